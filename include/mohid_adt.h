@@ -1,0 +1,188 @@
+/*
+ * mohid_adt.h -- C-ABI of the B200-native MOHID property transport step.
+ *
+ * This is the drop-in boundary for ModuleAdvectionDiffusion (reference paths are
+ * relative to /root/reference/Software):
+ *
+ *   AD  = MOHIDBase2/ModuleAdvectionDiffusion.F90
+ *   MF  = MOHIDBase1/ModuleFunctions.F90
+ *   MGD = MOHIDBase1/ModuleGlobalData.F90
+ *   MC  = MOHIDBase1/ModuleCuda.F90          (the reference's own ISO_C_BINDING precedent)
+ *   WP  = MOHIDWater/ModuleWaterProperties.F90
+ *
+ * Conventions (same as the reference's bind(C) interfaces, MC:49-121):
+ *   - every scalar is passed BY REFERENCE (Fortran default), arrays as the base address
+ *     of element (ILB,JLB,KLB) = (0,0,0);
+ *   - 3-D arrays are Fortran column-major (0:I+1, 0:J+1, 0:K+1), `i` contiguous, with an
+ *     explicit leading dimension ld_i >= I+2 (covers _PAD_MATRICES, MF:2832-2851);
+ *     2-D arrays are (0:I+1, 0:J+1) with the same ld_i;
+ *   - `real` is fp64 (compile_mohid.sh:185,209), masks are int32, Fortran logicals are
+ *     converted to int32 0/1 by the shim before the call;
+ *   - every function returns an int status: 0 = SUCCESS_ (MGD:181); non-zero = failure,
+ *     message available through mohid_adt_last_error().  The library never exit()s and has
+ *     NO CPU fallback: without a usable CUDA device every compute entry point fails.
+ */
+#ifndef MOHID_ADT_H
+#define MOHID_ADT_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes (MGD:180-199 style) ------------------------------------------- */
+#define MOHID_ADT_SUCCESS          0
+#define MOHID_ADT_ERR_UNKNOWN    (-99)  /* UNKNOWN_ */
+#define MOHID_ADT_ERR_HANDLE       9    /* IDLE_ERR_ analogue: bad / dead handle */
+#define MOHID_ADT_ERR_ARG         20    /* invalid argument (reference would `stop`) */
+#define MOHID_ADT_ERR_UNSUPPORTED 21    /* option exists in the reference, not on the GPU path */
+#define MOHID_ADT_ERR_CUDA        30    /* CUDA runtime failure (no device, OOM, launch error) */
+#define MOHID_ADT_ERR_STATE       31    /* call order violated (e.g. advect before set_step) */
+
+/* ---- numerical option ids (MGD:1810-1812, MGD:1831-1832, AD:152-158) -------------- */
+enum { MOHID_UpwindOrder1 = 1, MOHID_UpwindOrder2 = 2, MOHID_UpwindOrder3 = 3,
+       MOHID_P2_TVD = 4, MOHID_CentralDif = 5, MOHID_LeapFrog = 6 };
+enum { MOHID_MinMod = 1, MOHID_VanLeer = 2, MOHID_Muscl = 3, MOHID_SuperBee = 4, MOHID_PDM = 5 };
+enum { MOHID_BC_None = 0,              /* ReferenceProp not associated -> State%OpenBoundary OFF (AD:5816-5830) */
+       MOHID_BC_MassConservation = 1, MOHID_BC_ImposedValue = 2, MOHID_BC_NullGradient = 4,
+       MOHID_BC_SubModel = 5, MOHID_BC_Orlanski = 6, MOHID_BC_MassConservNullGrad = 7,
+       MOHID_BC_CyclicBoundary = 8 };
+#define MOHID_NULL_REAL   (-9.9e15)    /* MGD:143 */
+#define MOHID_FILL_INT    (-9999999)   /* MGD:131 FillValueInt */
+#define MOHID_DischUniform 5           /* MGD:1006 */
+
+/* T_Size3D (MGD:2041-2052, CudaWrapper/CuWrapperBinding.h:14-22) */
+typedef struct mohid_adt_size3d {
+    int ILB, IUB, JLB, JUB, KLB, KUB;
+} mohid_adt_size3d;
+
+/*
+ * Per-property argument block = the scalar dummy arguments of AdvectionDiffusion
+ * (AD:1108-1147) in the order the caller passes them (WP:14776-14822).
+ * Logical dummies are int 0/1.
+ */
+typedef struct mohid_adt_params {
+    double Schmidt_H;              /* AD:1110 */
+    double SchmidtCoef_V;
+    double SchmidtBackground_V;
+    int    AdvMethodH;             /* MOHID_UpwindOrder1 .. MOHID_LeapFrog */
+    int    TVDLimitationH;         /* MOHID_MinMod .. MOHID_PDM */
+    int    AdvMethodV;
+    int    TVDLimitationV;
+    int    Upwind2H;               /* logical */
+    int    Upwind2V;               /* logical */
+    double VolumeRelMax;
+    double DTProp;                 /* seconds */
+    double ImpExp_AdvV;            /* exactly 0 (explicit) or 1 (implicit), AD:3124 */
+    double ImpExp_DifV;            /* theta in [0,1] */
+    double ImpExp_AdvXX;           /* 0 explicit / 1 implicit, AD:4525 */
+    double ImpExp_AdvYY;
+    double ImpExp_DifH;            /* must be 0 (AD:1340-1343) */
+    int    NullDif;                /* logical */
+    int    BoundaryCondition;      /* MOHID_BC_*; MOHID_BC_None when ReferenceProp is absent */
+    double DecayTime;              /* seconds */
+    int    NoAdvFlux;              /* logical; needs NoFluxU/V/W (set_noflux) */
+    int    NoDifFlux;              /* logical */
+    int    reserved0;
+    int    reserved1;
+} mohid_adt_params;
+
+/* Instance-level flags = StartAdvectionDiffusion arguments (AD:400-411) */
+typedef struct mohid_adt_options {
+    int Vertical1D;                /* logical */
+    int XZFlow;                    /* logical */
+    int Docycle_method;            /* MM:641-643, default 1 */
+    int device;                    /* CUDA device ordinal, -1 = current device */
+    int max_properties;            /* upper bound of nprop in one batch (device buffers sized for it) */
+    int reserved[3];
+} mohid_adt_options;
+
+/* ---------------------------------------------------------------------------------- */
+/* Lifetime: replaces StartAdvectionDiffusion (AD:400-533) / KillAdvectionDiffusion     */
+/* (AD:5849-6010); the handle plays the role of ObjCudaID (CudaThomas/Thomas.cu:6-21).  */
+int mohid_adt_create(int *handle, const mohid_adt_size3d *size, const mohid_adt_size3d *worksize,
+                     const int *ld_i, const mohid_adt_options *opt);
+int mohid_adt_destroy(int *handle);
+
+/* Horizontal metrics / 2-D maps fetched by AdvectionDiffusion on every call (AD:1353-1384):
+ * GetHorizontalGrid DUX,DVY,DZX,DZY (fp64 2-D), GetGeometryKFloor Z (int 2-D),
+ * GetBoundaries BoundaryPoints2D (int 2-D).  Call once, or again when they change. */
+int mohid_adt_set_grid2d(const int *handle, const double *DUX, const double *DVY,
+                         const double *DZX, const double *DZY,
+                         const int *KFloorZ, const int *BoundaryPoints2D);
+
+/* Per-time-step shared inputs = array dummies of AdvectionDiffusion that are common to all
+ * properties of a step (AD:1132-1141) plus the Geometry getters (AD:1386-1401).
+ * HOST pointers; copied to the device inside the call.  SmallDepths may be NULL
+ * (SmallDepthsPresent = .false., AD:1297-1302); it is int32 0/1 (0:I+1,0:J+1). */
+int mohid_adt_set_step(const int *handle,
+                       const double *Wflux_X, const double *Wflux_Y, const double *Wflux_Z,
+                       const double *VolumeZOld, const double *VolumeZ,
+                       const double *Visc_H, const double *Diff_V,
+                       const double *DWZ, const double *DZZ,
+                       const double *AreaU, const double *AreaV,
+                       const int *OpenPoints3D, const int *LandPoints3D, const int *WaterPoints3D,
+                       const int *ComputeFacesU3D, const int *ComputeFacesV3D,
+                       const int *ComputeFacesW3D, const int *SmallDepths);
+
+/* SetDischarges / UnSetDischarges (AD:978-1095).  n_cells = sum(DischnCells). */
+int mohid_adt_set_discharges(const int *handle, const int *DischNumber, const int *n_cells,
+                             const double *DischFlow, const double *DischConc,
+                             const int *DischI, const int *DischJ, const int *DischK,
+                             const int *DischKmin, const int *DischKmax,
+                             const int *DischVert, const int *IgnoreDisch,
+                             const int *DischnCells, const int *ByPass,
+                             const double *DischConcMF);
+int mohid_adt_unset_discharges(const int *handle);
+
+/* The batched replacement of the per-property AdvectionDiffusion call loop
+ * (WP:14603-15143 -> AD:1108): advances `nprop` properties one transport step.
+ * prop[n] / reference_prop[n] are HOST arrays (0:I+1,0:J+1,0:K+1); prop[n] is updated
+ * in place exactly like PROP (MF:4101-4105); reference_prop may be NULL or hold NULL
+ * entries (ReferenceProp not associated).  All properties of one batch must share
+ * DTProp, the advection methods / limiters and VolumeRelMax (they are read FromFile,
+ * WP:9580-9632); Schmidt numbers, theta, BC and DecayTime are per property. */
+int mohid_adt_advect_batch(const int *handle, const int *nprop,
+                           double *const *prop, const double *const *reference_prop,
+                           const mohid_adt_params *params);
+
+/* ---- device-resident variants (benchmarks, device-side callers) ------------------- */
+/* Copy properties host->device / device->host without stepping. */
+int mohid_adt_upload_props(const int *handle, const int *nprop, const double *const *prop,
+                           const double *const *reference_prop);
+int mohid_adt_download_props(const int *handle, const int *nprop, double *const *prop);
+/* Advance the device-resident properties `nsteps` transport steps with the current
+ * set_step inputs; no host<->device traffic.  Includes the per-step coefficient pass. */
+int mohid_adt_advect_device(const int *handle, const int *nprop, const mohid_adt_params *params,
+                            const int *nsteps);
+/* Raw device pointer of property n (current buffer) and its leading dimension / plane
+ * stride in elements: element (i,j,k) is at ptr[i + ld*(j + nj*k)]. */
+int mohid_adt_prop_device_ptr(const int *handle, const int *n, void **dptr, int *ld, int *nj, int *nk);
+
+/* ---- halo exchange support for the j-slab decomposition (replaces               ---- */
+/* ---- ReceiveSendProperities3DMPIr8, HG:8479-8658)                                ---- */
+/* Pack `width` j-columns starting at j0 of all nprop device-resident properties into a
+ * contiguous DEVICE buffer (nprop * nk * width * ld doubles) / scatter them back. */
+int mohid_adt_pack_columns(const int *handle, const int *nprop, const int *j0, const int *width,
+                           void *device_buffer);
+int mohid_adt_unpack_columns(const int *handle, const int *nprop, const int *j0, const int *width,
+                             const void *device_buffer);
+/* Use the caller's CUDA stream (cudaStream_t passed as void*) for all work of this handle. */
+int mohid_adt_set_stream(const int *handle, void *cuda_stream);
+
+/* ---- diagnostics ------------------------------------------------------------------ */
+/* Copies the last error message of the handle (or of the library when handle is NULL). */
+int mohid_adt_last_error(const int *handle, char *buf, const int *buflen);
+/* counters[0] = kernels launched since create, [1] = zero-pivot rows seen by the column
+ * solver in the last batch (MF:4092-4098 leaves W,G stale; the GPU path counts them),
+ * [2] = mask-consistency violations found by set_step, [3] = bytes of device memory held. */
+int mohid_adt_get_counters(const int *handle, long long *counters, const int *n);
+/* Average device time in ms of the main transport kernel over the launches since the
+ * last call (CUDA events on the handle's stream) and the number of launches averaged. */
+int mohid_adt_kernel_time_ms(const int *handle, double *ms, int *launches);
+/* Library version / build info string. */
+int mohid_adt_version(char *buf, const int *buflen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOHID_ADT_H */

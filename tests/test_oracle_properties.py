@@ -1,0 +1,133 @@
+"""Self-consistency of the CPU oracle: the reference ships no golden
+vectors for this path, so the restatement is pinned by properties the scheme must have."""
+import numpy as np
+import pytest
+
+from mohid_b200.synthetic import make_case, default_params
+from helpers import oracle_for, NULL_REAL, water_mask
+
+CONFIGS = [  # (method_h, lim_h, method_v, lim_v, impexp_advv)
+    (1, 4, 1, 4, 1.0), (2, 4, 1, 4, 1.0), (3, 4, 3, 4, 0.0), (4, 1, 4, 1, 1.0), (4, 2, 4, 2, 1.0),
+    (4, 3, 4, 3, 0.0), (4, 4, 4, 4, 1.0), (4, 5, 4, 5, 1.0), (5, 4, 5, 4, 1.0),
+]
+
+
+def const_field(s, value):
+    p = np.where(s["LandPoints3D"] == 1, NULL_REAL, value)
+    p[0] = p[-1] = 0
+    p[:, 0] = p[:, -1] = 0
+    p[:, :, 0] = p[:, :, -1] = 0
+    return np.ascontiguousarray(p)
+
+
+@pytest.mark.parametrize("cfg", CONFIGS)
+def test_constant_field_preserved(oracle_lib, cfg):
+    """Continuity-consistent fluxes + MassConservation boundary with Ref = const keep a constant."""
+    mh, lh, mv, lv, adv_v = cfg
+    case = make_case(40, 36, 8, nprop=1, stepped_bottom=True)
+    o, g, s, props, refs = oracle_for(case)
+    p = const_field(s, 7.0)
+    ref = np.full_like(p, 7.0)
+    for step in range(3):
+        o.now += 30.0
+        o.advection_diffusion(p, default_params(mh, lh, mv, lv, bc=1, impexp_advv=adv_v), ref)
+    w = water_mask(s)
+    assert np.abs(p[w] - 7.0).max() < 1e-12
+    assert np.all(p[s["LandPoints3D"] == 1] == NULL_REAL)          # land: exactly null_real (AD:1753)
+    assert np.all(p[-1] == 0.0)                                    # PROP(:,:,KUB+1) = G(KUB+1) = 0
+
+
+@pytest.mark.parametrize("cfg", [(1, 4, 1, 4, 1.0), (4, 4, 4, 4, 1.0), (4, 4, 4, 4, 0.0), (2, 4, 1, 4, 1.0)])
+@pytest.mark.parametrize("theta", [1.0, 0.5])
+def test_mass_conserved_in_closed_basin(oracle_lib, cfg, theta):
+    mh, lh, mv, lv, adv_v = cfg
+    case = make_case(36, 32, 10, nprop=1, closed=True, volume_change=0.0)
+    o, g, s, props, refs = oracle_for(case)
+    p = props[0]
+    w = s["OpenPoints3D"] == 1
+    m0 = float((p[w] * s["VolumeZ"][w]).sum())
+    for step in range(5):
+        o.now += 30.0
+        o.advection_diffusion(p, default_params(mh, lh, mv, lv, impexp_advv=adv_v, theta_difv=theta))
+    m1 = float((p[w] * s["VolumeZ"][w]).sum())
+    assert abs(m1 - m0) / abs(m0) < 1e-12
+
+
+def test_upwind_is_monotone(oracle_lib):
+    case = make_case(36, 32, 10, nprop=1, closed=True, volume_change=0.0)
+    o, g, s, props, refs = oracle_for(case)
+    p = props[0]
+    w = s["OpenPoints3D"] == 1
+    lo, hi = p[w].min(), p[w].max()
+    for step in range(10):
+        o.now += 30.0
+        o.advection_diffusion(p, default_params(1, 4, 1, 4))
+        assert p[w].min() >= lo - 1e-12 and p[w].max() <= hi + 1e-12
+
+
+def test_optimize_path_matches_plain_path(oracle_lib):
+    """The Optimize code path (AD:5241-5245, MF:10642) only changes rounding order (quirk A.4-5)."""
+    case = make_case(40, 36, 12, nprop=3, stepped_bottom=True)
+    o1, g, s, props1, refs = oracle_for(case)
+    o2, _, _, props2, _ = oracle_for(case)
+    params = [default_params(4, 4, 4, 4, bc=4) for _ in range(3)]
+    for step in range(5):
+        o1.advect_batch(props1, params, refs, force_optimize=0)
+        o2.advect_batch(props2, params, refs, force_optimize=1)
+    w = water_mask(s)
+    for a, b in zip(props1, props2):
+        assert np.abs(a[w] - b[w]).max() / np.abs(a[w]).max() < 1e-12
+        assert np.array_equal(a == NULL_REAL, b == NULL_REAL)
+
+
+def test_batch_decides_optimize_like_the_caller(oracle_lib):
+    """WP:14580-14598: >= 2 properties, all P2_TVD + SuperBee, equal Schmidt_H -> Optimize."""
+    case = make_case(24, 20, 6, nprop=2)
+    o1, g, s, p1, refs = oracle_for(case)
+    o2, _, _, p2, _ = oracle_for(case)
+    params = [default_params(4, 4, 4, 4) for _ in range(2)]
+    o1.advect_batch(p1, params)                       # decides Optimize = True
+    o2.advect_batch(p2, params, force_optimize=1)
+    assert all(np.array_equal(a, b) for a, b in zip(p1, p2))
+
+
+def test_dry_columns_and_closed_cells_untouched(oracle_lib):
+    case = make_case(40, 36, 8, nprop=1)
+    o, g, s, props, refs = oracle_for(case)
+    p = props[0]
+    p0 = p.copy()
+    o.now += 30.0
+    o.advection_diffusion(p, default_params(4, 4, 4, 4))
+    water_col = s["WaterPoints3D"][case.K] == 1               # (nj, ld)
+    # columns with WaterPoints(i,j,KUB) /= 1 are not touched by the solver (MF:4086)
+    assert np.array_equal(p[:, ~water_col], p0[:, ~water_col])
+    # closed water cells (the lake cell) keep their concentration (AD:4003-4006)
+    closed = (s["WaterPoints3D"] == 1) & (s["OpenPoints3D"] == 0)
+    assert closed.any()
+    assert np.array_equal(p[closed], p0[closed])
+
+
+def test_reference_stop_conditions(oracle_lib):
+    case = make_case(16, 16, 4, nprop=1)
+    o, g, s, props, refs = oracle_for(case)
+    with pytest.raises(RuntimeError, match="ERR200"):          # implicit vertical + QUICK (AD:1234-1237)
+        o.advection_diffusion(props[0], default_params(1, 4, 2, 4, impexp_advv=1.0))
+    bad = default_params(1, 4, 1, 4)
+    bad["ImpExp_DifH"] = 1.0
+    with pytest.raises(RuntimeError, match="ERR02"):           # AD:1340-1343
+        o.advection_diffusion(props[0], bad)
+    bad = default_params(1, 4, 1, 4)
+    bad["ImpExp_AdvV"] = 0.5
+    with pytest.raises(RuntimeError, match="VerticalAdvection"):   # AD:3124
+        o.advection_diffusion(props[0], bad)
+
+
+def test_openmp_threads_do_not_change_results(oracle_lib):
+    case = make_case(40, 36, 8, nprop=2)
+    o1, g, s, p1, refs = oracle_for(case, nthreads=1)
+    o4, _, _, p4, _ = oracle_for(case, nthreads=4)
+    params = [default_params(4, 4, 4, 4, bc=7) for _ in range(2)]
+    for _ in range(3):
+        o1.advect_batch(p1, params, refs)
+        o4.advect_batch(p4, params, refs)
+    assert all(np.array_equal(a, b) for a, b in zip(p1, p4))
