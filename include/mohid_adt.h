@@ -158,6 +158,22 @@ int mohid_adt_advect_device(const int *handle, const int *nprop, const mohid_adt
  * stride in elements: element (i,j,k) is at ptr[i + ld*(j + nj*k)]. */
 int mohid_adt_prop_device_ptr(const int *handle, const int *n, void **dptr, int *ld, int *nj, int *nk);
 
+/* Every array pointer accepted above may be a host pointer (the Fortran caller) or, under CUDA
+ * unified virtual addressing, a device pointer (device-side producers, the benchmark generator):
+ * copies use cudaMemcpyDefault. */
+/* Wait for all work queued on the handle's stream. */
+int mohid_adt_synchronize(const int *handle);
+/* After writing a property in place through mohid_adt_prop_device_ptr: make the twin ping-pong
+ * buffer identical (halos, dry columns and closed cells are never rewritten by the kernels). */
+int mohid_adt_sync_prop_buffers(const int *handle, const int *nprop);
+/* Device pointer of the ReferenceProp mirror of property n (allocated on first use). */
+int mohid_adt_set_reference_device(const int *handle, const int *n, void **dptr);
+/* Device pointer of a staged input: which = 0..10 the fp64 arrays of set_step in argument order,
+ * 11..16 its int32 masks, 17 SmallDepths, 20..25 the set_grid2d arrays. */
+int mohid_adt_step_input_device_ptr(const int *handle, const int *which, void **dptr, int *ld, int *nj, int *nk);
+/* Declare the staged inputs valid after filling them through the pointers above. */
+int mohid_adt_mark_step_resident(const int *handle, const int *small_depths_present);
+
 /* ---- halo exchange support for the j-slab decomposition (replaces               ---- */
 /* ---- ReceiveSendProperities3DMPIr8, HG:8479-8658)                                ---- */
 /* Pack `width` j-columns starting at j0 of all nprop device-resident properties into a

@@ -1,0 +1,252 @@
+"""Host-side mirror of MOHID's ``ModuleAdvectionDiffusion`` public interface on top of the C-ABI.
+
+Reference interface (``/root/reference/Software/MOHIDBase2/ModuleAdvectionDiffusion.F90``):
+``StartAdvectionDiffusion`` (:400), ``AdvectionDiffusion`` (:1108), ``SetDischarges`` (:978),
+``UnSetDischarges`` (:1040), ``GetBoundaryConditionList`` (:855), ``KillAdvectionDiffusion`` (:5849).
+The module-level functions below keep those names, argument names and error behaviour (the
+reference's ``stop '... ERRnn'`` becomes :class:`mohid_b200.capi.AdtError` carrying the same text);
+:class:`TransportStep` is the batched / device-resident form the new path adds: all properties
+of a time step advance in one call (the loop of ``ModuleWaterProperties.F90:14603-15143``).
+
+Arrays are Fortran-ordered ``(0:I+1, 0:J+1, 0:K+1)`` with ``i`` contiguous, i.e. numpy / torch
+arrays of shape ``(K+2, J+2, ld)``; they may live in host memory or (torch CUDA tensors) on the
+device.  Everything is computed by the CUDA library; nothing here does arithmetic.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import capi
+from .capi import AdtError, Options, Params, Size3D, check, make_params
+
+# GetBoundaryConditionList (AD:855-893)
+MassConservation_, ImposedValue_, NullGradient_, SubModel_, Orlanski_, MassConservNullGrad_, CyclicBoundary_ = \
+    1, 2, 4, 5, 6, 7, 8
+UpwindOrder1, UpwindOrder2, UpwindOrder3, P2_TVD, CentralDif, LeapFrog = 1, 2, 3, 4, 5, 6
+MinMod, VanLeer, Muscl, SuperBee, PDM = 1, 2, 3, 4, 5
+SUCCESS_ = 0
+
+STEP_F64 = ["Wflux_X", "Wflux_Y", "Wflux_Z", "VolumeZOld", "VolumeZ", "Visc_H", "Diff_V", "DWZ", "DZZ", "AreaU", "AreaV"]
+STEP_I32 = ["OpenPoints3D", "LandPoints3D", "WaterPoints3D", "ComputeFacesU3D", "ComputeFacesV3D", "ComputeFacesW3D"]
+
+
+def _is_torch(a) -> bool:
+    return type(a).__module__.startswith("torch")
+
+
+def _ptr(a, dtype: str, nelem: int, name: str) -> C.c_void_p:
+    """Base address of a contiguous host (numpy / torch CPU) or device (torch CUDA) array."""
+    if a is None:
+        return C.c_void_p(None)
+    if _is_torch(a):
+        import torch
+        want = {"f8": torch.float64, "i4": torch.int32}[dtype]
+        if a.dtype != want or not a.is_contiguous() or a.numel() != nelem:
+            raise ValueError(f"{name}: expected contiguous {want} with {nelem} elements, got {a.dtype} {tuple(a.shape)}")
+        return C.c_void_p(a.data_ptr())
+    a_np = np.asarray(a)
+    want = np.dtype(dtype)
+    if a_np.dtype != want or not a_np.flags["C_CONTIGUOUS"] or a_np.size != nelem:
+        raise ValueError(f"{name}: expected C-contiguous {want} with {nelem} elements, got {a_np.dtype} {a_np.shape}")
+    return C.c_void_p(a_np.ctypes.data)
+
+
+class TransportStep:
+    """One ``ObjAdvectionDiffusion`` instance bound to one GPU."""
+
+    def __init__(self, I: int, J: int, K: int, ld: Optional[int] = None, *, vertical1d: bool = False,
+                 xzflow: bool = False, docycle_method: int = 1, device: int = -1, max_properties: int = 0):
+        self.lib = capi.load()
+        self.I, self.J, self.K = int(I), int(J), int(K)
+        self.ld = int(ld) if ld else self.I + 2
+        self.n2 = self.ld * (self.J + 2)
+        self.n3 = self.n2 * (self.K + 2)
+        self.h = C.c_int(0)
+        size = Size3D(0, I + 1, 0, J + 1, 0, K + 1)
+        work = Size3D(1, I, 1, J, 1, K)
+        opt = Options(int(vertical1d), int(xzflow), int(docycle_method), int(device), int(max_properties))
+        check(self.lib.mohid_adt_create(C.byref(self.h), C.byref(size), C.byref(work), C.byref(C.c_int(self.ld)),
+                                        C.byref(opt)))
+        self.nprop = 0
+
+    # ---- lifetime -------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.mohid_adt_destroy(C.byref(self.h))
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        check(rc, self.h)
+
+    # ---- inputs ---------------------------------------------------------------------
+    def set_grid2d(self, DUX, DVY, DZX, DZY, KFloorZ, BoundaryPoints2D):
+        """GetHorizontalGrid / GetGeometryKFloor / GetBoundaries results (AD:1353-1384)."""
+        self._check(self.lib.mohid_adt_set_grid2d(
+            C.byref(self.h), _ptr(DUX, "f8", self.n2, "DUX"), _ptr(DVY, "f8", self.n2, "DVY"),
+            _ptr(DZX, "f8", self.n2, "DZX"), _ptr(DZY, "f8", self.n2, "DZY"),
+            _ptr(KFloorZ, "i4", self.n2, "KFloorZ"), _ptr(BoundaryPoints2D, "i4", self.n2, "BoundaryPoints2D")))
+
+    def set_step(self, step: Dict[str, object], SmallDepths=None):
+        """Per-time-step shared inputs (AD:1132-1141, 1386-1401)."""
+        args = [_ptr(step[k], "f8", self.n3, k) for k in STEP_F64] + [_ptr(step[k], "i4", self.n3, k) for k in STEP_I32]
+        args.append(_ptr(SmallDepths, "i4", self.n2, "SmallDepths"))
+        self._check(self.lib.mohid_adt_set_step(C.byref(self.h), *args))
+
+    # ---- the batched transport step -------------------------------------------------
+    def _params(self, params: Sequence[dict]):
+        return (Params * len(params))(*[make_params(p) for p in params])
+
+    def _ptr_array(self, arrs: Optional[Sequence], name: str):
+        if arrs is None:
+            return None
+        n = len(arrs)
+        return (C.c_void_p * n)(*[_ptr(a, "f8", self.n3, f"{name}[{i}]") for i, a in enumerate(arrs)])
+
+    def advect_batch(self, props: Sequence, params: Sequence[dict], refs: Optional[Sequence] = None):
+        """Advance all ``props`` (updated in place, like PROP in the reference) one transport step."""
+        n = len(props)
+        self._check(self.lib.mohid_adt_advect_batch(C.byref(self.h), C.byref(C.c_int(n)),
+                                                    self._ptr_array(props, "prop"), self._ptr_array(refs, "ref"),
+                                                    self._params(params)))
+        self.nprop = n
+
+    def upload(self, props: Sequence, refs: Optional[Sequence] = None):
+        n = len(props)
+        self._check(self.lib.mohid_adt_upload_props(C.byref(self.h), C.byref(C.c_int(n)),
+                                                    self._ptr_array(props, "prop"), self._ptr_array(refs, "ref")))
+        self.nprop = n
+
+    def advect_device(self, params: Sequence[dict], nsteps: int = 1):
+        """Advance the device-resident properties ``nsteps`` steps; no host<->device traffic."""
+        self._check(self.lib.mohid_adt_advect_device(C.byref(self.h), C.byref(C.c_int(len(params))),
+                                                     self._params(params), C.byref(C.c_int(int(nsteps)))))
+
+    def download(self, props: Sequence):
+        self._check(self.lib.mohid_adt_download_props(C.byref(self.h), C.byref(C.c_int(len(props))),
+                                                      self._ptr_array(props, "prop")))
+
+    # ---- halo staging for the j-slab decomposition ----------------------------------
+    def pack_columns(self, nprop: int, j0: int, width: int, device_buffer):
+        self._check(self.lib.mohid_adt_pack_columns(C.byref(self.h), C.byref(C.c_int(nprop)), C.byref(C.c_int(j0)),
+                                                    C.byref(C.c_int(width)), C.c_void_p(device_buffer.data_ptr())))
+
+    def unpack_columns(self, nprop: int, j0: int, width: int, device_buffer):
+        self._check(self.lib.mohid_adt_unpack_columns(C.byref(self.h), C.byref(C.c_int(nprop)), C.byref(C.c_int(j0)),
+                                                      C.byref(C.c_int(width)), C.c_void_p(device_buffer.data_ptr())))
+
+    def halo_buffer_elems(self, nprop: int, width: int) -> int:
+        return nprop * (self.K + 2) * width * self.device_ld
+
+    @property
+    def device_ld(self) -> int:
+        return ((self.I + 2 + 15) // 16) * 16
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self.lib.mohid_adt_set_stream(C.byref(self.h), C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        self._check(self.lib.mohid_adt_synchronize(C.byref(self.h)))
+
+    # ---- diagnostics ----------------------------------------------------------------
+    def counters(self) -> Dict[str, int]:
+        v = (C.c_longlong * 4)()
+        self._check(self.lib.mohid_adt_get_counters(C.byref(self.h), v, C.byref(C.c_int(4))))
+        return dict(launches=v[0], zero_pivots=v[1], mask_violations=v[2], device_bytes=v[3])
+
+    def kernel_time_ms(self):
+        ms, n = C.c_double(0), C.c_int(0)
+        self._check(self.lib.mohid_adt_kernel_time_ms(C.byref(self.h), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+
+# =======================================================================================
+# Module-level mirror of the reference's procedural interface (integer instance IDs,
+# STAT-style returns).  One call of AdvectionDiffusion() = the reference's per-property call.
+# =======================================================================================
+_instances: Dict[int, TransportStep] = {}
+_next_id = 1
+
+
+def StartAdvectionDiffusion(I: int, J: int, K: int, *, Vertical1D: bool = False, XZFlow: bool = False,
+                            Docycle_method: int = 1, ld: Optional[int] = None, device: int = -1) -> int:
+    """AD:400-533.  The reference takes Geometry/Map/Grid/Time object IDs; here the sizes they carry."""
+    global _next_id
+    obj = TransportStep(I, J, K, ld, vertical1d=Vertical1D, xzflow=XZFlow, docycle_method=Docycle_method, device=device)
+    ident = _next_id
+    _next_id += 1
+    _instances[ident] = obj
+    return ident
+
+
+def _get(AdvectionDiffusionID: int) -> TransportStep:
+    try:
+        return _instances[AdvectionDiffusionID]
+    except KeyError:
+        raise AdtError(9, "AdvectionDiffusion - ModuleAdvectionDiffusion - instance not ready (IDLE_ERR_)")
+
+
+def GetTransportStep(AdvectionDiffusionID: int) -> TransportStep:
+    return _get(AdvectionDiffusionID)
+
+
+def AdvectionDiffusion(AdvectionDiffusionID: int, PROP, schmidt_H, SchmidtCoef_V, SchmidtBackground_V, AdvMethodH,
+                       TVDLimitationH, AdvMethodV, TVDLimitationV, Upwind2H, Upwind2V, VolumeRelMax,
+                       AdvectionNudging, AdvectionNudgingCells, DTProp, ImpExp_AdvV, ImpExp_DifV, ImpExp_AdvXX,
+                       ImpExp_AdvYY, ImpExp_DifH, NullDif, Wflux_X, Wflux_Y, Wflux_Z, VolumeZOld, VolumeZ,
+                       OpenPoints3D, LandPoints3D, ComputeFacesU3D, ComputeFacesV3D, ComputeFacesW3D, Visc_H, Diff_V,
+                       *, DWZ, DZZ, AreaU, AreaV, CellFluxes: bool = False, WaterPoints3D=None, ReferenceProp=None,
+                       BoundaryCondition: Optional[int] = None, DecayTime: float = 0.0, SmallDepths=None,
+                       NoAdvFlux: bool = False, NoDifFlux: bool = False) -> int:
+    """Same dummy arguments as AD:1108-1147 (DWZ, DZZ, AreaU, AreaV are what the reference fetches from
+    ModuleGeometry inside the call, AD:1386-1401).  ``PROP`` is updated in place.  Returns STAT."""
+    obj = _get(AdvectionDiffusionID)
+    if AdvectionNudging:
+        raise AdtError(21, "AdvectionNudging (AD:1989-2068) is not available on the GPU path")
+    if CellFluxes:
+        raise AdtError(21, "CellFluxes outputs (AD:3356-3954) are not available on the GPU path")
+    if WaterPoints3D is None:
+        raise AdtError(20, "WaterPoints3D is required (THOMASZ_NewType2 reads it, MF:4086)")
+    step = dict(Wflux_X=Wflux_X, Wflux_Y=Wflux_Y, Wflux_Z=Wflux_Z, VolumeZOld=VolumeZOld, VolumeZ=VolumeZ,
+                Visc_H=Visc_H, Diff_V=Diff_V, DWZ=DWZ, DZZ=DZZ, AreaU=AreaU, AreaV=AreaV, OpenPoints3D=OpenPoints3D,
+                LandPoints3D=LandPoints3D, WaterPoints3D=WaterPoints3D, ComputeFacesU3D=ComputeFacesU3D,
+                ComputeFacesV3D=ComputeFacesV3D, ComputeFacesW3D=ComputeFacesW3D)
+    obj.set_step(step, SmallDepths)
+    p = dict(Schmidt_H=schmidt_H, SchmidtCoef_V=SchmidtCoef_V, SchmidtBackground_V=SchmidtBackground_V,
+             AdvMethodH=AdvMethodH, TVDLimitationH=TVDLimitationH, AdvMethodV=AdvMethodV, TVDLimitationV=TVDLimitationV,
+             Upwind2H=int(Upwind2H), Upwind2V=int(Upwind2V), VolumeRelMax=VolumeRelMax, DTProp=DTProp,
+             ImpExp_AdvV=ImpExp_AdvV, ImpExp_DifV=ImpExp_DifV, ImpExp_AdvXX=ImpExp_AdvXX, ImpExp_AdvYY=ImpExp_AdvYY,
+             ImpExp_DifH=ImpExp_DifH, NullDif=int(NullDif),
+             BoundaryCondition=(BoundaryCondition if BoundaryCondition is not None else 0), DecayTime=DecayTime,
+             NoAdvFlux=int(NoAdvFlux), NoDifFlux=int(NoDifFlux))
+    obj.advect_batch([PROP], [p], [ReferenceProp] if ReferenceProp is not None else None)
+    return SUCCESS_
+
+
+def SetGrid2D(AdvectionDiffusionID: int, DUX, DVY, DZX, DZY, KFloorZ, BoundaryPoints2D) -> int:
+    """What AD:1353-1384 fetches from ModuleHorizontalGrid / ModuleGeometry / ModuleHorizontalMap."""
+    _get(AdvectionDiffusionID).set_grid2d(DUX, DVY, DZX, DZY, KFloorZ, BoundaryPoints2D)
+    return SUCCESS_
+
+
+def GetBoundaryConditionList() -> Dict[str, int]:
+    """AD:855-893."""
+    return dict(MassConservation=MassConservation_, ImposedValue=ImposedValue_, NullGradient=NullGradient_,
+                SubModel=SubModel_, Orlanski=Orlanski_, MassConservNullGrad=MassConservNullGrad_,
+                CyclicBoundary=CyclicBoundary_)
+
+
+def KillAdvectionDiffusion(AdvectionDiffusionID: int) -> int:
+    """AD:5849-6010."""
+    obj = _instances.pop(AdvectionDiffusionID, None)
+    if obj is None:
+        return 9
+    obj.close()
+    return SUCCESS_

@@ -1,0 +1,730 @@
+// =====================================================================================
+//  adt_api.cu -- C-ABI (include/mohid_adt.h) of the B200-native MOHID transport step.
+//  Host side: handle registry, device mirrors of the interface arrays, parameter validation
+//  (the reference's `stop` conditions become error codes), launches of the kernels in
+//  adt_kernels.cuh.  There is no CPU fallback: every compute entry point needs a CUDA device.
+// =====================================================================================
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "adt_kernels.cuh"
+
+using namespace adt;
+
+namespace {
+
+struct Handle {
+    int id = 0, dev = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    mohid_adt_options opt{};
+    int I = 0, J = 0, K = 0, ni = 0, nj = 0, nk = 0, ld_h = 0, ld = 0;
+    long n2 = 0, n3 = 0;
+    int maxprop = 0;
+    // 2-D
+    double *DUX = nullptr, *DVY = nullptr, *DZX = nullptr, *DZY = nullptr, *rdx = nullptr, *rdy = nullptr;
+    int *KFloorZ = nullptr, *Bnd = nullptr, *SmallDepths = nullptr;
+    bool have_small = false;
+    int *bnd_cols = nullptr;
+    int n_bnd_cols = 0;
+    // raw per-step inputs
+    double *raw_d[11] = {nullptr};
+    int *raw_i[6] = {nullptr};
+    // packed per-step coefficients (K1 outputs)
+    double *dtv = nullptr, *vr = nullptr, *dhu = nullptr, *dhv = nullptr, *dvz = nullptr, *rdz = nullptr;
+    uint8_t *mask = nullptr;
+    // properties: ping-pong pairs + reference fields
+    std::vector<double *> prop[2];
+    std::vector<double *> ref;
+    std::vector<int> cur;
+    std::vector<char> has_ref;
+    unsigned long long *d_zero_piv = nullptr;
+    bool have_grid = false, have_step = false;
+    long long launches = 0, bytes = 0, zero_piv_last = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;   // K2 timing
+    size_t ev_used = 0;
+    std::string err;
+    int smem_optin = 0, num_sms = 0;
+};
+
+std::mutex g_mu;
+std::map<int, Handle *> g_h;
+int g_next = 1;
+std::string g_err = "";
+
+int fail(Handle *h, int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_err = buf;
+    return code;
+}
+
+#define CU(h, call)                                                                                     \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return fail(h, MOHID_ADT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                            \
+    } while (0)
+
+Handle *get(const int *handle) {
+    if (!handle) return nullptr;
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_h.find(*handle);
+    return it == g_h.end() ? nullptr : it->second;
+}
+
+template <typename T>
+int dalloc(Handle *h, T **p, size_t n) {
+    CU(h, cudaMalloc((void **)p, n * sizeof(T)));
+    h->bytes += (long long)(n * sizeof(T));
+    return 0;
+}
+
+// caller (ld_h) -> device mirror (ld) copy of a (rows x ni) array, element size es.  cudaMemcpyDefault:
+// the caller's arrays may live in host memory (the Fortran case) or, under UVA, in device memory.
+int h2d(Handle *h, void *dst, const void *src, size_t es, long rows) {
+    if (h->ld_h == h->ld) {
+        CU(h, cudaMemcpyAsync(dst, src, es * (size_t)h->ld * rows, cudaMemcpyDefault, h->stream));
+    } else {
+        CU(h, cudaMemcpy2DAsync(dst, es * h->ld, src, es * h->ld_h, es * std::min(h->ld, h->ld_h), rows,
+                                cudaMemcpyDefault, h->stream));
+    }
+    return 0;
+}
+int d2h(Handle *h, void *dst, const void *src, size_t es, long rows) {
+    if (h->ld_h == h->ld) {
+        CU(h, cudaMemcpyAsync(dst, src, es * (size_t)h->ld * rows, cudaMemcpyDefault, h->stream));
+    } else {
+        CU(h, cudaMemcpy2DAsync(dst, es * h->ld_h, src, es * h->ld, es * std::min(h->ld, h->ld_h), rows,
+                                cudaMemcpyDefault, h->stream));
+    }
+    return 0;
+}
+
+int ensure_props(Handle *h, int nprop, bool need_ref_any) {
+    if (nprop > NPMAX) return fail(h, MOHID_ADT_ERR_ARG, "nprop %d exceeds the batch limit %d", nprop, NPMAX);
+    while ((int)h->prop[0].size() < nprop) {
+        double *a = nullptr, *b = nullptr;
+        if (int rc = dalloc(h, &a, h->n3)) return rc;
+        if (int rc = dalloc(h, &b, h->n3)) return rc;
+        h->prop[0].push_back(a);
+        h->prop[1].push_back(b);
+        h->ref.push_back(nullptr);
+        h->cur.push_back(0);
+        h->has_ref.push_back(0);
+    }
+    (void)need_ref_any;
+    return 0;
+}
+
+void free_all(Handle *h) {
+    cudaSetDevice(h->dev);
+    auto F = [](void *p) { if (p) cudaFree(p); };
+    F(h->DUX); F(h->DVY); F(h->DZX); F(h->DZY); F(h->rdx); F(h->rdy); F(h->KFloorZ); F(h->Bnd); F(h->SmallDepths);
+    F(h->bnd_cols);
+    for (auto p : h->raw_d) F(p);
+    for (auto p : h->raw_i) F(p);
+    F(h->dtv); F(h->vr); F(h->dhu); F(h->dhv); F(h->dvz); F(h->rdz); F(h->mask);
+    for (int b = 0; b < 2; ++b) for (auto p : h->prop[b]) F(p);
+    for (auto p : h->ref) F(p);
+    F(h->d_zero_piv);
+    for (auto &e : h->ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+}
+
+struct Batch {          // validated view of one advect call
+    int nprop = 0;
+    bool optimize = false;
+    const mohid_adt_params *p = nullptr;
+};
+
+// The reference's argument checks (AD:1229-1237, 1340-1349, 3124, 4525; MF:10869-10873) plus the
+// limits of the GPU path.
+int validate(Handle *h, int nprop, const mohid_adt_params *p, Batch &b) {
+    if (nprop < 1) return fail(h, MOHID_ADT_ERR_ARG, "nprop must be >= 1");
+    if (nprop > NPMAX) return fail(h, MOHID_ADT_ERR_ARG, "nprop %d exceeds the batch limit %d", nprop, NPMAX);
+    const mohid_adt_params &f = p[0];
+    bool optimize = nprop >= 2 && !h->opt.Vertical1D;
+    for (int n = 0; n < nprop; ++n) {
+        const mohid_adt_params &q = p[n];
+        if (q.ImpExp_DifH != 0.0)
+            return fail(h, MOHID_ADT_ERR_ARG, "AdvectionDiffusion - ModuleAdvectionDiffusion - ERR02 (horizontal diffusion must be explicit)");
+        if (q.ImpExp_AdvXX == 1.0 && q.ImpExp_AdvYY == 1.0)
+            return fail(h, MOHID_ADT_ERR_ARG, "AdvectionDiffusion - ModuleAdvectionDiffusion - ERR03 (both horizontal directions implicit)");
+        if ((q.ImpExp_AdvXX == 1.0 || q.ImpExp_AdvYY == 1.0) &&
+            (q.AdvMethodH == MOHID_UpwindOrder2 || q.AdvMethodH == MOHID_UpwindOrder3))
+            return fail(h, MOHID_ADT_ERR_ARG, "AdvectionDiffusion - ModuleAdvectionDiffusion - ERR100");
+        if (q.ImpExp_AdvV == 1.0 && (q.AdvMethodV == MOHID_UpwindOrder2 || q.AdvMethodV == MOHID_UpwindOrder3))
+            return fail(h, MOHID_ADT_ERR_ARG, "AdvectionDiffusion - ModuleAdvectionDiffusion - ERR200");
+        if (q.ImpExp_AdvXX != 0.0 && q.ImpExp_AdvXX != 1.0)
+            return fail(h, MOHID_ADT_ERR_ARG, "sub. HorizontalAdvectionXX - ModuleAdvectionDiffusion - ERR01");
+        if (q.ImpExp_AdvYY != 0.0 && q.ImpExp_AdvYY != 1.0)
+            return fail(h, MOHID_ADT_ERR_ARG, "sub. HorizontalAdvectionYY - ModuleAdvectionDiffusion - ERR01");
+        if (q.ImpExp_AdvV != 0.0 && q.ImpExp_AdvV != 1.0)
+            return fail(h, MOHID_ADT_ERR_ARG, "sub. VerticalAdvection - ModuleAdvectionDiffusion - ERR01");
+        if (q.ImpExp_AdvXX == 1.0 || q.ImpExp_AdvYY == 1.0)
+            return fail(h, MOHID_ADT_ERR_UNSUPPORTED,
+                        "horizontally implicit advection (AD:4167-4258) is not available on the GPU path");
+        for (int m : {q.AdvMethodH, q.AdvMethodV})
+            if (m < MOHID_UpwindOrder1 || m > MOHID_LeapFrog)
+                return fail(h, MOHID_ADT_ERR_ARG, "This method is not valid to compute Advection1D");
+        if (q.AdvMethodH == MOHID_P2_TVD && (q.TVDLimitationH < MOHID_MinMod || q.TVDLimitationH > MOHID_PDM))
+            return fail(h, MOHID_ADT_ERR_ARG, "This TVD Limitation option is not valid to compute Advection1D");
+        if (q.AdvMethodV == MOHID_P2_TVD && (q.TVDLimitationV < MOHID_MinMod || q.TVDLimitationV > MOHID_PDM))
+            return fail(h, MOHID_ADT_ERR_ARG, "This TVD Limitation option is not valid to compute Advection1D");
+        // near-boundary faces of methods 2/3/4 stop the reference unless Upwind2 is set (MF:10869-10873)
+        if ((q.AdvMethodH >= MOHID_UpwindOrder2 && q.AdvMethodH <= MOHID_P2_TVD && !q.Upwind2H) ||
+            (q.AdvMethodV >= MOHID_UpwindOrder2 && q.AdvMethodV <= MOHID_P2_TVD && !q.Upwind2V))
+            return fail(h, MOHID_ADT_ERR_ARG, "This method is not valid to compute Advection1D (Upwind2 must be set, WP:9638-9652)");
+        if (q.BoundaryCondition == MOHID_BC_Orlanski)
+            return fail(h, MOHID_ADT_ERR_UNSUPPORTED, "Orlanski boundary (AD:5504-5570) is not available on the GPU path");
+        const int bc = q.BoundaryCondition;
+        if (bc != MOHID_BC_None && bc != MOHID_BC_MassConservation && bc != MOHID_BC_ImposedValue &&
+            bc != MOHID_BC_NullGradient && bc != MOHID_BC_SubModel && bc != MOHID_BC_MassConservNullGrad &&
+            bc != MOHID_BC_CyclicBoundary)
+            return fail(h, MOHID_ADT_ERR_ARG, "Set_Internal_State - ModuleAdvectionDiffusion - ERR01");
+        if (q.NoAdvFlux || q.NoDifFlux)
+            return fail(h, MOHID_ADT_ERR_UNSUPPORTED, "NoAdvFlux / NoDifFlux cells are not available on the GPU path");
+        if (!(q.DTProp > 0.0)) return fail(h, MOHID_ADT_ERR_ARG, "DTProp must be positive");
+        // one kernel variant per batch: these keywords are read FromFile in the reference (WP:9580-9632)
+        if (q.AdvMethodH != f.AdvMethodH || q.AdvMethodV != f.AdvMethodV || q.TVDLimitationH != f.TVDLimitationH ||
+            q.TVDLimitationV != f.TVDLimitationV || q.VolumeRelMax != f.VolumeRelMax || q.DTProp != f.DTProp ||
+            q.Upwind2H != f.Upwind2H || q.Upwind2V != f.Upwind2V)
+            return fail(h, MOHID_ADT_ERR_ARG,
+                        "properties of one batch must share DTProp, advection methods, limiters and VolumeRelMax");
+        // OptimizeFlag (WP:14580-14598)
+        if (q.Schmidt_H != f.Schmidt_H || q.NullDif || q.AdvMethodH != MOHID_P2_TVD || q.AdvMethodV != MOHID_P2_TVD ||
+            q.TVDLimitationH != MOHID_SuperBee || q.TVDLimitationV != MOHID_SuperBee)
+            optimize = false;
+    }
+    b.nprop = nprop; b.optimize = optimize; b.p = p;
+    return 0;
+}
+
+int launch_coef(Handle *h, const mohid_adt_params &q, bool geom, bool diff) {
+    CoefArgs a{};
+    a.ni = h->ni; a.nj = h->nj; a.nk = h->nk; a.ld = h->ld; a.I = h->I; a.J = h->J; a.K = h->K;
+    a.dt = q.DTProp; a.schmidt_h = q.Schmidt_H; a.schmidt_coef_v = q.SchmidtCoef_V; a.schmidt_bg_v = q.SchmidtBackground_V;
+    a.nulldif = q.NullDif;
+    a.Wflux_X = h->raw_d[0]; a.Wflux_Y = h->raw_d[1]; a.Wflux_Z = h->raw_d[2]; a.VolumeZOld = h->raw_d[3];
+    a.VolumeZ = h->raw_d[4]; a.Visc_H = h->raw_d[5]; a.Diff_V = h->raw_d[6]; a.DWZ = h->raw_d[7]; a.DZZ = h->raw_d[8];
+    a.AreaU = h->raw_d[9]; a.AreaV = h->raw_d[10];
+    a.Open = h->raw_i[0]; a.Land = h->raw_i[1]; a.Water = h->raw_i[2]; a.CFU = h->raw_i[3]; a.CFV = h->raw_i[4];
+    a.CFW = h->raw_i[5]; a.SmallDepths = h->have_small ? h->SmallDepths : nullptr;
+    a.DUX = h->DUX; a.DVY = h->DVY; a.DZX = h->DZX; a.DZY = h->DZY; a.Bnd = h->Bnd;
+    a.dtv = h->dtv; a.vr = h->vr; a.dhu = h->dhu; a.dhv = h->dhv; a.dvz = h->dvz; a.rdz = h->rdz; a.mask = h->mask;
+    a.do_geom = geom; a.do_diff = diff;
+    const int threads = 256;
+    const long want = (h->n3 + threads - 1) / threads;
+    const int blocks = (int)std::min<long>(want, (long)h->num_sms * 32);
+    adt_coef_kernel<<<blocks, threads, 0, h->stream>>>(a);
+    CU(h, cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+int pick_wpb(Handle *h, int nprop) {
+    // W,G of the column solve: 2 * K * 32 doubles per warp; at most 12 warps (register budget)
+    const size_t per_warp = (size_t)2 * h->K * 32 * sizeof(double);
+    int wpb = (int)std::min<size_t>(12, (size_t)h->smem_optin / per_warp);
+    if (wpb >= nprop && nprop >= 6) wpb = nprop;                 // one block = all properties of a strip
+    else if (nprop < 6 && wpb >= 2 * nprop) wpb = (wpb / nprop) * nprop;
+    return wpb;
+}
+
+int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool timed) {
+    StepArgs s{};
+    s.I = h->I; s.J = h->J; s.K = h->K; s.ld = h->ld; s.nj = h->nj; s.sk = (long)h->ld * h->nj;
+    s.nprop = (int)idx.size();
+    s.ntile_i = (h->I + 30) / 31;
+    s.j_begin = 1; s.j_count = h->J;
+    const mohid_adt_params &f = b.p[idx[0]];
+    s.method_h = f.AdvMethodH; s.limiter_h = f.TVDLimitationH; s.method_v = f.AdvMethodV; s.limiter_v = f.TVDLimitationV;
+    s.upwind2_h = f.Upwind2H; s.upwind2_v = f.Upwind2V;
+    s.vertical1d = h->opt.Vertical1D; s.xzflow = h->opt.XZFlow;
+    s.vrelmax = f.VolumeRelMax; s.dt = f.DTProp;
+    s.qx = h->raw_d[0]; s.qy = h->raw_d[1]; s.qz = h->raw_d[2];
+    s.dtv = h->dtv; s.vr = h->vr; s.dhu = h->dhu; s.dhv = h->dhv; s.dvz = h->dvz; s.rdz = h->rdz; s.mask = h->mask;
+    s.rdx = h->rdx; s.rdy = h->rdy; s.DUX = h->DUX; s.DVY = h->DVY; s.DWZ = h->raw_d[7];
+    s.VolumeZ = h->raw_d[4]; s.VolumeZOld = h->raw_d[3];
+    s.zero_pivots = h->d_zero_piv;
+    for (int m = 0; m < s.nprop; ++m) {
+        const int n = idx[m];
+        const mohid_adt_params &q = b.p[n];
+        PropArgs &pa = s.p[m];
+        pa.pin = h->prop[h->cur[n]][n];
+        pa.pout = h->prop[h->cur[n] ^ 1][n];
+        pa.pref = h->has_ref[n] ? h->ref[n] : nullptr;
+        pa.theta_difv = (b.optimize && q.ImpExp_DifV > 0.0) ? 1.0 : q.ImpExp_DifV;     // AD:2797 vs AD:2741-2760
+        pa.tdec = 1.0 / (1.0 + q.DecayTime / q.DTProp);
+        pa.bc = h->has_ref[n] ? q.BoundaryCondition : MOHID_BC_None;                    // AD:5816-5830
+        pa.advv_implicit = (q.ImpExp_AdvV == 1.0) ? 1 : 0;
+    }
+    const int wpb = pick_wpb(h, s.nprop);
+    if (wpb < 1)
+        return fail(h, MOHID_ADT_ERR_UNSUPPORTED, "K = %d layers need more shared memory than one SM has", h->K);
+    const size_t smem = (size_t)2 * h->K * wpb * 32 * sizeof(double);
+    const long nunits = (long)s.nprop * s.ntile_i * h->J;
+    const long blocks = (nunits + wpb - 1) / wpb;
+    if (blocks > 2147483647L) return fail(h, MOHID_ADT_ERR_ARG, "grid too large");
+    CU(h, cudaFuncSetAttribute(adt_transport_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (timed) {
+        if (h->ev_used == h->ev.size()) {
+            cudaEvent_t a, c;
+            CU(h, cudaEventCreate(&a));
+            CU(h, cudaEventCreate(&c));
+            h->ev.emplace_back(a, c);
+        }
+        e0 = h->ev[h->ev_used].first; e1 = h->ev[h->ev_used].second;
+        h->ev_used++;
+        CU(h, cudaEventRecord(e0, h->stream));
+    }
+    adt_transport_kernel<<<(unsigned)blocks, wpb * 32, smem, h->stream>>>(s);
+    CU(h, cudaGetLastError());
+    if (timed) CU(h, cudaEventRecord(e1, h->stream));
+    h->launches++;
+
+    // post-solve boundary passes (AD:1874-1882)
+    for (int m = 0; m < s.nprop; ++m) {
+        const int n = idx[m];
+        const int bc = b.p[n].BoundaryCondition;
+        if ((bc == MOHID_BC_NullGradient || (bc == MOHID_BC_CyclicBoundary && h->has_ref[n])) && h->n_bnd_cols > 0) {
+            BndArgs ba{};
+            ba.I = h->I; ba.J = h->J; ba.K = h->K; ba.ld = h->ld; ba.nj = h->nj; ba.ncols = h->n_bnd_cols;
+            ba.sk = s.sk; ba.cols = h->bnd_cols; ba.kfloor = h->KFloorZ; ba.mask = h->mask;
+            ba.prop = s.p[m].pout; ba.pref = s.p[m].pref;
+            const long tot = (long)h->n_bnd_cols * h->K;
+            if (bc == MOHID_BC_NullGradient) {
+                adt_nullgrad_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(ba);
+                h->launches++;
+            } else {
+                adt_cyclic_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(ba, 0);
+                const long t1 = (long)std::max(h->I - 2, 0) * h->K, t2 = (long)std::max(h->J - 2, 0) * h->K;
+                if (t1 > 0) adt_cyclic_kernel<<<(unsigned)((t1 + 255) / 256), 256, 0, h->stream>>>(ba, 1);
+                if (t2 > 0) adt_cyclic_kernel<<<(unsigned)((t2 + 255) / 256), 256, 0, h->stream>>>(ba, 2);
+                h->launches += 3;
+            }
+            CU(h, cudaGetLastError());
+        }
+    }
+    for (int n : idx) h->cur[n] ^= 1;
+    return 0;
+}
+
+// One transport step of all properties of the batch: per-step coefficient pass + fused kernel,
+// one (K1 diff part + K2) group per distinct set of Schmidt numbers.
+int step_once(Handle *h, const Batch &b) {
+    std::vector<char> done(b.nprop, 0);
+    bool geom_done = false;
+    for (int n = 0; n < b.nprop; ++n) {
+        if (done[n]) continue;
+        std::vector<int> idx;
+        for (int m = n; m < b.nprop; ++m) {
+            if (done[m]) continue;
+            const auto &x = b.p[n], &y = b.p[m];
+            if (x.Schmidt_H == y.Schmidt_H && x.SchmidtCoef_V == y.SchmidtCoef_V &&
+                x.SchmidtBackground_V == y.SchmidtBackground_V && x.NullDif == y.NullDif) {
+                idx.push_back(m);
+                done[m] = 1;
+            }
+        }
+        if (int rc = launch_coef(h, b.p[n], !geom_done, true)) return rc;
+        geom_done = true;
+        if (int rc = launch_step(h, b, idx, true)) return rc;
+    }
+    return 0;
+}
+
+}  // namespace
+
+// =======================================================================================
+extern "C" {
+
+int mohid_adt_version(char *buf, const int *buflen) {
+    if (!buf || !buflen || *buflen <= 0) return MOHID_ADT_ERR_ARG;
+    snprintf(buf, (size_t)*buflen, "mohid_adt 0.1 (sm_100a, CUDA %d)", CUDART_VERSION);
+    return 0;
+}
+
+int mohid_adt_last_error(const int *handle, char *buf, const int *buflen) {
+    if (!buf || !buflen || *buflen <= 0) return MOHID_ADT_ERR_ARG;
+    Handle *h = get(handle);
+    std::lock_guard<std::mutex> lk(g_mu);
+    snprintf(buf, (size_t)*buflen, "%s", h ? h->err.c_str() : g_err.c_str());
+    return 0;
+}
+
+int mohid_adt_create(int *handle, const mohid_adt_size3d *size, const mohid_adt_size3d *worksize, const int *ld_i,
+                     const mohid_adt_options *opt) {
+    if (!handle || !size || !worksize) return fail(nullptr, MOHID_ADT_ERR_ARG, "null argument");
+    if (size->ILB != 0 || size->JLB != 0 || size->KLB != 0 || worksize->ILB != 1 || worksize->JLB != 1 ||
+        worksize->KLB != 1 || size->IUB != worksize->IUB + 1 || size->JUB != worksize->JUB + 1 ||
+        size->KUB != worksize->KUB + 1)
+        return fail(nullptr, MOHID_ADT_ERR_ARG, "Size must be (0:I+1,0:J+1,0:K+1) and WorkSize (1:I,1:J,1:K)");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, MOHID_ADT_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                    cudaGetErrorString(e));
+    Handle *h = new Handle();
+    if (opt) h->opt = *opt;
+    if (h->opt.Docycle_method == 0) h->opt.Docycle_method = 1;
+    int dev = h->opt.device;
+    if (dev < 0) cudaGetDevice(&dev);
+    if (dev >= ndev) { delete h; return fail(nullptr, MOHID_ADT_ERR_ARG, "device %d does not exist", dev); }
+    h->dev = dev;
+    CU(nullptr, cudaSetDevice(dev));
+    h->I = worksize->IUB; h->J = worksize->JUB; h->K = worksize->KUB;
+    h->ni = h->I + 2; h->nj = h->J + 2; h->nk = h->K + 2;
+    h->ld_h = (ld_i && *ld_i > 0) ? *ld_i : h->ni;
+    if (h->ld_h < h->ni) { delete h; return fail(nullptr, MOHID_ADT_ERR_ARG, "ld_i smaller than I+2"); }
+    h->ld = ((h->ni + 15) / 16) * 16;                // 128-byte aligned rows on the device
+    h->n2 = (long)h->ld * h->nj;
+    h->n3 = h->n2 * h->nk;
+    h->maxprop = h->opt.max_properties > 0 ? h->opt.max_properties : 0;
+    cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete h;
+        return fail(nullptr, MOHID_ADT_ERR_CUDA, "cudaStreamCreate failed");
+    }
+    h->own_stream = true;
+    int rc = 0;
+    rc |= dalloc(h, &h->DUX, h->n2); rc |= dalloc(h, &h->DVY, h->n2); rc |= dalloc(h, &h->DZX, h->n2);
+    rc |= dalloc(h, &h->DZY, h->n2); rc |= dalloc(h, &h->rdx, h->n2); rc |= dalloc(h, &h->rdy, h->n2);
+    rc |= dalloc(h, &h->KFloorZ, h->n2); rc |= dalloc(h, &h->Bnd, h->n2); rc |= dalloc(h, &h->SmallDepths, h->n2);
+    for (auto &p : h->raw_d) rc |= dalloc(h, &p, h->n3);
+    for (auto &p : h->raw_i) rc |= dalloc(h, &p, h->n3);
+    rc |= dalloc(h, &h->dtv, h->n3); rc |= dalloc(h, &h->vr, h->n3); rc |= dalloc(h, &h->dhu, h->n3);
+    rc |= dalloc(h, &h->dhv, h->n3); rc |= dalloc(h, &h->dvz, h->n3); rc |= dalloc(h, &h->rdz, h->n3);
+    rc |= dalloc(h, &h->mask, h->n3);
+    rc |= dalloc(h, &h->d_zero_piv, 1);
+    if (rc) { std::string m = h->err; free_all(h); delete h; return fail(nullptr, MOHID_ADT_ERR_CUDA, "%s", m.c_str()); }
+    // padded columns must read as zeros
+    for (auto p : h->raw_d) cudaMemsetAsync(p, 0, h->n3 * sizeof(double), h->stream);
+    for (auto p : h->raw_i) cudaMemsetAsync(p, 0, h->n3 * sizeof(int), h->stream);
+    for (auto p : {h->DUX, h->DVY, h->DZX, h->DZY}) cudaMemsetAsync(p, 0, h->n2 * sizeof(double), h->stream);
+    for (auto p : {h->KFloorZ, h->Bnd, h->SmallDepths}) cudaMemsetAsync(p, 0, h->n2 * sizeof(int), h->stream);
+    cudaMemsetAsync(h->d_zero_piv, 0, sizeof(unsigned long long), h->stream);
+    CU(h, cudaStreamSynchronize(h->stream));
+    std::lock_guard<std::mutex> lk(g_mu);
+    h->id = g_next++;
+    g_h[h->id] = h;
+    *handle = h->id;
+    return 0;
+}
+
+int mohid_adt_destroy(int *handle) {
+    if (!handle) return MOHID_ADT_ERR_ARG;
+    Handle *h = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_h.find(*handle);
+        if (it == g_h.end()) return MOHID_ADT_ERR_HANDLE;
+        h = it->second;
+        g_h.erase(it);
+    }
+    cudaSetDevice(h->dev);
+    cudaStreamSynchronize(h->stream);
+    free_all(h);
+    delete h;
+    *handle = 0;
+    return 0;
+}
+
+int mohid_adt_set_stream(const int *handle, void *cuda_stream) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    CU(h, cudaSetDevice(h->dev));
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    h->stream = (cudaStream_t)cuda_stream;
+    h->own_stream = false;
+    return 0;
+}
+
+int mohid_adt_set_grid2d(const int *handle, const double *DUX, const double *DVY, const double *DZX,
+                         const double *DZY, const int *KFloorZ, const int *BoundaryPoints2D) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    if (!DUX || !DVY || !DZX || !DZY || !KFloorZ || !BoundaryPoints2D) return fail(h, MOHID_ADT_ERR_ARG, "null array");
+    CU(h, cudaSetDevice(h->dev));
+    int rc = 0;
+    rc |= h2d(h, h->DUX, DUX, 8, h->nj); rc |= h2d(h, h->DVY, DVY, 8, h->nj);
+    rc |= h2d(h, h->DZX, DZX, 8, h->nj); rc |= h2d(h, h->DZY, DZY, 8, h->nj);
+    rc |= h2d(h, h->KFloorZ, KFloorZ, 4, h->nj); rc |= h2d(h, h->Bnd, BoundaryPoints2D, 4, h->nj);
+    if (rc) return rc;
+    adt_grid2d_kernel<<<std::max(1, (int)std::min<long>((h->n2 + 255) / 256, 4096)), 256, 0, h->stream>>>(
+        h->ni, h->nj, h->ld, h->DUX, h->DVY, h->rdx, h->rdy);
+    CU(h, cudaGetLastError());
+    h->launches++;
+    // compact list of boundary columns for the post-solve passes (built from the device mirror so the
+    // caller's array may be a host or a device pointer)
+    std::vector<int> bhost((size_t)h->n2);
+    CU(h, cudaMemcpyAsync(bhost.data(), h->Bnd, h->n2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    std::vector<int> cols;
+    for (int j = 1; j <= h->J; ++j)
+        for (int i = 1; i <= h->I; ++i)
+            if (bhost[(size_t)i + (size_t)h->ld * j] == 1) { cols.push_back(i); cols.push_back(j); }
+    if (h->bnd_cols) { cudaFree(h->bnd_cols); h->bnd_cols = nullptr; }
+    h->n_bnd_cols = (int)(cols.size() / 2);
+    if (h->n_bnd_cols) {
+        if (int r = dalloc(h, &h->bnd_cols, cols.size())) return r;
+        CU(h, cudaMemcpyAsync(h->bnd_cols, cols.data(), cols.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    }
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->have_grid = true;
+    return 0;
+}
+
+int mohid_adt_set_step(const int *handle, const double *Wflux_X, const double *Wflux_Y, const double *Wflux_Z,
+                       const double *VolumeZOld, const double *VolumeZ, const double *Visc_H, const double *Diff_V,
+                       const double *DWZ, const double *DZZ, const double *AreaU, const double *AreaV,
+                       const int *OpenPoints3D, const int *LandPoints3D, const int *WaterPoints3D,
+                       const int *ComputeFacesU3D, const int *ComputeFacesV3D, const int *ComputeFacesW3D,
+                       const int *SmallDepths) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    CU(h, cudaSetDevice(h->dev));
+    const double *d[11] = {Wflux_X, Wflux_Y, Wflux_Z, VolumeZOld, VolumeZ, Visc_H, Diff_V, DWZ, DZZ, AreaU, AreaV};
+    const int *m[6] = {OpenPoints3D, LandPoints3D, WaterPoints3D, ComputeFacesU3D, ComputeFacesV3D, ComputeFacesW3D};
+    for (auto p : d) if (!p) return fail(h, MOHID_ADT_ERR_ARG, "null array");
+    for (auto p : m) if (!p) return fail(h, MOHID_ADT_ERR_ARG, "null mask (WaterPoints3D is required: THOMASZ_NewType2 reads it, MF:4086)");
+    const long rows = (long)h->nj * h->nk;
+    for (int a = 0; a < 11; ++a) if (int rc = h2d(h, h->raw_d[a], d[a], 8, rows)) return rc;
+    for (int a = 0; a < 6; ++a) if (int rc = h2d(h, h->raw_i[a], m[a], 4, rows)) return rc;
+    h->have_small = SmallDepths != nullptr;
+    if (SmallDepths) if (int rc = h2d(h, h->SmallDepths, SmallDepths, 4, h->nj)) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));     // the host arrays are only borrowed for the call (AD:2229-2349)
+    h->have_step = true;
+    return 0;
+}
+
+int mohid_adt_step_input_device_ptr(const int *handle, const int *which, void **dptr, int *ld, int *nj, int *nk) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    if (!which || !dptr) return fail(h, MOHID_ADT_ERR_ARG, "null argument");
+    const int w = *which;
+    if (w >= 0 && w < 11) *dptr = h->raw_d[w];
+    else if (w >= 11 && w < 17) *dptr = h->raw_i[w - 11];
+    else if (w == 17) *dptr = h->SmallDepths;
+    else if (w >= 20 && w < 26) {
+        void *g[6] = {h->DUX, h->DVY, h->DZX, h->DZY, h->KFloorZ, h->Bnd};
+        *dptr = g[w - 20];
+    } else return fail(h, MOHID_ADT_ERR_ARG, "unknown array id %d", w);
+    if (ld) *ld = h->ld;
+    if (nj) *nj = h->nj;
+    if (nk) *nk = h->nk;
+    return 0;
+}
+
+int mohid_adt_mark_step_resident(const int *handle, const int *small_depths_present) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    h->have_step = true;
+    h->have_small = small_depths_present && *small_depths_present;
+    return 0;
+}
+
+int mohid_adt_set_discharges(const int *handle, const int *, const int *, const double *, const double *,
+                             const int *, const int *, const int *, const int *, const int *, const int *,
+                             const int *, const int *, const int *, const double *) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    return fail(h, MOHID_ADT_ERR_UNSUPPORTED, "discharges (AD:4025-4128) are not available on the GPU path yet");
+}
+int mohid_adt_unset_discharges(const int *handle) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    return 0;
+}
+
+int mohid_adt_upload_props(const int *handle, const int *nprop, const double *const *prop,
+                           const double *const *reference_prop) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    if (!nprop || !prop) return fail(h, MOHID_ADT_ERR_ARG, "null argument");
+    CU(h, cudaSetDevice(h->dev));
+    if (int rc = ensure_props(h, *nprop, reference_prop != nullptr)) return rc;
+    const long rows = (long)h->nj * h->nk;
+    for (int n = 0; n < *nprop; ++n) {
+        if (!prop[n]) return fail(h, MOHID_ADT_ERR_ARG, "prop[%d] is null", n);
+        double *a = h->prop[0][n], *b = h->prop[1][n];
+        if (h->ld != h->ld_h) CU(h, cudaMemsetAsync(a, 0, h->n3 * sizeof(double), h->stream));
+        if (int rc = h2d(h, a, prop[n], 8, rows)) return rc;
+        // both ping-pong buffers start identical: halos, dry columns and closed cells are never rewritten
+        CU(h, cudaMemcpyAsync(b, a, h->n3 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        h->cur[n] = 0;
+        const double *r = reference_prop ? reference_prop[n] : nullptr;
+        h->has_ref[n] = r != nullptr;
+        if (r) {
+            if (!h->ref[n]) {
+                if (int rc = dalloc(h, &h->ref[n], h->n3)) return rc;
+                CU(h, cudaMemsetAsync(h->ref[n], 0, h->n3 * sizeof(double), h->stream));
+            }
+            if (int rc = h2d(h, h->ref[n], r, 8, rows)) return rc;
+        }
+    }
+    CU(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int mohid_adt_download_props(const int *handle, const int *nprop, double *const *prop) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    if (!nprop || !prop) return fail(h, MOHID_ADT_ERR_ARG, "null argument");
+    if (*nprop > (int)h->prop[0].size()) return fail(h, MOHID_ADT_ERR_STATE, "properties were never uploaded");
+    CU(h, cudaSetDevice(h->dev));
+    const long rows = (long)h->nj * h->nk;
+    for (int n = 0; n < *nprop; ++n)
+        if (int rc = d2h(h, prop[n], h->prop[h->cur[n]][n], 8, rows)) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int mohid_adt_advect_device(const int *handle, const int *nprop, const mohid_adt_params *params, const int *nsteps) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    if (!nprop || !params) return fail(h, MOHID_ADT_ERR_ARG, "null argument");
+    if (!h->have_grid || !h->have_step) return fail(h, MOHID_ADT_ERR_STATE, "set_grid2d / set_step must precede advect");
+    if (*nprop > (int)h->prop[0].size()) return fail(h, MOHID_ADT_ERR_STATE, "properties were never uploaded");
+    CU(h, cudaSetDevice(h->dev));
+    Batch b;
+    if (int rc = validate(h, *nprop, params, b)) return rc;
+    const int ns = nsteps ? *nsteps : 1;
+    for (int s = 0; s < ns; ++s)
+        if (int rc = step_once(h, b)) return rc;
+    return 0;
+}
+
+int mohid_adt_advect_batch(const int *handle, const int *nprop, double *const *prop,
+                           const double *const *reference_prop, const mohid_adt_params *params) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    if (!nprop || !prop || !params) return fail(h, MOHID_ADT_ERR_ARG, "null argument");
+    if (!h->have_grid || !h->have_step) return fail(h, MOHID_ADT_ERR_STATE, "set_grid2d / set_step must precede advect");
+    Batch b;
+    if (int rc = validate(h, *nprop, params, b)) return rc;        // fail before moving any data
+    if (int rc = mohid_adt_upload_props(handle, nprop, prop, reference_prop)) return rc;
+    const int one = 1;
+    if (int rc = mohid_adt_advect_device(handle, nprop, params, &one)) return rc;
+    return mohid_adt_download_props(handle, nprop, prop);
+}
+
+int mohid_adt_prop_device_ptr(const int *handle, const int *n, void **dptr, int *ld, int *nj, int *nk) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    if (!n || !dptr) return fail(h, MOHID_ADT_ERR_ARG, "null argument");
+    CU(h, cudaSetDevice(h->dev));
+    if (int rc = ensure_props(h, *n + 1, false)) return rc;
+    *dptr = h->prop[h->cur[*n]][*n];
+    if (ld) *ld = h->ld;
+    if (nj) *nj = h->nj;
+    if (nk) *nk = h->nk;
+    return 0;
+}
+
+// after writing a property through mohid_adt_prop_device_ptr: make the twin buffer identical
+int mohid_adt_sync_prop_buffers(const int *handle, const int *nprop) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    CU(h, cudaSetDevice(h->dev));
+    for (int n = 0; n < *nprop && n < (int)h->prop[0].size(); ++n)
+        CU(h, cudaMemcpyAsync(h->prop[h->cur[n] ^ 1][n], h->prop[h->cur[n]][n], h->n3 * sizeof(double),
+                              cudaMemcpyDeviceToDevice, h->stream));
+    return 0;
+}
+
+int mohid_adt_set_reference_device(const int *handle, const int *n, void **dptr) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    CU(h, cudaSetDevice(h->dev));
+    if (int rc = ensure_props(h, *n + 1, true)) return rc;
+    if (!h->ref[*n]) {
+        if (int rc = dalloc(h, &h->ref[*n], h->n3)) return rc;
+        CU(h, cudaMemsetAsync(h->ref[*n], 0, h->n3 * sizeof(double), h->stream));
+    }
+    h->has_ref[*n] = 1;
+    *dptr = h->ref[*n];
+    return 0;
+}
+
+static int pack_common(const int *handle, const int *nprop, const int *j0, const int *width, double *buf, int unpack) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    if (!nprop || !j0 || !width || !buf) return fail(h, MOHID_ADT_ERR_ARG, "null argument");
+    if (*nprop > (int)h->prop[0].size() || *nprop > NPMAX) return fail(h, MOHID_ADT_ERR_STATE, "properties were never uploaded");
+    if (*j0 < 0 || *width < 1 || *j0 + *width > h->nj) return fail(h, MOHID_ADT_ERR_ARG, "column range out of bounds");
+    CU(h, cudaSetDevice(h->dev));
+    PackArgs a{};
+    a.ld = h->ld; a.nj = h->nj; a.nk = h->nk; a.nprop = *nprop; a.j0 = *j0; a.width = *width; a.sk = (long)h->ld * h->nj;
+    for (int n = 0; n < *nprop; ++n) a.prop[n] = h->prop[h->cur[n]][n];
+    const long tot = (long)a.nk * a.width * a.ld * a.nprop;
+    const int blocks = (int)std::min<long>((tot + 255) / 256, (long)h->num_sms * 16);
+    adt_pack_columns_kernel<<<blocks, 256, 0, h->stream>>>(a, buf, unpack);
+    CU(h, cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+int mohid_adt_pack_columns(const int *handle, const int *nprop, const int *j0, const int *width, void *device_buffer) {
+    return pack_common(handle, nprop, j0, width, (double *)device_buffer, 0);
+}
+int mohid_adt_unpack_columns(const int *handle, const int *nprop, const int *j0, const int *width,
+                             const void *device_buffer) {
+    return pack_common(handle, nprop, j0, width, (double *)device_buffer, 1);
+}
+
+int mohid_adt_synchronize(const int *handle) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    CU(h, cudaSetDevice(h->dev));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int mohid_adt_get_counters(const int *handle, long long *counters, const int *n) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    if (!counters || !n) return fail(h, MOHID_ADT_ERR_ARG, "null argument");
+    CU(h, cudaSetDevice(h->dev));
+    CU(h, cudaStreamSynchronize(h->stream));
+    unsigned long long zp = 0;
+    CU(h, cudaMemcpy(&zp, h->d_zero_piv, sizeof zp, cudaMemcpyDeviceToHost));
+    long long v[4] = {h->launches, (long long)zp, 0, h->bytes};
+    for (int i = 0; i < *n && i < 4; ++i) counters[i] = v[i];
+    return 0;
+}
+
+int mohid_adt_kernel_time_ms(const int *handle, double *ms, int *launches) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    CU(h, cudaSetDevice(h->dev));
+    CU(h, cudaStreamSynchronize(h->stream));
+    double tot = 0.;
+    for (size_t i = 0; i < h->ev_used; ++i) {
+        float t = 0.f;
+        CU(h, cudaEventElapsedTime(&t, h->ev[i].first, h->ev[i].second));
+        tot += t;
+    }
+    if (ms) *ms = h->ev_used ? tot / (double)h->ev_used : 0.;
+    if (launches) *launches = (int)h->ev_used;
+    h->ev_used = 0;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,234 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle on identical seeded inputs.
+
+Bar (BASELINE.json north_star): masks / indices bit-exact (land = null_real exactly, dry columns
+and closed cells untouched, KUB+1 row zero), property fields within 1e-10 relative after 100 steps
+(fp64).  Per step the reformulated arithmetic (shared reciprocals) must stay below 1e-12.
+"""
+import numpy as np
+import pytest
+
+from mohid_b200.synthetic import make_case, default_params
+from helpers import oracle_for, rel_err, water_mask, NULL_REAL
+
+pytestmark = pytest.mark.gpu
+
+TOL_STEP = 1e-12      # relative, one step
+TOL_100 = 1e-10       # relative, 100 steps (north star)
+
+
+def gpu_for(case, g, s, **kw):
+    from mohid_b200.advection_diffusion import TransportStep
+    ts = TransportStep(case.I, case.J, case.K, case.ld, **kw)
+    ts.set_grid2d(**g)
+    ts.set_step(s)
+    return ts
+
+
+def compare(gpu, cpu, s, tol):
+    w = water_mask(s)
+    worst = 0.0
+    for a, b in zip(gpu, cpu):
+        assert np.array_equal(a == NULL_REAL, b == NULL_REAL)            # land pattern bit-exact
+        assert np.array_equal(a[~w], b[~w])                              # everything that is not water: bit-exact
+        assert np.array_equal(a[-1], b[-1])                              # KUB+1 row
+        worst = max(worst, rel_err(a, b, w))
+    assert worst <= tol, worst
+    return worst
+
+
+CONFIGS = [  # (method_h, lim_h, method_v, lim_v, impexp_advv, theta)
+    (1, 4, 1, 4, 1.0, 1.0), (1, 4, 1, 4, 0.0, 0.5), (2, 4, 1, 4, 1.0, 1.0), (3, 4, 3, 4, 0.0, 1.0),
+    (2, 4, 2, 4, 0.0, 0.0), (4, 1, 4, 1, 1.0, 1.0), (4, 2, 4, 2, 1.0, 1.0), (4, 3, 4, 3, 0.0, 1.0),
+    (4, 4, 4, 4, 1.0, 1.0), (4, 4, 4, 4, 0.0, 0.3), (4, 5, 4, 5, 1.0, 1.0), (5, 4, 5, 4, 1.0, 1.0),
+    (6, 4, 1, 4, 1.0, 1.0),
+]
+
+
+@pytest.mark.parametrize("cfg", CONFIGS)
+def test_single_property_all_schemes(oracle_lib, cfg):
+    mh, lh, mv, lv, adv_v, theta = cfg
+    case = make_case(70, 45, 9, nprop=1, stepped_bottom=True)
+    o, g, s, props, refs = oracle_for(case)
+    ts = gpu_for(case, g, s)
+    gpu, cpu = [props[0].copy()], [props[0].copy()]
+    prm = [default_params(mh, lh, mv, lv, impexp_advv=adv_v, theta_difv=theta)]
+    for _ in range(2):
+        ts.advect_batch(gpu, prm)
+        o.advect_batch(cpu, prm)
+    compare(gpu, cpu, s, 2 * TOL_STEP)
+    assert ts.counters()["zero_pivots"] == 0
+    ts.close()
+
+
+@pytest.mark.parametrize("bc", [0, 1, 2, 4, 5, 7, 8])
+def test_batched_tvd_with_boundary_conditions(oracle_lib, bc):
+    case = make_case(66, 40, 8, nprop=3)
+    o, g, s, props, refs = oracle_for(case)
+    ts = gpu_for(case, g, s)
+    gpu, cpu = [p.copy() for p in props], [p.copy() for p in props]
+    prm = [default_params(4, 4, 4, 4, bc=bc, decay_time=900.0) for _ in range(3)]
+    for _ in range(2):
+        ts.advect_batch(gpu, prm, refs)
+        o.advect_batch(cpu, prm, refs)       # Optimize path, decided like WP:14580-14598
+    compare(gpu, cpu, s, 2 * TOL_STEP)
+    ts.close()
+
+
+def test_mixed_boundary_conditions_and_schmidt_groups(oracle_lib):
+    """Coastal3D-like: T,S with NullGradient, a tracer with MassConservNullGrad and another Schmidt number."""
+    case = make_case(50, 38, 7, nprop=3)
+    o, g, s, props, refs = oracle_for(case)
+    ts = gpu_for(case, g, s)
+    gpu, cpu = [p.copy() for p in props], [p.copy() for p in props]
+    prm = [default_params(4, 4, 4, 4, bc=4), default_params(4, 4, 4, 4, bc=4),
+           default_params(4, 4, 4, 4, bc=7, schmidt_h=0.7)]
+    prm[2]["SchmidtCoef_V"] = 0.5
+    ts.advect_batch(gpu, prm, refs)
+    o.advect_batch(cpu, prm, refs)
+    compare(gpu, cpu, s, TOL_STEP)
+    ts.close()
+
+
+def test_hundred_steps_within_1e10(oracle_lib):
+    """North-star tolerance: <= 1e-10 relative after 100 steps on identical inputs."""
+    case = make_case(64, 48, 10, nprop=2)
+    o, g, s, props, refs = oracle_for(case)
+    ts = gpu_for(case, g, s)
+    prm = [default_params(4, 4, 4, 4, bc=1, decay_time=3600.0) for _ in range(2)]
+    cpu = [p.copy() for p in props]
+    ts.upload(props, refs)
+    for _ in range(100):
+        o.advect_batch(cpu, prm, refs)
+    ts.advect_device(prm, nsteps=100)
+    gpu = [np.empty_like(p) for p in props]
+    ts.download(gpu)
+    worst = compare(gpu, cpu, s, TOL_100)
+    print("100-step max relative difference:", worst)
+    ts.close()
+
+
+def test_upwind_100_steps(oracle_lib):
+    """Config C2 numerics (upwind + implicit vertical, 1 tracer)."""
+    case = make_case(64, 64, 10, nprop=1)
+    o, g, s, props, refs = oracle_for(case)
+    ts = gpu_for(case, g, s)
+    prm = [default_params(1, 4, 1, 4)]
+    cpu = [props[0].copy()]
+    ts.upload(props)
+    for _ in range(100):
+        o.advect_batch(cpu, prm)
+    ts.advect_device(prm, nsteps=100)
+    gpu = [np.empty_like(props[0])]
+    ts.download(gpu)
+    compare(gpu, cpu, s, TOL_100)
+    ts.close()
+
+
+def test_padded_leading_dimension_and_ragged_tiles(oracle_lib):
+    """_PAD_MATRICES-style ld > I+2, and I not a multiple of the 31-cell strip."""
+    for I, ld in [(31, 40), (32, 48), (61, 64), (95, 97)]:
+        case = make_case(I, 20, 5, nprop=2, ld=ld)
+        o, g, s, props, refs = oracle_for(case)
+        ts = gpu_for(case, g, s)
+        gpu, cpu = [p.copy() for p in props], [p.copy() for p in props]
+        prm = [default_params(4, 4, 4, 4) for _ in range(2)]
+        ts.advect_batch(gpu, prm)
+        o.advect_batch(cpu, prm)
+        compare(gpu, cpu, s, TOL_STEP)
+        ts.close()
+
+
+def test_two_dimensional_case(oracle_lib):
+    """K = 1: no vertical processes, the column solve degenerates to a division by E."""
+    case = make_case(40, 33, 1, nprop=1)
+    o, g, s, props, refs = oracle_for(case)
+    ts = gpu_for(case, g, s)
+    gpu, cpu = [props[0].copy()], [props[0].copy()]
+    prm = [default_params(4, 4, 1, 4)]
+    ts.advect_batch(gpu, prm)
+    o.advect_batch(cpu, prm)
+    compare(gpu, cpu, s, TOL_STEP)
+    ts.close()
+
+
+def test_small_depths_and_flags(oracle_lib):
+    case = make_case(40, 30, 6, nprop=1)
+    g_small = None
+    for kw in (dict(xzflow=True), dict(vertical1d=True), dict()):
+        o, g, s, props, refs = oracle_for(case, **kw)
+        ts = gpu_for(case, g, s, **kw)
+        small = np.zeros_like(g["KFloorZ"])
+        small[5:15, 5:20] = 1
+        o.set_step(s, small)
+        ts.set_step(s, small)
+        gpu, cpu = [props[0].copy()], [props[0].copy()]
+        prm = [default_params(1, 4, 1, 4)]
+        ts.advect_batch(gpu, prm)
+        o.advect_batch(cpu, prm)
+        compare(gpu, cpu, s, TOL_STEP)
+        ts.close()
+
+
+def test_device_resident_equals_host_path(oracle_lib):
+    case = make_case(45, 37, 6, nprop=2)
+    o, g, s, props, refs = oracle_for(case)
+    ts = gpu_for(case, g, s)
+    prm = [default_params(4, 4, 4, 4, bc=4) for _ in range(2)]
+    a = [p.copy() for p in props]
+    for _ in range(3):
+        ts.advect_batch(a, prm, refs)
+    ts.upload(props, refs)
+    ts.advect_device(prm, nsteps=3)
+    b = [np.empty_like(p) for p in props]
+    ts.download(b)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    ts.close()
+
+
+def test_reference_stop_conditions_become_errors(oracle_lib):
+    from mohid_b200.capi import AdtError
+    case = make_case(16, 16, 4, nprop=1)
+    o, g, s, props, refs = oracle_for(case)
+    ts = gpu_for(case, g, s)
+    p0 = props[0].copy()
+    with pytest.raises(AdtError, match="ERR200"):
+        ts.advect_batch([p0], [default_params(1, 4, 2, 4, impexp_advv=1.0)])
+    bad = default_params(1, 4, 1, 4); bad["ImpExp_DifH"] = 1.0
+    with pytest.raises(AdtError, match="ERR02"):
+        ts.advect_batch([p0], [bad])
+    bad = default_params(1, 4, 1, 4); bad["ImpExp_AdvV"] = 0.5
+    with pytest.raises(AdtError, match="VerticalAdvection"):
+        ts.advect_batch([p0], [bad])
+    bad = default_params(1, 4, 1, 4); bad["ImpExp_AdvXX"] = 1.0
+    with pytest.raises(AdtError) as e:
+        ts.advect_batch([p0], [bad])
+    assert e.value.code == 21                          # exists in the reference, not on the GPU path
+    assert np.array_equal(p0, props[0])                # nothing was touched
+    ts.close()
+
+
+def test_torch_cuda_inputs(oracle_lib):
+    """The same entry points accept device pointers (UVA): inputs generated on the GPU."""
+    import torch
+    from mohid_b200.advection_diffusion import TransportStep
+    case = make_case(48, 40, 6, nprop=2, device="cuda")
+    ts = TransportStep(case.I, case.J, case.K)
+    ts.set_grid2d(**case.grid2d)
+    ts.set_step(case.step)
+    ts.upload(case.props)
+    prm = [default_params(4, 4, 4, 4) for _ in range(2)]
+    ts.advect_device(prm, nsteps=2)
+    out = [torch.empty_like(p) for p in case.props]
+    ts.download(out)
+    torch.cuda.synchronize()
+    cpu_case = make_case(48, 40, 6, nprop=2)
+    o, g, s, props, refs = oracle_for(cpu_case)
+    # the generator is device independent up to libm rounding of sin/cos: feed the oracle the GPU-made inputs
+    from oracle.oracle import case_to_numpy
+    g, s, props, refs = case_to_numpy(case)
+    o.set_grid2d(g); o.set_step(s)
+    cpu = [p.copy() for p in props]
+    for _ in range(2):
+        o.advect_batch(cpu, prm)
+    compare([t.cpu().numpy() for t in out], cpu, s, 2 * TOL_STEP)
+    ts.close()
