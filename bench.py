@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""Benchmark of the batched MOHID property transport step (BASELINE.json metric:
+"Gcell-property updates/s per transport step; % of HBM roofline").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4s|...]
+
+One "step" = one batched transport step (per-step coefficient pass K1 + fused kernel K2 + boundary
+passes) of all N_prop properties over the whole grid.  Workload at 1 GPU: config C3 of BASELINE.json
+(2048 x 2048 x 40 sigma grid, 10 properties, P2_TVD + SuperBee horizontal and vertical, implicit
+vertical).  With --gpus N > 1 (launched by torchrun, one rank per GPU) the same global grid is split
+into j-slabs (strong scaling) and the 2-column property halos are exchanged with NCCL every step.
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the reference path
+(oracle/, OpenMP, all host cores) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (I, J, K, nprop, method, limiter)
+    "c2": (512, 512, 20, 1, 1, 4),          # upwind + implicit vertical, 1 tracer
+    "c3": (2048, 2048, 40, 10, 4, 4),       # 10 properties, TVD SuperBee  (headline, 1 GPU)
+    "c3pdm": (2048, 2048, 40, 10, 4, 5),    # ULTIMATE-QUICKEST style limiter
+    "c1": (305, 232, 75, 2, 4, 4),          # Coastal3D-like dimensions
+    "c4": (4096, 4096, 40, 10, 4, 4),       # needs >= 2 GPUs
+    "small": (256, 256, 20, 4, 4, 4),
+}
+
+
+def b_alg(nprop: int) -> float:
+    """Algorithmic bytes per cell-property update: 16 + 112 / N."""
+    return 16.0 + 112.0 / nprop
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def params_for(nprop, method, limiter, dt):
+    from mohid_b200.synthetic import default_params
+    mv = method if method not in (2, 3) else 1          # implicit vertical forbids QUICK/QUICKEST (AD:1234)
+    return [default_params(method, limiter, mv, limiter, dt=dt) for _ in range(nprop)]
+
+
+# -----------------------------------------------------------------------------------------
+# CPU arm: the oracle (C++ restatement of the reference path, OpenMP) on a bounded sample
+# -----------------------------------------------------------------------------------------
+def cpu_reference_run(workload: str, steps: int, warmup: int, budget_s: float = 20.0):
+    import numpy as np
+    from mohid_b200.synthetic import make_case
+    from oracle.oracle import OracleAdvectionDiffusion, case_to_numpy
+    I, J, K, nprop, method, limiter = WORKLOADS[workload]
+    # bounded sample: same K, N, numerics; horizontal extent cut so one step is ~1 s of CPU work
+    si, sj = min(I, 384), min(J, 384)
+    case = make_case(si, sj, K, nprop=nprop)
+    g, s, props, refs = case_to_numpy(case)
+    o = OracleAdvectionDiffusion(si, sj, K)
+    o.set_grid2d(g)
+    o.set_step(s)
+    prm = params_for(nprop, method, limiter, case.dt)
+    for _ in range(max(1, min(warmup, 2))):
+        o.advect_batch(props, prm)
+    t0 = time.perf_counter()
+    done = 0
+    while done < max(1, steps) and (time.perf_counter() - t0) < budget_s:
+        o.advect_batch(props, prm)
+        done += 1
+    dt = time.perf_counter() - t0
+    units = si * sj * K * nprop * done
+    return {"value": units / dt / 1e9, "unit": "Gcell-property updates/s", "cores": o.nthreads, "kind": "port",
+            "sample": f"{si}x{sj}x{K} x {nprop} properties, {done} steps in {dt:.1f} s (oracle, g++ -O2 -fopenmp, "
+                      f"{o.nthreads} threads)", "ms_per_step": dt / done * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(args.workload, args.steps, args.warmup, budget_s=60.0)
+    I, J, K, nprop, method, limiter = WORKLOADS[args.workload]
+    line = {"impl": "reference", "metric": "Gcell-property updates/s per transport step", "value": r["value"],
+            "unit": r["unit"], "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {I}x{J}x{K} sigma grid, {nprop} properties (bounded sample)",
+                       "adv_method": method, "tvd_limiter": limiter},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": r["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# -----------------------------------------------------------------------------------------
+# GPU arm
+# -----------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from mohid_b200 import capi
+    from mohid_b200.advection_diffusion import TransportStep
+    from mohid_b200.synthetic import make_case, STEP_ORDER
+    from mohid_b200.partition import SlabDecomposition, HaloExchanger
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the GPU arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    capi.load(build_if_missing=True)
+
+    I, J, K, nprop, method, limiter = WORKLOADS[args.workload]
+    dec = SlabDecomposition(J, world, ghost=2)
+    sl = dec.slab(rank)
+    # every rank generates its slab (+ghost columns) of the same global case
+    case = make_case(I, J, K, nprop=nprop, device=str(dev), make_refs=False, j_range=(sl.j_lo_ext, sl.j_hi_ext))
+    prm = params_for(nprop, method, limiter, case.dt)
+
+    ts = TransportStep(I, case.J, K, device=local)
+    stream = torch.cuda.current_stream()
+    ts.set_stream(stream.cuda_stream)
+    ts.set_grid2d(**case.grid2d)
+    ts.set_step(case.step)
+    ts.upload(case.props)
+    halo = HaloExchanger(ts, dec, rank, nprop, dev) if world > 1 else None
+
+    # pinned host copies for the end-to-end leg (what a Fortran host would own)
+    e2e_steps = max(1, min(args.steps, 3))
+    host = None
+    if args.e2e:
+        host = {"step": {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v) for k, v in case.step.items()},
+                "props": [torch.empty(p.shape, dtype=p.dtype, pin_memory=True).copy_(p) for p in case.props]}
+    cells_local = I * sl.n_owned * K
+    del case
+    torch.cuda.empty_cache()
+
+    def one_step():
+        ts.advect_device(prm, 1)
+        if halo is not None:
+            halo.exchange()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    barrier()
+    ts.kernel_time_ms()                       # reset the K2 event accumulator
+    c0 = ts.counters()["launches"]
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        one_step()
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    k2_ms, k2_n = ts.kernel_time_ms()
+    launches = ts.counters()["launches"] - c0 + (halo.launches if halo else 0)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        k = torch.tensor([k2_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(k, op=dist.ReduceOp.MAX)
+        k2_ms = float(k.item())
+    ms_step = ms_total / args.steps
+    units_global = I * J * K * nprop
+    value = units_global / (ms_step * 1e-3) / 1e9
+
+    # ---- end-to-end leg: host buffers through the C-ABI, H2D + D2H inside the timed region ----
+    e2e = None
+    if host is not None:
+        h2d = sum(v.numel() * v.element_size() for v in host["step"].values()) + \
+            sum(p.numel() * p.element_size() for p in host["props"])
+        d2h = sum(p.numel() * p.element_size() for p in host["props"])
+
+        def e2e_step():
+            ts.set_step(host["step"])                       # per-step inputs: host -> device (H2D)
+            ts.upload(host["props"])                        # properties: host -> device (H2D)
+            ts.advect_device(prm, 1)
+            if halo is not None:
+                halo.exchange()
+            ts.download(host["props"])                      # updated properties: device -> host (D2H), in place
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": units_global * e2e_steps / dt / 1e9, "unit": "Gcell-property updates/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+               "ms_per_step": dt / e2e_steps * 1e3,
+               "note": "mohid_adt_set_step + upload_props + advect_device + download_props (= advect_batch) with pinned host arrays"}
+
+    if rank == 0:
+        peak, peak_src = measured_hbm_peak()
+        bytes_per_launch = b_alg(nprop) * cells_local * nprop
+        achieved = bytes_per_launch / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else 0.0
+        step_achieved = b_alg(nprop) * cells_local * nprop / (ms_step * 1e-3) / 1e9
+        cpu = cpu_reference_run(args.workload, 5, 1) if (world == 1 and args.cpu_baseline) else None
+        line = {"metric": "Gcell-property updates/s per transport step", "value": value,
+                "unit": "Gcell-property updates/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"{args.workload}: {I}x{J}x{K} sigma grid, {nprop} properties",
+                           "adv_method_h_v": method, "tvd_limiter": limiter, "vertical": "implicit",
+                           "partition": f"{world} j-slab(s), ghost 2, NCCL halo" if world > 1 else "single GPU",
+                           "l2": "inputs >> L2 (each field %.2f GB)" % (8.0 * (I + 2) * (J + 2) * (K + 2) / 1e9),
+                           "step_includes": "K1 coefficient pass + K2 fused kernel + boundary passes"},
+                "roofline": {"bound": "hbm", "kernel": "adt_transport_kernel", "achieved": achieved, "peak": peak,
+                             "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                             "bytes_per_unit": b_alg(nprop), "kernel_ms": k2_ms, "kernel_launches_timed": k2_n,
+                             "step_achieved": step_achieved, "step_frac": step_achieved / peak},
+                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(line))
+    ts.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-e2e", dest="e2e", action="store_false")
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -176,6 +176,10 @@ int mohid_adt_mark_step_resident(const int *handle, const int *small_depths_pres
 
 /* ---- halo exchange support for the j-slab decomposition (replaces               ---- */
 /* ---- ReceiveSendProperities3DMPIr8, HG:8479-8658)                                ---- */
+/* Restrict the columns this handle advances to j_begin .. j_begin+j_count-1 (default 1..J): the
+ * owned columns of a j-slab whose remaining work columns are ghost copies of the neighbours
+ * (the reference instead recomputes overlapping HALOPOINTS columns, HG:1048-1105). */
+int mohid_adt_set_active_columns(const int *handle, const int *j_begin, const int *j_count);
 /* Pack `width` j-columns starting at j0 of all nprop device-resident properties into a
  * contiguous DEVICE buffer (nprop * nk * width * ld doubles) / scatter them back. */
 int mohid_adt_pack_columns(const int *handle, const int *nprop, const int *j0, const int *width,

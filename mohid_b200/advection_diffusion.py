@@ -142,6 +142,11 @@ class TransportStep:
         self._check(self.lib.mohid_adt_unpack_columns(C.byref(self.h), C.byref(C.c_int(nprop)), C.byref(C.c_int(j0)),
                                                       C.byref(C.c_int(width)), C.c_void_p(device_buffer.data_ptr())))
 
+    def set_active_columns(self, j_begin: int, j_count: int):
+        """Advance only local columns j_begin .. j_begin+j_count-1 (the owned columns of a j-slab)."""
+        self._check(self.lib.mohid_adt_set_active_columns(C.byref(self.h), C.byref(C.c_int(j_begin)),
+                                                          C.byref(C.c_int(j_count))))
+
     def halo_buffer_elems(self, nprop: int, width: int) -> int:
         return nprop * (self.K + 2) * width * self.device_ld
 

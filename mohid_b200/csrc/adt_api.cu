@@ -52,6 +52,8 @@ struct Handle {
     size_t ev_used = 0;
     std::string err;
     int smem_optin = 0, num_sms = 0;
+    int j_begin = 1, j_count = 0;                       // columns advanced by this handle (slab decomposition)
+    std::vector<int> bnd_host;                          // (i,j) of all boundary columns
 };
 
 std::mutex g_mu;
@@ -143,6 +145,22 @@ void free_all(Handle *h) {
     F(h->d_zero_piv);
     for (auto &e : h->ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+}
+
+// boundary columns inside the active j-range -> device list used by the post-solve passes
+int upload_bnd_cols(Handle *h) {
+    std::vector<int> cols;
+    for (size_t c = 0; c + 1 < h->bnd_host.size(); c += 2) {
+        const int j = h->bnd_host[c + 1];
+        if (j >= h->j_begin && j < h->j_begin + h->j_count) { cols.push_back(h->bnd_host[c]); cols.push_back(j); }
+    }
+    if (h->bnd_cols) { cudaFree(h->bnd_cols); h->bnd_cols = nullptr; }
+    h->n_bnd_cols = (int)(cols.size() / 2);
+    if (h->n_bnd_cols) {
+        if (int r = dalloc(h, &h->bnd_cols, cols.size())) return r;
+        CU(h, cudaMemcpy(h->bnd_cols, cols.data(), cols.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    return 0;
 }
 
 struct Batch {          // validated view of one advect call
@@ -250,7 +268,7 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
     s.I = h->I; s.J = h->J; s.K = h->K; s.ld = h->ld; s.nj = h->nj; s.sk = (long)h->ld * h->nj;
     s.nprop = (int)idx.size();
     s.ntile_i = (h->I + 30) / 31;
-    s.j_begin = 1; s.j_count = h->J;
+    s.j_begin = h->j_begin; s.j_count = h->j_count;
     const mohid_adt_params &f = b.p[idx[0]];
     s.method_h = f.AdvMethodH; s.limiter_h = f.TVDLimitationH; s.method_v = f.AdvMethodV; s.limiter_v = f.TVDLimitationV;
     s.upwind2_h = f.Upwind2H; s.upwind2_v = f.Upwind2V;
@@ -277,7 +295,7 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
     if (wpb < 1)
         return fail(h, MOHID_ADT_ERR_UNSUPPORTED, "K = %d layers need more shared memory than one SM has", h->K);
     const size_t smem = (size_t)2 * h->K * wpb * 32 * sizeof(double);
-    const long nunits = (long)s.nprop * s.ntile_i * h->J;
+    const long nunits = (long)s.nprop * s.ntile_i * h->j_count;
     const long blocks = (nunits + wpb - 1) / wpb;
     if (blocks > 2147483647L) return fail(h, MOHID_ADT_ERR_ARG, "grid too large");
     CU(h, cudaFuncSetAttribute(adt_transport_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -390,6 +408,7 @@ int mohid_adt_create(int *handle, const mohid_adt_size3d *size, const mohid_adt_
     CU(nullptr, cudaSetDevice(dev));
     h->I = worksize->IUB; h->J = worksize->JUB; h->K = worksize->KUB;
     h->ni = h->I + 2; h->nj = h->J + 2; h->nk = h->K + 2;
+    h->j_begin = 1; h->j_count = h->J;
     h->ld_h = (ld_i && *ld_i > 0) ? *ld_i : h->ni;
     if (h->ld_h < h->ni) { delete h; return fail(nullptr, MOHID_ADT_ERR_ARG, "ld_i smaller than I+2"); }
     h->ld = ((h->ni + 15) / 16) * 16;                // 128-byte aligned rows on the device
@@ -477,16 +496,11 @@ int mohid_adt_set_grid2d(const int *handle, const double *DUX, const double *DVY
     std::vector<int> bhost((size_t)h->n2);
     CU(h, cudaMemcpyAsync(bhost.data(), h->Bnd, h->n2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
-    std::vector<int> cols;
+    h->bnd_host.clear();
     for (int j = 1; j <= h->J; ++j)
         for (int i = 1; i <= h->I; ++i)
-            if (bhost[(size_t)i + (size_t)h->ld * j] == 1) { cols.push_back(i); cols.push_back(j); }
-    if (h->bnd_cols) { cudaFree(h->bnd_cols); h->bnd_cols = nullptr; }
-    h->n_bnd_cols = (int)(cols.size() / 2);
-    if (h->n_bnd_cols) {
-        if (int r = dalloc(h, &h->bnd_cols, cols.size())) return r;
-        CU(h, cudaMemcpyAsync(h->bnd_cols, cols.data(), cols.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    }
+            if (bhost[(size_t)i + (size_t)h->ld * j] == 1) { h->bnd_host.push_back(i); h->bnd_host.push_back(j); }
+    if (int r = upload_bnd_cols(h)) return r;
     CU(h, cudaStreamSynchronize(h->stream));
     h->have_grid = true;
     return 0;
@@ -687,6 +701,17 @@ int mohid_adt_pack_columns(const int *handle, const int *nprop, const int *j0, c
 int mohid_adt_unpack_columns(const int *handle, const int *nprop, const int *j0, const int *width,
                              const void *device_buffer) {
     return pack_common(handle, nprop, j0, width, (double *)device_buffer, 1);
+}
+
+int mohid_adt_set_active_columns(const int *handle, const int *j_begin, const int *j_count) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    if (!j_begin || !j_count || *j_begin < 1 || *j_count < 1 || *j_begin + *j_count - 1 > h->J)
+        return fail(h, MOHID_ADT_ERR_ARG, "active column range must lie inside 1..J");
+    CU(h, cudaSetDevice(h->dev));
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->j_begin = *j_begin; h->j_count = *j_count;
+    return upload_bnd_cols(h);
 }
 
 int mohid_adt_synchronize(const int *handle) {

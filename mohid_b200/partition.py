@@ -1,0 +1,141 @@
+"""Horizontal j-slab decomposition of the transport step across the GPUs of one box.
+
+Replaces MOHID's MPI domain decomposition for this path (``ModuleHorizontalGrid.F90:966-1110``
+ConstructDDecomp, ``:1690`` AutomaticDDecompColumns, ``:8479-8658`` ReceiveSendProperities3DMPIr8):
+
+* one rank (= one GPU) owns a contiguous range of global columns ``j``;
+* its local arrays additionally carry ``ghost`` (= 2, the reach of the 4-point advection stencil,
+  ``ModuleFunctions.F90:10572-10574``) columns of each interior neighbour instead of MOHID's
+  recomputed ``HALOPOINTS`` overlap;
+* after every batched step each rank sends its first / last ``ghost`` owned columns of all
+  properties to the left / right neighbour (one grouped send+recv pair per neighbour,
+  NCCL on GPUs, gloo on CPU for the tests).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+
+@dataclass(frozen=True)
+class Slab:
+    rank: int
+    world: int
+    j_lo: int           # first owned global column
+    j_hi: int           # last owned global column
+    ghost_left: int
+    ghost_right: int
+
+    @property
+    def n_owned(self) -> int:
+        return self.j_hi - self.j_lo + 1
+
+    @property
+    def j_lo_ext(self) -> int:      # first global column present as a local work column
+        return self.j_lo - self.ghost_left
+
+    @property
+    def j_hi_ext(self) -> int:
+        return self.j_hi + self.ghost_right
+
+    @property
+    def J_local(self) -> int:
+        return self.j_hi_ext - self.j_lo_ext + 1
+
+    @property
+    def j_begin(self) -> int:       # local index of the first owned column (local j=0 is the array halo)
+        return 1 + self.ghost_left
+
+    def local_j(self, j_global: int) -> int:
+        return j_global - self.j_lo_ext + 1
+
+
+class SlabDecomposition:
+    """Split columns 1..J into ``world`` contiguous slabs of (almost) equal width."""
+
+    def __init__(self, J: int, world: int, ghost: int = 2):
+        if world < 1 or J < world * max(ghost, 1):
+            raise ValueError(f"cannot split J={J} into {world} slabs with ghost width {ghost}")
+        self.J, self.world, self.ghost = J, world, ghost
+        base, rem = divmod(J, world)
+        self.bounds = []
+        lo = 1
+        for r in range(world):
+            n = base + (1 if r < rem else 0)
+            self.bounds.append((lo, lo + n - 1))
+            lo += n
+
+    def slab(self, rank: int) -> Slab:
+        lo, hi = self.bounds[rank]
+        return Slab(rank, self.world, lo, hi, self.ghost if rank > 0 else 0,
+                    self.ghost if rank < self.world - 1 else 0)
+
+    def owner(self, j_global: int) -> int:
+        for r, (lo, hi) in enumerate(self.bounds):
+            if lo <= j_global <= hi:
+                return r
+        raise ValueError(j_global)
+
+
+def _p2p_exchange(dist, send_left, recv_left, send_right, recv_right, rank: int, world: int):
+    """One grouped send/recv pair per neighbour (HG:8554-8640 does this with blocking MPI calls)."""
+    ops = []
+    if rank > 0:
+        ops.append(dist.P2POp(dist.isend, send_left, rank - 1))
+        ops.append(dist.P2POp(dist.irecv, recv_left, rank - 1))
+    if rank < world - 1:
+        ops.append(dist.P2POp(dist.isend, send_right, rank + 1))
+        ops.append(dist.P2POp(dist.irecv, recv_right, rank + 1))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
+class HaloExchanger:
+    """Device-resident halo exchange of all properties of a :class:`TransportStep` (NCCL)."""
+
+    def __init__(self, ts, dec: SlabDecomposition, rank: int, nprop: int, device):
+        import torch
+        self.ts, self.dec, self.rank, self.nprop = ts, dec, rank, nprop
+        self.sl = dec.slab(rank)
+        g = dec.ghost
+        n = ts.halo_buffer_elems(nprop, g)
+        mk = lambda: torch.empty(n, dtype=torch.float64, device=device)
+        self.send_l, self.recv_l, self.send_r, self.recv_r = mk(), mk(), mk(), mk()
+        self.launches = 0
+        ts.set_active_columns(self.sl.j_begin, self.sl.n_owned)
+
+    def exchange(self):
+        import torch.distributed as dist
+        sl, g, ts = self.sl, self.dec.ghost, self.ts
+        if sl.ghost_left:
+            ts.pack_columns(self.nprop, sl.j_begin, g, self.send_l)
+            self.launches += 1
+        if sl.ghost_right:
+            ts.pack_columns(self.nprop, sl.j_begin + sl.n_owned - g, g, self.send_r)
+            self.launches += 1
+        _p2p_exchange(dist, self.send_l, self.recv_l, self.send_r, self.recv_r, self.rank, self.dec.world)
+        if sl.ghost_left:
+            ts.unpack_columns(self.nprop, sl.j_begin - g, g, self.recv_l)
+            self.launches += 1
+        if sl.ghost_right:
+            ts.unpack_columns(self.nprop, sl.j_begin + sl.n_owned, g, self.recv_r)
+            self.launches += 1
+
+
+def exchange_host_arrays(props: Sequence, dec: SlabDecomposition, rank: int):
+    """Same exchange on host arrays (torch CPU tensors of shape (K+2, J_local+2, ld)) over the default
+    process group (gloo): used to validate the decomposition logic on CPU."""
+    import torch
+    import torch.distributed as dist
+    sl, g = dec.slab(rank), dec.ghost
+    jb, n = sl.j_begin, sl.n_owned
+    stack = lambda j0: torch.stack([p[:, j0:j0 + g, :] for p in props]).contiguous()
+    send_l, send_r = stack(jb), stack(jb + n - g)
+    recv_l, recv_r = torch.empty_like(send_l), torch.empty_like(send_r)
+    _p2p_exchange(dist, send_l, recv_l, send_r, recv_r, rank, dec.world)
+    for m, p in enumerate(props):
+        if sl.ghost_left:
+            p[:, jb - g:jb, :] = recv_l[m]
+        if sl.ghost_right:
+            p[:, jb + n:jb + n + g, :] = recv_r[m]

@@ -23,7 +23,7 @@ from __future__ import annotations
 
 import math
 from dataclasses import dataclass, field
-from typing import Dict, List, Optional
+from typing import Dict, List, Optional, Tuple
 
 import torch
 
@@ -84,72 +84,121 @@ def make_case(I: int, J: int, K: int, nprop: int = 1, *, dt: float = 30.0, seed:
               ld: Optional[int] = None, device: str = "cpu", islands: bool = True,
               stepped_bottom: bool = False, courant_h: float = 0.4, courant_v: float = 0.3,
               volume_change: float = 2.0e-3, dx: float = 500.0, dy: float = 500.0,
-              depth: float = 50.0, make_refs: bool = True, closed: bool = False) -> Case:
+              depth: float = 50.0, make_refs: bool = True, closed: bool = False,
+              j_range: Optional[Tuple[int, int]] = None) -> Case:
+    """Build a case on the global grid ``I x J x K``.
+
+    ``j_range=(lo, hi)`` returns only the j-slab whose work columns are the global columns
+    ``lo..hi`` (local ``J = hi-lo+1``, local column ``j`` is global ``lo-1+j``): every formula uses
+    global coordinates and hashes, so a slab is bit-identical to the same columns of the global case.
+    """
     dev = torch.device(device)
     f64 = dict(dtype=torch.float64, device=dev)
-    i32 = dict(dtype=torch.int32, device=dev)
-    ni, nj, nk = I + 2, J + 2, K + 2
+    lo, hi = (1, J) if j_range is None else (int(j_range[0]), int(j_range[1]))
+    assert 1 <= lo <= hi <= J
+    Jg, Jl = J, hi - lo + 1
+    ni, nj, nk = I + 2, Jl + 2, K + 2
     ld = ni if ld is None else int(ld)
     assert ld >= ni
-    c = Case(I=I, J=J, K=K, ld=ld, dt=float(dt), J_global=J)
+    c = Case(I=I, J=Jl, K=K, ld=ld, dt=float(dt), J_global=Jg, j_offset=lo - 1)
 
-    ii = torch.arange(ld, **f64).view(1, ld)          # i index along the last dim
-    jj = torch.arange(nj, **f64).view(nj, 1)
-    valid_i = (torch.arange(ld, device=dev) < ni).view(1, ld)
-
-    # ---------------- horizontal metrics (HG:6283-6345) ----------------
-    DUX = dx * (1.0 + 0.1 * torch.sin(TWO_PI * jj / J)) + 0.0 * ii
-    DVY = dy * (1.0 + 0.1 * torch.cos(TWO_PI * ii / I)) + 0.0 * jj
-    DZX = torch.empty_like(DUX)
-    DZX[:-1, :] = 0.5 * (DUX[:-1, :] + DUX[1:, :])
-    DZX[-1, :] = DUX[-1, :]
-    DZY = torch.empty_like(DVY)
-    DZY[:, :-1] = 0.5 * (DVY[:, :-1] + DVY[:, 1:])
-    DZY[:, -1] = DVY[:, -1]
-
-    # ---------------- 2-D water mask, islands, boundary ring ----------------
-    ji = torch.arange(nj, device=dev).view(nj, 1)
+    # ---- 2-D stage on a j-range extended by a margin (the coastal taper below has an 8-cell reach) ----
+    MARGIN = 12
+    e_lo, e_hi = max(0, lo - 1 - MARGIN), min(Jg + 1, hi + 1 + MARGIN)      # global columns generated
+    nje = e_hi - e_lo + 1
+    crop = slice(lo - 1 - e_lo, lo - 1 - e_lo + nj)
+    ii = torch.arange(ld, **f64).view(1, ld)
+    jj = (torch.arange(nje, **f64) + e_lo).view(nje, 1)                     # GLOBAL j
+    ji = (torch.arange(nje, device=dev) + e_lo).view(nje, 1)
     iw = torch.arange(ld, device=dev).view(1, ld)
-    water2d = (ji >= 1) & (ji <= J) & (iw >= 1) & (iw <= I)
-    if islands and I >= 16 and J >= 16:
+    valid_i = (iw < ni)
+
+    # horizontal metrics (HG:6283-6345); DZX/DZY use the next cell, replicated on the last one
+    def dux_of(j):
+        return dx * (1.0 + 0.1 * torch.sin(TWO_PI * j / Jg))
+
+    def dvy_of(i):
+        return dy * (1.0 + 0.1 * torch.cos(TWO_PI * i / I))
+    DUX = dux_of(jj) + 0.0 * ii
+    DVY = dvy_of(ii) + 0.0 * jj
+    DZX = torch.where(jj < Jg + 1, 0.5 * (dux_of(jj) + dux_of(jj + 1.0)), dux_of(jj)) + 0.0 * ii
+    DZY = torch.where(ii < I + 1, 0.5 * (dvy_of(ii) + dvy_of(ii + 1.0)), dvy_of(ii)) + 0.0 * jj
+
+    # 2-D water mask, islands, boundary ring
+    water2d = (ji >= 1) & (ji <= Jg) & (iw >= 1) & (iw <= I)
+    if islands and I >= 16 and Jg >= 16:
         def rect(i0, i1, j0, j1):
-            return (iw >= int(i0 * I)) & (iw <= int(i1 * I)) & (ji >= int(j0 * J)) & (ji <= int(j1 * J))
+            return (iw >= int(i0 * I)) & (iw <= int(i1 * I)) & (ji >= int(j0 * Jg)) & (ji <= int(j1 * Jg))
         land = rect(0.20, 0.30, 0.25, 0.40) | rect(0.55, 0.70, 0.60, 0.70) | rect(0.75, 0.80, 0.15, 0.30)
         # one enclosed lake cell: water point that never becomes an open point (AD:4003-4006)
-        lake = (iw == int(0.25 * I)) & (ji == int(0.32 * J))
+        lake = (iw == int(0.25 * I)) & (ji == int(0.32 * Jg))
         water2d = water2d & (~land | lake)
-    bnd2d = water2d & ((ji == 1) | (ji == J) | (iw == 1) | (iw == I))
+    bnd2d = water2d & ((ji == 1) | (ji == Jg) | (iw == 1) | (iw == I))
     if closed:                                   # closed basin: no open-boundary ring
         bnd2d = torch.zeros_like(bnd2d)
 
-    # ---------------- bottom level ----------------
+    # bottom level
     if stepped_bottom and K >= 4:
-        bump = 0.5 * (1.0 + torch.sin(TWO_PI * 2.0 * ii / I) * torch.sin(TWO_PI * 1.5 * jj / J))
+        bump = 0.5 * (1.0 + torch.sin(TWO_PI * 2.0 * ii / I) * torch.sin(TWO_PI * 1.5 * jj / Jg))
         kfloor = (1 + torch.floor(bump * (K // 3))).to(torch.int32)
         kfloor = torch.where(bnd2d, torch.ones_like(kfloor), kfloor)
     else:
-        kfloor = torch.ones((nj, ld), **i32)
+        kfloor = torch.ones((nje, ld), dtype=torch.int32, device=dev)
     kfloor = torch.where(water2d, kfloor, torch.ones_like(kfloor))
 
-    c.grid2d = dict(DUX=DUX.contiguous(), DVY=DVY.contiguous(), DZX=DZX, DZY=DZY,
-                    KFloorZ=kfloor.contiguous(), BoundaryPoints2D=bnd2d.to(torch.int32).contiguous())
+    # stream function at cell corners (SW corner of cell (i,j)): 24 x 20-cell eddies, tapered to zero on
+    # every corner that touches a non-water cell, so the discrete flow stays exactly non-divergent per
+    # layer and tangent to the coasts (no column-integrated convergence next to islands).
+    psi = torch.sin(TWO_PI * (ii - 0.5) / 24.0) * torch.sin(TWO_PI * (jj - 0.5) / 20.0)
+    cm = torch.zeros((nje, ld), dtype=torch.bool, device=dev)
+    cm[1:, 1:] = water2d[1:, 1:] & water2d[:-1, 1:] & water2d[1:, :-1] & water2d[:-1, :-1]
+    taper = cm.to(torch.float64).view(1, 1, nje, ld)
+    for _ in range(8):
+        taper = torch.nn.functional.avg_pool2d(taper, 3, stride=1, padding=1) * cm
+    psi = psi * taper.view(nje, ld)
+    qx2 = torch.zeros((nje, ld), **f64)
+    qx2[:, :-1] = psi[:, 1:] - psi[:, :-1]            # Qx(i,j) = psi(i+1,j) - psi(i,j)
+    qy2 = torch.zeros((nje, ld), **f64)
+    qy2[:-1, :] = -(psi[1:, :] - psi[:-1, :])         # Qy(i,j) = -(psi(i,j+1) - psi(i,j))
+    # divergent part from a potential whose sign changes over depth (column mean ~ 0)
+    phi = torch.sin(TWO_PI * ii / 32.0) * torch.sin(TWO_PI * jj / 32.0)
+    dxp = torch.zeros((nje, ld), **f64)
+    dxp[1:, :] = phi[1:, :] - phi[:-1, :]             # across U face j
+    dyp = torch.zeros((nje, ld), **f64)
+    dyp[:, 1:] = phi[:, 1:] - phi[:, :-1]             # across V face i
+    h = depth * (1.0 + 0.4 * torch.sin(TWO_PI * ii / I) * torch.cos(TWO_PI * jj / Jg))
+    dvol2 = volume_change * torch.sin(TWO_PI * (ii / I + jj / Jg))
+    blobs = []
+    for n in range(nprop):
+        ci = I * (0.35 + 0.3 * ((n * 0.37) % 1.0))
+        cj = Jg * (0.35 + 0.3 * ((n * 0.61) % 1.0))
+        sig_i, sig_j = 0.12 * I + 2.0, 0.12 * Jg + 2.0
+        blobs.append(torch.exp(-0.5 * (((ii - ci) / sig_i) ** 2 + ((jj - cj) / sig_j) ** 2))[crop].contiguous())
+
+    # ---- crop the 2-D fields to the slab (+1 halo column each side) ----
+    DUX, DVY, DZX, DZY = (t[crop].contiguous() for t in (DUX, DVY, DZX, DZY))
+    water2d, bnd2d, kfloor = water2d[crop].contiguous(), bnd2d[crop].contiguous(), kfloor[crop].contiguous()
+    qx2, qy2, dxp, dyp, h, dvol2 = (t[crop].contiguous() for t in (qx2, qy2, dxp, dyp, h, dvol2))
+    ji = ji[crop]                                       # global j of the local columns
+    del psi, phi, taper, cm
+    c.grid2d = dict(DUX=DUX, DVY=DVY, DZX=DZX, DZY=DZY, KFloorZ=kfloor,
+                    BoundaryPoints2D=bnd2d.to(torch.int32).contiguous())
 
     # ---------------- vertical geometry: uniform sigma (GEO:5047-5170) ----------------
-    h = depth * (1.0 + 0.4 * torch.sin(TWO_PI * ii / I) * torch.cos(TWO_PI * jj / J))   # (nj, ld)
     DWZ = (h / K).unsqueeze(0).expand(nk, nj, ld).contiguous()
     DZZ = torch.empty_like(DWZ)
     DZZ[:-1] = 0.5 * (DWZ[1:] + DWZ[:-1])
     DZZ[-1] = DWZ[-1]
     VolumeZ = DWZ * (DUX * DVY).unsqueeze(0)
-    lin = (torch.arange(nk, device=dev).view(nk, 1, 1) * nj + (ji.view(1, nj, 1) + c.j_offset)) * ni + iw.view(1, 1, ld)
+    kidx = torch.arange(nk, device=dev).view(nk, 1, 1)
+    lin = (kidx * (Jg + 2) + ji.view(1, nj, 1)) * ni + iw.view(1, 1, ld)      # global linear index (hash key)
     kk = torch.arange(nk, **f64).view(nk, 1, 1)
-    VolumeZOld = VolumeZ * (1.0 + volume_change * torch.sin(TWO_PI * (ii / I + jj / J)).unsqueeze(0))
+    VolumeZOld = VolumeZ * (1.0 + dvol2.unsqueeze(0))
 
     # ---------------- 3-D masks ----------------
-    kidx = torch.arange(nk, device=dev).view(nk, 1, 1)
     inside_k = (kidx >= 1) & (kidx <= K)
     water3 = water2d.unsqueeze(0) & inside_k & (kidx >= kfloor.unsqueeze(0))
-    inwork = ((ji >= 1) & (ji <= J) & (iw >= 1) & (iw <= I)).unsqueeze(0) & inside_k
+    inwork = ((ji >= 1) & (ji <= Jg) & (iw >= 1) & (iw <= I)).unsqueeze(0) & inside_k
     land3 = inwork & ~water3
     # 2-D compute faces: both sides water and not between two boundary points (HM:939-942)
     cf2u = torch.zeros((nj, ld), dtype=torch.bool, device=dev)
@@ -172,48 +221,19 @@ def make_case(I: int, J: int, K: int, nprop: int = 1, *, dt: float = 30.0, seed:
     openp &= inwork
 
     # ---------------- water fluxes ----------------
-    Vref = dx * dy * depth / K
-    # stream function at cell corners (SW corner of cell (i,j)): 24 x 20-cell eddies.  psi is tapered to
-    # zero on every corner that touches a non-water cell, so the discrete flow stays exactly non-divergent
-    # per layer and tangent to the coasts (no column-integrated convergence next to islands).
-    psi = torch.sin(TWO_PI * (ii - 0.5) / 24.0) * torch.sin(TWO_PI * (jj + c.j_offset - 0.5) / 20.0)
-    cm = torch.zeros((nj, ld), dtype=torch.bool, device=dev)
-    cm[1:, 1:] = water2d[1:, 1:] & water2d[:-1, 1:] & water2d[1:, :-1] & water2d[:-1, :-1]
-    taper = cm.to(torch.float64).view(1, 1, nj, ld)
-    for _ in range(8):
-        taper = torch.nn.functional.avg_pool2d(taper, 3, stride=1, padding=1) * cm
-    psi = psi * taper.view(nj, ld)
+    # amplitudes from analytic bounds (identical on every slab): |d psi| <= 2 sin(pi/24) + taper slope,
+    # smallest cell volume = 0.9 dx * 0.9 dy * 0.6 depth / K
+    vmin = 0.81 * dx * dy * 0.6 * depth / K
+    amp = courant_h * vmin / dt / 0.40 * 0.85
+    # peak of the potential-driven vertical flux: sum_k cos(.) <= K/pi, horizontal divergence <= 8 sin^2(pi/32)
+    div_unit = 8.0 * math.sin(math.pi / 32.0) ** 2
+    ampv = min(courant_v * vmin / dt / (div_unit * K / math.pi), 0.15 * courant_h * vmin / dt / (2.0 * math.sin(math.pi / 32.0)))
     g = (0.6 + 0.4 * kk / K)
-    qx2 = torch.zeros((nj, ld), **f64)
-    qx2[:, :-1] = psi[:, 1:] - psi[:, :-1]            # Qx(i,j) = psi(i+1,j) - psi(i,j)
-    qy2 = torch.zeros((nj, ld), **f64)
-    qy2[:-1, :] = -(psi[1:, :] - psi[:-1, :])         # Qy(i,j) = -(psi(i,j+1) - psi(i,j))
-    # divergent part from a potential, sign changes over depth so the column mean is ~0
-    Bv = courant_v * Vref / dt
-    phi = Bv * torch.sin(TWO_PI * ii / 32.0) * torch.sin(TWO_PI * (jj + c.j_offset) / 32.0)
-    dxp = torch.zeros((nj, ld), **f64)
-    dxp[1:, :] = phi[1:, :] - phi[:-1, :]             # across U face j
-    dyp = torch.zeros((nj, ld), **f64)
-    dyp[:, 1:] = phi[:, 1:] - phi[:, :-1]             # across V face i
     s = torch.cos(math.pi * (kk - 0.5) / K)
-    # scale the rotational part so that the peak horizontal Courant number is `courant_h`
-    vmin = VolumeZ[1].clamp_min(1.0)
-    peak = max(float((qx2.abs() * dt / vmin).max()), float((qy2.abs() * dt / vmin).max()), 1e-30)
-    amp = courant_h / peak * 0.85        # the divergent part below adds up to ~15 %
-    # scale the divergent part so that the peak vertical Courant number it induces is `courant_v`
-    colmask = (surf & ~bnd2d).unsqueeze(0) & water3        # interior columns with W faces
-    fx = dxp.unsqueeze(0) * s * CFU
-    fy = dyp.unsqueeze(0) * s * CFV
-    conv = torch.zeros(c.shape3, **f64)
-    conv[:, :-1, :-1] = fx[:, :-1, :-1] - fx[:, 1:, :-1] + fy[:, :-1, :-1] - fy[:, :-1, 1:]
-    qz_unit = torch.cumsum(conv * colmask, dim=0)
-    peak_v = max(float((qz_unit.abs() * dt / VolumeZ.clamp_min(1.0)).max()), 1e-30)
-    ampv = min(courant_v / peak_v, 0.15 * courant_h / max(float((fx.abs() * dt / VolumeZ.clamp_min(1.0)).max()), 1e-30))
-    del conv, qz_unit
-    Wflux_X = qx2.unsqueeze(0) * (g * amp) * CFU + fx * ampv
-    Wflux_Y = qy2.unsqueeze(0) * (g * amp) * CFV + fy * ampv
-    del fx, fy
+    Wflux_X = (qx2.unsqueeze(0) * (g * amp) + dxp.unsqueeze(0) * (s * ampv)) * CFU
+    Wflux_Y = (qy2.unsqueeze(0) * (g * amp) + dyp.unsqueeze(0) * (s * ampv)) * CFV
     # continuity: Qz(k+1) = Qz(k) + Qx(j) - Qx(j+1) + Qy(i) - Qy(i+1) - (V - Vold)/dt   (AD:5718-5727 sign convention)
+    colmask = (surf & ~bnd2d).unsqueeze(0) & water3        # interior columns with W faces
     conv = torch.zeros(c.shape3, **f64)
     conv[:, :-1, :-1] = (Wflux_X[:, :-1, :-1] - Wflux_X[:, 1:, :-1] + Wflux_Y[:, :-1, :-1] - Wflux_Y[:, :-1, 1:])
     conv = conv - (VolumeZ - VolumeZOld) / dt
@@ -250,26 +270,23 @@ def make_case(I: int, J: int, K: int, nprop: int = 1, *, dt: float = 30.0, seed:
         OpenPoints3D=fin(openp, torch.int32), LandPoints3D=fin(land3, torch.int32),
         WaterPoints3D=fin(water3, torch.int32), ComputeFacesU3D=fin(CFU, torch.int32),
         ComputeFacesV3D=fin(CFV, torch.int32), ComputeFacesW3D=fin(CFW, torch.int32))
-    # padded volumes must stay non-zero (they are divisors in unmasked lanes of nobody, but keep them finite)
-    if ld > ni:
+    del Wflux_X, Wflux_Y, Wflux_Z, VolumeZOld, Visc_H, Diff_V, AreaU, AreaV, openp, CFU, CFV, CFW
+    if ld > ni:                                   # padded volumes / thicknesses stay finite divisors
         for name in ("VolumeZ", "VolumeZOld", "DWZ", "DZZ"):
             c.step[name].masked_fill_(pad.expand_as(c.step[name]), 1.0)
 
     # ---------------- tracers ----------------
     ranges = [(10.0, 20.0), (30.0, 36.0)]
     for n in range(nprop):
-        lo, hi = ranges[n] if n < len(ranges) else (0.0, 1.0)
-        ci = I * (0.35 + 0.3 * ((n * 0.37) % 1.0))
-        cj = c.J_global * (0.35 + 0.3 * ((n * 0.61) % 1.0))
-        sig_i, sig_j = 0.12 * I + 2.0, 0.12 * c.J_global + 2.0
-        blob = torch.exp(-0.5 * (((ii - ci) / sig_i) ** 2 + ((jj + c.j_offset - cj) / sig_j) ** 2)).unsqueeze(0)
+        lo_v, hi_v = ranges[n] if n < len(ranges) else (0.0, 1.0)
         vert = 0.5 + 0.5 * kk / K
-        p = lo + (hi - lo) * (0.15 + 0.7 * blob * vert + 0.01 * _splitmix64_uniform(lin, seed + 1000 + n))
+        p = lo_v + (hi_v - lo_v) * (0.15 + 0.7 * blobs[n].unsqueeze(0) * vert +
+                                    0.01 * _splitmix64_uniform(lin, seed + 1000 + n))
         p = torch.where(land3, torch.full_like(p, -9.9e15), p)      # land carries null_real (AD:1753)
         p = torch.where(inwork, p, torch.zeros_like(p))              # halos 0
         c.props.append(fin(p))
         if make_refs:
-            r = lo + (hi - lo) * (0.5 + 0.1 * torch.sin(TWO_PI * kk / K)) + 0.0 * blob
+            r = lo_v + (hi_v - lo_v) * (0.5 + 0.1 * torch.sin(TWO_PI * kk / K)) + 0.0 * blobs[n].unsqueeze(0)
             c.refs.append(fin(r.expand(c.shape3)))
     return c
 
