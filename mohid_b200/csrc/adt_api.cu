@@ -39,7 +39,7 @@ struct Handle {
     int *raw_i[6] = {nullptr};
     // packed per-step coefficients (K1 outputs)
     double *dtv = nullptr, *vr = nullptr, *dhu = nullptr, *dhv = nullptr, *dvz = nullptr, *rdz = nullptr;
-    uint8_t *mask = nullptr;
+    uint32_t *mask = nullptr;
     // properties: ping-pong pairs + reference fields
     std::vector<double *> prop[2];
     std::vector<double *> ref;
@@ -298,7 +298,14 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
     const long nunits = (long)s.nprop * s.ntile_i * h->j_count;
     const long blocks = (nunits + wpb - 1) / wpb;
     if (blocks > 2147483647L) return fail(h, MOHID_ADT_ERR_ARG, "grid too large");
-    CU(h, cudaFuncSetAttribute(adt_transport_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // kernel variant: the two headline schemes are compiled with fixed method / limiter
+    void (*kern)(const StepArgs) = adt_transport_kernel<0, 0, 0, 0>;
+    if (s.method_h == MOHID_P2_TVD && s.method_v == MOHID_P2_TVD && s.limiter_h == MOHID_SuperBee &&
+        s.limiter_v == MOHID_SuperBee)
+        kern = adt_transport_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee>;
+    else if (s.method_h == MOHID_UpwindOrder1 && s.method_v == MOHID_UpwindOrder1)
+        kern = adt_transport_kernel<MOHID_UpwindOrder1, MOHID_SuperBee, MOHID_UpwindOrder1, MOHID_SuperBee>;
+    CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (timed) {
         if (h->ev_used == h->ev.size()) {
@@ -311,7 +318,7 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
         h->ev_used++;
         CU(h, cudaEventRecord(e0, h->stream));
     }
-    adt_transport_kernel<<<(unsigned)blocks, wpb * 32, smem, h->stream>>>(s);
+    kern<<<(unsigned)blocks, wpb * 32, smem, h->stream>>>(s);
     CU(h, cudaGetLastError());
     if (timed) CU(h, cudaEventRecord(e1, h->stream));
     h->launches++;

@@ -7,7 +7,7 @@
 //  K1  adt_coef_kernel      per-step shared coefficients (property independent):
 //                           Convert_Dif_Vertical / Convert_Visc_Dif_Horizontal (AD:2364-2675),
 //                           Compute_DifH/DifV_Constants (AD:1514-1619), DT/V, Vold/V, the packed
-//                           1-byte mask and 1/(DWZ(k)+DWZ(k-1)).
+//                           32-bit neighbourhood mask and 1/(DWZ(k)+DWZ(k-1)).
 //  K2  adt_transport_kernel the fused step, one thread per (water column, property):
 //                           VolumeVariation (AD:3966) + explicit horizontal diffusion/advection
 //                           (AD:5123-5365, 4368-4953; face weights MF:10702-10894) + vertical
@@ -36,16 +36,25 @@ constexpr int NPMAX = 32;                 // max properties per launch (kernel-p
 constexpr double NULL_REAL = MOHID_NULL_REAL;
 constexpr double MIN_VALUE = 1.e-16;      // MGD:1812
 
-// packed per-cell mask byte written by K1
+// Packed per-cell 32-bit neighbourhood mask written by K1: everything K2 has to know about the cell and
+// the compute-point state of its stencil neighbours, so one load replaces six mask loads.
 enum : unsigned {
-    M_OPEN = 1u,      // OpenPoints3D == 1
-    M_CFU = 2u,       // ComputeFacesU3D == 1 (west face of the cell)
-    M_CFV = 4u,       // ComputeFacesV3D == 1 (south face)
-    M_CFW = 8u,       // ComputeFacesW3D == 1 (bottom face)
-    M_LAND = 16u,     // LandPoints3D == 1
-    M_BND = 32u,      // BoundaryPoints2D(i,j) == 1
-    M_COLWET = 64u,   // WaterPoints3D(i,j,KUB) == 1: the column is solved (MF:4086)
-    M_COLOPEN = 128u  // OpenPoints3D(i,j,KUB) == 1: vertical advection coefficients are built (AD:2966)
+    M_OPEN = 1u << 0,      // OpenPoints3D == 1
+    M_CFU = 1u << 1,       // ComputeFacesU3D(i,j,k)   == 1 (west face)
+    M_CFUE = 1u << 2,      // ComputeFacesU3D(i,j+1,k) == 1 (east face)
+    M_CFV = 1u << 3,       // ComputeFacesV3D(i,j,k)   == 1 (south face)
+    M_CFVN = 1u << 4,      // ComputeFacesV3D(i+1,j,k) == 1 (north face)
+    M_CFW = 1u << 5,       // ComputeFacesW3D(i,j,k)   == 1 (bottom face)
+    M_CFWT = 1u << 6,      // ComputeFacesW3D(i,j,k+1) == 1 (top face)
+    M_LAND = 1u << 7,      // LandPoints3D == 1
+    M_BND = 1u << 8,       // BoundaryPoints2D(i,j) == 1
+    M_COLWET = 1u << 9,    // WaterPoints3D(i,j,KUB) == 1: the column is solved (MF:4086)
+    M_COLOPEN = 1u << 10,  // OpenPoints3D(i,j,KUB) == 1: vertical advection coefficients are built (AD:2966)
+    M_O_JM2 = 1u << 11, M_O_JM1 = 1u << 12, M_O_JP1 = 1u << 13, M_O_JP2 = 1u << 14,   // OpenPoints3D of j-2..j+2
+    M_O_IM2 = 1u << 15, M_O_IM1 = 1u << 16, M_O_IP1 = 1u << 17, M_O_IP2 = 1u << 18,   // ... of i-2..i+2
+    M_O_KM1 = 1u << 19, M_O_KP1 = 1u << 20, M_O_KP2 = 1u << 21,                       // ... of k-1, k+1, k+2
+    // interior (open, non-boundary) neighbours for the ImposedValue boundary (AD:5462-5470)
+    M_A_IP1 = 1u << 22, M_A_IM1 = 1u << 23, M_A_JP1 = 1u << 24, M_A_JM1 = 1u << 25
 };
 
 struct CoefArgs {
@@ -60,12 +69,12 @@ struct CoefArgs {
     const int *Bnd;
     // outputs
     double *dtv, *vr, *dhu, *dhv, *dvz, *rdz;
-    uint8_t *mask;
+    uint32_t *mask;
     int do_geom, do_diff;            // which parts to (re)build
 };
 
 // -------------------------------------------------------------------------------------
-// K1: one thread per allocated cell, i fastest (coalesced); memory bound (112 B in, 49 B out).
+// K1: one thread per allocated cell, i fastest (coalesced); memory bound (112 B in, 52 B out).
 // -------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) adt_coef_kernel(const CoefArgs a) {
     const long n3 = (long)a.ld * a.nj * a.nk;
@@ -82,17 +91,46 @@ __global__ void __launch_bounds__(256) adt_coef_kernel(const CoefArgs a) {
         const long q2 = (long)i + sj * j;
         const bool cfu = a.CFU[q] == 1, cfv = a.CFV[q] == 1, cfw = a.CFW[q] == 1;
         if (a.do_geom) {
+            // neighbour lookups stay inside the allocation: clamp the probe to the array and test the range
+            auto open_at = [&](int di, int dj, int dk) -> bool {
+                const int ii = i + di, jj = j + dj, kk = k + dk;
+                if (ii < 0 || ii >= a.ni || jj < 0 || jj >= a.nj || kk < 0 || kk >= a.nk) return false;
+                return a.Open[q + di + sj * dj + sk * dk] == 1;
+            };
+            auto bnd_at = [&](int di, int dj) -> bool {
+                const int ii = i + di, jj = j + dj;
+                if (ii < 0 || ii >= a.ni || jj < 0 || jj >= a.nj) return false;
+                return a.Bnd[q2 + di + sj * dj] == 1;
+            };
             unsigned m = 0;
             if (a.Open[q] == 1) m |= M_OPEN;
             if (cfu) m |= M_CFU;
             if (cfv) m |= M_CFV;
             if (cfw) m |= M_CFW;
+            if (j + 1 < a.nj && a.CFU[q + sj] == 1) m |= M_CFUE;
+            if (i + 1 < a.ni && a.CFV[q + 1] == 1) m |= M_CFVN;
+            if (k + 1 < a.nk && a.CFW[q + sk] == 1) m |= M_CFWT;
             if (a.Land[q] == 1) m |= M_LAND;
             if (a.Bnd[q2] == 1) m |= M_BND;
             const long qtop = q2 + sk * a.K;
             if (a.Water[qtop] == 1) m |= M_COLWET;
             if (a.Open[qtop] == 1) m |= M_COLOPEN;
-            a.mask[q] = (uint8_t)m;
+            if (open_at(0, -2, 0)) m |= M_O_JM2;
+            if (open_at(0, -1, 0)) m |= M_O_JM1;
+            if (open_at(0, 1, 0)) m |= M_O_JP1;
+            if (open_at(0, 2, 0)) m |= M_O_JP2;
+            if (open_at(-2, 0, 0)) m |= M_O_IM2;
+            if (open_at(-1, 0, 0)) m |= M_O_IM1;
+            if (open_at(1, 0, 0)) m |= M_O_IP1;
+            if (open_at(2, 0, 0)) m |= M_O_IP2;
+            if (open_at(0, 0, -1)) m |= M_O_KM1;
+            if (open_at(0, 0, 1)) m |= M_O_KP1;
+            if (open_at(0, 0, 2)) m |= M_O_KP2;
+            if (open_at(1, 0, 0) && !bnd_at(1, 0)) m |= M_A_IP1;
+            if (open_at(-1, 0, 0) && !bnd_at(-1, 0)) m |= M_A_IM1;
+            if (open_at(0, 1, 0) && !bnd_at(0, 1)) m |= M_A_JP1;
+            if (open_at(0, -1, 0) && !bnd_at(0, -1)) m |= M_A_JM1;
+            a.mask[q] = m;
             const double V = a.VolumeZ[q];
             const bool inwork = (i >= 1 && i <= a.I && j >= 1 && j <= a.J && k >= 1 && k <= a.K);
             a.dtv[q] = (inwork && V != 0.) ? a.dt / V : 0.;
@@ -162,7 +200,7 @@ struct StepArgs {
     int vertical1d, xzflow;
     double vrelmax, dt;
     const double *qx, *qy, *qz, *dtv, *vr, *dhu, *dhv, *dvz, *rdz;
-    const uint8_t *mask;
+    const uint32_t *mask;
     const double *rdx, *rdy, *DUX, *DVY, *DWZ;
     const double *VolumeZ, *VolumeZOld;         // open-boundary flux only (AD:5718-5727)
     unsigned long long *zero_pivots;
@@ -171,102 +209,153 @@ struct StepArgs {
 
 __device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
 __device__ __forceinline__ double shfl_dn_d(double v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ double sel(bool c, double a, double b) { return c ? a : b; }
 
-// TVD limiter psi(r) (MF:10812-10856); Cr may be overwritten by the PDM branch (quirk A.4-1)
-__device__ __forceinline__ double tvd_psi(int limiter, double r, double &Cr) {
-    switch (limiter) {
-        case MOHID_MinMod: return fmax(0., fmin(1., r));
-        case MOHID_VanLeer: return (r < 0.) ? 0. : 2. * r / (1. + r);
-        case MOHID_Muscl: return fmax(0., fmin(fmin(2., 2. * r), (1. + r) / 2.));
-        case MOHID_SuperBee: return fmax(fmax(0., fmin(1., 2. * r)), fmin(r, 2.));
-        default: {  // PDM
-            const double c = (1. - 2. * fabs(Cr)) / 6.;
-            const double a = 0.5 + c, b = 0.5 - c;
-            const double aux = a + b * r;
-            if (fabs(Cr) < MIN_VALUE) Cr = MIN_VALUE;
-            return fmax(0., fmin(fmin(aux, 2. / (1. - Cr)), 2. * r / Cr));
-        }
-    }
+// 1/x for normal, finite x without the IEEE slow path: MUFU.RCP64H seed (2^-20) + two Newton steps
+// (relative error <= ~2 ulp).  Callers guarantee |x| is far from 0, Inf and the denormal range.
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
 }
 
-// Face weights CFace(1..4) of ComputeAdvectionFace (MF:10702-10894) for the stencil cells
-// (f-2, f-1, f, f+1) = (1,2,3,4).  o1/o4: the outer cells are compute points (near-boundary test,
-// MF:10563-10570).  dtv1..4 = DT/V of the four cells (signed Courant = Q*dtv, MF:11045-11053;
-// VolumeRel of methods 2/3 = max(dtv)/min(dtv)); rd12, rd23, rd34 = 1/(du_a+du_b); du2, du3 only
-// for the centred schemes.
-__device__ __forceinline__ void face_weights(int method, int limiter, bool upwind2, double vrelmax, double Q,
-                                             double P1, double P2, double P3, double P4, bool o1, bool o4,
-                                             double dtv1, double dtv2, double dtv3, double dtv4, double rd12,
-                                             double rd23, double rd34, double du2, double du3, double &c1,
-                                             double &c2, double &c3, double &c4) {
-    const bool pos = Q > 0.;
-    const bool near = pos ? !o1 : !o4;
-    c1 = 0.; c4 = 0.;
-    if (method == MOHID_UpwindOrder1 || (near && upwind2)) {
-        c2 = pos ? 1. : 0.;
-        c3 = pos ? 0. : 1.;
-        return;
-    }
+// TVD limiter psi(r) (MF:10812-10856); Cr may be overwritten by the PDM branch (quirk A.4-1)
+template <int L>
+__device__ __forceinline__ double tvd_psi(int limiter_rt, double r, double &Cr) {
+    const int limiter = (L > 0) ? L : limiter_rt;
+    if (limiter == MOHID_SuperBee) return fmax(fmax(0., fmin(1., 2. * r)), fmin(r, 2.));
+    if (limiter == MOHID_MinMod) return fmax(0., fmin(1., r));
+    if (limiter == MOHID_VanLeer) return (r < 0.) ? 0. : 2. * r * fast_rcp(1. + r);
+    if (limiter == MOHID_Muscl) return fmax(0., fmin(fmin(2., 2. * r), (1. + r) * 0.5));
+    // PDM
+    const double c = (1. - 2. * fabs(Cr)) / 6.;
+    const double a = 0.5 + c, b = 0.5 - c;
+    const double aux = a + b * r;
+    if (fabs(Cr) < MIN_VALUE) Cr = MIN_VALUE;
+    return fmax(0., fmin(fmin(aux, 2. * fast_rcp(1. - Cr)), 2. * r * fast_rcp(Cr)));
+}
+
+// Face weights of ComputeAdvectionFace (MF:10702-10894) in UPWIND-ORIENTED form: the face flux of
+// property is Q * (wuu*Puu + wu*Pu + wd*Pd) with (uu, u, d) = (2nd upwind, upwind, downwind) cell.
+// For Q > 0 that is (f-2, f-1, f), otherwise (f+1, f, f-1) -- Q == 0 counts as negative (MF:11127-11141).
+//   near   : the 2nd upwind cell is not a compute point (MF:10563-10570)
+//   t_*    : DT/V of the cells (signed Courant = Q*t_u, MF:11045-11053; VolumeRel = max/min of t)
+//   rd_u   : 1/(du_u+du_uu), rd_c : 1/(du_u+du_d); du_u, du_d only for the centred schemes
+template <int M, int L>
+__device__ __forceinline__ void oriented_weights(int method_rt, int limiter_rt, bool upwind2, double vrelmax,
+                                                 double Q, double Puu, double Pu, double Pd, bool near,
+                                                 double t_uu, double t_u, double t_d, double rd_u, double rd_c,
+                                                 double du_u, double du_d, double &wuu, double &wu, double &wd) {
+    const int method = (M > 0) ? M : method_rt;
+    wuu = 0.; wu = 1.; wd = 0.;
+    if (method == MOHID_UpwindOrder1) return;
     if (method == MOHID_P2_TVD) {
-        double Cr = Q * (pos ? dtv2 : dtv3);
-        const double dP = pos ? (P3 - P2) : (P2 - P3);
-        double dC = dP * rd23;
+        double Cr = Q * t_u;
+        double dC = (Pd - Pu) * rd_c;
         if (fabs(dC) < MIN_VALUE) dC = (dC >= 0.) ? MIN_VALUE : -MIN_VALUE;
-        const double up = pos ? (P2 - P1) * rd12 : (P3 - P4) * rd34;
-        const double r = up / dC;
-        double theta = tvd_psi(limiter, r, Cr);
+        const double r = (Pu - Puu) * rd_u * fast_rcp(dC);
+        double theta = tvd_psi<L>(limiter_rt, r, Cr);
         theta = 0.5 * theta * (1. - Cr);
-        c2 = pos ? (1. - theta) : theta;
-        c3 = pos ? theta : (1. - theta);
+        theta = (near && upwind2) ? 0. : theta;
+        wu = 1. - theta;
+        wd = theta;
         return;
     }
     if (method == MOHID_CentralDif || method == MOHID_LeapFrog) {
-        c2 = du3 * rd23;
-        c3 = du2 * rd23;
+        if (!(near && upwind2)) { wu = du_d * rd_c; wd = du_u * rd_c; }
         return;
     }
-    // UpwindOrder2 (QUICK) / UpwindOrder3 (QUICKEST), interior faces (MF:10751-10770, 11055-11125)
-    {
-        const double ta = pos ? dtv1 : dtv2, tb = pos ? dtv2 : dtv3, tc = pos ? dtv3 : dtv4;
-        const double tmax = fmax(fmax(ta, tb), tc), tmin = fmin(fmin(ta, tb), tc);
-        const bool first_order = (tmax / tmin > vrelmax) || (Q == 0.);
-        if (first_order) {
-            c2 = pos ? 1. : 0.;
-            c3 = pos ? 0. : 1.;
-            return;
-        }
-        double h1, h2, h3;      // weights of (2nd upwind, upwind, downwind)
-        if (method == MOHID_UpwindOrder2) {
-            h1 = -1. / 8.; h2 = 6. / 8.; h3 = 3. / 8.;
-        } else {
-            const double Cr = Q * (pos ? dtv2 : dtv3);
-            const double c = (1. - 2. * fabs(Cr)) / 6.;
-            const double a = 0.5 + c, b = 0.5 - c, d = (1. - fabs(Cr)) / 2.;
-            h1 = -d * b; h2 = 1. + d * (b - a); h3 = d * a;
-        }
-        c2 = pos ? h2 : h3;
-        c3 = pos ? h3 : h2;
-        if (pos) c1 = h1; else c4 = h1;
+    // UpwindOrder2 (QUICK) / UpwindOrder3 (QUICKEST), MF:10751-10770, 11055-11125
+    const double tmax = fmax(fmax(t_uu, t_u), t_d), tmin = fmin(fmin(t_uu, t_u), t_d);
+    const bool first_order = near || (tmax > vrelmax * tmin) || (Q == 0.);
+    if (first_order) return;
+    if (method == MOHID_UpwindOrder2) {
+        wuu = -1. / 8.; wu = 6. / 8.; wd = 3. / 8.;
+    } else {
+        const double Cr = Q * t_u;
+        const double c = (1. - 2. * fabs(Cr)) / 6.;
+        const double a = 0.5 + c, b = 0.5 - c, d = (1. - fabs(Cr)) / 2.;
+        wuu = -d * b; wu = 1. + d * (b - a); wd = d * a;
     }
 }
 
-// Total (advective - diffusive) property flux through a horizontal face, positive toward +index.
-// Applied iff the face is a compute face; advective weights exist iff both adjacent cells are open
-// (MF:10559, AD:4467, AD:5188).
-__device__ __forceinline__ double hface_flux(const StepArgs &s, bool cf, bool o2, bool o3, double Q, double dh,
-                                             double P1, double P2, double P3, double P4, bool o1, bool o4,
-                                             double dtv1, double dtv2, double dtv3, double dtv4, double rd12,
-                                             double rd23, double rd34, double du2, double du3) {
-    if (!cf) return 0.;
-    double f = -dh * (P3 - P2);
-    if (o2 && o3) {
-        double c1, c2, c3, c4;
-        face_weights(s.method_h, s.limiter_h, s.upwind2_h != 0, s.vrelmax, Q, P1, P2, P3, P4, o1, o4, dtv1, dtv2,
-                     dtv3, dtv4, rd12, rd23, rd34, du2, du3, c1, c2, c3, c4);
-        f += Q * (c1 * P1 + c2 * P2 + c3 * P3 + c4 * P4);
-    }
-    return f;
+// Total (advective - diffusive) property flux through a horizontal face between cells 2 and 3 of the
+// stencil (1,2,3,4), positive toward cell 3.  adv_on = face is a compute face AND both cells are open
+// (MF:10559, AD:4467); the diffusive conductance dh is already zero on non-compute faces (K1).
+template <int M, int L>
+__device__ __forceinline__ double hface_flux(const StepArgs &s, bool adv_on, double Q, double dh, double P1,
+                                             double P2, double P3, double P4, bool o1, bool o4, double t1,
+                                             double t2, double t3, double t4, double rd12, double rd23,
+                                             double rd34, double du2, double du3) {
+    const bool pos = Q > 0.;
+    const double Puu = sel(pos, P1, P4), Pu = sel(pos, P2, P3), Pd = sel(pos, P3, P2);
+    double wuu, wu, wd;
+    oriented_weights<M, L>(s.method_h, s.limiter_h, s.upwind2_h != 0, s.vrelmax, Q, Puu, Pu, Pd, pos ? !o1 : !o4,
+                           sel(pos, t1, t4), sel(pos, t2, t3), sel(pos, t3, t2), sel(pos, rd12, rd34), rd23,
+                           sel(pos, du2, du3), sel(pos, du3, du2), wuu, wu, wd);
+    const double fadv = Q * (wuu * Puu + wu * Pu + wd * Pd);
+    return sel(adv_on, fadv, 0.) - dh * (P3 - P2);
 }
+
+// Rows of open-boundary cells (AD:5369-5672); rare (boundary ring only): a predicated-off branch elsewhere.
+struct Row { double D, E, F, TI; };
+__device__ __forceinline__ void open_boundary_row(const StepArgs &s, const PropArgs &pa, long q, unsigned m, double Pc,
+                                               double qz_c, double qz_p, double dtv_c, Row &row) {
+    const double *__restrict__ P = pa.pin;
+    const long sj = s.ld;
+    const int bc = pa.bc;
+    if (bc == MOHID_BC_NullGradient || bc == MOHID_BC_CyclicBoundary) {
+        row.TI = Pc; row.D = 0.; row.E = 1.; row.F = 0.;
+    } else if (bc == MOHID_BC_ImposedValue || bc == MOHID_BC_SubModel) {
+        const double A1 = (m & M_A_IP1) ? 1. : 0., A2 = (m & M_A_IM1) ? 1. : 0.;
+        const double A3 = (m & M_A_JP1) ? 1. : 0., A4 = (m & M_A_JM1) ? 1. : 0.;
+        const double At = A1 + A2 + A3 + A4;
+        double ext;
+        if (At > 0.) {
+            const double pin_ = (P[q + 1] * A1 + P[q - 1] * A2 + P[q + sj] * A3 + P[q - sj] * A4) / At;
+            ext = pin_ * (1.0 - pa.tdec) + pa.pref[q] * pa.tdec;
+        } else {
+            ext = pa.pref[q];
+        }
+        row.TI = ext; row.D = 0.; row.E = 1.; row.F = 0.;
+    } else {
+        // WaterFluxOBoundary (AD:5718-5727)
+        const double qb = s.qx[q] * ((m & M_CFU) ? 1. : 0.) - s.qx[q + sj] * ((m & M_CFUE) ? 1. : 0.) +
+                          s.qy[q] * ((m & M_CFV) ? 1. : 0.) - s.qy[q + 1] * ((m & M_CFVN) ? 1. : 0.) +
+                          qz_c * ((m & M_CFW) ? 1. : 0.) - qz_p * ((m & M_CFWT) ? 1. : 0.) -
+                          (s.VolumeZ[q] - s.VolumeZOld[q]) / s.dt;
+        if (qb < 0.) {
+            if (bc == MOHID_BC_MassConservation) {
+                const double ext = Pc * (1.0 - pa.tdec) + pa.pref[q] * pa.tdec;
+                row.TI -= qb * ext * dtv_c;
+            } else {                               // MassConservNullGrad: NullGradProp of the old field
+                const int cVn = (m & M_CFVN) ? 1 : 0, cVs = (m & M_CFV) ? 1 : 0;
+                const int cUe = (m & M_CFUE) ? 1 : 0, cUw = (m & M_CFU) ? 1 : 0;
+                const int aux = cVn + cVs + cUe + cUw;
+                if (aux > 0)
+                    row.TI = (P[q + 1] * cVn + P[q - 1] * cVs + P[q + sj] * cUe + P[q - sj] * cUw) / (double)aux;
+                else
+                    row.TI = Pc;
+                row.D = 0.; row.E = 1.; row.F = 0.;
+            }
+        } else {
+            row.E += qb * dtv_c;
+        }
+    }
+}
+
+// Horizontal data of one level of one column, fetched one level ahead of its use (software pipeline).
+struct Level {
+    double Pw2, Pw1, Pe1, Pe2, hP;      // property at j-2, j-1, j+1, j+2 and the strip-halo value
+    double t_w, t_e, t_h;               // DT/V at j-1, j+1 and of the south neighbour of lane 0
+    double t_w2, t_e2, t_h2;            // DT/V at j-2, j+2, strip halo (QUICK / QUICKEST only)
+    double qxw, qxe, qys, dhw, dhe, dhs, vr;
+    unsigned m;
+};
 
 // -------------------------------------------------------------------------------------
 // K2: fused transport step.
@@ -276,7 +365,9 @@ __device__ __forceinline__ double hface_flux(const StepArgs &s, bool cf, bool o2
 //   back-substitutes and writes the new property.  Units are ordered property-fastest so the
 //   warps of a block read the same shared coefficients (L1 hits).
 //   blockDim.x = 32 * WPB; dynamic shared memory = 2 * K * WPB * 32 doubles.
+//   MH/LH/MV/LV > 0 fix the advection method / limiter at compile time; 0 = read from StepArgs.
 // -------------------------------------------------------------------------------------
+template <int MH, int LH, int MV, int LV>
 __global__ void __launch_bounds__(384, 1) adt_transport_kernel(const __grid_constant__ StepArgs s) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, WPB = blockDim.x >> 5;
@@ -292,207 +383,165 @@ __global__ void __launch_bounds__(384, 1) adt_transport_kernel(const __grid_cons
     const int i = 1 + tile * 31 + lane;
     const bool writer = (lane < 31) && (i <= s.I);
     const int ic = min(i, s.I + 1);                       // clamped column: every load stays in bounds
-    const PropArgs &pa = s.p[n];
+    const PropArgs pa = s.p[n];
     const double *__restrict__ P = pa.pin;
     const long sj = s.ld, sk = s.sk;
     const long c2d = (long)ic + sj * j;
-    const bool jp2 = (j + 2 <= s.J + 1);
+    const long je2 = (j + 2 <= s.J + 1) ? 2 * sj : sj;     // offset of column j+2 (clamped at the array edge)
+
+    const int method_h = MH > 0 ? MH : s.method_h, method_v = MV > 0 ? MV : s.method_v;
+    const bool central_h = (method_h == MOHID_CentralDif || method_h == MOHID_LeapFrog);
+    const bool central_v = (method_v == MOHID_CentralDif || method_v == MOHID_LeapFrog);
+    const bool far_h = (method_h == MOHID_UpwindOrder2 || method_h == MOHID_UpwindOrder3);
+    const bool far_v = (method_v == MOHID_UpwindOrder2 || method_v == MOHID_UpwindOrder3);
+    const bool do_h = !s.vertical1d, do_y = do_h && !s.xzflow;
 
     // ---- 2-D metrics of the column ----
-    const double rdx_m = s.rdx[c2d - sj], rdx_c = s.rdx[c2d], rdx_p = s.rdx[c2d + sj];
-    const double rdx_pp = jp2 ? s.rdx[c2d + 2 * sj] : 0.;
+    const double rdx_m = s.rdx[c2d - sj], rdx_c = s.rdx[c2d], rdx_p = s.rdx[c2d + sj], rdx_pp = s.rdx[c2d + je2];
     const double rdy_c = s.rdy[c2d];
     double rdy_m = shfl_up_d(rdy_c, 1), rdy_p = shfl_dn_d(rdy_c, 1);
     if (lane == 0) rdy_m = s.rdy[c2d - 1];
     if (lane == 31) rdy_p = s.rdy[c2d + (ic <= s.I ? 1 : 0)];
     double dux_m = 0., dux_c = 0., dux_p = 0., dvy_m = 0., dvy_c = 0.;
-    const bool central_h = (s.method_h == MOHID_CentralDif || s.method_h == MOHID_LeapFrog);
-    const bool central_v = (s.method_v == MOHID_CentralDif || s.method_v == MOHID_LeapFrog);
     if (central_h) {
         dux_m = s.DUX[c2d - sj]; dux_c = s.DUX[c2d]; dux_p = s.DUX[c2d + sj];
         dvy_c = s.DVY[c2d]; dvy_m = s.DVY[c2d - 1];
     }
-    const bool far_h = (s.method_h == MOHID_UpwindOrder2 || s.method_h == MOHID_UpwindOrder3);
-    const bool far_v = (s.method_v == MOHID_UpwindOrder2 || s.method_v == MOHID_UpwindOrder3);
 
     const unsigned mtop = s.mask[c2d + sk * s.K];
     const bool colwet = (mtop & M_COLWET) != 0;
     const bool colopen = (mtop & M_COLOPEN) != 0;
-    const bool bnd = (mtop & M_BND) != 0;
-    const int bc = pa.bc;
-    const double theta = pa.theta_difv;
+    const bool obc = (mtop & M_BND) != 0 && pa.bc != MOHID_BC_None;
+    const double theta = pa.theta_difv, omt = 1. - pa.theta_difv;
     const bool advv_imp = pa.advv_implicit != 0;
     // halo lanes of the strip: lanes 0,1 fetch cell i-2, lane 31 fetches cell i+1
     const bool halo_lane = (lane < 2) || (lane == 31);
-    const int halo_off = (lane == 31) ? ((ic <= s.I) ? 1 : 0) : -2;
+    const long halo_off = (lane == 31) ? ((ic <= s.I) ? 1 : 0) : -2;
+
+    // fetch the horizontal data of level k at cell offset q (all loads independent of computed values)
+    auto fetch = [&](long q, Level &L) {
+        L.m = s.mask[q];
+        L.vr = s.vr[q];
+        if (do_h) {
+            L.Pw2 = P[q - 2 * sj]; L.Pw1 = P[q - sj]; L.Pe1 = P[q + sj]; L.Pe2 = P[q + je2];
+            L.t_w = s.dtv[q - sj]; L.t_e = s.dtv[q + sj];
+            L.qxw = s.qx[q]; L.qxe = s.qx[q + sj]; L.dhw = s.dhu[q]; L.dhe = s.dhu[q + sj];
+            if (far_h) { L.t_w2 = s.dtv[q - 2 * sj]; L.t_e2 = s.dtv[q + je2]; }
+            if (do_y) {
+                L.qys = s.qy[q]; L.dhs = s.dhv[q];
+                L.hP = halo_lane ? P[q + halo_off] : 0.;
+                L.t_h = (lane == 0) ? s.dtv[q - 1] : 0.;
+                if (far_h) L.t_h2 = halo_lane ? s.dtv[q + halo_off] : 0.;
+            }
+        }
+    };
 
     // ---- rolling registers along k (cells k-1 .. k+2 of this column) ----
     long q = c2d + sk;                                    // cell (i,j,1)
     double Pm1 = P[c2d], Pc = P[q], Pp1 = P[q + sk];
-    unsigned mm1 = s.mask[c2d], mc = s.mask[q], mp1 = s.mask[q + sk];
     double dtv_m = 0., dtv_c = s.dtv[q], dtv_p = s.dtv[q + sk];
     double rdz_c = s.rdz[q], rdz_p = s.rdz[q + sk];
     double qz_c = s.qz[q], qz_p = s.qz[q + sk];
+    double dvz_p = s.dvz[q + sk];
     double Dk = 0., Ek_b = 0., TIk_b = 0.;                // contributions of the bottom face to row k
     double Wprev = 0., Gprev = 0.;
     unsigned long long zp = 0;
+    Level cur, nxt;
+    fetch(q, cur);
 
     for (int k = 1; k <= s.K; ++k, q += sk) {
-        const bool has2 = (k + 2 <= s.K + 1);
-        const long q2 = has2 ? q + 2 * sk : q;
-        const double Pp2 = has2 ? P[q2] : 0.;
-        const unsigned mp2 = has2 ? s.mask[q2] : 0u;
-        const double rdz_pp = has2 ? s.rdz[q2] : 0.;
-        const double dtv_pp = has2 ? s.dtv[q2] : 0.;
-        const double qz_pp = has2 ? s.qz[q2] : 0.;
+        // ---- prefetch: level k+1 (horizontal) and level k+2 (vertical rolling values) ----
+        const long q2 = (k + 2 <= s.K + 1) ? q + 2 * sk : q + sk;
+        const double Pp2 = P[q2], rdz_pp = s.rdz[q2], dtv_pp = s.dtv[q2], qz_pp = s.qz[q2], dvz_pp = s.dvz[q2];
+        if (k < s.K) fetch(q + sk, nxt);
 
-        const bool open_c = (mc & M_OPEN) != 0;
+        const unsigned m = cur.m;
+        const bool open_c = (m & M_OPEN) != 0;
         // ---------------- VolumeVariation (AD:3966-4021) ----------------
-        double TI = open_c ? Pc * s.vr[q] : Pc;
-        double E = 1.0;
-        if (open_c && k == s.K) E = 1.0 + dtv_c * qz_p;
-        double D = Dk, F = 0.;
-        E += Ek_b;
-        TI += TIk_b;
+        Row row;
+        row.TI = sel(open_c, Pc * cur.vr, Pc) + TIk_b;
+        row.E = sel(open_c && k == s.K, 1.0 + dtv_c * qz_p, 1.0) + Ek_b;
+        row.D = Dk;
+        row.F = 0.;
 
         // ---------------- horizontal faces (explicit) ----------------
-        if (!s.vertical1d) {
-            // X direction: west face j and east face j+1 of this cell
-            const double Pw2 = P[q - 2 * sj], Pw1 = P[q - sj], Pe1 = P[q + sj];
-            const double Pe2 = jp2 ? P[q + 2 * sj] : 0.;
-            const unsigned mw2 = s.mask[q - 2 * sj], mw1 = s.mask[q - sj], me1 = s.mask[q + sj];
-            const unsigned me2 = jp2 ? s.mask[q + 2 * sj] : 0u;
-            const double dtv_w = s.dtv[q - sj], dtv_e = s.dtv[q + sj];
-            double dtv_w2 = 0., dtv_e2 = 0.;
-            if (far_h) {
-                dtv_w2 = s.dtv[q - 2 * sj];
-                dtv_e2 = jp2 ? s.dtv[q + 2 * sj] : 0.;
-            }
-            const double fw = hface_flux(s, (mc & M_CFU) != 0, (mw1 & M_OPEN) != 0, open_c, s.qx[q], s.dhu[q], Pw2,
-                                         Pw1, Pc, Pe1, (mw2 & M_OPEN) != 0, (me1 & M_OPEN) != 0, dtv_w2, dtv_w,
-                                         dtv_c, dtv_e, rdx_m, rdx_c, rdx_p, dux_m, dux_c);
-            const double fe = hface_flux(s, (me1 & M_CFU) != 0, open_c, (me1 & M_OPEN) != 0, s.qx[q + sj],
-                                         s.dhu[q + sj], Pw1, Pc, Pe1, Pe2, (mw1 & M_OPEN) != 0,
-                                         (me2 & M_OPEN) != 0, dtv_w, dtv_c, dtv_e, dtv_e2, rdx_c, rdx_p, rdx_pp,
-                                         dux_c, dux_p);
-            TI += (fw - fe) * dtv_c;
-
-            if (!s.xzflow) {
-                // Y direction: each lane builds its south face; the north face comes from lane+1
+        if (do_h) {
+            const bool o_w1 = (m & M_O_JM1) != 0, o_e1 = (m & M_O_JP1) != 0;
+            const double fw = hface_flux<MH, LH>(s, (m & M_CFU) && o_w1 && open_c, cur.qxw, cur.dhw, cur.Pw2, cur.Pw1,
+                                                 Pc, cur.Pe1, (m & M_O_JM2) != 0, o_e1, cur.t_w2, cur.t_w, dtv_c,
+                                                 cur.t_e, rdx_m, rdx_c, rdx_p, dux_m, dux_c);
+            const double fe = hface_flux<MH, LH>(s, (m & M_CFUE) && open_c && o_e1, cur.qxe, cur.dhe, cur.Pw1, Pc,
+                                                 cur.Pe1, cur.Pe2, o_w1, (m & M_O_JP2) != 0, cur.t_w, dtv_c, cur.t_e,
+                                                 cur.t_e2, rdx_c, rdx_p, rdx_pp, dux_c, dux_p);
+            double fsum = fw - fe;
+            if (do_y) {
+                // each lane builds its south face; the north face is the south face of lane+1
                 double Ps1 = shfl_up_d(Pc, 1), Ps2 = shfl_up_d(Pc, 2), Pn1 = shfl_dn_d(Pc, 1);
-                unsigned ms1 = __shfl_up_sync(0xffffffffu, mc, 1), ms2 = __shfl_up_sync(0xffffffffu, mc, 2);
-                unsigned mn1 = __shfl_down_sync(0xffffffffu, mc, 1);
-                double dtv_s = shfl_up_d(dtv_c, 1), dtv_n = shfl_dn_d(dtv_c, 1), dtv_s2 = 0.;
-                if (far_h) dtv_s2 = shfl_up_d(dtv_c, 2);
-                // strip halo
-                double hP = 0., hT = 0.;
-                unsigned hM = 0;
-                if (halo_lane) { hP = P[q + halo_off]; hM = s.mask[q + halo_off]; }
-                if (lane == 0) dtv_s = s.dtv[q - 1];
-                if (far_h && halo_lane) hT = s.dtv[q + halo_off];
-                const double hP1 = __shfl_sync(0xffffffffu, hP, 1);
-                const unsigned hM1 = __shfl_sync(0xffffffffu, hM, 1);
-                if (lane == 0) { Ps2 = hP; ms2 = hM; Ps1 = hP1; ms1 = hM1; dtv_s2 = hT; }
-                else if (lane == 1) { Ps2 = hP; ms2 = hM; dtv_s2 = hT; }
-                else if (lane == 31) { Pn1 = hP; mn1 = hM; dtv_n = far_h ? hT : dtv_n; }
-                const double fs = hface_flux(s, (mc & M_CFV) != 0, (ms1 & M_OPEN) != 0, open_c, s.qy[q], s.dhv[q],
-                                             Ps2, Ps1, Pc, Pn1, (ms2 & M_OPEN) != 0, (mn1 & M_OPEN) != 0, dtv_s2,
-                                             dtv_s, dtv_c, dtv_n, rdy_m, rdy_c, rdy_p, dvy_m, dvy_c);
-                const double fn = shfl_dn_d(fs, 1);
-                TI += (fs - fn) * dtv_c;
+                double t_s = shfl_up_d(dtv_c, 1), t_n = 0., t_s2 = 0.;
+                if (far_h) { t_n = shfl_dn_d(dtv_c, 1); t_s2 = shfl_up_d(dtv_c, 2); }
+                const double hP1 = __shfl_sync(0xffffffffu, cur.hP, 1);
+                if (lane == 0) { Ps2 = cur.hP; Ps1 = hP1; t_s = cur.t_h; t_s2 = cur.t_h2; }
+                else if (lane == 1) { Ps2 = cur.hP; t_s2 = cur.t_h2; }
+                else if (lane == 31) { Pn1 = cur.hP; t_n = cur.t_h2; }
+                const bool o_s1 = (m & M_O_IM1) != 0;
+                const double fs = hface_flux<MH, LH>(s, (m & M_CFV) && o_s1 && open_c, cur.qys, cur.dhs, Ps2, Ps1, Pc,
+                                                     Pn1, (m & M_O_IM2) != 0, (m & M_O_IP1) != 0, t_s2, t_s, dtv_c, t_n,
+                                                     rdy_m, rdy_c, rdy_p, dvy_m, dvy_c);
+                fsum += fs - shfl_dn_d(fs, 1);
             }
+            row.TI += fsum * dtv_c;
         }
 
         // ---------------- vertical face k+1 (top of this cell) ----------------
         double Dn = 0., En_b = 0., TIn_b = 0.;            // contributions to row k+1
-        if (s.K > 1 && (mp1 & M_CFW)) {
-            // diffusion (AD:2708-2775 / 2779-2937)
-            const double a = s.dvz[q + sk];
-            const double aux1 = a * dtv_c, aux2 = a * dtv_p;
+        if (s.K > 1) {
+            // diffusion (AD:2708-2775 / 2779-2937): dvz is zero on non-compute W faces and in SmallDepths columns
+            const double aux1 = dvz_p * dtv_c, aux2 = dvz_p * dtv_p;
             const double dP = Pp1 - Pc;
-            E += aux1 * theta;
-            F -= aux1 * theta;
-            TI += aux1 * dP * (1. - theta);
-            Dn -= aux2 * theta;
-            En_b += aux2 * theta;
-            TIn_b -= aux2 * dP * (1. - theta);
-            // advection (AD:2941-3144); weights exist iff both cells are open (MF:10559)
-            if (!s.vertical1d && colopen && open_c && (mp1 & M_OPEN)) {
-                double c1, c2, c3, c4, dwz_c = 0., dwz_p = 0.;
-                if (central_v) { dwz_c = s.DWZ[q]; dwz_p = s.DWZ[q + sk]; }
-                face_weights(s.method_v, s.limiter_v, s.upwind2_v != 0, s.vrelmax, qz_p, Pm1, Pc, Pp1, Pp2,
-                             (mm1 & M_OPEN) != 0, (mp2 & M_OPEN) != 0, dtv_m, dtv_c, dtv_p, dtv_pp, rdz_c, rdz_p,
-                             rdz_pp, dwz_c, dwz_p, c1, c2, c3, c4);
-                if (advv_imp) {
-                    const double dfl = qz_p * c2, efl = qz_p * c3;     // D_flux, E_flux (MF:10583-10586)
-                    E += dfl * dtv_c;
-                    F += efl * dtv_c;
-                    Dn -= dfl * dtv_p;
-                    En_b -= efl * dtv_p;
-                } else {
-                    const double fz = qz_p * (c1 * Pm1 + c2 * Pc + c3 * Pp1 + c4 * Pp2);
-                    TI -= fz * dtv_c;
-                    TIn_b += fz * dtv_p;
-                }
+            row.E += aux1 * theta;
+            row.F -= aux1 * theta;
+            row.TI += aux1 * dP * omt;
+            Dn = -aux2 * theta;
+            En_b = aux2 * theta;
+            TIn_b = -aux2 * dP * omt;
+            // advection (AD:2941-3144); weights exist iff both cells are open (MF:10559), applied on compute faces
+            const bool adv_on = do_h && colopen && open_c && (m & M_O_KP1) && (m & M_CFWT);
+            const bool pos = qz_p > 0.;
+            const double Puu = sel(pos, Pm1, Pp2), Pu = sel(pos, Pc, Pp1), Pd = sel(pos, Pp1, Pc);
+            double du_u = 0., du_d = 0.;
+            if (central_v) { const double a = s.DWZ[q], b = s.DWZ[q + sk]; du_u = sel(pos, a, b); du_d = sel(pos, b, a); }
+            double wuu, wu, wd;
+            oriented_weights<MV, LV>(s.method_v, s.limiter_v, s.upwind2_v != 0, s.vrelmax, qz_p, Puu, Pu, Pd,
+                                     pos ? !(m & M_O_KM1) : !(m & M_O_KP2), sel(pos, dtv_m, dtv_pp),
+                                     sel(pos, dtv_c, dtv_p), sel(pos, dtv_p, dtv_c), sel(pos, rdz_c, rdz_pp), rdz_p,
+                                     du_u, du_d, wuu, wu, wd);
+            const double qa = sel(adv_on, qz_p, 0.);
+            if (advv_imp) {
+                const double dfl = qa * sel(pos, wu, wd), efl = qa * sel(pos, wd, wu);   // D_flux, E_flux (MF:10583-10586)
+                row.E += dfl * dtv_c;
+                row.F += efl * dtv_c;
+                Dn -= dfl * dtv_p;
+                En_b -= efl * dtv_p;
+            } else {
+                const double fz = qa * (wuu * Puu + wu * Pu + wd * Pd);
+                row.TI -= fz * dtv_c;
+                TIn_b += fz * dtv_p;
             }
         }
         (void)far_v;
 
         // ---------------- open boundary rows (AD:5369-5672) ----------------
-        if (bnd && bc != MOHID_BC_None && open_c) {
-            if (bc == MOHID_BC_NullGradient || bc == MOHID_BC_CyclicBoundary) {
-                TI = Pc; D = 0.; E = 1.; F = 0.;
-            } else if (bc == MOHID_BC_ImposedValue || bc == MOHID_BC_SubModel) {
-                const unsigned mN = s.mask[q + 1], mS = s.mask[q - 1], mE = s.mask[q + sj], mW = s.mask[q - sj];
-                const double A1 = ((mN & M_OPEN) && !(mN & M_BND)) ? 1. : 0.;
-                const double A2 = ((mS & M_OPEN) && !(mS & M_BND)) ? 1. : 0.;
-                const double A3 = ((mE & M_OPEN) && !(mE & M_BND)) ? 1. : 0.;
-                const double A4 = ((mW & M_OPEN) && !(mW & M_BND)) ? 1. : 0.;
-                const double At = A1 + A2 + A3 + A4;
-                double ext;
-                if (At > 0.) {
-                    const double pin_ = (P[q + 1] * A1 + P[q - 1] * A2 + P[q + sj] * A3 + P[q - sj] * A4) / At;
-                    ext = pin_ * (1.0 - pa.tdec) + pa.pref[q] * pa.tdec;
-                } else {
-                    ext = pa.pref[q];
-                }
-                TI = ext; D = 0.; E = 1.; F = 0.;
-            } else {
-                // WaterFluxOBoundary (AD:5718-5727)
-                const unsigned mE = s.mask[q + sj], mN = s.mask[q + 1];
-                const double qb = s.qx[q] * ((mc & M_CFU) ? 1. : 0.) - s.qx[q + sj] * ((mE & M_CFU) ? 1. : 0.) +
-                                  s.qy[q] * ((mc & M_CFV) ? 1. : 0.) - s.qy[q + 1] * ((mN & M_CFV) ? 1. : 0.) +
-                                  qz_c * ((mc & M_CFW) ? 1. : 0.) - qz_p * ((mp1 & M_CFW) ? 1. : 0.) -
-                                  (s.VolumeZ[q] - s.VolumeZOld[q]) / s.dt;
-                if (qb < 0.) {
-                    if (bc == MOHID_BC_MassConservation) {
-                        const double ext = Pc * (1.0 - pa.tdec) + pa.pref[q] * pa.tdec;
-                        TI -= qb * ext * dtv_c;
-                    } else {                               // MassConservNullGrad: NullGradProp of the old field
-                        const int cVn = (mN & M_CFV) ? 1 : 0, cVs = (mc & M_CFV) ? 1 : 0;
-                        const int cUe = (mE & M_CFU) ? 1 : 0, cUw = (mc & M_CFU) ? 1 : 0;
-                        const int aux = cVn + cVs + cUe + cUw;
-                        if (aux > 0)
-                            TI = (P[q + 1] * cVn + P[q - 1] * cVs + P[q + sj] * cUe + P[q - sj] * cUw) / (double)aux;
-                        else
-                            TI = Pc;
-                        D = 0.; E = 1.; F = 0.;
-                    }
-                } else {
-                    E += qb * dtv_c;
-                }
-            }
-        }
+        if (obc && open_c) open_boundary_row(s, pa, q, m, Pc, qz_c, qz_p, dtv_c, row);
 
         // ---------------- land fill (AD:1753) ----------------
-        if (mc & M_LAND) TI = NULL_REAL;
+        if (m & M_LAND) row.TI = NULL_REAL;
 
         // ---------------- Thomas forward elimination, row k (MF:4087-4099) ----------------
-        const double aux = E + D * Wprev;
+        const double aux = row.E + row.D * Wprev;
         if (fabs(aux) > 0.) {
-            const double ra = 1.0 / aux;
-            Wprev = -F * ra;
-            Gprev = (TI - D * Gprev) * ra;
+            const double ra = fast_rcp(aux);
+            Wprev = -row.F * ra;
+            Gprev = (row.TI - row.D * Gprev) * ra;
         } else {
             ++zp;                                          // reference leaves W,G stale (MF:4092-4098)
         }
@@ -502,10 +551,11 @@ __global__ void __launch_bounds__(384, 1) adt_transport_kernel(const __grid_cons
         // ---------------- roll ----------------
         Dk = Dn; Ek_b = En_b; TIk_b = TIn_b;
         Pm1 = Pc; Pc = Pp1; Pp1 = Pp2;
-        mm1 = mc; mc = mp1; mp1 = mp2;
         dtv_m = dtv_c; dtv_c = dtv_p; dtv_p = dtv_pp;
         rdz_c = rdz_p; rdz_p = rdz_pp;
         qz_c = qz_p; qz_p = qz_pp;
+        dvz_p = dvz_pp;
+        cur = nxt;
     }
 
     // ---------------- back substitution (MF:4100-4105) ----------------
@@ -533,7 +583,7 @@ struct BndArgs {
     long sk;
     const int *cols;          // packed (i,j) of boundary columns
     const int *kfloor;
-    const uint8_t *mask;
+    const uint32_t *mask;
     double *prop;             // new field (in place)
     const double *pref;
 };
@@ -548,8 +598,9 @@ __global__ void adt_nullgrad_kernel(const BndArgs b) {
     kf = kf < 0 ? -kf : kf;
     if (k < kf) return;
     const long q = q2 + b.sk * k;
-    const int cVn = (b.mask[q + 1] & M_CFV) ? 1 : 0, cVs = (b.mask[q] & M_CFV) ? 1 : 0;
-    const int cUe = (b.mask[q + b.ld] & M_CFU) ? 1 : 0, cUw = (b.mask[q] & M_CFU) ? 1 : 0;
+    const unsigned m = b.mask[q];
+    const int cVn = (m & M_CFVN) ? 1 : 0, cVs = (m & M_CFV) ? 1 : 0;
+    const int cUe = (m & M_CFUE) ? 1 : 0, cUw = (m & M_CFU) ? 1 : 0;
     const int aux = cVn + cVs + cUe + cUw;
     if (aux > 0)
         b.prop[q] = (b.prop[q + 1] * cVn + b.prop[q - 1] * cVs + b.prop[q + b.ld] * cUe + b.prop[q - b.ld] * cUw) /
