@@ -368,7 +368,7 @@ struct Level {
 //   MH/LH/MV/LV > 0 fix the advection method / limiter at compile time; 0 = read from StepArgs.
 // -------------------------------------------------------------------------------------
 template <int MH, int LH, int MV, int LV>
-__global__ void __launch_bounds__(384, 1) adt_transport_kernel(const __grid_constant__ StepArgs s) {
+__global__ void __launch_bounds__(256, 1) adt_transport_kernel(const __grid_constant__ StepArgs s) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, WPB = blockDim.x >> 5;
     double *__restrict__ Wsm = smem + warp * 32 + lane;                  // [K][WPB][32]
@@ -446,10 +446,11 @@ __global__ void __launch_bounds__(384, 1) adt_transport_kernel(const __grid_cons
     double Dk = 0., Ek_b = 0., TIk_b = 0.;                // contributions of the bottom face to row k
     double Wprev = 0., Gprev = 0.;
     unsigned long long zp = 0;
-    Level cur, nxt;
-    fetch(q, cur);
+    Level lvA, lvB;
+    fetch(q, lvA);
 
-    for (int k = 1; k <= s.K; ++k, q += sk) {
+    // one level of the march: consumes `cur`, prefetches the next level into `nxt`
+    auto level = [&](const int k, const Level &cur, Level &nxt) {
         // ---- prefetch: level k+1 (horizontal) and level k+2 (vertical rolling values) ----
         const long q2 = (k + 2 <= s.K + 1) ? q + 2 * sk : q + sk;
         const double Pp2 = P[q2], rdz_pp = s.rdz[q2], dtv_pp = s.dtv[q2], qz_pp = s.qz[q2], dvz_pp = s.dvz[q2];
@@ -555,7 +556,11 @@ __global__ void __launch_bounds__(384, 1) adt_transport_kernel(const __grid_cons
         rdz_c = rdz_p; rdz_p = rdz_pp;
         qz_c = qz_p; qz_p = qz_pp;
         dvz_p = dvz_pp;
-        cur = nxt;
+        q += sk;
+    };
+    for (int k = 1; k <= s.K; k += 2) {
+        level(k, lvA, lvB);
+        if (k + 1 <= s.K) level(k + 1, lvB, lvA);
     }
 
     // ---------------- back substitution (MF:4100-4105) ----------------
