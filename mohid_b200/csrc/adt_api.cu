@@ -245,10 +245,8 @@ int launch_coef(Handle *h, const mohid_adt_params &q, bool geom, bool diff) {
     a.DUX = h->DUX; a.DVY = h->DVY; a.DZX = h->DZX; a.DZY = h->DZY; a.Bnd = h->Bnd;
     a.dtv = h->dtv; a.vr = h->vr; a.dhu = h->dhu; a.dhv = h->dhv; a.dvz = h->dvz; a.rdz = h->rdz; a.mask = h->mask;
     a.do_geom = geom; a.do_diff = diff;
-    const int threads = 256;
-    const long want = (h->n3 + threads - 1) / threads;
-    const int blocks = (int)std::min<long>(want, (long)h->num_sms * 32);
-    adt_coef_kernel<<<blocks, threads, 0, h->stream>>>(a);
+    const dim3 grid((unsigned)((h->ld + 127) / 128), (unsigned)h->nj, (unsigned)h->nk);
+    adt_coef_kernel<<<grid, 128, 0, h->stream>>>(a);
     CU(h, cudaGetLastError());
     h->launches++;
     return 0;
@@ -421,6 +419,10 @@ int mohid_adt_create(int *handle, const mohid_adt_size3d *size, const mohid_adt_
     h->ld = ((h->ni + 15) / 16) * 16;                // 128-byte aligned rows on the device
     h->n2 = (long)h->ld * h->nj;
     h->n3 = h->n2 * h->nk;
+    if (h->n3 >= 2147483647L || h->nj > 65535 || h->nk > 65535) {
+        delete h;
+        return fail(nullptr, MOHID_ADT_ERR_ARG, "one field must hold fewer than 2^31 elements (32-bit cell indices)");
+    }
     h->maxprop = h->opt.max_properties > 0 ? h->opt.max_properties : 0;
     cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, dev);

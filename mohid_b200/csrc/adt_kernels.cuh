@@ -74,94 +74,91 @@ struct CoefArgs {
 };
 
 // -------------------------------------------------------------------------------------
-// K1: one thread per allocated cell, i fastest (coalesced); memory bound (112 B in, 52 B out).
+// K1: one thread per allocated cell; grid = (ceil(ld/128), nj, nk) so no index divisions are needed,
+// i fastest (coalesced).  Memory bound: 112 B in, 52 B out per cell.
 // -------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) adt_coef_kernel(const CoefArgs a) {
-    const long n3 = (long)a.ld * a.nj * a.nk;
-    const long sj = a.ld, sk = (long)a.ld * a.nj;
-    for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < n3; q += (long)gridDim.x * blockDim.x) {
-        const int i = (int)(q % a.ld);
-        const int j = (int)((q / a.ld) % a.nj);
-        const int k = (int)(q / sk);
-        if (i >= a.ni) {                                  // leading-dimension padding
-            if (a.do_geom) { a.mask[q] = 0; a.dtv[q] = 0.; a.vr[q] = 1.; a.rdz[q] = 0.; }
-            if (a.do_diff) { a.dhu[q] = 0.; a.dhv[q] = 0.; a.dvz[q] = 0.; }
-            continue;
+__global__ void __launch_bounds__(128) adt_coef_kernel(const CoefArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y, k = blockIdx.z;
+    if (i >= a.ld) return;
+    const int sj = a.ld, sk = a.ld * a.nj;
+    const int q2 = i + sj * j;
+    const int q = q2 + sk * k;
+    if (i >= a.ni) {                                  // leading-dimension padding
+        if (a.do_geom) { a.mask[q] = 0; a.dtv[q] = 0.; a.vr[q] = 1.; a.rdz[q] = 0.; }
+        if (a.do_diff) { a.dhu[q] = 0.; a.dhv[q] = 0.; a.dvz[q] = 0.; }
+        return;
+    }
+    const bool cfu = a.CFU[q] == 1, cfv = a.CFV[q] == 1, cfw = a.CFW[q] == 1;
+    if (a.do_geom) {
+        // neighbour probes stay inside the allocation
+        const bool im1 = i >= 1, im2 = i >= 2, ip1 = i + 1 < a.ni, ip2 = i + 2 < a.ni;
+        const bool jm1 = j >= 1, jm2 = j >= 2, jp1 = j + 1 < a.nj, jp2 = j + 2 < a.nj;
+        const bool km1 = k >= 1, kp1 = k + 1 < a.nk, kp2 = k + 2 < a.nk;
+        const bool o_jm1 = jm1 && a.Open[q - sj] == 1, o_jp1 = jp1 && a.Open[q + sj] == 1;
+        const bool o_im1 = im1 && a.Open[q - 1] == 1, o_ip1 = ip1 && a.Open[q + 1] == 1;
+        unsigned m = 0;
+        if (a.Open[q] == 1) m |= M_OPEN;
+        if (cfu) m |= M_CFU;
+        if (cfv) m |= M_CFV;
+        if (cfw) m |= M_CFW;
+        if (jp1 && a.CFU[q + sj] == 1) m |= M_CFUE;
+        if (ip1 && a.CFV[q + 1] == 1) m |= M_CFVN;
+        if (kp1 && a.CFW[q + sk] == 1) m |= M_CFWT;
+        if (a.Land[q] == 1) m |= M_LAND;
+        const bool bnd = a.Bnd[q2] == 1;
+        if (bnd) m |= M_BND;
+        const int qtop = q2 + sk * a.K;
+        if (a.Water[qtop] == 1) m |= M_COLWET;
+        if (a.Open[qtop] == 1) m |= M_COLOPEN;
+        if (jm2 && a.Open[q - 2 * sj] == 1) m |= M_O_JM2;
+        if (o_jm1) m |= M_O_JM1;
+        if (o_jp1) m |= M_O_JP1;
+        if (jp2 && a.Open[q + 2 * sj] == 1) m |= M_O_JP2;
+        if (im2 && a.Open[q - 2] == 1) m |= M_O_IM2;
+        if (o_im1) m |= M_O_IM1;
+        if (o_ip1) m |= M_O_IP1;
+        if (ip2 && a.Open[q + 2] == 1) m |= M_O_IP2;
+        if (km1 && a.Open[q - sk] == 1) m |= M_O_KM1;
+        if (kp1 && a.Open[q + sk] == 1) m |= M_O_KP1;
+        if (kp2 && a.Open[q + 2 * sk] == 1) m |= M_O_KP2;
+        if (bnd) {                                        // interior neighbours: only boundary rows need them
+            if (o_ip1 && a.Bnd[q2 + 1] != 1) m |= M_A_IP1;
+            if (o_im1 && a.Bnd[q2 - 1] != 1) m |= M_A_IM1;
+            if (o_jp1 && a.Bnd[q2 + sj] != 1) m |= M_A_JP1;
+            if (o_jm1 && a.Bnd[q2 - sj] != 1) m |= M_A_JM1;
         }
-        const long q2 = (long)i + sj * j;
-        const bool cfu = a.CFU[q] == 1, cfv = a.CFV[q] == 1, cfw = a.CFW[q] == 1;
-        if (a.do_geom) {
-            // neighbour lookups stay inside the allocation: clamp the probe to the array and test the range
-            auto open_at = [&](int di, int dj, int dk) -> bool {
-                const int ii = i + di, jj = j + dj, kk = k + dk;
-                if (ii < 0 || ii >= a.ni || jj < 0 || jj >= a.nj || kk < 0 || kk >= a.nk) return false;
-                return a.Open[q + di + sj * dj + sk * dk] == 1;
-            };
-            auto bnd_at = [&](int di, int dj) -> bool {
-                const int ii = i + di, jj = j + dj;
-                if (ii < 0 || ii >= a.ni || jj < 0 || jj >= a.nj) return false;
-                return a.Bnd[q2 + di + sj * dj] == 1;
-            };
-            unsigned m = 0;
-            if (a.Open[q] == 1) m |= M_OPEN;
-            if (cfu) m |= M_CFU;
-            if (cfv) m |= M_CFV;
-            if (cfw) m |= M_CFW;
-            if (j + 1 < a.nj && a.CFU[q + sj] == 1) m |= M_CFUE;
-            if (i + 1 < a.ni && a.CFV[q + 1] == 1) m |= M_CFVN;
-            if (k + 1 < a.nk && a.CFW[q + sk] == 1) m |= M_CFWT;
-            if (a.Land[q] == 1) m |= M_LAND;
-            if (a.Bnd[q2] == 1) m |= M_BND;
-            const long qtop = q2 + sk * a.K;
-            if (a.Water[qtop] == 1) m |= M_COLWET;
-            if (a.Open[qtop] == 1) m |= M_COLOPEN;
-            if (open_at(0, -2, 0)) m |= M_O_JM2;
-            if (open_at(0, -1, 0)) m |= M_O_JM1;
-            if (open_at(0, 1, 0)) m |= M_O_JP1;
-            if (open_at(0, 2, 0)) m |= M_O_JP2;
-            if (open_at(-2, 0, 0)) m |= M_O_IM2;
-            if (open_at(-1, 0, 0)) m |= M_O_IM1;
-            if (open_at(1, 0, 0)) m |= M_O_IP1;
-            if (open_at(2, 0, 0)) m |= M_O_IP2;
-            if (open_at(0, 0, -1)) m |= M_O_KM1;
-            if (open_at(0, 0, 1)) m |= M_O_KP1;
-            if (open_at(0, 0, 2)) m |= M_O_KP2;
-            if (open_at(1, 0, 0) && !bnd_at(1, 0)) m |= M_A_IP1;
-            if (open_at(-1, 0, 0) && !bnd_at(-1, 0)) m |= M_A_IM1;
-            if (open_at(0, 1, 0) && !bnd_at(0, 1)) m |= M_A_JP1;
-            if (open_at(0, -1, 0) && !bnd_at(0, -1)) m |= M_A_JM1;
-            a.mask[q] = m;
-            const double V = a.VolumeZ[q];
-            const bool inwork = (i >= 1 && i <= a.I && j >= 1 && j <= a.J && k >= 1 && k <= a.K);
-            a.dtv[q] = (inwork && V != 0.) ? a.dt / V : 0.;
-            a.vr[q] = (inwork && V != 0.) ? a.VolumeZOld[q] / V : 1.;
-            double s = (k >= 1) ? (a.DWZ[q] + a.DWZ[q - sk]) : 0.;
-            a.rdz[q] = (s != 0.) ? 1.0 / s : 0.;
+        a.mask[q] = m;
+        const double V = a.VolumeZ[q];
+        const bool inwork = (i >= 1 && i <= a.I && j >= 1 && j <= a.J && k >= 1 && k <= a.K);
+        a.dtv[q] = (inwork && V != 0.) ? a.dt / V : 0.;
+        a.vr[q] = (inwork && V != 0.) ? a.VolumeZOld[q] / V : 1.;
+        double s = (k >= 1) ? (a.DWZ[q] + a.DWZ[q - sk]) : 0.;
+        a.rdz[q] = (s != 0.) ? 1.0 / s : 0.;
+    }
+    if (a.do_diff) {
+        double hu = 0., hv = 0., vz = 0.;
+        if (cfu && j >= 1) {
+            // DifX (AD:2486-2495) then Diff_H_Const_U (AD:1549-1553), same operation order
+            const double dux = a.DUX[q2], duxm = a.DUX[q2 - sj];
+            double difx = a.schmidt_h * (a.Visc_H[q] * duxm + a.Visc_H[q - sj] * dux) / (dux + duxm);
+            if (a.nulldif && a.Wflux_X[q] == 0.) difx = 0.;
+            hu = difx * a.AreaU[q] / a.DZX[q2 - sj];
         }
-        if (a.do_diff) {
-            double hu = 0., hv = 0., vz = 0.;
-            if (cfu && j >= 1) {
-                // DifX (AD:2486-2495) then Diff_H_Const_U (AD:1549-1553), same operation order
-                const double dux = a.DUX[q2], duxm = a.DUX[q2 - sj];
-                double difx = a.schmidt_h * (a.Visc_H[q] * duxm + a.Visc_H[q - sj] * dux) / (dux + duxm);
-                if (a.nulldif && a.Wflux_X[q] == 0.) difx = 0.;
-                hu = difx * a.AreaU[q] / a.DZX[q2 - sj];
-            }
-            if (cfv && i >= 1) {
-                const double dvy = a.DVY[q2], dvym = a.DVY[q2 - 1];
-                double dify = a.schmidt_h * (a.Visc_H[q] * dvym + a.Visc_H[q - 1] * dvy) / (dvy + dvym);
-                if (a.nulldif && a.Wflux_Y[q] == 0.) dify = 0.;
-                hv = dify * a.AreaV[q] / a.DZY[q2 - 1];
-            }
-            if (cfw && k >= 1 && !(a.SmallDepths && a.SmallDepths[q2] != 0)) {
-                // DifZ (AD:2397-2405) then Diff_V_Const (AD:1591-1597)
-                double difz = (a.schmidt_coef_v * a.Diff_V[q] + a.schmidt_bg_v);
-                if (a.nulldif && a.Wflux_Z[q] == 0.) difz = 0.;
-                const double auxk = difz * a.DUX[q2] * a.DVY[q2];
-                vz = auxk / a.DZZ[q - sk];
-            }
-            a.dhu[q] = hu; a.dhv[q] = hv; a.dvz[q] = vz;
+        if (cfv && i >= 1) {
+            const double dvy = a.DVY[q2], dvym = a.DVY[q2 - 1];
+            double dify = a.schmidt_h * (a.Visc_H[q] * dvym + a.Visc_H[q - 1] * dvy) / (dvy + dvym);
+            if (a.nulldif && a.Wflux_Y[q] == 0.) dify = 0.;
+            hv = dify * a.AreaV[q] / a.DZY[q2 - 1];
         }
+        if (cfw && k >= 1 && !(a.SmallDepths && a.SmallDepths[q2] != 0)) {
+            // DifZ (AD:2397-2405) then Diff_V_Const (AD:1591-1597)
+            double difz = (a.schmidt_coef_v * a.Diff_V[q] + a.schmidt_bg_v);
+            if (a.nulldif && a.Wflux_Z[q] == 0.) difz = 0.;
+            const double auxk = difz * a.DUX[q2] * a.DVY[q2];
+            vz = auxk / a.DZZ[q - sk];
+        }
+        a.dhu[q] = hu; a.dhv[q] = hv; a.dvz[q] = vz;
     }
 }
 
@@ -303,10 +300,10 @@ __device__ __forceinline__ double hface_flux(const StepArgs &s, bool adv_on, dou
 
 // Rows of open-boundary cells (AD:5369-5672); rare (boundary ring only): a predicated-off branch elsewhere.
 struct Row { double D, E, F, TI; };
-__device__ __forceinline__ void open_boundary_row(const StepArgs &s, const PropArgs &pa, long q, unsigned m, double Pc,
+__device__ __forceinline__ void open_boundary_row(const StepArgs &s, const PropArgs &pa, int q, unsigned m, double Pc,
                                                double qz_c, double qz_p, double dtv_c, Row &row) {
     const double *__restrict__ P = pa.pin;
-    const long sj = s.ld;
+    const int sj = s.ld;
     const int bc = pa.bc;
     if (bc == MOHID_BC_NullGradient || bc == MOHID_BC_CyclicBoundary) {
         row.TI = Pc; row.D = 0.; row.E = 1.; row.F = 0.;
@@ -385,9 +382,9 @@ __global__ void __launch_bounds__(256, 1) adt_transport_kernel(const __grid_cons
     const int ic = min(i, s.I + 1);                       // clamped column: every load stays in bounds
     const PropArgs pa = s.p[n];
     const double *__restrict__ P = pa.pin;
-    const long sj = s.ld, sk = s.sk;
-    const long c2d = (long)ic + sj * j;
-    const long je2 = (j + 2 <= s.J + 1) ? 2 * sj : sj;     // offset of column j+2 (clamped at the array edge)
+    const int sj = s.ld, sk = (int)s.sk;                  // 32-bit cell indices (n3 < 2^31 is checked at create)
+    const int c2d = ic + sj * j;
+    const int je2 = (j + 2 <= s.J + 1) ? 2 * sj : sj;     // offset of column j+2 (clamped at the array edge)
 
     const int method_h = MH > 0 ? MH : s.method_h, method_v = MV > 0 ? MV : s.method_v;
     const bool central_h = (method_h == MOHID_CentralDif || method_h == MOHID_LeapFrog);
@@ -416,10 +413,10 @@ __global__ void __launch_bounds__(256, 1) adt_transport_kernel(const __grid_cons
     const bool advv_imp = pa.advv_implicit != 0;
     // halo lanes of the strip: lanes 0,1 fetch cell i-2, lane 31 fetches cell i+1
     const bool halo_lane = (lane < 2) || (lane == 31);
-    const long halo_off = (lane == 31) ? ((ic <= s.I) ? 1 : 0) : -2;
+    const int halo_off = (lane == 31) ? ((ic <= s.I) ? 1 : 0) : -2;
 
     // fetch the horizontal data of level k at cell offset q (all loads independent of computed values)
-    auto fetch = [&](long q, Level &L) {
+    auto fetch = [&](int q, Level &L) {
         L.m = s.mask[q];
         L.vr = s.vr[q];
         if (do_h) {
@@ -437,7 +434,7 @@ __global__ void __launch_bounds__(256, 1) adt_transport_kernel(const __grid_cons
     };
 
     // ---- rolling registers along k (cells k-1 .. k+2 of this column) ----
-    long q = c2d + sk;                                    // cell (i,j,1)
+    int q = c2d + sk;                                     // cell (i,j,1)
     double Pm1 = P[c2d], Pc = P[q], Pp1 = P[q + sk];
     double dtv_m = 0., dtv_c = s.dtv[q], dtv_p = s.dtv[q + sk];
     double rdz_c = s.rdz[q], rdz_p = s.rdz[q + sk];
@@ -452,7 +449,7 @@ __global__ void __launch_bounds__(256, 1) adt_transport_kernel(const __grid_cons
     // one level of the march: consumes `cur`, prefetches the next level into `nxt`
     auto level = [&](const int k, const Level &cur, Level &nxt) {
         // ---- prefetch: level k+1 (horizontal) and level k+2 (vertical rolling values) ----
-        const long q2 = (k + 2 <= s.K + 1) ? q + 2 * sk : q + sk;
+        const int q2 = (k + 2 <= s.K + 1) ? q + 2 * sk : q + sk;
         const double Pp2 = P[q2], rdz_pp = s.rdz[q2], dtv_pp = s.dtv[q2], qz_pp = s.qz[q2], dvz_pp = s.dvz[q2];
         if (k < s.K) fetch(q + sk, nxt);
 
@@ -566,7 +563,7 @@ __global__ void __launch_bounds__(256, 1) adt_transport_kernel(const __grid_cons
     // ---------------- back substitution (MF:4100-4105) ----------------
     if (writer && colwet) {
         double *__restrict__ O = pa.pout;
-        long qo = (long)i + sj * j + sk * (s.K + 1);
+        int qo = i + sj * j + sk * (s.K + 1);
         double x = 0.0;                                   // RES(KUB+1) = G(KUB+1) = 0 (halo row is the identity)
         O[qo] = x;
         for (int k = s.K; k >= 1; --k) {
