@@ -124,8 +124,14 @@ int mohid_adt_set_step(const int *handle,
                        const int *ComputeFacesU3D, const int *ComputeFacesV3D,
                        const int *ComputeFacesW3D, const int *SmallDepths);
 
-/* SetDischarges / UnSetDischarges (AD:978-1095).  n_cells = sum(DischnCells). */
-int mohid_adt_set_discharges(const int *handle, const int *DischNumber, const int *n_cells,
+/* SetDischarges / UnSetDischarges (AD:978-1095), same arguments as the reference plus the position
+ * `prop_index` (0-based) of the property in the next advect batch: the caller invokes SetDischarges
+ * once per property with that property's DischConc / DischConcMF (WP:14761-14773); the discharge
+ * geometry (flows, cells, vertical distribution, Ignore, nCells, ByPass) is the caller's single
+ * Me%Discharge and must be the same in every call of a step.  n_cells = number of entries of the
+ * per-cell arrays (cells of ignored discharges are not listed, AD:4039-4041).  Logical arrays
+ * (IgnoreDisch, ByPass) are int32 0/1.  unset clears the discharges of all properties. */
+int mohid_adt_set_discharges(const int *handle, const int *prop_index, const int *DischNumber, const int *n_cells,
                              const double *DischFlow, const double *DischConc,
                              const int *DischI, const int *DischJ, const int *DischK,
                              const int *DischKmin, const int *DischKmax,

@@ -100,6 +100,26 @@ class TransportStep:
         args.append(_ptr(SmallDepths, "i4", self.n2, "SmallDepths"))
         self._check(self.lib.mohid_adt_set_step(C.byref(self.h), *args))
 
+    def set_discharges(self, prop_index: int, d: Dict[str, object]):
+        """SetDischarges (AD:978-1034) for the property at position ``prop_index`` of the next batch.
+        ``d`` holds the reference's argument names: DischFlow, DischConc, DischI, DischJ, DischK, DischKmin,
+        DischKmax, DischVert, IgnoreDisch, DischnCells, ByPass, DischConcMF."""
+        f8 = lambda k: np.ascontiguousarray(d[k], dtype=np.float64)
+        i4 = lambda k: np.ascontiguousarray(d[k], dtype=np.int32)
+        a = {k: f8(k) for k in ("DischFlow", "DischConc", "DischConcMF")}
+        a.update({k: i4(k) for k in ("DischI", "DischJ", "DischK", "DischKmin", "DischKmax", "DischVert",
+                                     "IgnoreDisch", "DischnCells", "ByPass")})
+        nd, nc = len(a["DischnCells"]), len(a["DischFlow"])
+        P = lambda k: C.c_void_p(a[k].ctypes.data)
+        self._check(self.lib.mohid_adt_set_discharges(
+            C.byref(self.h), C.byref(C.c_int(prop_index)), C.byref(C.c_int(nd)), C.byref(C.c_int(nc)),
+            P("DischFlow"), P("DischConc"), P("DischI"), P("DischJ"), P("DischK"), P("DischKmin"), P("DischKmax"),
+            P("DischVert"), P("IgnoreDisch"), P("DischnCells"), P("ByPass"), P("DischConcMF")))
+
+    def unset_discharges(self):
+        """UnSetDischarges (AD:1040-1095)."""
+        self._check(self.lib.mohid_adt_unset_discharges(C.byref(self.h)))
+
     # ---- the batched transport step -------------------------------------------------
     def _params(self, params: Sequence[dict]):
         return (Params * len(params))(*[make_params(p) for p in params])
@@ -232,6 +252,23 @@ def AdvectionDiffusion(AdvectionDiffusionID: int, PROP, schmidt_H, SchmidtCoef_V
              BoundaryCondition=(BoundaryCondition if BoundaryCondition is not None else 0), DecayTime=DecayTime,
              NoAdvFlux=int(NoAdvFlux), NoDifFlux=int(NoDifFlux))
     obj.advect_batch([PROP], [p], [ReferenceProp] if ReferenceProp is not None else None)
+    return SUCCESS_
+
+
+def SetDischarges(AdvectionDiffusionID: int, DischFlow, DischConc, DischI, DischJ, DischK, DischKmin, DischKmax, DischVert,
+                  DischNumber, IgnoreDisch, DischnCells, ByPass, DischConcMF) -> int:
+    """AD:978-1034 (applies to the next AdvectionDiffusion call, i.e. property 0 of a batch of one)."""
+    assert DischNumber == len(DischnCells)
+    _get(AdvectionDiffusionID).set_discharges(0, dict(
+        DischFlow=DischFlow, DischConc=DischConc, DischI=DischI, DischJ=DischJ, DischK=DischK, DischKmin=DischKmin,
+        DischKmax=DischKmax, DischVert=DischVert, IgnoreDisch=IgnoreDisch, DischnCells=DischnCells, ByPass=ByPass,
+        DischConcMF=DischConcMF))
+    return SUCCESS_
+
+
+def UnSetDischarges(AdvectionDiffusionID: int) -> int:
+    """AD:1040-1095."""
+    _get(AdvectionDiffusionID).unset_discharges()
     return SUCCESS_
 
 

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -53,6 +54,12 @@ struct Handle {
     std::string err;
     int smem_optin = 0, num_sms = 0;
     int j_begin = 1, j_count = 0;                       // columns advanced by this handle (slab decomposition)
+    // point discharges: shared geometry (per listed cell) + per-property concentrations
+    int d_ncell = 0;
+    int *d_ci = nullptr, *d_cj = nullptr, *d_ck = nullptr, *d_ckmin = nullptr, *d_ckmax = nullptr, *d_cvert = nullptr,
+        *d_cbypass = nullptr, *d_kmin_eff = nullptr, *d_kmax_eff = nullptr;
+    double *d_cflow = nullptr, *d_flow_k = nullptr;
+    std::vector<double *> d_conc, d_concmf;             // per property (nullptr = no discharges)
     std::vector<int> bnd_host;                          // (i,j) of all boundary columns
 };
 
@@ -143,6 +150,10 @@ void free_all(Handle *h) {
     for (int b = 0; b < 2; ++b) for (auto p : h->prop[b]) F(p);
     for (auto p : h->ref) F(p);
     F(h->d_zero_piv);
+    F(h->d_ci); F(h->d_cj); F(h->d_ck); F(h->d_ckmin); F(h->d_ckmax); F(h->d_cvert); F(h->d_cbypass);
+    F(h->d_kmin_eff); F(h->d_kmax_eff); F(h->d_cflow); F(h->d_flow_k);
+    for (auto p : h->d_conc) F(p);
+    for (auto p : h->d_concmf) F(p);
     for (auto &e : h->ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
 }
@@ -255,7 +266,7 @@ int launch_coef(Handle *h, const mohid_adt_params &q, bool geom, bool diff) {
 int pick_wpb(Handle *h, int nprop) {
     // W,G of the column solve: 2 * K * 32 doubles per warp; at most 8 warps = 2 per SM sub-partition (16K registers each), so a thread may use up to 255 registers
     const size_t per_warp = (size_t)2 * h->K * 32 * sizeof(double);
-    int wpb = (int)std::min<size_t>(8, (size_t)h->smem_optin / per_warp);
+    int wpb = (int)std::min<size_t>(getenv("MOHID_ADT_WPB12") ? 12 : 8, (size_t)h->smem_optin / per_warp);
     if (wpb >= nprop && nprop >= 6) wpb = nprop;                 // one block = all properties of a strip
     else if (nprop < 6 && wpb >= 2 * nprop) wpb = (wpb / nprop) * nprop;
     return wpb;
@@ -277,6 +288,9 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
     s.rdx = h->rdx; s.rdy = h->rdy; s.DUX = h->DUX; s.DVY = h->DVY; s.DWZ = h->raw_d[7];
     s.VolumeZ = h->raw_d[4]; s.VolumeZOld = h->raw_d[3];
     s.zero_pivots = h->d_zero_piv;
+    s.disch.ncell = h->d_ncell; s.disch.K = h->K; s.disch.ci = h->d_ci; s.disch.cj = h->d_cj;
+    s.disch.kmin_eff = h->d_kmin_eff; s.disch.kmax_eff = h->d_kmax_eff; s.disch.cbypass = h->d_cbypass;
+    s.disch.flow_k = h->d_flow_k;
     for (int m = 0; m < s.nprop; ++m) {
         const int n = idx[m];
         const mohid_adt_params &q = b.p[n];
@@ -288,6 +302,9 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
         pa.tdec = 1.0 / (1.0 + q.DecayTime / q.DTProp);
         pa.bc = h->has_ref[n] ? q.BoundaryCondition : MOHID_BC_None;                    // AD:5816-5830
         pa.advv_implicit = (q.ImpExp_AdvV == 1.0) ? 1 : 0;
+        const bool hd = h->d_ncell > 0 && n < (int)h->d_conc.size() && h->d_conc[n];
+        pa.dconc = hd ? h->d_conc[n] : nullptr;
+        pa.dconcmf = hd ? h->d_concmf[n] : nullptr;
     }
     const int wpb = pick_wpb(h, s.nprop);
     if (wpb < 1)
@@ -297,12 +314,22 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
     const long blocks = (nunits + wpb - 1) / wpb;
     if (blocks > 2147483647L) return fail(h, MOHID_ADT_ERR_ARG, "grid too large");
     // kernel variant: the two headline schemes are compiled with fixed method / limiter
-    void (*kern)(const StepArgs) = adt_transport_kernel<0, 0, 0, 0>;
-    if (s.method_h == MOHID_P2_TVD && s.method_v == MOHID_P2_TVD && s.limiter_h == MOHID_SuperBee &&
-        s.limiter_v == MOHID_SuperBee)
-        kern = adt_transport_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee>;
-    else if (s.method_h == MOHID_UpwindOrder1 && s.method_v == MOHID_UpwindOrder1)
-        kern = adt_transport_kernel<MOHID_UpwindOrder1, MOHID_SuperBee, MOHID_UpwindOrder1, MOHID_SuperBee>;
+    bool any_disch = false;
+    for (int m = 0; m < s.nprop; ++m) any_disch = any_disch || s.p[m].dconc != nullptr;
+    void (*kern)(const StepArgs);
+    const bool tvd_sb = s.method_h == MOHID_P2_TVD && s.method_v == MOHID_P2_TVD && s.limiter_h == MOHID_SuperBee &&
+                        s.limiter_v == MOHID_SuperBee;
+    const bool upw = s.method_h == MOHID_UpwindOrder1 && s.method_v == MOHID_UpwindOrder1;
+    if (any_disch)
+        kern = tvd_sb ? adt_transport_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, true>
+             : upw    ? adt_transport_kernel<MOHID_UpwindOrder1, MOHID_SuperBee, MOHID_UpwindOrder1, MOHID_SuperBee, true>
+                      : adt_transport_kernel<0, 0, 0, 0, true>;
+    else if (getenv("MOHID_ADT_WPB12") && tvd_sb)
+        kern = adt_transport_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, false, 12>;
+    else
+        kern = tvd_sb ? adt_transport_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, false>
+             : upw    ? adt_transport_kernel<MOHID_UpwindOrder1, MOHID_SuperBee, MOHID_UpwindOrder1, MOHID_SuperBee, false>
+                      : adt_transport_kernel<0, 0, 0, 0, false>;
     CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (timed) {
@@ -366,6 +393,17 @@ int step_once(Handle *h, const Batch &b) {
             }
         }
         if (int rc = launch_coef(h, b.p[n], !geom_done, true)) return rc;
+        if (!geom_done && h->d_ncell > 0) {               // flag the receiving cells, per-layer flows (AD:4063-4077)
+            DischArgs d{};
+            d.ncell = h->d_ncell; d.K = h->K; d.ld = h->ld; d.nj = h->nj;
+            d.ci = h->d_ci; d.cj = h->d_cj; d.ck = h->d_ck; d.ckmin = h->d_ckmin; d.ckmax = h->d_ckmax;
+            d.cvert = h->d_cvert; d.cbypass = h->d_cbypass; d.cflow = h->d_cflow;
+            d.kmin_eff = h->d_kmin_eff; d.kmax_eff = h->d_kmax_eff; d.flow_k = h->d_flow_k;
+            d.kfloor = h->KFloorZ; d.DWZ = h->raw_d[7]; d.mask = h->mask;
+            adt_discharge_prep_kernel<<<(h->d_ncell + 127) / 128, 128, 0, h->stream>>>(d);
+            CU(h, cudaGetLastError());
+            h->launches++;
+        }
         geom_done = true;
         if (int rc = launch_step(h, b, idx, true)) return rc;
     }
@@ -564,16 +602,74 @@ int mohid_adt_mark_step_resident(const int *handle, const int *small_depths_pres
     return 0;
 }
 
-int mohid_adt_set_discharges(const int *handle, const int *, const int *, const double *, const double *,
-                             const int *, const int *, const int *, const int *, const int *, const int *,
-                             const int *, const int *, const int *, const double *) {
+int mohid_adt_set_discharges(const int *handle, const int *prop_index, const int *DischNumber, const int *n_cells,
+                             const double *DischFlow, const double *DischConc, const int *DischI, const int *DischJ,
+                             const int *DischK, const int *DischKmin, const int *DischKmax, const int *DischVert,
+                             const int *IgnoreDisch, const int *DischnCells, const int *ByPass,
+                             const double *DischConcMF) {
     Handle *h = get(handle);
     if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
-    return fail(h, MOHID_ADT_ERR_UNSUPPORTED, "discharges (AD:4025-4128) are not available on the GPU path yet");
+    if (!prop_index || !DischNumber || !n_cells) return fail(h, MOHID_ADT_ERR_ARG, "null argument");
+    const int nd = *DischNumber, nc = *n_cells, pi = *prop_index;
+    if (pi < 0 || pi >= NPMAX) return fail(h, MOHID_ADT_ERR_ARG, "prop_index out of range");
+    if (nd < 0 || nc < 0) return fail(h, MOHID_ADT_ERR_ARG, "negative discharge count");
+    if (nc > 0 && (!DischFlow || !DischConc || !DischI || !DischJ || !DischK || !DischKmin || !DischKmax ||
+                   !DischVert || !IgnoreDisch || !DischnCells || !ByPass || !DischConcMF))
+        return fail(h, MOHID_ADT_ERR_ARG, "null discharge array");
+    CU(h, cudaSetDevice(h->dev));
+    // expand (discharge, cell) pairs exactly like the serial loop AD:4037-4045 (ignored discharges do not advance n)
+    std::vector<int> vert, byp;
+    int n = 0;
+    for (int dis = 0; dis < nd; ++dis) {
+        if (IgnoreDisch[dis]) continue;
+        for (int c = 0; c < DischnCells[dis]; ++c, ++n) {
+            if (n >= nc) return fail(h, MOHID_ADT_ERR_ARG, "DischnCells lists more cells than n_cells");
+            if (DischI[n] < 1 || DischI[n] > h->I || DischJ[n] < 1 || DischJ[n] > h->J)
+                return fail(h, MOHID_ADT_ERR_ARG, "discharge cell %d lies outside the work range", n);
+            vert.push_back(DischVert[dis]);
+            byp.push_back(ByPass[dis] ? 1 : 0);
+        }
+    }
+    const int ncell = n;
+    auto up_i = [&](int *&d, const int *src) -> int {
+        if (d) { cudaFree(d); d = nullptr; }
+        if (ncell == 0) return 0;
+        if (int rc = dalloc(h, &d, (size_t)ncell)) return rc;
+        CU(h, cudaMemcpy(d, src, ncell * sizeof(int), cudaMemcpyHostToDevice));
+        return 0;
+    };
+    auto up_d = [&](double *&d, const double *src, size_t cnt) -> int {
+        if (d) { cudaFree(d); d = nullptr; }
+        if (cnt == 0) return 0;
+        if (int rc = dalloc(h, &d, cnt)) return rc;
+        if (src) CU(h, cudaMemcpy(d, src, cnt * sizeof(double), cudaMemcpyHostToDevice));
+        return 0;
+    };
+    CU(h, cudaStreamSynchronize(h->stream));
+    int rc = 0;
+    rc |= up_i(h->d_ci, DischI); rc |= up_i(h->d_cj, DischJ); rc |= up_i(h->d_ck, DischK);
+    rc |= up_i(h->d_ckmin, DischKmin); rc |= up_i(h->d_ckmax, DischKmax);
+    rc |= up_i(h->d_cvert, vert.data()); rc |= up_i(h->d_cbypass, byp.data());
+    rc |= up_i(h->d_kmin_eff, DischKmin); rc |= up_i(h->d_kmax_eff, DischKmax);
+    rc |= up_d(h->d_cflow, DischFlow, (size_t)ncell);
+    rc |= up_d(h->d_flow_k, nullptr, (size_t)ncell * (h->K + 2));
+    if (rc) return rc;
+    if ((int)h->d_conc.size() <= pi) { h->d_conc.resize(pi + 1, nullptr); h->d_concmf.resize(pi + 1, nullptr); }
+    rc |= up_d(h->d_conc[pi], DischConc, (size_t)ncell);
+    rc |= up_d(h->d_concmf[pi], DischConcMF, (size_t)ncell);
+    if (rc) return rc;
+    h->d_ncell = ncell;
+    return 0;
 }
+
 int mohid_adt_unset_discharges(const int *handle) {
     Handle *h = get(handle);
     if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    cudaSetDevice(h->dev);
+    cudaStreamSynchronize(h->stream);
+    h->d_ncell = 0;
+    for (auto &p : h->d_conc) { if (p) cudaFree(p); p = nullptr; }
+    for (auto &p : h->d_concmf) { if (p) cudaFree(p); p = nullptr; }
     return 0;
 }
 

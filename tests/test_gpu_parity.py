@@ -232,3 +232,43 @@ def test_torch_cuda_inputs(oracle_lib):
         o.advect_batch(cpu, prm)
     compare([t.cpu().numpy() for t in out], cpu, s, 2 * TOL_STEP)
     ts.close()
+
+
+def _discharge_set(case, s, conc, concmf):
+    """Three discharges: a bottom point source, a uniform-over-the-column source (kmin/kmax = FillValueInt), an
+    ignored one, and a withdrawal (negative flow) that by-passes nothing."""
+    K = case.K
+    FILL = -9999999
+    water = np.argwhere((s["OpenPoints3D"][K] == 1) & (s["OpenPoints3D"][1] == 1))
+    (j1, i1), (j2, i2), (j3, i3) = water[len(water) // 5], water[len(water) // 2], water[4 * len(water) // 5]
+    return dict(DischFlow=[40.0, 25.0, -30.0], DischConc=conc, DischConcMF=concmf,
+                DischI=[i1, i2, i3], DischJ=[j1, j2, j3], DischK=[1, K, 2], DischKmin=[FILL, FILL, FILL],
+                DischKmax=[FILL, FILL, FILL], DischVert=[1, 5, 9, 1], IgnoreDisch=[0, 0, 1, 0],
+                DischnCells=[1, 1, 7, 1], ByPass=[0, 1, 0, 0])
+
+
+def test_discharges_per_property(oracle_lib):
+    """SetDischarges with property-specific concentrations (WP:14761-14773, AD:4025-4128)."""
+    case = make_case(50, 40, 7, nprop=2)
+    o, g, s, props, refs = oracle_for(case)
+    ts = gpu_for(case, g, s)
+    prm = [default_params(1, 4, 1, 4), default_params(1, 4, 1, 4)]
+    sets = [_discharge_set(case, s, [35.0, 2.0, 0.0], [1.0, 1.0, 0.5]),
+            _discharge_set(case, s, [0.5, 7.5, 0.0], [0.0, 1.0, 1.0])]
+    gpu, cpu = [p.copy() for p in props], [p.copy() for p in props]
+    for n in range(2):
+        ts.set_discharges(n, sets[n])
+    for _ in range(3):
+        ts.advect_batch(gpu, prm)
+        for n in range(2):                      # the reference's per-property call sequence
+            o.set_discharges(sets[n])
+            o.now += 30.0 if n == 0 else 0.0
+            o.advection_diffusion(cpu[n], prm[n], optimize=False, first_property=(n == 0))
+            o.unset_discharges()
+    compare(gpu, cpu, s, 3 * TOL_STEP)
+    # discharges really acted
+    ref_o, _, _, p0, _ = oracle_for(case)
+    ref_o.advect_batch(p0, prm)
+    assert not np.array_equal(p0[0], cpu[0])
+    ts.unset_discharges()
+    ts.close()
