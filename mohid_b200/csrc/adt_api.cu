@@ -266,7 +266,7 @@ int launch_coef(Handle *h, const mohid_adt_params &q, bool geom, bool diff) {
 int pick_wpb(Handle *h, int nprop) {
     // W,G of the column solve: 2 * K * 32 doubles per warp; at most 8 warps = 2 per SM sub-partition (16K registers each), so a thread may use up to 255 registers
     const size_t per_warp = (size_t)2 * h->K * 32 * sizeof(double);
-    int wpb = (int)std::min<size_t>(getenv("MOHID_ADT_WPB12") ? 12 : 8, (size_t)h->smem_optin / per_warp);
+    int wpb = (int)std::min<size_t>(8, (size_t)h->smem_optin / per_warp);
     if (wpb >= nprop && nprop >= 6) wpb = nprop;                 // one block = all properties of a strip
     else if (nprop < 6 && wpb >= 2 * nprop) wpb = (wpb / nprop) * nprop;
     return wpb;
@@ -324,8 +324,6 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
         kern = tvd_sb ? adt_transport_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, true>
              : upw    ? adt_transport_kernel<MOHID_UpwindOrder1, MOHID_SuperBee, MOHID_UpwindOrder1, MOHID_SuperBee, true>
                       : adt_transport_kernel<0, 0, 0, 0, true>;
-    else if (getenv("MOHID_ADT_WPB12") && tvd_sb)
-        kern = adt_transport_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, false, 12>;
     else
         kern = tvd_sb ? adt_transport_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, false>
              : upw    ? adt_transport_kernel<MOHID_UpwindOrder1, MOHID_SuperBee, MOHID_UpwindOrder1, MOHID_SuperBee, false>

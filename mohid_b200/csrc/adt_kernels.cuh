@@ -257,7 +257,20 @@ struct StepArgs {
 __device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
 __device__ __forceinline__ double shfl_dn_d(double v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
 __device__ __forceinline__ double sel(bool c, double a, double b) { return c ? a : b; }
+__device__ __forceinline__ bool all_set(unsigned m, unsigned bits) { return (m & bits) == bits; }
 __device__ __forceinline__ double ratio_or_zero(double a, double b) { return b != 0. ? a / b : 0.; }
+// min / max as one compare + select (fmin/fmax expand to a NaN-propagation sequence of ~7 instructions;
+// operands here are never NaN)
+__device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
+__device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
+// x with the sign of s flipped in when s < 0 (s = -0.0 counts as negative; callers pass differences, where
+// a zero difference makes the result irrelevant), and |x| with the sign of s: one LOP3 each on the high word
+__device__ __forceinline__ double flip_sign_by(double x, double s) {
+    return __hiloint2double(__double2hiint(x) ^ (__double2hiint(s) & 0x80000000), __double2loint(x));
+}
+__device__ __forceinline__ double with_sign_of(double x, double s) {
+    return __hiloint2double((__double2hiint(x) & 0x7fffffff) | (__double2hiint(s) & 0x80000000), __double2loint(x));
+}
 
 // 1/x for normal, finite x without the IEEE slow path: MUFU.RCP64H seed (2^-20) + two Newton steps
 // (relative error <= ~2 ulp).  Callers guarantee |x| is far from 0, Inf and the denormal range.
@@ -275,16 +288,16 @@ __device__ __forceinline__ double fast_rcp(double x) {
 template <int L>
 __device__ __forceinline__ double tvd_psi(int limiter_rt, double r, double &Cr) {
     const int limiter = (L > 0) ? L : limiter_rt;
-    if (limiter == MOHID_SuperBee) return fmax(fmax(0., fmin(1., 2. * r)), fmin(r, 2.));
-    if (limiter == MOHID_MinMod) return fmax(0., fmin(1., r));
+    if (limiter == MOHID_SuperBee) return dmax(dmax(0., dmin(1., 2. * r)), dmin(r, 2.));
+    if (limiter == MOHID_MinMod) return dmax(0., dmin(1., r));
     if (limiter == MOHID_VanLeer) return (r < 0.) ? 0. : 2. * r * fast_rcp(1. + r);
-    if (limiter == MOHID_Muscl) return fmax(0., fmin(fmin(2., 2. * r), (1. + r) * 0.5));
+    if (limiter == MOHID_Muscl) return dmax(0., dmin(dmin(2., 2. * r), (1. + r) * 0.5));
     // PDM
     const double c = (1. - 2. * fabs(Cr)) / 6.;
     const double a = 0.5 + c, b = 0.5 - c;
     const double aux = a + b * r;
     if (fabs(Cr) < MIN_VALUE) Cr = MIN_VALUE;
-    return fmax(0., fmin(fmin(aux, 2. * fast_rcp(1. - Cr)), 2. * r * fast_rcp(Cr)));
+    return dmax(0., dmin(dmin(aux, 2. * fast_rcp(1. - Cr)), 2. * r * fast_rcp(Cr)));
 }
 
 // Face weights of ComputeAdvectionFace (MF:10702-10894) in UPWIND-ORIENTED form: the face flux of
@@ -304,7 +317,7 @@ __device__ __forceinline__ void oriented_weights(int method_rt, int limiter_rt, 
     if (method == MOHID_P2_TVD) {
         double Cr = Q * t_u;
         double dC = (Pd - Pu) * rd_c;
-        if (fabs(dC) < MIN_VALUE) dC = (dC >= 0.) ? MIN_VALUE : -MIN_VALUE;
+        dC = (fabs(dC) < MIN_VALUE) ? with_sign_of(MIN_VALUE, dC) : dC;   // MF:10795-10803 (dC is never -0.0)
         const double r = (Pu - Puu) * rd_u * fast_rcp(dC);
         double theta = tvd_psi<L>(limiter_rt, r, Cr);
         theta = 0.5 * theta * (1. - Cr);
@@ -318,7 +331,7 @@ __device__ __forceinline__ void oriented_weights(int method_rt, int limiter_rt, 
         return;
     }
     // UpwindOrder2 (QUICK) / UpwindOrder3 (QUICKEST), MF:10751-10770, 11055-11125
-    const double tmax = fmax(fmax(t_uu, t_u), t_d), tmin = fmin(fmin(t_uu, t_u), t_d);
+    const double tmax = dmax(dmax(t_uu, t_u), t_d), tmin = dmin(dmin(t_uu, t_u), t_d);
     const bool first_order = near || (tmax > vrelmax * tmin) || (Q == 0.);
     if (first_order) return;
     if (method == MOHID_UpwindOrder2) {
@@ -347,11 +360,10 @@ __device__ __forceinline__ double hface_flux(const StepArgs &s, bool adv_on, dou
         // rho = (du_u+du_d)/(du_u+du_uu) (passed in the rd12 / rd34 slots).  Face flux = Q*(Pu + 0.5(1-Cr)*psi*dP)
         // (MF:10785-10858, 10889-10892); the |dC| < 1e-16 clamp only matters below 1e-13 in the property.
         const double dP = Pd - Pu;
-        double aS = (Pu - Puu) * sel(pos, rd12, rd34);
-        aS = (dP >= 0.) ? aS : -aS;
+        const double aS = flip_sign_by((Pu - Puu) * sel(pos, rd12, rd34), dP);
         const double ad = fabs(dP);
-        double lim = fmax(fmax(0., fmin(ad, aS + aS)), fmin(aS, ad + ad));
-        lim = (dP >= 0.) ? lim : -lim;
+        double lim = dmax(dmax(0., dmin(ad, aS + aS)), dmin(aS, ad + ad));
+        lim = with_sign_of(lim, dP);
         const bool near = pos ? !o1 : !o4;
         lim = (near && s.upwind2_h) ? 0. : lim;
         const double homc = fma(-0.5 * Q, sel(pos, t2, t3), 0.5);          // 0.5*(1 - Cr), Cr = Q*DT/V_upwind
@@ -500,6 +512,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
     const bool colwet = (mtop & M_COLWET) != 0;
     const bool colopen = (mtop & M_COLOPEN) != 0;
     const bool obc = (mtop & M_BND) != 0 && pa.bc != MOHID_BC_None;
+    // vertical advection acts on a top face iff both cells are open, the face is a compute face, the column's
+    // surface cell is open and the run is not Vertical1D (AD:2966, 3041; MF:10559); bit 31 is never set in a mask
+    const unsigned top_req = (do_h && colopen) ? (M_OPEN | M_O_KP1 | M_CFWT) : (1u << 31);
     const double theta = pa.theta_difv, omt = 1. - pa.theta_difv;
     const bool advv_imp = pa.advv_implicit != 0;
     // halo lanes of the strip: lanes 0,1 fetch cell i-2, lane 31 fetches cell i+1
@@ -561,10 +576,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
         // ---------------- horizontal faces (explicit) ----------------
         if (do_h) {
             const bool o_w1 = (m & M_O_JM1) != 0, o_e1 = (m & M_O_JP1) != 0;
-            const double fw = hface_flux<MH, LH>(s, (m & M_CFU) && o_w1 && open_c, cur.qxw, cur.dhw, cur.Pw2, cur.Pw1,
+            const double fw = hface_flux<MH, LH>(s, all_set(m, M_CFU | M_O_JM1 | M_OPEN), cur.qxw, cur.dhw, cur.Pw2, cur.Pw1,
                                                  Pc, cur.Pe1, (m & M_O_JM2) != 0, o_e1, cur.t_w2, cur.t_w, dtv_c,
                                                  cur.t_e, rho_wp, rdx_c, rho_wn, dux_m, dux_c);
-            const double fe = hface_flux<MH, LH>(s, (m & M_CFUE) && open_c && o_e1, cur.qxe, cur.dhe, cur.Pw1, Pc,
+            const double fe = hface_flux<MH, LH>(s, all_set(m, M_CFUE | M_O_JP1 | M_OPEN), cur.qxe, cur.dhe, cur.Pw1, Pc,
                                                  cur.Pe1, cur.Pe2, o_w1, (m & M_O_JP2) != 0, cur.t_w, dtv_c, cur.t_e,
                                                  cur.t_e2, rho_ep, rdx_p, rho_en, dux_c, dux_p);
             double fsum = fw - fe;
@@ -574,11 +589,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
                 double t_s = shfl_up_d(dtv_c, 1), t_n = 0., t_s2 = 0.;
                 if (far_h) { t_n = shfl_dn_d(dtv_c, 1); t_s2 = shfl_up_d(dtv_c, 2); }
                 const double hP1 = __shfl_sync(0xffffffffu, cur.hP, 1);
-                if (lane == 0) { Ps2 = cur.hP; Ps1 = hP1; t_s = cur.t_h; t_s2 = cur.t_h2; }
-                else if (lane == 1) { Ps2 = cur.hP; t_s2 = cur.t_h2; }
-                else if (lane == 31) { Pn1 = cur.hP; t_n = cur.t_h2; }
+                // strip halo, branch free: lanes 0,1 take cell i-2 (and lane 0 cell i-1) from the halo loads,
+                // lane 31 takes cell i+1
+                Ps2 = sel(lane < 2, cur.hP, Ps2);
+                Ps1 = sel(lane == 0, hP1, Ps1);
+                Pn1 = sel(lane == 31, cur.hP, Pn1);
+                t_s = sel(lane == 0, cur.t_h, t_s);
+                if (far_h) { t_s2 = sel(lane < 2, cur.t_h2, t_s2); t_n = sel(lane == 31, cur.t_h2, t_n); }
                 const bool o_s1 = (m & M_O_IM1) != 0;
-                const double fs = hface_flux<MH, LH>(s, (m & M_CFV) && o_s1 && open_c, cur.qys, cur.dhs, Ps2, Ps1, Pc,
+                const double fs = hface_flux<MH, LH>(s, all_set(m, M_CFV | M_O_IM1 | M_OPEN), cur.qys, cur.dhs, Ps2, Ps1, Pc,
                                                      Pn1, (m & M_O_IM2) != 0, (m & M_O_IP1) != 0, t_s2, t_s, dtv_c, t_n,
                                                      rho_sp, rdy_c, rho_sn, dvy_m, dvy_c);
                 fsum += fs - shfl_dn_d(fs, 1);
@@ -599,7 +618,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
             En_b = aux2 * theta;
             TIn_b = -aux2 * dP * omt;
             // advection (AD:2941-3144); weights exist iff both cells are open (MF:10559), applied on compute faces
-            const bool adv_on = do_h && colopen && open_c && (m & M_O_KP1) && (m & M_CFWT);
+            const bool adv_on = all_set(m, top_req);
             const bool pos = qz_p > 0.;
             const double Puu = sel(pos, Pm1, Pp2), Pu = sel(pos, Pc, Pp1), Pd = sel(pos, Pp1, Pc);
             double du_u = 0., du_d = 0.;
