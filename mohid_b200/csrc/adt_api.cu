@@ -314,20 +314,25 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
     const long blocks = (nunits + wpb - 1) / wpb;
     if (blocks > 2147483647L) return fail(h, MOHID_ADT_ERR_ARG, "grid too large");
     // kernel variant: the two headline schemes are compiled with fixed method / limiter
-    bool any_disch = false;
-    for (int m = 0; m < s.nprop; ++m) any_disch = any_disch || s.p[m].dconc != nullptr;
+    bool any_disch = false, all_impv = true;
+    for (int m = 0; m < s.nprop; ++m) {
+        any_disch = any_disch || s.p[m].dconc != nullptr;
+        all_impv = all_impv && s.p[m].advv_implicit;
+    }
+    // FULL: 3-D, both horizontal directions, implicit vertical advection for every property of the launch
+    const bool full = !s.vertical1d && !s.xzflow && s.K > 1 && all_impv;
     void (*kern)(const StepArgs);
     const bool tvd_sb = s.method_h == MOHID_P2_TVD && s.method_v == MOHID_P2_TVD && s.limiter_h == MOHID_SuperBee &&
                         s.limiter_v == MOHID_SuperBee;
     const bool upw = s.method_h == MOHID_UpwindOrder1 && s.method_v == MOHID_UpwindOrder1;
-    if (any_disch)
-        kern = tvd_sb ? adt_transport_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, true>
-             : upw    ? adt_transport_kernel<MOHID_UpwindOrder1, MOHID_SuperBee, MOHID_UpwindOrder1, MOHID_SuperBee, true>
-                      : adt_transport_kernel<0, 0, 0, 0, true>;
-    else
-        kern = tvd_sb ? adt_transport_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, false>
-             : upw    ? adt_transport_kernel<MOHID_UpwindOrder1, MOHID_SuperBee, MOHID_UpwindOrder1, MOHID_SuperBee, false>
-                      : adt_transport_kernel<0, 0, 0, 0, false>;
+#define ADT_PICK(D, F)                                                                                              \
+    (tvd_sb ? adt_transport_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, D, F>                \
+     : upw  ? adt_transport_kernel<MOHID_UpwindOrder1, MOHID_SuperBee, MOHID_UpwindOrder1, MOHID_SuperBee, D, F>    \
+            : adt_transport_kernel<0, 0, 0, 0, D, F>)
+    if (any_disch) kern = ADT_PICK(true, false);
+    else if (full) kern = ADT_PICK(false, true);
+    else kern = ADT_PICK(false, false);
+#undef ADT_PICK
     CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (timed) {

@@ -461,8 +461,10 @@ struct Level {
 //   blockDim.x = 32 * WPB; dynamic shared memory = 2 * K * WPB * 32 doubles.
 //   MH/LH/MV/LV > 0 fix the advection method / limiter at compile time; 0 = read from StepArgs.
 //   DISCH = the batch has point discharges (keeps the rare out-of-line call out of the common kernels).
+//   FULL  = 3-D run with both horizontal directions and implicit vertical advection for every property:
+//           the level body becomes one basic block (no uniform branches), which lets ptxas interleave the faces.
 // -------------------------------------------------------------------------------------
-template <int MH, int LH, int MV, int LV, bool DISCH, int WARPS = 8>
+template <int MH, int LH, int MV, int LV, bool DISCH, bool FULL, int WARPS = 8>
 __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __grid_constant__ StepArgs s) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, WPB = blockDim.x >> 5;
@@ -489,7 +491,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
     const bool central_v = (method_v == MOHID_CentralDif || method_v == MOHID_LeapFrog);
     const bool far_h = (method_h == MOHID_UpwindOrder2 || method_h == MOHID_UpwindOrder3);
     const bool far_v = (method_v == MOHID_UpwindOrder2 || method_v == MOHID_UpwindOrder3);
-    const bool do_h = !s.vertical1d, do_y = do_h && !s.xzflow;
+    const bool do_h = FULL || !s.vertical1d, do_y = FULL || (do_h && !s.xzflow);
 
     // ---- 2-D metrics of the column ----
     const double rdx_m = s.rdx[c2d - sj], rdx_c = s.rdx[c2d], rdx_p = s.rdx[c2d + sj], rdx_pp = s.rdx[c2d + je2];
@@ -516,7 +518,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
     // surface cell is open and the run is not Vertical1D (AD:2966, 3041; MF:10559); bit 31 is never set in a mask
     const unsigned top_req = (do_h && colopen) ? (M_OPEN | M_O_KP1 | M_CFWT) : (1u << 31);
     const double theta = pa.theta_difv, omt = 1. - pa.theta_difv;
-    const bool advv_imp = pa.advv_implicit != 0;
+    const bool advv_imp = FULL || pa.advv_implicit != 0;
     // halo lanes of the strip: lanes 0,1 fetch cell i-2, lane 31 fetches cell i+1
     const bool halo_lane = (lane < 2) || (lane == 31);
     const int halo_off = (lane == 31) ? ((ic <= s.I) ? 1 : 0) : -2;
@@ -548,7 +550,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
     double dvz_p = s.dvz[q + sk];
     double Dk = 0., Ek_b = 0., TIk_b = 0.;                // contributions of the bottom face to row k
     double Wprev = 0., Gprev = 0.;
-    unsigned long long zp = 0;
+    unsigned zp = 0;
     Level lvA, lvB;
     fetch(q, lvA);
 
@@ -557,7 +559,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
         // ---- prefetch: level k+1 (horizontal) and level k+2 (vertical rolling values) ----
         const int q2 = (k + 2 <= s.K + 1) ? q + 2 * sk : q + sk;
         const double Pp2 = P[q2], rdz_pp = s.rdz[q2], dtv_pp = s.dtv[q2], qz_pp = s.qz[q2], dvz_pp = s.dvz[q2];
-        if (k < s.K) fetch(q + sk, nxt);
+        fetch(q + sk, nxt);                               // plane K+1 exists, so the look-ahead is always in bounds
 
         const unsigned m = cur.m;
         const bool open_c = (m & M_OPEN) != 0;
@@ -607,7 +609,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
 
         // ---------------- vertical face k+1 (top of this cell) ----------------
         double Dn = 0., En_b = 0., TIn_b = 0.;            // contributions to row k+1
-        if (s.K > 1) {
+        if (FULL || s.K > 1) {
             // diffusion (AD:2708-2775 / 2779-2937): dvz is zero on non-compute W faces and in SmallDepths columns
             const double aux1 = dvz_p * dtv_c, aux2 = dvz_p * dtv_p;
             const double dP = Pp1 - Pc;
@@ -643,20 +645,33 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
         }
         (void)far_v;
 
-        // ---------------- open boundary rows (AD:5369-5672) ----------------
-        if (obc && open_c) open_boundary_row(s, pa, q, m, Pc, qz_c, qz_p, dtv_c, row);
-
         // ---------------- land fill (AD:1753) ----------------
-        if (m & M_LAND) row.TI = NULL_REAL;
+        row.TI = sel((m & M_LAND) != 0, NULL_REAL, row.TI);
 
         // ---------------- Thomas forward elimination, row k (MF:4087-4099) ----------------
-        const double aux = row.E + row.D * Wprev;
-        if (fabs(aux) > 0.) {
+        // branch free: a zero pivot keeps the previous W,G (the reference leaves them stale, MF:4092-4098)
+        const double Wp0 = Wprev, Gp0 = Gprev;
+        {
+            const double aux = row.E + row.D * Wp0;
+            const bool ok = aux != 0.;
             const double ra = fast_rcp(aux);
-            Wprev = -row.F * ra;
-            Gprev = (row.TI - row.D * Gprev) * ra;
-        } else {
-            ++zp;                                          // reference leaves W,G stale (MF:4092-4098)
+            Wprev = sel(ok, -row.F * ra, Wp0);
+            Gprev = sel(ok, (row.TI - row.D * Gp0) * ra, Gp0);
+            zp += ok ? 0u : 1u;
+        }
+        // ---------------- open boundary rows (AD:5369-5672) ----------------
+        // Rare (boundary ring only): the row is amended and eliminated again, so the common path stays one
+        // basic block.  Open boundary cells are never land.
+        if (obc && open_c) {
+            open_boundary_row(s, pa, q, m, Pc, qz_c, qz_p, dtv_c, row);
+            const double aux = row.E + row.D * Wp0;
+            if (aux != 0.) {
+                const double ra = 1.0 / aux;
+                Wprev = -row.F * ra;
+                Gprev = (row.TI - row.D * Gp0) * ra;
+            } else {
+                Wprev = Wp0; Gprev = Gp0;
+            }
         }
         Wsm[(size_t)(k - 1) * wstride] = Wprev;
         Gsm[(size_t)(k - 1) * wstride] = Gprev;
@@ -670,9 +685,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
         dvz_p = dvz_pp;
         q += sk;
     };
-    for (int k = 1; k <= s.K; k += 2) {
-        level(k, lvA, lvB);
-        if (k + 1 <= s.K) level(k + 1, lvB, lvA);
+    {
+        int k = 1;
+        for (; k + 1 <= s.K; k += 2) {
+            level(k, lvA, lvB);
+            level(k + 1, lvB, lvA);
+        }
+        if (k <= s.K) level(k, lvA, lvB);
     }
 
     // ---------------- back substitution (MF:4100-4105) ----------------
@@ -686,7 +705,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
             x = Wsm[(size_t)(k - 1) * wstride] * x + Gsm[(size_t)(k - 1) * wstride];
             O[qo] = x;
         }
-        if (zp) atomicAdd(s.zero_pivots, zp);
+        if (zp) atomicAdd(s.zero_pivots, (unsigned long long)zp);
     }
 }
 
