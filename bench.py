@@ -35,6 +35,9 @@ WORKLOADS = {
     "c1": (305, 232, 75, 2, 4, 4),          # Coastal3D-like dimensions
     "c4": (4096, 4096, 40, 10, 4, 4),       # needs >= 2 GPUs
     "small": (256, 256, 20, 4, 4, 4),
+    "c3q": (1024, 1024, 40, 10, 4, 4),      # quarter of C3 (size-sensitivity checks)
+    "c3s": (512, 512, 40, 10, 4, 4),
+    "strip": (62, 16384, 40, 10, 4, 4),     # narrow in i: a k-plane is only 1 MB (TLB / page-locality probe)
 }
 
 

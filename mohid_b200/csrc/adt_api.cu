@@ -263,15 +263,6 @@ int launch_coef(Handle *h, const mohid_adt_params &q, bool geom, bool diff) {
     return 0;
 }
 
-int pick_wpb(Handle *h, int nprop) {
-    // W,G of the column solve: 2 * K * 32 doubles per warp; at most 8 warps = 2 per SM sub-partition (16K registers each), so a thread may use up to 255 registers
-    const size_t per_warp = (size_t)2 * h->K * 32 * sizeof(double);
-    int wpb = (int)std::min<size_t>(8, (size_t)h->smem_optin / per_warp);
-    if (wpb >= nprop && nprop >= 6) wpb = nprop;                 // one block = all properties of a strip
-    else if (nprop < 6 && wpb >= 2 * nprop) wpb = (wpb / nprop) * nprop;
-    return wpb;
-}
-
 int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool timed) {
     StepArgs s{};
     s.I = h->I; s.J = h->J; s.K = h->K; s.ld = h->ld; s.nj = h->nj; s.sk = (long)h->ld * h->nj;
@@ -306,14 +297,7 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
         pa.dconc = hd ? h->d_conc[n] : nullptr;
         pa.dconcmf = hd ? h->d_concmf[n] : nullptr;
     }
-    const int wpb = pick_wpb(h, s.nprop);
-    if (wpb < 1)
-        return fail(h, MOHID_ADT_ERR_UNSUPPORTED, "K = %d layers need more shared memory than one SM has", h->K);
-    const size_t smem = (size_t)2 * h->K * wpb * 32 * sizeof(double);
-    const long nunits = (long)s.nprop * s.ntile_i * h->j_count;
-    const long blocks = (nunits + wpb - 1) / wpb;
-    if (blocks > 2147483647L) return fail(h, MOHID_ADT_ERR_ARG, "grid too large");
-    // kernel variant: the two headline schemes are compiled with fixed method / limiter
+    // ---- kernel variant and launch shape ----
     bool any_disch = false, all_impv = true;
     for (int m = 0; m < s.nprop; ++m) {
         any_disch = any_disch || s.p[m].dconc != nullptr;
@@ -321,18 +305,38 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
     }
     // FULL: 3-D, both horizontal directions, implicit vertical advection for every property of the launch
     const bool full = !s.vertical1d && !s.xzflow && s.K > 1 && all_impv;
-    void (*kern)(const StepArgs);
     const bool tvd_sb = s.method_h == MOHID_P2_TVD && s.method_v == MOHID_P2_TVD && s.limiter_h == MOHID_SuperBee &&
                         s.limiter_v == MOHID_SuperBee;
     const bool upw = s.method_h == MOHID_UpwindOrder1 && s.method_v == MOHID_UpwindOrder1;
+    void (*kern)(const StepArgs);
+    int wpb;
+    size_t smem;
+    // Occupancy is bounded by registers (16K per SM sub-partition): 8 warps allow 255 registers per thread,
+    // 12 warps 168.  The two headline variants fit 168 registers once G of the column solve is parked in the
+    // output array instead of shared memory (W needs K*32 doubles per warp, W+G twice that).
+    const size_t w_bytes = (size_t)h->K * 32 * sizeof(double);
+    if (full && !any_disch && (tvd_sb || upw) && 12 * w_bytes <= (size_t)h->smem_optin) {
+        kern = tvd_sb ? adt_transport_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, false, true, 12, true, true>
+                      : adt_transport_kernel<MOHID_UpwindOrder1, MOHID_SuperBee, MOHID_UpwindOrder1, MOHID_SuperBee, false, true, 12, true, true>;
+        wpb = 12;
+        smem = wpb * w_bytes;
+    } else {
 #define ADT_PICK(D, F)                                                                                              \
     (tvd_sb ? adt_transport_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, D, F>                \
      : upw  ? adt_transport_kernel<MOHID_UpwindOrder1, MOHID_SuperBee, MOHID_UpwindOrder1, MOHID_SuperBee, D, F>    \
             : adt_transport_kernel<0, 0, 0, 0, D, F>)
-    if (any_disch) kern = ADT_PICK(true, false);
-    else if (full) kern = ADT_PICK(false, true);
-    else kern = ADT_PICK(false, false);
+        if (any_disch) kern = ADT_PICK(true, false);
+        else if (full) kern = ADT_PICK(false, true);
+        else kern = ADT_PICK(false, false);
 #undef ADT_PICK
+        wpb = (int)std::min<size_t>(8, (size_t)h->smem_optin / (2 * w_bytes));
+        smem = (size_t)2 * wpb * w_bytes;
+    }
+    if (wpb < 1)
+        return fail(h, MOHID_ADT_ERR_UNSUPPORTED, "K = %d layers need more shared memory than one SM has", h->K);
+    const long nunits = (long)s.nprop * s.ntile_i * h->j_count;
+    const long blocks = (nunits + wpb - 1) / wpb;
+    if (blocks > 2147483647L) return fail(h, MOHID_ADT_ERR_ARG, "grid too large");
     CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (timed) {

@@ -464,7 +464,7 @@ struct Level {
 //   FULL  = 3-D run with both horizontal directions and implicit vertical advection for every property:
 //           the level body becomes one basic block (no uniform branches), which lets ptxas interleave the faces.
 // -------------------------------------------------------------------------------------
-template <int MH, int LH, int MV, int LV, bool DISCH, bool FULL, int WARPS = 8>
+template <int MH, int LH, int MV, int LV, bool DISCH, bool FULL, int WARPS = 8, bool PF = true, bool GGLOB = false>
 __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __grid_constant__ StepArgs s) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, WPB = blockDim.x >> 5;
@@ -552,14 +552,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
     double Wprev = 0., Gprev = 0.;
     unsigned zp = 0;
     Level lvA, lvB;
-    fetch(q, lvA);
+    if (PF) fetch(q, lvA);
 
     // one level of the march: consumes `cur`, prefetches the next level into `nxt`
-    auto level = [&](const int k, const Level &cur, Level &nxt) {
+    auto level = [&](const int k, const Level &cur_, Level &nxt) {
         // ---- prefetch: level k+1 (horizontal) and level k+2 (vertical rolling values) ----
         const int q2 = (k + 2 <= s.K + 1) ? q + 2 * sk : q + sk;
         const double Pp2 = P[q2], rdz_pp = s.rdz[q2], dtv_pp = s.dtv[q2], qz_pp = s.qz[q2], dvz_pp = s.dvz[q2];
-        fetch(q + sk, nxt);                               // plane K+1 exists, so the look-ahead is always in bounds
+        if (PF) fetch(q + sk, nxt);                       // plane K+1 exists, so the look-ahead is always in bounds
+        else fetch(q, nxt);
+        const Level &cur = PF ? cur_ : nxt;
 
         const unsigned m = cur.m;
         const bool open_c = (m & M_OPEN) != 0;
@@ -598,7 +600,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
                 Pn1 = sel(lane == 31, cur.hP, Pn1);
                 t_s = sel(lane == 0, cur.t_h, t_s);
                 if (far_h) { t_s2 = sel(lane < 2, cur.t_h2, t_s2); t_n = sel(lane == 31, cur.t_h2, t_n); }
-                const bool o_s1 = (m & M_O_IM1) != 0;
                 const double fs = hface_flux<MH, LH>(s, all_set(m, M_CFV | M_O_IM1 | M_OPEN), cur.qys, cur.dhs, Ps2, Ps1, Pc,
                                                      Pn1, (m & M_O_IM2) != 0, (m & M_O_IP1) != 0, t_s2, t_s, dtv_c, t_n,
                                                      rho_sp, rdy_c, rho_sn, dvy_m, dvy_c);
@@ -674,7 +675,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
             }
         }
         Wsm[(size_t)(k - 1) * wstride] = Wprev;
-        Gsm[(size_t)(k - 1) * wstride] = Gprev;
+        if (GGLOB) { if (writer && colwet) pa.pout[q] = Gprev; }      // G parked in the output array
+        else Gsm[(size_t)(k - 1) * wstride] = Gprev;
 
         // ---------------- roll ----------------
         Dk = Dn; Ek_b = En_b; TIk_b = TIn_b;
@@ -700,10 +702,31 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
         int qo = i + sj * j + sk * (s.K + 1);
         double x = 0.0;                                   // RES(KUB+1) = G(KUB+1) = 0 (halo row is the identity)
         O[qo] = x;
-        for (int k = s.K; k >= 1; --k) {
-            qo -= sk;
-            x = Wsm[(size_t)(k - 1) * wstride] * x + Gsm[(size_t)(k - 1) * wstride];
-            O[qo] = x;
+        if (GGLOB) {
+            // G comes back from the output array: fetch 8 levels at a time so the loads overlap
+            int k = s.K;
+            for (; k >= 8; k -= 8) {
+                double g[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) g[u] = O[qo - (u + 1) * sk];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    qo -= sk;
+                    x = Wsm[(size_t)(k - 1 - u) * wstride] * x + g[u];
+                    O[qo] = x;
+                }
+            }
+            for (; k >= 1; --k) {
+                qo -= sk;
+                x = Wsm[(size_t)(k - 1) * wstride] * x + O[qo];
+                O[qo] = x;
+            }
+        } else {
+            for (int k = s.K; k >= 1; --k) {
+                qo -= sk;
+                x = Wsm[(size_t)(k - 1) * wstride] * x + Gsm[(size_t)(k - 1) * wstride];
+                O[qo] = x;
+            }
         }
         if (zp) atomicAdd(s.zero_pivots, (unsigned long long)zp);
     }
