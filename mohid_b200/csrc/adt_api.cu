@@ -316,10 +316,14 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
     // output array instead of shared memory (W needs K*32 doubles per warp, W+G twice that).
     const size_t w_bytes = (size_t)h->K * 32 * sizeof(double);
     if (full && !any_disch && (tvd_sb || upw) && 12 * w_bytes <= (size_t)h->smem_optin) {
-        kern = tvd_sb ? adt_transport_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, false, true, 12, true, true>
-                      : adt_transport_kernel<MOHID_UpwindOrder1, MOHID_SuperBee, MOHID_UpwindOrder1, MOHID_SuperBee, false, true, 12, true, true>;
+        kern = tvd_sb ? adt_transport_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, false, true, 12, 1, true>
+                      : adt_transport_kernel<MOHID_UpwindOrder1, MOHID_SuperBee, MOHID_UpwindOrder1, MOHID_SuperBee, false, true, 12, 1, true>;
         wpb = 12;
         smem = wpb * w_bytes;
+        if (getenv("MOHID_ADT_PF2") && tvd_sb && wpb * (w_bytes + 2 * 16 * 32 * sizeof(double)) <= (size_t)h->smem_optin) {
+            kern = adt_transport_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, false, true, 12, 2, true>;
+            smem = wpb * (w_bytes + 2 * 16 * 32 * sizeof(double));
+        }
     } else {
 #define ADT_PICK(D, F)                                                                                              \
     (tvd_sb ? adt_transport_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, D, F>                \

@@ -27,6 +27,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <cuda_pipeline.h>
 
 #include "../../include/mohid_adt.h"
 
@@ -461,16 +462,21 @@ struct Level {
 //   blockDim.x = 32 * WPB; dynamic shared memory = 2 * K * WPB * 32 doubles.
 //   MH/LH/MV/LV > 0 fix the advection method / limiter at compile time; 0 = read from StepArgs.
 //   DISCH = the batch has point discharges (keeps the rare out-of-line call out of the common kernels).
+//   PF    = 0 no look-ahead, 1 next level fetched into registers, 2 next two levels staged in shared memory
+//           with cp.async (in-flight loads hold no registers; needs FULL and a non-QUICK scheme).
+//   GGLOB = G of the column solve is parked in the output array instead of shared memory.
 //   FULL  = 3-D run with both horizontal directions and implicit vertical advection for every property:
 //           the level body becomes one basic block (no uniform branches), which lets ptxas interleave the faces.
 // -------------------------------------------------------------------------------------
-template <int MH, int LH, int MV, int LV, bool DISCH, bool FULL, int WARPS = 8, bool PF = true, bool GGLOB = false>
+template <int MH, int LH, int MV, int LV, bool DISCH, bool FULL, int WARPS = 8, int PF = 1, bool GGLOB = false>
 __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __grid_constant__ StepArgs s) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, WPB = blockDim.x >> 5;
     double *__restrict__ Wsm = smem + warp * 32 + lane;                  // [K][WPB][32]
     double *__restrict__ Gsm = Wsm + (size_t)s.K * WPB * 32;
     const int wstride = WPB * 32;
+    constexpr int NV = 16, NSTAGE = 2;                       // PF == 2: staged values per level, ring depth
+    double *__restrict__ Stg = smem + (size_t)s.K * WPB * 32 * (GGLOB ? 1 : 2) + warp * 32 + lane;
     const long nunits = (long)s.nprop * s.ntile_i * s.j_count;
     const long unit = (long)blockIdx.x * WPB + warp;
     if (unit >= nunits) return;
@@ -541,27 +547,56 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
         }
     };
 
+    // PF == 2: the same data, copied global -> shared by cp.async (one private slot per thread and value)
+    auto fetch_async = [&](int q, int st) {
+        double *d = Stg + (size_t)st * NV * wstride;
+        auto cp8 = [&](int slot, const double *g) { __pipeline_memcpy_async(d + slot * wstride, g, 8); };
+        cp8(0, P + q - 2 * sj); cp8(1, P + q - sj); cp8(2, P + q + sj); cp8(3, P + q + je2);
+        if (halo_lane) cp8(4, P + q + halo_off);
+        cp8(5, s.dtv + q - sj); cp8(6, s.dtv + q + sj);
+        if (lane == 0) cp8(7, s.dtv + q - 1);
+        cp8(8, s.qx + q); cp8(9, s.qx + q + sj); cp8(10, s.qy + q);
+        cp8(11, s.dhu + q); cp8(12, s.dhu + q + sj); cp8(13, s.dhv + q); cp8(14, s.vr + q);
+        __pipeline_memcpy_async(reinterpret_cast<uint32_t *>(d + 15 * wstride), s.mask + q, 4);
+        __pipeline_commit();
+    };
+    auto load_stage = [&](int st, Level &L) {
+        const double *d = Stg + (size_t)st * NV * wstride;
+        L.Pw2 = d[0]; L.Pw1 = d[wstride]; L.Pe1 = d[2 * wstride]; L.Pe2 = d[3 * wstride]; L.hP = d[4 * wstride];
+        L.t_w = d[5 * wstride]; L.t_e = d[6 * wstride]; L.t_h = d[7 * wstride];
+        L.qxw = d[8 * wstride]; L.qxe = d[9 * wstride]; L.qys = d[10 * wstride];
+        L.dhw = d[11 * wstride]; L.dhe = d[12 * wstride]; L.dhs = d[13 * wstride]; L.vr = d[14 * wstride];
+        L.m = *reinterpret_cast<const uint32_t *>(d + 15 * wstride);
+        L.t_w2 = 0.; L.t_e2 = 0.; L.t_h2 = 0.;
+    };
+
     // ---- rolling registers along k (cells k-1 .. k+2 of this column) ----
     int q = c2d + sk;                                     // cell (i,j,1)
-    double Pm1 = P[c2d], Pc = P[q], Pp1 = P[q + sk];
+    double Pm1 = P[c2d], Pc = P[q], Pp1 = P[q + sk], Pp2 = P[q + ((s.K >= 2) ? 2 * sk : sk)];
     double dtv_m = 0., dtv_c = s.dtv[q], dtv_p = s.dtv[q + sk];
-    double rdz_c = s.rdz[q], rdz_p = s.rdz[q + sk];
+    double rdz_c = s.rdz[q], rdz_p = s.rdz[q + sk], rdz_pp = s.rdz[q + ((s.K >= 2) ? 2 * sk : sk)];
     double qz_c = s.qz[q], qz_p = s.qz[q + sk];
     double dvz_p = s.dvz[q + sk];
     double Dk = 0., Ek_b = 0., TIk_b = 0.;                // contributions of the bottom face to row k
     double Wprev = 0., Gprev = 0.;
     unsigned zp = 0;
     Level lvA, lvB;
-    if (PF) fetch(q, lvA);
+    if (PF == 1) fetch(q, lvA);
+    if (PF == 2) { fetch_async(q, 0); fetch_async(q + sk, 1); }
 
     // one level of the march: consumes `cur`, prefetches the next level into `nxt`
     auto level = [&](const int k, const Level &cur_, Level &nxt) {
         // ---- prefetch: level k+1 (horizontal) and level k+2 (vertical rolling values) ----
+        // vertical look-ahead: the values of plane k+2 that this level itself uses (stencil cell k+2, its metric sum)
+        // were loaded one level ago; here plane k+3 is requested for the next level (clamped to plane K+1)
         const int q2 = (k + 2 <= s.K + 1) ? q + 2 * sk : q + sk;
-        const double Pp2 = P[q2], rdz_pp = s.rdz[q2], dtv_pp = s.dtv[q2], qz_pp = s.qz[q2], dvz_pp = s.dvz[q2];
-        if (PF) fetch(q + sk, nxt);                       // plane K+1 exists, so the look-ahead is always in bounds
-        else fetch(q, nxt);
-        const Level &cur = PF ? cur_ : nxt;
+        const int q3 = (k + 3 <= s.K + 1) ? q + 3 * sk : q2;
+        const double Pp3 = P[q3], rdz_p3 = s.rdz[q3];
+        const double dtv_pp = s.dtv[q2], qz_pp = s.qz[q2], dvz_pp = s.dvz[q2];
+        if (PF == 1) fetch(q + sk, nxt);                  // plane K+1 exists, so the look-ahead is always in bounds
+        else if (PF == 0) fetch(q, nxt);
+        else { __pipeline_wait_prior(NSTAGE - 1); load_stage((k - 1) & 1, nxt); }
+        const Level &cur = (PF == 1) ? cur_ : nxt;
 
         const unsigned m = cur.m;
         const bool open_c = (m & M_OPEN) != 0;
@@ -680,12 +715,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
 
         // ---------------- roll ----------------
         Dk = Dn; Ek_b = En_b; TIk_b = TIn_b;
-        Pm1 = Pc; Pc = Pp1; Pp1 = Pp2;
+        Pm1 = Pc; Pc = Pp1; Pp1 = Pp2; Pp2 = Pp3;
         dtv_m = dtv_c; dtv_c = dtv_p; dtv_p = dtv_pp;
-        rdz_c = rdz_p; rdz_p = rdz_pp;
+        rdz_c = rdz_p; rdz_p = rdz_pp; rdz_pp = rdz_p3;
         qz_c = qz_p; qz_p = qz_pp;
         dvz_p = dvz_pp;
         q += sk;
+        // PF == 2: every value of this level has been consumed, so its stage can be refilled with level k+2
+        // (addresses are clamped to plane K+1; the surplus copies of the last two levels are never read)
+        if (PF == 2) fetch_async(min(q + sk, c2d + sk * (s.K + 1)), (k - 1) & 1);
     };
     {
         int k = 1;
@@ -696,6 +734,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
         if (k <= s.K) level(k, lvA, lvB);
     }
 
+    if (PF == 2) __pipeline_wait_prior(0);
     // ---------------- back substitution (MF:4100-4105) ----------------
     if (writer && colwet) {
         double *__restrict__ O = pa.pout;
