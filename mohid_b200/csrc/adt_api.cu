@@ -28,6 +28,8 @@ struct Handle {
     mohid_adt_options opt{};
     int I = 0, J = 0, K = 0, ni = 0, nj = 0, nk = 0, ld_h = 0, ld = 0;
     long n2 = 0, n3 = 0;
+    int sj = 0, sk = 0;                                 // element strides of j and k in the 3-D device arrays
+    bool kmid = false;                                  // optional device layout (i, k, j) (MOHID_ADT_LAYOUT=1); measured: no gain
     int maxprop = 0;
     // 2-D
     double *DUX = nullptr, *DVY = nullptr, *DZX = nullptr, *DZY = nullptr, *rdx = nullptr, *rdy = nullptr;
@@ -102,24 +104,27 @@ int dalloc(Handle *h, T **p, size_t n) {
     return 0;
 }
 
-// caller (ld_h) -> device mirror (ld) copy of a (rows x ni) array, element size es.  cudaMemcpyDefault:
+// caller -> device mirror copy of a 2-D array (nj rows of ni elements, element size es).  cudaMemcpyDefault:
 // the caller's arrays may live in host memory (the Fortran case) or, under UVA, in device memory.
-int h2d(Handle *h, void *dst, const void *src, size_t es, long rows) {
-    if (h->ld_h == h->ld) {
-        CU(h, cudaMemcpyAsync(dst, src, es * (size_t)h->ld * rows, cudaMemcpyDefault, h->stream));
-    } else {
-        CU(h, cudaMemcpy2DAsync(dst, es * h->ld, src, es * h->ld_h, es * std::min(h->ld, h->ld_h), rows,
-                                cudaMemcpyDefault, h->stream));
-    }
+int h2d2(Handle *h, void *dst, const void *src, size_t es) {
+    CU(h, cudaMemcpy2DAsync(dst, es * h->ld, src, es * h->ld_h, es * std::min(h->ld, h->ld_h), h->nj,
+                            cudaMemcpyDefault, h->stream));
     return 0;
 }
-int d2h(Handle *h, void *dst, const void *src, size_t es, long rows) {
-    if (h->ld_h == h->ld) {
-        CU(h, cudaMemcpyAsync(dst, src, es * (size_t)h->ld * rows, cudaMemcpyDefault, h->stream));
-    } else {
-        CU(h, cudaMemcpy2DAsync(dst, es * h->ld_h, src, es * h->ld, es * std::min(h->ld, h->ld_h), rows,
-                                cudaMemcpyDefault, h->stream));
-    }
+// 3-D arrays: the caller's layout is Fortran (i, j, k); the device mirror is (i, k, j) when kmid, so each k-plane
+// of the caller is one strided 2-D copy (row pitch sj on the device).
+int h2d3(Handle *h, void *dst, const void *src, size_t es) {
+    for (int k = 0; k < h->nk; ++k)
+        CU(h, cudaMemcpy2DAsync((char *)dst + es * (size_t)h->sk * k, es * h->sj,
+                                (const char *)src + es * (size_t)h->ld_h * h->nj * k, es * h->ld_h,
+                                es * std::min(h->ld, h->ld_h), h->nj, cudaMemcpyDefault, h->stream));
+    return 0;
+}
+int d2h3(Handle *h, void *dst, const void *src, size_t es) {
+    for (int k = 0; k < h->nk; ++k)
+        CU(h, cudaMemcpy2DAsync((char *)dst + es * (size_t)h->ld_h * h->nj * k, es * h->ld_h,
+                                (const char *)src + es * (size_t)h->sk * k, es * h->sj,
+                                es * std::min(h->ld, h->ld_h), h->nj, cudaMemcpyDefault, h->stream));
     return 0;
 }
 
@@ -246,6 +251,7 @@ int validate(Handle *h, int nprop, const mohid_adt_params *p, Batch &b) {
 int launch_coef(Handle *h, const mohid_adt_params &q, bool geom, bool diff) {
     CoefArgs a{};
     a.ni = h->ni; a.nj = h->nj; a.nk = h->nk; a.ld = h->ld; a.I = h->I; a.J = h->J; a.K = h->K;
+    a.sj = h->sj; a.sk = h->sk;
     a.dt = q.DTProp; a.schmidt_h = q.Schmidt_H; a.schmidt_coef_v = q.SchmidtCoef_V; a.schmidt_bg_v = q.SchmidtBackground_V;
     a.nulldif = q.NullDif;
     a.Wflux_X = h->raw_d[0]; a.Wflux_Y = h->raw_d[1]; a.Wflux_Z = h->raw_d[2]; a.VolumeZOld = h->raw_d[3];
@@ -265,7 +271,7 @@ int launch_coef(Handle *h, const mohid_adt_params &q, bool geom, bool diff) {
 
 int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool timed) {
     StepArgs s{};
-    s.I = h->I; s.J = h->J; s.K = h->K; s.ld = h->ld; s.nj = h->nj; s.sk = (long)h->ld * h->nj;
+    s.I = h->I; s.J = h->J; s.K = h->K; s.ld = h->ld; s.nj = h->nj; s.sj = h->sj; s.sk = h->sk;
     s.nprop = (int)idx.size();
     s.ntile_i = (h->I + 30) / 31;
     s.j_begin = h->j_begin; s.j_count = h->j_count;
@@ -366,7 +372,7 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
         if ((bc == MOHID_BC_NullGradient || (bc == MOHID_BC_CyclicBoundary && h->has_ref[n])) && h->n_bnd_cols > 0) {
             BndArgs ba{};
             ba.I = h->I; ba.J = h->J; ba.K = h->K; ba.ld = h->ld; ba.nj = h->nj; ba.ncols = h->n_bnd_cols;
-            ba.sk = s.sk; ba.cols = h->bnd_cols; ba.kfloor = h->KFloorZ; ba.mask = h->mask;
+            ba.sj = s.sj; ba.sk = s.sk; ba.cols = h->bnd_cols; ba.kfloor = h->KFloorZ; ba.mask = h->mask;
             ba.prop = s.p[m].pout; ba.pref = s.p[m].pref;
             const long tot = (long)h->n_bnd_cols * h->K;
             if (bc == MOHID_BC_NullGradient) {
@@ -406,7 +412,7 @@ int step_once(Handle *h, const Batch &b) {
         if (int rc = launch_coef(h, b.p[n], !geom_done, true)) return rc;
         if (!geom_done && h->d_ncell > 0) {               // flag the receiving cells, per-layer flows (AD:4063-4077)
             DischArgs d{};
-            d.ncell = h->d_ncell; d.K = h->K; d.ld = h->ld; d.nj = h->nj;
+            d.ncell = h->d_ncell; d.K = h->K; d.ld = h->ld; d.sj = h->sj; d.sk = h->sk;
             d.ci = h->d_ci; d.cj = h->d_cj; d.ck = h->d_ck; d.ckmin = h->d_ckmin; d.ckmax = h->d_ckmax;
             d.cvert = h->d_cvert; d.cbypass = h->d_cbypass; d.cflow = h->d_cflow;
             d.kmin_eff = h->d_kmin_eff; d.kmax_eff = h->d_kmax_eff; d.flow_k = h->d_flow_k;
@@ -468,6 +474,9 @@ int mohid_adt_create(int *handle, const mohid_adt_size3d *size, const mohid_adt_
     h->ld = ((h->ni + 15) / 16) * 16;                // 128-byte aligned rows on the device
     h->n2 = (long)h->ld * h->nj;
     h->n3 = h->n2 * h->nk;
+    if (const char *e = getenv("MOHID_ADT_LAYOUT")) h->kmid = atoi(e) != 0;
+    if (h->kmid) { h->sk = h->ld; h->sj = h->ld * h->nk; }          // element (i,j,k) at i + ld*(k + nk*j)
+    else         { h->sj = h->ld; h->sk = h->ld * h->nj; }          // element (i,j,k) at i + ld*(j + nj*k)
     if (h->n3 >= 2147483647L || h->nj > 65535 || h->nk > 65535) {
         delete h;
         return fail(nullptr, MOHID_ADT_ERR_ARG, "one field must hold fewer than 2^31 elements (32-bit cell indices)");
@@ -541,9 +550,9 @@ int mohid_adt_set_grid2d(const int *handle, const double *DUX, const double *DVY
     if (!DUX || !DVY || !DZX || !DZY || !KFloorZ || !BoundaryPoints2D) return fail(h, MOHID_ADT_ERR_ARG, "null array");
     CU(h, cudaSetDevice(h->dev));
     int rc = 0;
-    rc |= h2d(h, h->DUX, DUX, 8, h->nj); rc |= h2d(h, h->DVY, DVY, 8, h->nj);
-    rc |= h2d(h, h->DZX, DZX, 8, h->nj); rc |= h2d(h, h->DZY, DZY, 8, h->nj);
-    rc |= h2d(h, h->KFloorZ, KFloorZ, 4, h->nj); rc |= h2d(h, h->Bnd, BoundaryPoints2D, 4, h->nj);
+    rc |= h2d2(h, h->DUX, DUX, 8); rc |= h2d2(h, h->DVY, DVY, 8);
+    rc |= h2d2(h, h->DZX, DZX, 8); rc |= h2d2(h, h->DZY, DZY, 8);
+    rc |= h2d2(h, h->KFloorZ, KFloorZ, 4); rc |= h2d2(h, h->Bnd, BoundaryPoints2D, 4);
     if (rc) return rc;
     adt_grid2d_kernel<<<std::max(1, (int)std::min<long>((h->n2 + 255) / 256, 4096)), 256, 0, h->stream>>>(
         h->ni, h->nj, h->ld, h->DUX, h->DVY, h->rdx, h->rdy);
@@ -577,11 +586,10 @@ int mohid_adt_set_step(const int *handle, const double *Wflux_X, const double *W
     const int *m[6] = {OpenPoints3D, LandPoints3D, WaterPoints3D, ComputeFacesU3D, ComputeFacesV3D, ComputeFacesW3D};
     for (auto p : d) if (!p) return fail(h, MOHID_ADT_ERR_ARG, "null array");
     for (auto p : m) if (!p) return fail(h, MOHID_ADT_ERR_ARG, "null mask (WaterPoints3D is required: THOMASZ_NewType2 reads it, MF:4086)");
-    const long rows = (long)h->nj * h->nk;
-    for (int a = 0; a < 11; ++a) if (int rc = h2d(h, h->raw_d[a], d[a], 8, rows)) return rc;
-    for (int a = 0; a < 6; ++a) if (int rc = h2d(h, h->raw_i[a], m[a], 4, rows)) return rc;
+    for (int a = 0; a < 11; ++a) if (int rc = h2d3(h, h->raw_d[a], d[a], 8)) return rc;
+    for (int a = 0; a < 6; ++a) if (int rc = h2d3(h, h->raw_i[a], m[a], 4)) return rc;
     h->have_small = SmallDepths != nullptr;
-    if (SmallDepths) if (int rc = h2d(h, h->SmallDepths, SmallDepths, 4, h->nj)) return rc;
+    if (SmallDepths) if (int rc = h2d2(h, h->SmallDepths, SmallDepths, 4)) return rc;
     CU(h, cudaStreamSynchronize(h->stream));     // the host arrays are only borrowed for the call (AD:2229-2349)
     h->have_step = true;
     return 0;
@@ -691,12 +699,11 @@ int mohid_adt_upload_props(const int *handle, const int *nprop, const double *co
     if (!nprop || !prop) return fail(h, MOHID_ADT_ERR_ARG, "null argument");
     CU(h, cudaSetDevice(h->dev));
     if (int rc = ensure_props(h, *nprop, reference_prop != nullptr)) return rc;
-    const long rows = (long)h->nj * h->nk;
     for (int n = 0; n < *nprop; ++n) {
         if (!prop[n]) return fail(h, MOHID_ADT_ERR_ARG, "prop[%d] is null", n);
         double *a = h->prop[0][n], *b = h->prop[1][n];
-        if (h->ld != h->ld_h) CU(h, cudaMemsetAsync(a, 0, h->n3 * sizeof(double), h->stream));
-        if (int rc = h2d(h, a, prop[n], 8, rows)) return rc;
+        if (h->ld != h->ld_h) CU(h, cudaMemsetAsync(a, 0, h->n3 * sizeof(double), h->stream));   // ld padding reads as zero
+        if (int rc = h2d3(h, a, prop[n], 8)) return rc;
         // both ping-pong buffers start identical: halos, dry columns and closed cells are never rewritten
         CU(h, cudaMemcpyAsync(b, a, h->n3 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
         h->cur[n] = 0;
@@ -707,7 +714,7 @@ int mohid_adt_upload_props(const int *handle, const int *nprop, const double *co
                 if (int rc = dalloc(h, &h->ref[n], h->n3)) return rc;
                 CU(h, cudaMemsetAsync(h->ref[n], 0, h->n3 * sizeof(double), h->stream));
             }
-            if (int rc = h2d(h, h->ref[n], r, 8, rows)) return rc;
+            if (int rc = h2d3(h, h->ref[n], r, 8)) return rc;
         }
     }
     CU(h, cudaStreamSynchronize(h->stream));
@@ -720,9 +727,8 @@ int mohid_adt_download_props(const int *handle, const int *nprop, double *const 
     if (!nprop || !prop) return fail(h, MOHID_ADT_ERR_ARG, "null argument");
     if (*nprop > (int)h->prop[0].size()) return fail(h, MOHID_ADT_ERR_STATE, "properties were never uploaded");
     CU(h, cudaSetDevice(h->dev));
-    const long rows = (long)h->nj * h->nk;
     for (int n = 0; n < *nprop; ++n)
-        if (int rc = d2h(h, prop[n], h->prop[h->cur[n]][n], 8, rows)) return rc;
+        if (int rc = d2h3(h, prop[n], h->prop[h->cur[n]][n], 8)) return rc;
     CU(h, cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -802,7 +808,7 @@ static int pack_common(const int *handle, const int *nprop, const int *j0, const
     if (*j0 < 0 || *width < 1 || *j0 + *width > h->nj) return fail(h, MOHID_ADT_ERR_ARG, "column range out of bounds");
     CU(h, cudaSetDevice(h->dev));
     PackArgs a{};
-    a.ld = h->ld; a.nj = h->nj; a.nk = h->nk; a.nprop = *nprop; a.j0 = *j0; a.width = *width; a.sk = (long)h->ld * h->nj;
+    a.ld = h->ld; a.nj = h->nj; a.nk = h->nk; a.nprop = *nprop; a.j0 = *j0; a.width = *width; a.sj = h->sj; a.sk = h->sk;
     for (int n = 0; n < *nprop; ++n) a.prop[n] = h->prop[h->cur[n]][n];
     const long tot = (long)a.nk * a.width * a.ld * a.nprop;
     const int blocks = (int)std::min<long>((tot + 255) / 256, (long)h->num_sms * 16);

@@ -61,6 +61,7 @@ enum : unsigned {
 
 struct CoefArgs {
     int ni, nj, nk, ld;              // allocated extents (I+2, J+2, K+2) and leading dimension
+    int sj, sk;                      // element strides of j and k in the 3-D device arrays
     int I, J, K;
     double dt, schmidt_h, schmidt_coef_v, schmidt_bg_v;
     int nulldif;
@@ -83,9 +84,9 @@ __global__ void __launch_bounds__(128) adt_coef_kernel(const CoefArgs a) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y, k = blockIdx.z;
     if (i >= a.ld) return;
-    const int sj = a.ld, sk = a.ld * a.nj;
-    const int q2 = i + sj * j;
-    const int q = q2 + sk * k;
+    const int sj = a.sj, sk = a.sk, sj2 = a.ld;          // 3-D strides; 2-D arrays are (i + ld*j)
+    const int q2 = i + sj2 * j;
+    const int q = i + sj * j + sk * k;
     if (i >= a.ni) {                                  // leading-dimension padding
         if (a.do_geom) { a.mask[q] = 0; a.dtv[q] = 0.; a.vr[q] = 1.; a.rdz[q] = 0.; }
         if (a.do_diff) { a.dhu[q] = 0.; a.dhv[q] = 0.; a.dvz[q] = 0.; }
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(128) adt_coef_kernel(const CoefArgs a) {
         if (a.Land[q] == 1) m |= M_LAND;
         const bool bnd = a.Bnd[q2] == 1;
         if (bnd) m |= M_BND;
-        const int qtop = q2 + sk * a.K;
+        const int qtop = i + sj * j + sk * a.K;
         if (a.Water[qtop] == 1) m |= M_COLWET;
         if (a.Open[qtop] == 1) m |= M_COLOPEN;
         if (jm2 && a.Open[q - 2 * sj] == 1) m |= M_O_JM2;
@@ -127,8 +128,8 @@ __global__ void __launch_bounds__(128) adt_coef_kernel(const CoefArgs a) {
         if (bnd) {                                        // interior neighbours: only boundary rows need them
             if (o_ip1 && a.Bnd[q2 + 1] != 1) m |= M_A_IP1;
             if (o_im1 && a.Bnd[q2 - 1] != 1) m |= M_A_IM1;
-            if (o_jp1 && a.Bnd[q2 + sj] != 1) m |= M_A_JP1;
-            if (o_jm1 && a.Bnd[q2 - sj] != 1) m |= M_A_JM1;
+            if (o_jp1 && a.Bnd[q2 + sj2] != 1) m |= M_A_JP1;
+            if (o_jm1 && a.Bnd[q2 - sj2] != 1) m |= M_A_JM1;
         }
         a.mask[q] = m;
         const double V = a.VolumeZ[q];
@@ -142,10 +143,10 @@ __global__ void __launch_bounds__(128) adt_coef_kernel(const CoefArgs a) {
         double hu = 0., hv = 0., vz = 0.;
         if (cfu && j >= 1) {
             // DifX (AD:2486-2495) then Diff_H_Const_U (AD:1549-1553), same operation order
-            const double dux = a.DUX[q2], duxm = a.DUX[q2 - sj];
+            const double dux = a.DUX[q2], duxm = a.DUX[q2 - sj2];
             double difx = a.schmidt_h * (a.Visc_H[q] * duxm + a.Visc_H[q - sj] * dux) / (dux + duxm);
             if (a.nulldif && a.Wflux_X[q] == 0.) difx = 0.;
-            hu = difx * a.AreaU[q] / a.DZX[q2 - sj];
+            hu = difx * a.AreaU[q] / a.DZX[q2 - sj2];
         }
         if (cfv && i >= 1) {
             const double dvy = a.DVY[q2], dvym = a.DVY[q2 - 1];
@@ -185,7 +186,7 @@ __global__ void adt_grid2d_kernel(int ni, int nj, int ld, const double *DUX, con
 // -------------------------------------------------------------------------------------
 struct DischArgs {
     int ncell;                 // discharge cells that are not ignored (AD:4039-4041)
-    int K, ld, nj;
+    int K, ld, sj, sk;
     const int *ci, *cj, *ck, *ckmin, *ckmax, *cvert, *cbypass;   // per listed cell (vert / bypass of its discharge)
     const double *cflow;
     int *kmin_eff, *kmax_eff;  // out: effective k-range
@@ -199,7 +200,7 @@ __global__ void adt_discharge_prep_kernel(const DischArgs d) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= d.ncell) return;
     const int i = d.ci[n], j = d.cj[n];
-    const int q2 = i + d.ld * j, sk = d.ld * d.nj;
+    const int q2 = i + d.ld * j, q3 = i + d.sj * j, sk = d.sk;
     int kmin = d.ckmin[n], kmax = d.ckmax[n];
     const bool uniform = d.cvert[n] == MOHID_DischUniform;
     if (uniform) {
@@ -210,10 +211,10 @@ __global__ void adt_discharge_prep_kernel(const DischArgs d) {
     }
     d.kmin_eff[n] = kmin; d.kmax_eff[n] = kmax;
     double wc = 0.0;
-    for (int k = kmin; k <= kmax; ++k) wc = wc + d.DWZ[q2 + sk * k];
+    for (int k = kmin; k <= kmax; ++k) wc = wc + d.DWZ[q3 + sk * k];
     for (int k = kmin; k <= kmax; ++k) {
-        d.flow_k[(size_t)n * (d.K + 2) + k] = uniform ? d.cflow[n] * d.DWZ[q2 + sk * k] / wc : d.cflow[n];
-        atomicOr(&d.mask[q2 + sk * k], M_DISCH);
+        d.flow_k[(size_t)n * (d.K + 2) + k] = uniform ? d.cflow[n] * d.DWZ[q3 + sk * k] / wc : d.cflow[n];
+        atomicOr(&d.mask[q3 + sk * k], M_DISCH);
     }
 }
 
@@ -240,7 +241,7 @@ struct PropArgs {
 
 struct StepArgs {
     int I, J, K, ld, nj;
-    long sk;                                    // plane stride ld*nj
+    int sj, sk;                                 // element strides of j and k in the 3-D device arrays
     int nprop, ntile_i;                         // tiles of 31 cells along i
     int j_begin, j_count;                       // columns j_begin .. j_begin+j_count-1 are advanced
     int method_h, limiter_h, method_v, limiter_v, upwind2_h, upwind2_v;
@@ -401,7 +402,7 @@ struct Row { double D, E, F, TI; };
 __device__ __forceinline__ void open_boundary_row(const StepArgs &s, const PropArgs &pa, int q, unsigned m, double Pc,
                                                double qz_c, double qz_p, double dtv_c, Row &row) {
     const double *__restrict__ P = pa.pin;
-    const int sj = s.ld;
+    const int sj = s.sj;
     const int bc = pa.bc;
     if (bc == MOHID_BC_NullGradient || bc == MOHID_BC_CyclicBoundary) {
         row.TI = Pc; row.D = 0.; row.E = 1.; row.F = 0.;
@@ -488,9 +489,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
     const int ic = min(i, s.I + 1);                       // clamped column: every load stays in bounds
     const PropArgs pa = s.p[n];
     const double *__restrict__ P = pa.pin;
-    const int sj = s.ld, sk = (int)s.sk;                  // 32-bit cell indices (n3 < 2^31 is checked at create)
-    const int c2d = ic + sj * j;
-    const int je2 = (j + 2 <= s.J + 1) ? 2 * sj : sj;     // offset of column j+2 (clamped at the array edge)
+    const int sj = s.sj, sk = s.sk, sj2 = s.ld;          // 32-bit cell indices (n3 < 2^31 is checked at create)
+    const int c2 = ic + sj2 * j;                          // column in the 2-D arrays
+    const int c2d = ic + sj * j;                          // column base (k = 0) in the 3-D arrays
+    const int je2 = (j + 2 <= s.J + 1) ? 2 * sj : sj;
+    const int je2_2 = (j + 2 <= s.J + 1) ? 2 * sj2 : sj2;
+    const int jw2 = (j >= 2) ? 2 * sj : sj;               // offset of column j-2 (clamped: column -1 does not exist)
 
     const int method_h = MH > 0 ? MH : s.method_h, method_v = MV > 0 ? MV : s.method_v;
     const bool central_h = (method_h == MOHID_CentralDif || method_h == MOHID_LeapFrog);
@@ -500,11 +504,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
     const bool do_h = FULL || !s.vertical1d, do_y = FULL || (do_h && !s.xzflow);
 
     // ---- 2-D metrics of the column ----
-    const double rdx_m = s.rdx[c2d - sj], rdx_c = s.rdx[c2d], rdx_p = s.rdx[c2d + sj], rdx_pp = s.rdx[c2d + je2];
-    const double rdy_c = s.rdy[c2d];
+    const double rdx_m = s.rdx[c2 - sj2], rdx_c = s.rdx[c2], rdx_p = s.rdx[c2 + sj2], rdx_pp = s.rdx[c2 + je2_2];
+    const double rdy_c = s.rdy[c2];
     double rdy_m = shfl_up_d(rdy_c, 1), rdy_p = shfl_dn_d(rdy_c, 1);
-    if (lane == 0) rdy_m = s.rdy[c2d - 1];
-    if (lane == 31) rdy_p = s.rdy[c2d + (ic <= s.I ? 1 : 0)];
+    if (lane == 0) rdy_m = s.rdy[c2 - 1];
+    if (lane == 31) rdy_p = s.rdy[c2 + (ic <= s.I ? 1 : 0)];
     constexpr bool FAST_H = (MH == MOHID_P2_TVD && LH == MOHID_SuperBee);
     // fast path operands: rho = (du_u+du_d)/(du_u+du_uu) for both flow directions of the west, east and south face
     const double rho_wp = FAST_H ? ratio_or_zero(rdx_m, rdx_c) : rdx_m, rho_wn = FAST_H ? ratio_or_zero(rdx_p, rdx_c) : rdx_p;
@@ -512,8 +516,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
     const double rho_sp = FAST_H ? ratio_or_zero(rdy_m, rdy_c) : rdy_m, rho_sn = FAST_H ? ratio_or_zero(rdy_p, rdy_c) : rdy_p;
     double dux_m = 0., dux_c = 0., dux_p = 0., dvy_m = 0., dvy_c = 0.;
     if (central_h) {
-        dux_m = s.DUX[c2d - sj]; dux_c = s.DUX[c2d]; dux_p = s.DUX[c2d + sj];
-        dvy_c = s.DVY[c2d]; dvy_m = s.DVY[c2d - 1];
+        dux_m = s.DUX[c2 - sj2]; dux_c = s.DUX[c2]; dux_p = s.DUX[c2 + sj2];
+        dvy_c = s.DVY[c2]; dvy_m = s.DVY[c2 - 1];
     }
 
     const unsigned mtop = s.mask[c2d + sk * s.K];
@@ -534,10 +538,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
         L.m = s.mask[q];
         L.vr = s.vr[q];
         if (do_h) {
-            L.Pw2 = P[q - 2 * sj]; L.Pw1 = P[q - sj]; L.Pe1 = P[q + sj]; L.Pe2 = P[q + je2];
+            L.Pw2 = P[q - jw2]; L.Pw1 = P[q - sj]; L.Pe1 = P[q + sj]; L.Pe2 = P[q + je2];
             L.t_w = s.dtv[q - sj]; L.t_e = s.dtv[q + sj];
             L.qxw = s.qx[q]; L.qxe = s.qx[q + sj]; L.dhw = s.dhu[q]; L.dhe = s.dhu[q + sj];
-            if (far_h) { L.t_w2 = s.dtv[q - 2 * sj]; L.t_e2 = s.dtv[q + je2]; }
+            if (far_h) { L.t_w2 = s.dtv[q - jw2]; L.t_e2 = s.dtv[q + je2]; }
             if (do_y) {
                 L.qys = s.qy[q]; L.dhs = s.dhv[q];
                 L.hP = halo_lane ? P[q + halo_off] : 0.;
@@ -551,7 +555,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
     auto fetch_async = [&](int q, int st) {
         double *d = Stg + (size_t)st * NV * wstride;
         auto cp8 = [&](int slot, const double *g) { __pipeline_memcpy_async(d + slot * wstride, g, 8); };
-        cp8(0, P + q - 2 * sj); cp8(1, P + q - sj); cp8(2, P + q + sj); cp8(3, P + q + je2);
+        cp8(0, P + q - jw2); cp8(1, P + q - sj); cp8(2, P + q + sj); cp8(3, P + q + je2);
         if (halo_lane) cp8(4, P + q + halo_off);
         cp8(5, s.dtv + q - sj); cp8(6, s.dtv + q + sj);
         if (lane == 0) cp8(7, s.dtv + q - 1);
@@ -738,7 +742,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
     // ---------------- back substitution (MF:4100-4105) ----------------
     if (writer && colwet) {
         double *__restrict__ O = pa.pout;
-        int qo = i + sj * j + sk * (s.K + 1);
+        int qo = c2d + sk * (s.K + 1);
         double x = 0.0;                                   // RES(KUB+1) = G(KUB+1) = 0 (halo row is the identity)
         O[qo] = x;
         if (GGLOB) {
@@ -778,7 +782,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
 // -------------------------------------------------------------------------------------
 struct BndArgs {
     int I, J, K, ld, nj, ncols;
-    long sk;
+    int sj, sk;               // element strides of j and k in the 3-D device arrays
     const int *cols;          // packed (i,j) of boundary columns
     const int *kfloor;
     const uint32_t *mask;
@@ -795,13 +799,13 @@ __global__ void adt_nullgrad_kernel(const BndArgs b) {
     int kf = b.kfloor[q2];
     kf = kf < 0 ? -kf : kf;
     if (k < kf) return;
-    const long q = q2 + b.sk * k;
+    const long q = (long)i + (long)b.sj * j + (long)b.sk * k;
     const unsigned m = b.mask[q];
     const int cVn = (m & M_CFVN) ? 1 : 0, cVs = (m & M_CFV) ? 1 : 0;
     const int cUe = (m & M_CFUE) ? 1 : 0, cUw = (m & M_CFU) ? 1 : 0;
     const int aux = cVn + cVs + cUe + cUw;
     if (aux > 0)
-        b.prop[q] = (b.prop[q + 1] * cVn + b.prop[q - 1] * cVs + b.prop[q + b.ld] * cUe + b.prop[q - b.ld] * cUw) /
+        b.prop[q] = (b.prop[q + 1] * cVn + b.prop[q - 1] * cVs + b.prop[q + b.sj] * cUe + b.prop[q - b.sj] * cUw) /
                     (double)aux;
 }
 
@@ -809,26 +813,29 @@ __global__ void adt_nullgrad_kernel(const BndArgs b) {
 // phase 1: wrap j (per i), phase 2: wrap i (per j).  Launched as three ordered kernels.
 __global__ void adt_cyclic_kernel(const BndArgs b, int phase) {
     const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long sj = b.sj, sk = b.sk;
     if (phase == 0) {
         if (t >= (long)b.ncols * b.K) return;
         const int c = (int)(t / b.K), k = (int)(t % b.K) + 1;
-        const long q = (long)b.cols[2 * c] + (long)b.ld * b.cols[2 * c + 1] + b.sk * k;
+        const long q = (long)b.cols[2 * c] + sj * b.cols[2 * c + 1] + sk * k;
         b.prop[q] = b.pref[q];
     } else if (phase == 1) {
         if (t >= (long)(b.I - 2) * b.K) return;
         const int i = (int)(t / b.K) + 2, k = (int)(t % b.K) + 1;
-        const long r1 = (long)i + (long)b.ld * 1, rJ = (long)i + (long)b.ld * b.J;
-        if ((b.mask[r1 + b.sk * b.K] & M_BND) && (b.mask[rJ + b.sk * b.K] & M_BND)) {
-            if (k >= b.kfloor[rJ - b.ld]) b.prop[r1 + b.sk * k] = b.prop[rJ - b.ld + b.sk * k];
-            if (k >= b.kfloor[r1 + b.ld]) b.prop[rJ + b.sk * k] = b.prop[r1 + b.ld + b.sk * k];
+        const long r1 = (long)i + sj * 1, rJ = (long)i + sj * b.J;                 // 3-D column bases of (i,1), (i,J)
+        const long f1 = (long)i + (long)b.ld * 1, fJ = (long)i + (long)b.ld * b.J;   // the same columns in 2-D arrays
+        if ((b.mask[r1 + sk * b.K] & M_BND) && (b.mask[rJ + sk * b.K] & M_BND)) {
+            if (k >= b.kfloor[fJ - b.ld]) b.prop[r1 + sk * k] = b.prop[rJ - sj + sk * k];
+            if (k >= b.kfloor[f1 + b.ld]) b.prop[rJ + sk * k] = b.prop[r1 + sj + sk * k];
         }
     } else {
         if (t >= (long)(b.J - 2) * b.K) return;
         const int j = (int)(t / b.K) + 2, k = (int)(t % b.K) + 1;
-        const long r1 = 1 + (long)b.ld * j, rI = (long)b.I + (long)b.ld * j;
-        if ((b.mask[r1 + b.sk * b.K] & M_BND) && (b.mask[rI + b.sk * b.K] & M_BND)) {
-            if (k >= b.kfloor[rI - 1]) b.prop[r1 + b.sk * k] = b.prop[rI - 1 + b.sk * k];
-            if (k >= b.kfloor[r1 + 1]) b.prop[rI + b.sk * k] = b.prop[r1 + 1 + b.sk * k];
+        const long r1 = 1 + sj * j, rI = (long)b.I + sj * j;
+        const long f1 = 1 + (long)b.ld * j, fI = (long)b.I + (long)b.ld * j;
+        if ((b.mask[r1 + sk * b.K] & M_BND) && (b.mask[rI + sk * b.K] & M_BND)) {
+            if (k >= b.kfloor[fI - 1]) b.prop[r1 + sk * k] = b.prop[rI - 1 + sk * k];
+            if (k >= b.kfloor[f1 + 1]) b.prop[rI + sk * k] = b.prop[r1 + 1 + sk * k];
         }
     }
 }
@@ -839,7 +846,7 @@ __global__ void adt_cyclic_kernel(const BndArgs b, int phase) {
 // -------------------------------------------------------------------------------------
 struct PackArgs {
     int ld, nj, nk, nprop, j0, width;
-    long sk;
+    int sj, sk;               // element strides of j and k in the 3-D device arrays
     double *prop[NPMAX];
 };
 __global__ void adt_pack_columns_kernel(const PackArgs a, double *buf, int unpack) {
@@ -851,7 +858,7 @@ __global__ void adt_pack_columns_kernel(const PackArgs a, double *buf, int unpac
         const int i = (int)(r % a.ld);
         const int w = (int)((r / a.ld) % a.width);
         const int k = (int)(r / ((long)a.ld * a.width));
-        const long q = (long)i + (long)a.ld * (a.j0 + w) + a.sk * k;
+        const long q = (long)i + (long)a.sj * (a.j0 + w) + (long)a.sk * k;
         if (unpack) a.prop[n][q] = buf[t];
         else buf[t] = a.prop[n][q];
     }
