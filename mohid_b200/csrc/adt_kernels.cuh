@@ -92,74 +92,100 @@ __global__ void __launch_bounds__(128) adt_coef_kernel(const CoefArgs a) {
         if (a.do_diff) { a.dhu[q] = 0.; a.dhv[q] = 0.; a.dvz[q] = 0.; }
         return;
     }
-    const bool cfu = a.CFU[q] == 1, cfv = a.CFV[q] == 1, cfw = a.CFW[q] == 1;
+    // ---- neighbour offsets, clamped to the allocation (a clamped probe is masked out below) ----
+    const bool im1 = i >= 1, im2 = i >= 2, ip1 = i + 1 < a.ni, ip2 = i + 2 < a.ni;
+    const bool jm1 = j >= 1, jm2 = j >= 2, jp1 = j + 1 < a.nj, jp2 = j + 2 < a.nj;
+    const bool km1 = k >= 1, kp1 = k + 1 < a.nk, kp2 = k + 2 < a.nk;
+    const int oim1 = im1 ? -1 : 0, oim2 = im2 ? -2 : 0, oip1 = ip1 ? 1 : 0, oip2 = ip2 ? 2 : 0;
+    const int ojm1 = jm1 ? -sj : 0, ojm2 = jm2 ? -2 * sj : 0, ojp1 = jp1 ? sj : 0, ojp2 = jp2 ? 2 * sj : 0;
+    const int okm1 = km1 ? -sk : 0, okp1 = kp1 ? sk : 0, okp2 = kp2 ? 2 * sk : 0;
+    const int qtop = i + sj * j + sk * a.K;
+
+    // ---- all loads up front (independent, so they overlap) ----
+    const int open_c = a.Open[q], cfu_c = a.CFU[q], cfv_c = a.CFV[q], cfw_c = a.CFW[q], land_c = a.Land[q];
+    const int bnd_c = a.Bnd[q2];
+    int cfu_e = 0, cfv_n = 0, cfw_t = 0, wat_top = 0, open_top = 0;
+    int o_jm2 = 0, o_jm1 = 0, o_jp1 = 0, o_jp2 = 0, o_im2 = 0, o_im1 = 0, o_ip1 = 0, o_ip2 = 0, o_km1 = 0, o_kp1 = 0, o_kp2 = 0;
+    double V = 0., Vold = 0., dwz = 0., dwz_m = 0.;
     if (a.do_geom) {
-        // neighbour probes stay inside the allocation
-        const bool im1 = i >= 1, im2 = i >= 2, ip1 = i + 1 < a.ni, ip2 = i + 2 < a.ni;
-        const bool jm1 = j >= 1, jm2 = j >= 2, jp1 = j + 1 < a.nj, jp2 = j + 2 < a.nj;
-        const bool km1 = k >= 1, kp1 = k + 1 < a.nk, kp2 = k + 2 < a.nk;
-        const bool o_jm1 = jm1 && a.Open[q - sj] == 1, o_jp1 = jp1 && a.Open[q + sj] == 1;
-        const bool o_im1 = im1 && a.Open[q - 1] == 1, o_ip1 = ip1 && a.Open[q + 1] == 1;
+        cfu_e = a.CFU[q + ojp1]; cfv_n = a.CFV[q + oip1]; cfw_t = a.CFW[q + okp1];
+        wat_top = a.Water[qtop]; open_top = a.Open[qtop];
+        o_jm2 = a.Open[q + ojm2]; o_jm1 = a.Open[q + ojm1]; o_jp1 = a.Open[q + ojp1]; o_jp2 = a.Open[q + ojp2];
+        o_im2 = a.Open[q + oim2]; o_im1 = a.Open[q + oim1]; o_ip1 = a.Open[q + oip1]; o_ip2 = a.Open[q + oip2];
+        o_km1 = a.Open[q + okm1]; o_kp1 = a.Open[q + okp1]; o_kp2 = a.Open[q + okp2];
+        V = a.VolumeZ[q]; Vold = a.VolumeZOld[q]; dwz = a.DWZ[q]; dwz_m = a.DWZ[q + okm1];
+    }
+    double visc = 0., visc_w = 0., visc_s = 0., areau = 0., areav = 0., diffv = 0., dzz_m = 0.;
+    double dux = 0., dux_w = 0., dvy = 0., dvy_s = 0., dzx_w = 0., dzy_s = 0., wx = 1., wy = 1., wz = 1.;
+    int small = 0;
+    if (a.do_diff) {
+        visc = a.Visc_H[q]; visc_w = a.Visc_H[q + ojm1]; visc_s = a.Visc_H[q + oim1];
+        areau = a.AreaU[q]; areav = a.AreaV[q]; diffv = a.Diff_V[q]; dzz_m = a.DZZ[q + okm1];
+        dux = a.DUX[q2]; dux_w = a.DUX[q2 - (jm1 ? sj2 : 0)]; dvy = a.DVY[q2]; dvy_s = a.DVY[q2 + oim1];
+        dzx_w = a.DZX[q2 - (jm1 ? sj2 : 0)]; dzy_s = a.DZY[q2 + oim1];
+        if (a.nulldif) { wx = a.Wflux_X[q]; wy = a.Wflux_Y[q]; wz = a.Wflux_Z[q]; }
+        if (a.SmallDepths) small = a.SmallDepths[q2];
+    }
+
+    const bool cfu = cfu_c == 1, cfv = cfv_c == 1, cfw = cfw_c == 1;
+    if (a.do_geom) {
+        const bool bnd = bnd_c == 1;
+        const bool ojm1b = jm1 && o_jm1 == 1, ojp1b = jp1 && o_jp1 == 1, oim1b = im1 && o_im1 == 1, oip1b = ip1 && o_ip1 == 1;
         unsigned m = 0;
-        if (a.Open[q] == 1) m |= M_OPEN;
+        if (open_c == 1) m |= M_OPEN;
         if (cfu) m |= M_CFU;
         if (cfv) m |= M_CFV;
         if (cfw) m |= M_CFW;
-        if (jp1 && a.CFU[q + sj] == 1) m |= M_CFUE;
-        if (ip1 && a.CFV[q + 1] == 1) m |= M_CFVN;
-        if (kp1 && a.CFW[q + sk] == 1) m |= M_CFWT;
-        if (a.Land[q] == 1) m |= M_LAND;
-        const bool bnd = a.Bnd[q2] == 1;
+        if (jp1 && cfu_e == 1) m |= M_CFUE;
+        if (ip1 && cfv_n == 1) m |= M_CFVN;
+        if (kp1 && cfw_t == 1) m |= M_CFWT;
+        if (land_c == 1) m |= M_LAND;
         if (bnd) m |= M_BND;
-        const int qtop = i + sj * j + sk * a.K;
-        if (a.Water[qtop] == 1) m |= M_COLWET;
-        if (a.Open[qtop] == 1) m |= M_COLOPEN;
-        if (jm2 && a.Open[q - 2 * sj] == 1) m |= M_O_JM2;
-        if (o_jm1) m |= M_O_JM1;
-        if (o_jp1) m |= M_O_JP1;
-        if (jp2 && a.Open[q + 2 * sj] == 1) m |= M_O_JP2;
-        if (im2 && a.Open[q - 2] == 1) m |= M_O_IM2;
-        if (o_im1) m |= M_O_IM1;
-        if (o_ip1) m |= M_O_IP1;
-        if (ip2 && a.Open[q + 2] == 1) m |= M_O_IP2;
-        if (km1 && a.Open[q - sk] == 1) m |= M_O_KM1;
-        if (kp1 && a.Open[q + sk] == 1) m |= M_O_KP1;
-        if (kp2 && a.Open[q + 2 * sk] == 1) m |= M_O_KP2;
-        if (bnd) {                                        // interior neighbours: only boundary rows need them
-            if (o_ip1 && a.Bnd[q2 + 1] != 1) m |= M_A_IP1;
-            if (o_im1 && a.Bnd[q2 - 1] != 1) m |= M_A_IM1;
-            if (o_jp1 && a.Bnd[q2 + sj2] != 1) m |= M_A_JP1;
-            if (o_jm1 && a.Bnd[q2 - sj2] != 1) m |= M_A_JM1;
+        if (wat_top == 1) m |= M_COLWET;
+        if (open_top == 1) m |= M_COLOPEN;
+        if (jm2 && o_jm2 == 1) m |= M_O_JM2;
+        if (ojm1b) m |= M_O_JM1;
+        if (ojp1b) m |= M_O_JP1;
+        if (jp2 && o_jp2 == 1) m |= M_O_JP2;
+        if (im2 && o_im2 == 1) m |= M_O_IM2;
+        if (oim1b) m |= M_O_IM1;
+        if (oip1b) m |= M_O_IP1;
+        if (ip2 && o_ip2 == 1) m |= M_O_IP2;
+        if (km1 && o_km1 == 1) m |= M_O_KM1;
+        if (kp1 && o_kp1 == 1) m |= M_O_KP1;
+        if (kp2 && o_kp2 == 1) m |= M_O_KP2;
+        if (bnd) {                                        // interior neighbours: only boundary rows need them (rare)
+            if (oip1b && a.Bnd[q2 + 1] != 1) m |= M_A_IP1;
+            if (oim1b && a.Bnd[q2 - 1] != 1) m |= M_A_IM1;
+            if (ojp1b && a.Bnd[q2 + sj2] != 1) m |= M_A_JP1;
+            if (ojm1b && a.Bnd[q2 - sj2] != 1) m |= M_A_JM1;
         }
         a.mask[q] = m;
-        const double V = a.VolumeZ[q];
         const bool inwork = (i >= 1 && i <= a.I && j >= 1 && j <= a.J && k >= 1 && k <= a.K);
         a.dtv[q] = (inwork && V != 0.) ? a.dt / V : 0.;
-        a.vr[q] = (inwork && V != 0.) ? a.VolumeZOld[q] / V : 1.;
-        double s = (k >= 1) ? (a.DWZ[q] + a.DWZ[q - sk]) : 0.;
-        a.rdz[q] = (s != 0.) ? 1.0 / s : 0.;
+        a.vr[q] = (inwork && V != 0.) ? Vold / V : 1.;
+        const double sd = km1 ? (dwz + dwz_m) : 0.;
+        a.rdz[q] = (sd != 0.) ? 1.0 / sd : 0.;
     }
     if (a.do_diff) {
         double hu = 0., hv = 0., vz = 0.;
-        if (cfu && j >= 1) {
+        if (cfu && jm1) {
             // DifX (AD:2486-2495) then Diff_H_Const_U (AD:1549-1553), same operation order
-            const double dux = a.DUX[q2], duxm = a.DUX[q2 - sj2];
-            double difx = a.schmidt_h * (a.Visc_H[q] * duxm + a.Visc_H[q - sj] * dux) / (dux + duxm);
-            if (a.nulldif && a.Wflux_X[q] == 0.) difx = 0.;
-            hu = difx * a.AreaU[q] / a.DZX[q2 - sj2];
+            double difx = a.schmidt_h * (visc * dux_w + visc_w * dux) / (dux + dux_w);
+            if (a.nulldif && wx == 0.) difx = 0.;
+            hu = difx * areau / dzx_w;
         }
-        if (cfv && i >= 1) {
-            const double dvy = a.DVY[q2], dvym = a.DVY[q2 - 1];
-            double dify = a.schmidt_h * (a.Visc_H[q] * dvym + a.Visc_H[q - 1] * dvy) / (dvy + dvym);
-            if (a.nulldif && a.Wflux_Y[q] == 0.) dify = 0.;
-            hv = dify * a.AreaV[q] / a.DZY[q2 - 1];
+        if (cfv && im1) {
+            double dify = a.schmidt_h * (visc * dvy_s + visc_s * dvy) / (dvy + dvy_s);
+            if (a.nulldif && wy == 0.) dify = 0.;
+            hv = dify * areav / dzy_s;
         }
-        if (cfw && k >= 1 && !(a.SmallDepths && a.SmallDepths[q2] != 0)) {
+        if (cfw && km1 && small == 0) {
             // DifZ (AD:2397-2405) then Diff_V_Const (AD:1591-1597)
-            double difz = (a.schmidt_coef_v * a.Diff_V[q] + a.schmidt_bg_v);
-            if (a.nulldif && a.Wflux_Z[q] == 0.) difz = 0.;
-            const double auxk = difz * a.DUX[q2] * a.DVY[q2];
-            vz = auxk / a.DZZ[q - sk];
+            double difz = (a.schmidt_coef_v * diffv + a.schmidt_bg_v);
+            if (a.nulldif && wz == 0.) difz = 0.;
+            const double auxk = difz * dux * dvy;
+            vz = auxk / dzz_m;
         }
         a.dhu[q] = hu; a.dhv[q] = hv; a.dvz[q] = vz;
     }
