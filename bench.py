@@ -46,6 +46,15 @@ def b_alg(nprop: int) -> float:
     return 16.0 + 112.0 / nprop
 
 
+def measured_traffic(workload: str):
+    """DRAM bytes per K2 launch from the committed ncu capture of this workload (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            return float(json.load(f)[workload]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def measured_hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -116,7 +125,9 @@ def params_for(nprop, method, limiter, dt):
 def cpu_reference_run(workload: str, steps: int, warmup: int, budget_s: float = 20.0):
     import numpy as np
     from mohid_b200.synthetic import make_case
+    from oracle import oracle as _oracle
     from oracle.oracle import OracleAdvectionDiffusion, case_to_numpy
+    _oracle.use_fast_build(True)                       # g++ -O3 -mavx2 -fopenmp -ffp-contract=off
     I, J, K, nprop, method, limiter = WORKLOADS[workload]
     # bounded sample: same K, N, numerics; horizontal extent cut so one step is ~1 s of CPU work
     si, sj = min(I, 384), min(J, 384)
@@ -136,7 +147,7 @@ def cpu_reference_run(workload: str, steps: int, warmup: int, budget_s: float = 
     dt = time.perf_counter() - t0
     units = si * sj * K * nprop * done
     return {"value": units / dt / 1e9, "unit": "Gcell-property updates/s", "cores": o.nthreads, "kind": "port",
-            "sample": f"{si}x{sj}x{K} x {nprop} properties, {done} steps in {dt:.1f} s (oracle, g++ -O2 -fopenmp, "
+            "sample": f"{si}x{sj}x{K} x {nprop} properties, {done} steps in {dt:.1f} s (oracle, g++ -O3 -mavx2 -fopenmp, "
                       f"{o.nthreads} threads)", "ms_per_step": dt / done * 1e3}
 
 
@@ -291,7 +302,8 @@ def run_ours(args):
                            "l2": "inputs >> L2 (each field %.2f GB)" % (8.0 * (I + 2) * (J + 2) * (K + 2) / 1e9),
                            "step_includes": "K1 coefficient pass + K2 fused kernel + boundary passes"},
                 "roofline": {"bound": "hbm", "kernel": "adt_transport_kernel", "achieved": achieved, "peak": peak,
-                             "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                             "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": (measured_traffic(args.workload) if world == 1 else None), "peak_source": peak_src,
                              "bytes_per_unit": b_alg(nprop), "kernel_ms": k2_ms, "kernel_launches_timed": k2_n,
                              "step_achieved": step_achieved, "step_frac": step_achieved / peak},
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}

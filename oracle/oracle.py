@@ -15,6 +15,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libmohid_oracle.so")
+LIB_FAST = os.path.join(HERE, "libmohid_oracle_fast.so")      # -O3 -mavx2 build used for CPU timing
 
 
 class Size3D(C.Structure):
@@ -40,12 +41,20 @@ class Options(C.Structure):
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (g++ -O2 -ffp-contract=off -fopenmp)."""
     src = os.path.join(HERE, "adv_diff_oracle.cpp")
-    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
-        subprocess.run(["make", "-C", HERE, "-B", "libmohid_oracle.so"], check=True, capture_output=True)
+    stale = lambda f: not os.path.exists(f) or os.path.getmtime(f) < os.path.getmtime(src)
+    if force or stale(LIB) or stale(LIB_FAST):
+        subprocess.run(["make", "-C", HERE, "-B", "all"], check=True, capture_output=True)
     return LIB
 
 
 _lib = None
+
+
+def use_fast_build(on: bool = True):
+    """Switch to the -O3 -mavx2 build (timing only; must be called before the first oracle call)."""
+    global _lib
+    build()
+    _lib = C.CDLL(LIB_FAST if on else LIB)
 
 
 def lib():
