@@ -65,8 +65,10 @@ def measured_hbm_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled every 25 ms while the GPU is under the benchmark load.
+    Samples inside the timed region are used when there are at least three of them; for very short timed
+    regions the samples of the (identical) warm-up steps are included and the window says so."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -74,11 +76,12 @@ class ClockSampler:
         self.idx = gpu_index
         self.proc = None
         self.lines = []
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "25", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
         except Exception:
@@ -86,31 +89,44 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark_timed(self, t0: float, t1: float):
+        self.t0, self.t1 = t0, t1
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons, pw = [], [], set(), []
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+
+        def parse(lines):
+            sm, mx, pw, reasons = [], [], [], set()
+            for _, ln in lines:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, pw, reasons
+        inside = [x for x in self.lines if self.t0 is not None and self.t0 <= x[0] <= self.t1 + 0.03]
+        window = "timed region"
+        if len(inside) < 3:
+            inside, window = self.lines, "warm-up + timed region (timed region shorter than 3 samples)"
+        sm, mx, pw, reasons = parse(inside)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "window": window,
+                "reasons": sorted(reasons)}
 
 
 def params_for(nprop, method, limiter, dt):
@@ -227,24 +243,27 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         one_step()
     barrier()
     ts.kernel_time_ms()                       # reset the K2 event accumulator
     c0 = ts.counters()["launches"]
-    sampler = ClockSampler(local)
-    sampler.start()
+    h0 = halo.launches if halo else 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    w0 = time.time()
     e0.record(stream)
     for _ in range(args.steps):
         one_step()
     e1.record(stream)
     barrier()
+    sampler.mark_timed(w0, time.time())
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop()
     k2_ms, k2_n = ts.kernel_time_ms()
-    launches = ts.counters()["launches"] - c0 + (halo.launches if halo else 0)
+    launches = ts.counters()["launches"] - c0 + ((halo.launches - h0) if halo else 0)
     if world > 1:
         t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
