@@ -82,7 +82,7 @@ typedef struct mohid_adt_params {
     double DecayTime;              /* seconds */
     int    NoAdvFlux;              /* logical; needs NoFluxU/V/W (set_noflux) */
     int    NoDifFlux;              /* logical */
-    int    reserved0;
+    int    CellFluxes;             /* logical: also produce the six cell-face fluxes (AD:1457-1470, 3356-3954) */
     int    reserved1;
 } mohid_adt_params;
 
@@ -150,6 +150,13 @@ int mohid_adt_unset_discharges(const int *handle);
 int mohid_adt_advect_batch(const int *handle, const int *nprop,
                            double *const *prop, const double *const *reference_prop,
                            const mohid_adt_params *params);
+
+/* GetAdvFlux / GetDifFlux (AD:697-851): the six cell-face mass fluxes of property `prop_index` of the last
+ * batch, for properties whose params carried CellFluxes = 1 (box budgets, WP:14956-15032).  Arrays are
+ * (0:I+1,0:J+1,0:K+1) like the properties; flux (i,j,k) belongs to the U / V / W face (i,j,k).  Any pointer
+ * may be NULL. */
+int mohid_adt_get_cell_fluxes(const int *handle, const int *prop_index, double *AdvFluxX, double *AdvFluxY,
+                              double *AdvFluxZ, double *DifFluxX, double *DifFluxY, double *DifFluxZ);
 
 /* ---- device-resident variants (benchmarks, device-side callers) ------------------- */
 /* Copy properties host->device / device->host without stepping. */

@@ -153,6 +153,14 @@ class TransportStep:
         self._check(self.lib.mohid_adt_download_props(C.byref(self.h), C.byref(C.c_int(len(props))),
                                                       self._ptr_array(props, "prop")))
 
+    def get_cell_fluxes(self, prop_index: int) -> Dict[str, np.ndarray]:
+        """GetAdvFlux + GetDifFlux (AD:697-851) of a property advanced with ``CellFluxes = 1``."""
+        names = ("AdvFluxX", "AdvFluxY", "AdvFluxZ", "DifFluxX", "DifFluxY", "DifFluxZ")
+        out = {k: np.zeros((self.K + 2, self.J + 2, self.ld)) for k in names}
+        self._check(self.lib.mohid_adt_get_cell_fluxes(C.byref(self.h), C.byref(C.c_int(prop_index)),
+                                                       *[C.c_void_p(out[k].ctypes.data) for k in names]))
+        return out
+
     # ---- halo staging for the j-slab decomposition ----------------------------------
     def pack_columns(self, nprop: int, j0: int, width: int, device_buffer):
         self._check(self.lib.mohid_adt_pack_columns(C.byref(self.h), C.byref(C.c_int(nprop)), C.byref(C.c_int(j0)),
@@ -235,8 +243,6 @@ def AdvectionDiffusion(AdvectionDiffusionID: int, PROP, schmidt_H, SchmidtCoef_V
     obj = _get(AdvectionDiffusionID)
     if AdvectionNudging:
         raise AdtError(21, "AdvectionNudging (AD:1989-2068) is not available on the GPU path")
-    if CellFluxes:
-        raise AdtError(21, "CellFluxes outputs (AD:3356-3954) are not available on the GPU path")
     if WaterPoints3D is None:
         raise AdtError(20, "WaterPoints3D is required (THOMASZ_NewType2 reads it, MF:4086)")
     step = dict(Wflux_X=Wflux_X, Wflux_Y=Wflux_Y, Wflux_Z=Wflux_Z, VolumeZOld=VolumeZOld, VolumeZ=VolumeZ,
@@ -250,7 +256,7 @@ def AdvectionDiffusion(AdvectionDiffusionID: int, PROP, schmidt_H, SchmidtCoef_V
              ImpExp_AdvV=ImpExp_AdvV, ImpExp_DifV=ImpExp_DifV, ImpExp_AdvXX=ImpExp_AdvXX, ImpExp_AdvYY=ImpExp_AdvYY,
              ImpExp_DifH=ImpExp_DifH, NullDif=int(NullDif),
              BoundaryCondition=(BoundaryCondition if BoundaryCondition is not None else 0), DecayTime=DecayTime,
-             NoAdvFlux=int(NoAdvFlux), NoDifFlux=int(NoDifFlux))
+             NoAdvFlux=int(NoAdvFlux), NoDifFlux=int(NoDifFlux), CellFluxes=int(CellFluxes))
     obj.advect_batch([PROP], [p], [ReferenceProp] if ReferenceProp is not None else None)
     return SUCCESS_
 
@@ -270,6 +276,18 @@ def UnSetDischarges(AdvectionDiffusionID: int) -> int:
     """AD:1040-1095."""
     _get(AdvectionDiffusionID).unset_discharges()
     return SUCCESS_
+
+
+def GetAdvFlux(AdvectionDiffusionID: int):
+    """AD:697-776: (AdvFluxX, AdvFluxY, AdvFluxZ) of the last AdvectionDiffusion call made with CellFluxes."""
+    f = _get(AdvectionDiffusionID).get_cell_fluxes(0)
+    return f["AdvFluxX"], f["AdvFluxY"], f["AdvFluxZ"]
+
+
+def GetDifFlux(AdvectionDiffusionID: int):
+    """AD:780-851."""
+    f = _get(AdvectionDiffusionID).get_cell_fluxes(0)
+    return f["DifFluxX"], f["DifFluxY"], f["DifFluxZ"]
 
 
 def SetGrid2D(AdvectionDiffusionID: int, DUX, DVY, DZX, DZY, KFloorZ, BoundaryPoints2D) -> int:

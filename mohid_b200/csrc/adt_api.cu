@@ -62,6 +62,7 @@ struct Handle {
         *d_cbypass = nullptr, *d_kmin_eff = nullptr, *d_kmax_eff = nullptr;
     double *d_cflow = nullptr, *d_flow_k = nullptr;
     std::vector<double *> d_conc, d_concmf;             // per property (nullptr = no discharges)
+    std::vector<double *> flux[6];                      // per property: AdvFluxX/Y/Z, DifFluxX/Y/Z (allocated on demand)
     std::vector<int> bnd_host;                          // (i,j) of all boundary columns
 };
 
@@ -159,6 +160,7 @@ void free_all(Handle *h) {
     F(h->d_kmin_eff); F(h->d_kmax_eff); F(h->d_cflow); F(h->d_flow_k);
     for (auto p : h->d_conc) F(p);
     for (auto p : h->d_concmf) F(p);
+    for (auto &v : h->flux) for (auto p : v) F(p);
     for (auto &e : h->ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
 }
@@ -387,6 +389,31 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
             }
             CU(h, cudaGetLastError());
         }
+    }
+    // cell-face fluxes of the properties that asked for them (AD:1885-1916: after the boundary passes)
+    for (int m = 0; m < s.nprop; ++m) {
+        const int n = idx[m];
+        const mohid_adt_params &q = b.p[n];
+        if (!q.CellFluxes) continue;
+        for (auto &v : h->flux) if ((int)v.size() <= n) v.resize(n + 1, nullptr);
+        for (auto &v : h->flux) {
+            if (!v[n]) if (int rc = dalloc(h, &v[n], h->n3)) return rc;
+            CU(h, cudaMemsetAsync(v[n], 0, h->n3 * sizeof(double), h->stream));       // AD:1457-1470
+        }
+        FluxArgs fa{};
+        fa.I = h->I; fa.J = h->J; fa.K = h->K; fa.ld = h->ld; fa.sj = h->sj; fa.sk = h->sk;
+        fa.method_h = q.AdvMethodH; fa.limiter_h = q.TVDLimitationH; fa.method_v = q.AdvMethodV; fa.limiter_v = q.TVDLimitationV;
+        fa.upwind2_h = q.Upwind2H; fa.upwind2_v = q.Upwind2V; fa.vertical1d = h->opt.Vertical1D; fa.xzflow = h->opt.XZFlow;
+        fa.vrelmax = q.VolumeRelMax; fa.w_advv = q.ImpExp_AdvV; fa.theta = q.ImpExp_DifV;
+        fa.pold = s.p[m].pin; fa.pnew = s.p[m].pout;
+        fa.qx = s.qx; fa.qy = s.qy; fa.qz = s.qz; fa.dtv = s.dtv; fa.dhu = s.dhu; fa.dhv = s.dhv; fa.dvz = s.dvz;
+        fa.rdz = s.rdz; fa.rdx = s.rdx; fa.rdy = s.rdy; fa.DUX = s.DUX; fa.DVY = s.DVY; fa.DWZ = s.DWZ; fa.mask = s.mask;
+        fa.ax = h->flux[0][n]; fa.ay = h->flux[1][n]; fa.az = h->flux[2][n];
+        fa.dx = h->flux[3][n]; fa.dy = h->flux[4][n]; fa.dz = h->flux[5][n];
+        const dim3 grid((unsigned)((h->I + 127) / 128), (unsigned)h->J, (unsigned)h->K);
+        adt_cell_flux_kernel<<<grid, 128, 0, h->stream>>>(fa);
+        CU(h, cudaGetLastError());
+        h->launches++;
     }
     for (int n : idx) h->cur[n] ^= 1;
     return 0;
@@ -823,6 +850,22 @@ int mohid_adt_pack_columns(const int *handle, const int *nprop, const int *j0, c
 int mohid_adt_unpack_columns(const int *handle, const int *nprop, const int *j0, const int *width,
                              const void *device_buffer) {
     return pack_common(handle, nprop, j0, width, (double *)device_buffer, 1);
+}
+
+int mohid_adt_get_cell_fluxes(const int *handle, const int *prop_index, double *AdvFluxX, double *AdvFluxY,
+                              double *AdvFluxZ, double *DifFluxX, double *DifFluxY, double *DifFluxZ) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    if (!prop_index) return fail(h, MOHID_ADT_ERR_ARG, "null argument");
+    const int n = *prop_index;
+    if (n < 0 || n >= (int)h->flux[0].size() || !h->flux[0][n])
+        return fail(h, MOHID_ADT_ERR_STATE, "GetAdvFlux - ModuleAdvectionDiffusion: no fluxes were computed for property %d (CellFluxes was not set)", n);
+    CU(h, cudaSetDevice(h->dev));
+    double *out[6] = {AdvFluxX, AdvFluxY, AdvFluxZ, DifFluxX, DifFluxY, DifFluxZ};
+    for (int w = 0; w < 6; ++w)
+        if (out[w]) if (int rc = d2h3(h, out[w], h->flux[w][n], 8)) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    return 0;
 }
 
 int mohid_adt_set_active_columns(const int *handle, const int *j_begin, const int *j_count) {

@@ -867,6 +867,103 @@ __global__ void adt_cyclic_kernel(const BndArgs b, int phase) {
 }
 
 // -------------------------------------------------------------------------------------
+// K5: cell-face mass fluxes for the box budgets (CalcHorizontal/Vertical Adv/Dif Flux, AD:3356-3954;
+// GetAdvFlux / GetDifFlux, AD:697-851).  Only launched for properties whose call carries CellFluxes (box
+// time-series output steps, WP:14956-15032).  One thread per work cell: its west U face, south V face and
+// top W face.  Explicit shares use the old field, implicit shares (vertical) the new one (AD:1885-1916);
+// the face weights always come from the old field (AD:2966-3001).
+// -------------------------------------------------------------------------------------
+struct FluxArgs {
+    int I, J, K, ld, sj, sk;
+    int method_h, limiter_h, method_v, limiter_v, upwind2_h, upwind2_v, vertical1d, xzflow;
+    double vrelmax, w_advv, theta;                 // ImpExp_AdvV (0 or 1), ImpExp_DifV as passed by the caller
+    const double *pold, *pnew;
+    const double *qx, *qy, *qz, *dtv, *dhu, *dhv, *dvz, *rdz, *rdx, *rdy, *DUX, *DVY, *DWZ;
+    const uint32_t *mask;
+    double *ax, *ay, *az, *dx, *dy, *dz;
+};
+
+__device__ __forceinline__ double adv_face_flux(int method, int limiter, bool up2, double vrelmax, double Q,
+                                                const double Pw[4], const double Pa[4], bool o1, bool o4,
+                                                const double t[4], double rd12, double rd23, double rd34, double du2,
+                                                double du3) {
+    // weights from the stencil Pw (old field); they multiply the stencil Pa (old or new field)
+    const bool pos = Q > 0.;
+    double wuu, wu, wd;
+    oriented_weights<0, 0>(method, limiter, up2, vrelmax, Q, sel(pos, Pw[0], Pw[3]), sel(pos, Pw[1], Pw[2]),
+                           sel(pos, Pw[2], Pw[1]), pos ? !o1 : !o4, sel(pos, t[0], t[3]), sel(pos, t[1], t[2]),
+                           sel(pos, t[2], t[1]), sel(pos, rd12, rd34), rd23, sel(pos, du2, du3), sel(pos, du3, du2),
+                           wuu, wu, wd);
+    return Q * (wuu * sel(pos, Pa[0], Pa[3]) + wu * sel(pos, Pa[1], Pa[2]) + wd * sel(pos, Pa[2], Pa[1]));
+}
+
+__global__ void __launch_bounds__(128) adt_cell_flux_kernel(const FluxArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int j = blockIdx.y + 1, k = blockIdx.z + 1;
+    if (i > a.I) return;
+    const int sj = a.sj, sk = a.sk, sj2 = a.ld;
+    const int q = i + sj * j + sk * k, q2 = i + sj2 * j;
+    const unsigned m = a.mask[q];
+    const double *__restrict__ P = a.pold;
+    const double *__restrict__ N = a.pnew;
+    const int jw2 = (j >= 2) ? 2 * sj : sj;
+    if (!a.vertical1d) {
+        // ---- U face (i,j,k), between cells j-1 and j ----
+        if (m & M_CFU) {
+            const double Pw[4] = {P[q - jw2], P[q - sj], P[q], P[q + sj]};
+            double adv = 0.;
+            if (all_set(m, M_O_JM1 | M_OPEN)) {
+                const double t[4] = {a.dtv[q - jw2], a.dtv[q - sj], a.dtv[q], a.dtv[q + sj]};
+                adv = adv_face_flux(a.method_h, a.limiter_h, a.upwind2_h != 0, a.vrelmax, a.qx[q], Pw, Pw,
+                                    (m & M_O_JM2) != 0, (m & M_O_JP1) != 0, t, a.rdx[q2 - sj2], a.rdx[q2],
+                                    a.rdx[q2 + sj2], a.DUX[q2 - sj2], a.DUX[q2]);
+            }
+            a.ax[q] = adv;
+            a.dx[q] = -a.dhu[q] * (Pw[2] - Pw[1]);
+        }
+        // ---- V face (i,j,k), between cells i-1 and i ----
+        if (!a.xzflow && (m & M_CFV)) {
+            const double Pw[4] = {P[q - (i >= 2 ? 2 : 1)], P[q - 1], P[q], P[q + 1]};
+            double adv = 0.;
+            if (all_set(m, M_O_IM1 | M_OPEN)) {
+                const double t[4] = {a.dtv[q - (i >= 2 ? 2 : 1)], a.dtv[q - 1], a.dtv[q], a.dtv[q + 1]};
+                adv = adv_face_flux(a.method_h, a.limiter_h, a.upwind2_h != 0, a.vrelmax, a.qy[q], Pw, Pw,
+                                    (m & M_O_IM2) != 0, (m & M_O_IP1) != 0, t, a.rdy[q2 - 1], a.rdy[q2], a.rdy[q2 + 1],
+                                    a.DVY[q2 - 1], a.DVY[q2]);
+            }
+            a.ay[q] = adv;
+            a.dy[q] = -a.dhv[q] * (Pw[2] - Pw[1]);
+        }
+    }
+    // ---- W face (i,j,k+1), between cells k and k+1 ----
+    if (a.K > 1 && (m & M_CFWT)) {
+        const int qt = q + sk;
+        const int q2k = (k + 2 <= a.K + 1) ? q + 2 * sk : qt;
+        const double Pw[4] = {P[q - sk], P[q], P[qt], P[q2k]};
+        const double Pn[4] = {N[q - sk], N[q], N[qt], N[q2k]};
+        double dif = 0.;
+        if (a.theta < 1.) dif = dif - (1. - a.theta) * a.dvz[qt] * (Pw[2] - Pw[1]);      // VerticalDiffusion share (AD:2768)
+        if (a.theta > 0.) dif = dif - a.theta * a.dvz[qt] * (Pn[2] - Pn[1]);               // after the solve (AD:1893)
+        a.dz[qt] = dif;
+        double adv = 0.;
+        const unsigned mtop = a.mask[i + sj * j + sk * a.K];
+        if (!a.vertical1d && (mtop & M_COLOPEN) && all_set(m, M_OPEN | M_O_KP1)) {
+            const double t[4] = {a.dtv[q - sk], a.dtv[q], a.dtv[qt], a.dtv[q2k]};
+            double du2 = 0., du3 = 0.;
+            if (a.method_v == MOHID_CentralDif || a.method_v == MOHID_LeapFrog) { du2 = a.DWZ[q]; du3 = a.DWZ[qt]; }
+            const bool o1 = (m & M_O_KM1) != 0, o4 = (m & M_O_KP2) != 0;
+            if (a.w_advv < 1.)
+                adv += (1. - a.w_advv) * adv_face_flux(a.method_v, a.limiter_v, a.upwind2_v != 0, a.vrelmax, a.qz[qt],
+                                                       Pw, Pw, o1, o4, t, a.rdz[q], a.rdz[qt], a.rdz[q2k], du2, du3);
+            if (a.w_advv > 0.)
+                adv += a.w_advv * adv_face_flux(a.method_v, a.limiter_v, a.upwind2_v != 0, a.vrelmax, a.qz[qt], Pw,
+                                                Pn, o1, o4, t, a.rdz[q], a.rdz[qt], a.rdz[q2k], du2, du3);
+        }
+        a.az[qt] = adv;
+    }
+}
+
+// -------------------------------------------------------------------------------------
 // K4: gather / scatter `width` j-columns of nprop properties to / from a contiguous buffer
 // laid out [n][k][w][i] (i fastest).  Coalesced on both sides.
 // -------------------------------------------------------------------------------------

@@ -300,4 +300,4 @@ def default_params(method_h: int = 4, limiter_h: int = 4, method_v: int = 4, lim
                 Upwind2H=1, Upwind2V=1, VolumeRelMax=1.5, DTProp=dt,
                 ImpExp_AdvV=impexp_advv, ImpExp_DifV=theta_difv, ImpExp_AdvXX=0.0, ImpExp_AdvYY=0.0,
                 ImpExp_DifH=0.0, NullDif=0, BoundaryCondition=bc, DecayTime=decay_time,
-                NoAdvFlux=0, NoDifFlux=0)
+                NoAdvFlux=0, NoDifFlux=0, CellFluxes=0)

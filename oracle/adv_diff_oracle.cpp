@@ -23,7 +23,7 @@
 //
 //  Not restated (returns ORACLE_ERR_UNSUPPORTED): horizontally implicit advection
 //  (AD:4167-4258, THOMAS_3D MF:3667-3875), AdvectionNudging (AD:1989-2068), Orlanski
-//  boundary (MF:4129-4500), CellFluxes outputs (AD:3356-3954).
+//  boundary (MF:4129-4500).
 // =====================================================================================
 #include <algorithm>
 #include <cmath>
@@ -98,6 +98,8 @@ struct Oracle {
     std::vector<double> XC, XD, XE, XF;                    // COEF3_HorAdvXX
     std::vector<double> YC, YD, YE, YF;                    // COEF3_HorAdvYY
     std::vector<double> QB;                                // WaterFluxOBoundary
+    std::vector<double> AdvFluxX, AdvFluxY, AdvFluxZ, DifFluxX, DifFluxY, DifFluxZ;   // T_CellFluxes (AD:229-240)
+    bool st_CellFluxes = false;
     std::vector<double> DHU, DHV, DVC;                     // Diff_H_Const_U/V, Diff_V_Const (AD:1474-1477)
     bool FirstTime = true;
     std::vector<std::vector<double>> VEC_G, VEC_W;         // per-thread Thomas scratch (AD:626-637)
@@ -1240,6 +1242,98 @@ void Prop_CyclicBoundary(Oracle &o) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Cell-face mass fluxes for the box budgets (AD:3356-3954).  `field` is the property the weights multiply:
+// the old field for the explicit shares (called from inside the flux passes), the new one after the solve.
+// ---------------------------------------------------------------------------------------
+void CalcVerticalAdvFlux(Oracle &o, double Weigth) {          // AD:3356-3396 and _opt AD:3400-3463
+    const auto &W = o.W;
+    for (int k = W.KLB; k <= W.KUB; ++k)
+        for (int j = W.JLB; j <= W.JUB; ++j)
+            for (int i = W.ILB; i <= W.IUB; ++i) {
+                long q = o.i3(i, j, k);
+                if (o.ComputeFacesW3D[q] == 1) {
+                    if (o.Optimize)
+                        o.AdvFluxZ[q] = o.AdvFluxZ[q] + Weigth * (o.VD[q] * o.PROP[o.i3(i, j, k - 1)] + o.VE[q] * o.PROP[q]);
+                    else
+                        o.AdvFluxZ[q] = o.AdvFluxZ[q] + Weigth * (o.VC[q] * o.PROP[o.i3(i, j, k - 2)] + o.VD[q] * o.PROP[o.i3(i, j, k - 1)] +
+                                                                  o.VE[q] * o.PROP[q] + o.VF[q] * o.PROP[o.i3(i, j, k + 1)]);
+                }
+            }
+}
+void CalcHorizontalAdvFluxXX(Oracle &o, double Weigth) {      // AD:3467-3540
+    const auto &W = o.W;
+    for (int k = W.KLB; k <= W.KUB; ++k)
+        for (int j = W.JLB; j <= W.JUB; ++j)
+            for (int i = W.ILB; i <= W.IUB; ++i) {
+                long q = o.i3(i, j, k);
+                if (o.ComputeFacesU3D[q] == 1) {
+                    if (o.Optimize)
+                        o.AdvFluxX[q] = o.AdvFluxX[q] + Weigth * (o.XD[q] * o.PROP[o.i3(i, j - 1, k)] + o.XE[q] * o.PROP[q]);
+                    else
+                        o.AdvFluxX[q] = o.AdvFluxX[q] + Weigth * (o.XC[q] * o.PROP[o.i3(i, j - 2, k)] + o.XD[q] * o.PROP[o.i3(i, j - 1, k)] +
+                                                                  o.XE[q] * o.PROP[q] + o.XF[q] * o.PROP[o.i3(i, j + 1, k)]);
+                }
+            }
+}
+void CalcHorizontalAdvFluxYY(Oracle &o, double Weigth) {      // AD:3544-3660
+    const auto &W = o.W;
+    for (int k = W.KLB; k <= W.KUB; ++k)
+        for (int j = W.JLB; j <= W.JUB; ++j)
+            for (int i = W.ILB; i <= W.IUB; ++i) {
+                long q = o.i3(i, j, k);
+                if (o.ComputeFacesV3D[q] == 1) {
+                    if (o.Optimize)
+                        o.AdvFluxY[q] = o.AdvFluxY[q] + Weigth * (o.YD[q] * o.PROP[o.i3(i - 1, j, k)] + o.YE[q] * o.PROP[q]);
+                    else
+                        o.AdvFluxY[q] = o.AdvFluxY[q] + Weigth * (o.YC[q] * o.PROP[o.i3(i - 2, j, k)] + o.YD[q] * o.PROP[o.i3(i - 1, j, k)] +
+                                                                  o.YE[q] * o.PROP[q] + o.YF[q] * o.PROP[o.i3(i + 1, j, k)]);
+                }
+            }
+}
+void CalcVerticalDifFlux(Oracle &o, double Weigth) {          // AD:3664-3703 and CalcVerticalDifFlux2 AD:3705-3753
+    const auto &W = o.W;
+    for (int k = W.KLB; k <= W.KUB; ++k)
+        for (int j = W.JLB; j <= W.JUB; ++j)
+            for (int i = W.ILB; i <= W.IUB; ++i) {
+                long q = o.i3(i, j, k);
+                if (o.ComputeFacesW3D[q] == 1) {
+                    long qm = o.i3(i, j, k - 1);
+                    if (o.Optimize)
+                        o.DifFluxZ[q] = o.DifFluxZ[q] - Weigth * o.DVC[q] * (o.PROP[q] - o.PROP[qm]);
+                    else
+                        o.DifFluxZ[q] = o.DifFluxZ[q] - Weigth * o.DifZ[q] * o.DUX[o.i2(i, j)] * o.DVY[o.i2(i, j)] / o.DZZ[qm] *
+                                                            (o.PROP[q] - o.PROP[qm]);
+                }
+            }
+}
+void CalcHorizontalDifFluxXX(Oracle &o) {                     // AD:3755-3809
+    const auto &W = o.W;
+    for (int k = W.KLB; k <= W.KUB; ++k)
+        for (int j = W.JLB; j <= W.JUB; ++j)
+            for (int i = W.ILB; i <= W.IUB; ++i) {
+                long q = o.i3(i, j, k);
+                if (o.ComputeFacesU3D[q] == 1) {
+                    long qm = o.i3(i, j - 1, k);
+                    if (o.Optimize) o.DifFluxX[q] = o.DifFluxX[q] - o.DHU[q] * (o.PROP[q] - o.PROP[qm]);
+                    else o.DifFluxX[q] = o.DifFluxX[q] - o.DifX[q] * o.AreaU[q] / o.DZX[o.i2(i, j - 1)] * (o.PROP[q] - o.PROP[qm]);
+                }
+            }
+}
+void CalcHorizontalDifFluxYY(Oracle &o) {                     // AD:3811-3866
+    const auto &W = o.W;
+    for (int k = W.KLB; k <= W.KUB; ++k)
+        for (int j = W.JLB; j <= W.JUB; ++j)
+            for (int i = W.ILB; i <= W.IUB; ++i) {
+                long q = o.i3(i, j, k);
+                if (o.ComputeFacesV3D[q] == 1) {
+                    long qm = o.i3(i - 1, j, k);
+                    if (o.Optimize) o.DifFluxY[q] = o.DifFluxY[q] - o.DHV[q] * (o.PROP[q] - o.PROP[qm]);
+                    else o.DifFluxY[q] = o.DifFluxY[q] - o.DifY[q] * o.AreaV[q] / o.DZY[o.i2(i - 1, j)] * (o.PROP[q] - o.PROP[qm]);
+                }
+            }
+}
+
+// ---------------------------------------------------------------------------------------
 // AdvectionDiffusionIteration (AD:1624-1922)
 // ---------------------------------------------------------------------------------------
 int AdvectionDiffusionIteration(Oracle &o) {
@@ -1277,15 +1371,27 @@ int AdvectionDiffusionIteration(Oracle &o) {
     if (!o.opt.Vertical1D) {
         // HorizontalDiffusion (AD:5123-5152)
         if (o.Optimize) HorizontalDiffusionXX2(o); else HorizontalDiffusionXX(o);
-        if (!o.opt.XZFlow) { if (o.Optimize) HorizontalDiffusionYY2(o); else HorizontalDiffusionYY(o); }
+        if (o.st_CellFluxes) CalcHorizontalDifFluxXX(o);                        // AD:5201, 5254
+        if (!o.opt.XZFlow) {
+            if (o.Optimize) HorizontalDiffusionYY2(o); else HorizontalDiffusionYY(o);
+            if (o.st_CellFluxes) CalcHorizontalDifFluxYY(o);                    // AD:5309, 5360
+        }
         // HorizontalAdvection (AD:4132-4265)
         if ((rc = HorizontalAdvectionXX(o))) return rc;
-        if (!o.opt.XZFlow) if ((rc = HorizontalAdvectionYY(o))) return rc;
+        if (o.st_CellFluxes && o.P.ImpExp_AdvXX == ExplicitScheme) CalcHorizontalAdvFluxXX(o, 1. - o.P.ImpExp_AdvXX);   // AD:4519-4525
+        if (!o.opt.XZFlow) {
+            if ((rc = HorizontalAdvectionYY(o))) return rc;
+            if (o.st_CellFluxes && o.P.ImpExp_AdvYY == ExplicitScheme) CalcHorizontalAdvFluxYY(o, 1. - o.P.ImpExp_AdvYY);   // AD:4902-4908
+        }
     }
 
     if (o.W.KUB > 1) {
         if (o.Optimize) VerticalDiffusion2(o); else VerticalDiffusion(o);
-        if (!o.opt.Vertical1D) if ((rc = VerticalAdvection(o))) return rc;
+        if (o.st_CellFluxes && o.P.ImpExp_DifV < 1.) CalcVerticalDifFlux(o, 1. - o.P.ImpExp_DifV);          // AD:2768, 2930
+        if (!o.opt.Vertical1D) {
+            if ((rc = VerticalAdvection(o))) return rc;
+            if (o.st_CellFluxes && o.P.ImpExp_AdvV < 1.) CalcVerticalAdvFlux(o, 1. - o.P.ImpExp_AdvV);     // AD:3131-3137
+        }
     }
 
     if (o.st_OpenBoundary) if ((rc = OpenBoundaryCondition(o))) return rc;
@@ -1300,6 +1406,11 @@ int AdvectionDiffusionIteration(Oracle &o) {
 
     if (o.P.BoundaryCondition == MOHID_BC_NullGradient) ImposeNullGradient(o);
     else if (o.P.BoundaryCondition == MOHID_BC_CyclicBoundary) Prop_CyclicBoundary(o);
+    // implicit shares of the cell fluxes, with the new field (AD:1885-1916)
+    if (o.st_CellFluxes) {
+        if (o.P.ImpExp_AdvV > 0.0 && o.W.KUB > 1) CalcVerticalAdvFlux(o, o.P.ImpExp_AdvV);
+        if (o.P.ImpExp_DifV > 0.0 && o.W.KUB > 1) CalcVerticalDifFlux(o, o.P.ImpExp_DifV);
+    }
     return 0;
 }
 
@@ -1359,6 +1470,10 @@ int AdvectionDiffusion(Oracle &o, double *PROP, const double *ReferenceProp, con
             SetMatrixValue(o, o.VC, 0.0); SetMatrixValue(o, o.VD, 0.0);
             SetMatrixValue(o, o.VE, 0.0); SetMatrixValue(o, o.VF, 0.0);
         }
+    }
+    o.st_CellFluxes = p.CellFluxes != 0;                      // Set_Internal_State cd3 (AD:5809-5813)
+    if (o.st_CellFluxes) {                                    // AD:1457-1470
+        for (auto *v : {&o.AdvFluxX, &o.AdvFluxY, &o.AdvFluxZ, &o.DifFluxX, &o.DifFluxY, &o.DifFluxZ}) v->assign(o.n3, 0.0);
     }
     if (o.Optimize) {
         if (o.FirstTime) {
@@ -1549,6 +1664,17 @@ int mohid_oracle_last_error(const int *handle, char *buf, const int *buflen) {
     const std::string &e = o ? o->err : g_err;
     if (!buf || !buflen || *buflen <= 0) return ORACLE_ERR_ARG;
     std::snprintf(buf, (size_t)*buflen, "%s", e.c_str());
+    return 0;
+}
+
+// GetAdvFlux / GetDifFlux (AD:697-851): which = 0..5 -> AdvFluxX, AdvFluxY, AdvFluxZ, DifFluxX, DifFluxY, DifFluxZ
+// of the LAST AdvectionDiffusion call that had CellFluxes set.
+int mohid_oracle_get_cell_flux(const int *handle, const int *which, double *out) {
+    Oracle *o = get(handle);
+    if (!o) return MOHID_ADT_ERR_HANDLE;
+    std::vector<double> *v[6] = {&o->AdvFluxX, &o->AdvFluxY, &o->AdvFluxZ, &o->DifFluxX, &o->DifFluxY, &o->DifFluxZ};
+    if (*which < 0 || *which > 5 || (long)v[*which]->size() != o->n3) return ORACLE_ERR_ARG;
+    std::memcpy(out, v[*which]->data(), sizeof(double) * o->n3);
     return 0;
 }
 

@@ -30,7 +30,7 @@ class Params(C.Structure):
                 ("ImpExp_DifV", C.c_double), ("ImpExp_AdvXX", C.c_double), ("ImpExp_AdvYY", C.c_double),
                 ("ImpExp_DifH", C.c_double), ("NullDif", C.c_int), ("BoundaryCondition", C.c_int),
                 ("DecayTime", C.c_double), ("NoAdvFlux", C.c_int), ("NoDifFlux", C.c_int),
-                ("reserved0", C.c_int), ("reserved1", C.c_int)]
+                ("CellFluxes", C.c_int), ("reserved1", C.c_int)]
 
 
 class Options(C.Structure):
@@ -163,6 +163,16 @@ class OracleAdvectionDiffusion:
         self._check(lib().mohid_oracle_advect_batch(C.byref(self.h), C.byref(C.c_int(n)), pp, rp, pa,
                                                     C.byref(C.c_double(self.now)), C.byref(C.c_int(force_optimize))))
         self.now += float(params[0]["DTProp"])
+
+    def get_cell_fluxes(self):
+        """GetAdvFlux + GetDifFlux (AD:697-851) of the last call made with CellFluxes = 1."""
+        out = {}
+        n3 = (self.K + 2) * (self.J + 2) * self.ld
+        for w, name in enumerate(("AdvFluxX", "AdvFluxY", "AdvFluxZ", "DifFluxX", "DifFluxY", "DifFluxZ")):
+            a = np.zeros((self.K + 2, self.J + 2, self.ld))
+            self._check(lib().mohid_oracle_get_cell_flux(C.byref(self.h), C.byref(C.c_int(w)), _dp(a)))
+            out[name] = a
+        return out
 
     def zero_pivots(self) -> int:
         n = C.c_longlong(0)

@@ -272,3 +272,39 @@ def test_discharges_per_property(oracle_lib):
     assert not np.array_equal(p0[0], cpu[0])
     ts.unset_discharges()
     ts.close()
+
+
+@pytest.mark.parametrize("cfg", [(4, 4, 4, 4, 1.0, 1.0, 2), (4, 4, 4, 4, 0.0, 0.4, 1), (1, 4, 1, 4, 1.0, 1.0, 1),
+                                 (2, 4, 1, 4, 1.0, 0.0, 1), (5, 4, 5, 4, 1.0, 1.0, 1)])
+def test_cell_fluxes_match_oracle_and_close_the_budget(oracle_lib, cfg):
+    """CellFluxes outputs (AD:3356-3954, GetAdvFlux / GetDifFlux AD:697-851)."""
+    mh, lh, mv, lv, adv_v, theta, nprop = cfg
+    case = make_case(44, 38, 7, nprop=nprop, stepped_bottom=True)
+    o, g, s, props, refs = oracle_for(case)
+    ts = gpu_for(case, g, s)
+    prm = [default_params(mh, lh, mv, lv, impexp_advv=adv_v, theta_difv=theta) for _ in range(nprop)]
+    for p in prm:
+        p["CellFluxes"] = 1
+    gpu, cpu = [p.copy() for p in props], [p.copy() for p in props]
+    old = [p.copy() for p in props]
+    ts.advect_batch(gpu, prm)
+    o.advect_batch(cpu, prm)
+    compare(gpu, cpu, s, TOL_STEP)
+    n = nprop - 1                                      # the oracle keeps the fluxes of its last call
+    fg, fc = ts.get_cell_fluxes(n), o.get_cell_fluxes()
+    for name in fc:
+        scale = max(np.abs(fc[name]).max(), 1e-30)
+        assert np.abs(fg[name] - fc[name]).max() / scale < 1e-12, name
+        assert np.array_equal(fg[name] == 0, fc[name] == 0), name          # same faces carry a flux
+    # budget of every open cell below the surface layer: V (Pnew - Pold Vold/V) / dt = sum of face fluxes
+    K, J, I = case.K, case.J, case.I
+    tot = {d: fg["AdvFlux" + d] + fg["DifFlux" + d] for d in "XYZ"}
+    c = (slice(1, K + 1), slice(1, J + 1), slice(1, I + 1))
+    net = (tot["X"][c] - tot["X"][1:K + 1, 2:J + 2, 1:I + 1] + tot["Y"][c] - tot["Y"][1:K + 1, 1:J + 1, 2:I + 2] +
+           tot["Z"][c] - tot["Z"][2:K + 2, 1:J + 1, 1:I + 1])
+    V = s["VolumeZ"]
+    lhs = (V * (gpu[n] - old[n] * s["VolumeZOld"] / V) / case.dt)[c]
+    w = (s["OpenPoints3D"][c] == 1) & (g["BoundaryPoints2D"][1:J + 1, 1:I + 1] == 0)[None]
+    w[K - 1] = False                                   # the surface layer also exchanges through its free surface
+    assert np.abs(lhs - net)[w].max() / np.abs(tot["X"]).max() < 1e-11
+    ts.close()

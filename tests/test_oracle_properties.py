@@ -131,3 +131,27 @@ def test_openmp_threads_do_not_change_results(oracle_lib):
         o1.advect_batch(p1, params, refs)
         o4.advect_batch(p4, params, refs)
     assert all(np.array_equal(a, b) for a, b in zip(p1, p4))
+
+
+@pytest.mark.parametrize("optimize", [False, True])
+def test_cell_fluxes_close_the_cell_budget(oracle_lib, optimize):
+    """CellFluxes (AD:3356-3954): V (Pnew - Pold Vold/V) / dt equals the net face flux of every open cell."""
+    case = make_case(30, 26, 6, nprop=1, closed=True)
+    o, g, s, props, refs = oracle_for(case)
+    p = props[0]
+    p0 = p.copy()
+    prm = default_params(4, 4, 4, 4)
+    prm["CellFluxes"] = 1
+    o.now += 30.0
+    o.advection_diffusion(p, prm, optimize=optimize, first_property=True)
+    fl = o.get_cell_fluxes()
+    K, J, I = case.K, case.J, case.I
+    tot = {d: fl["AdvFlux" + d] + fl["DifFlux" + d] for d in "XYZ"}
+    c = (slice(1, K + 1), slice(1, J + 1), slice(1, I + 1))
+    net = (tot["X"][c] - tot["X"][1:K + 1, 2:J + 2, 1:I + 1] + tot["Y"][c] - tot["Y"][1:K + 1, 1:J + 1, 2:I + 2] +
+           tot["Z"][c] - tot["Z"][2:K + 2, 1:J + 1, 1:I + 1])
+    V = s["VolumeZ"]
+    lhs = (V * (p - p0 * s["VolumeZOld"] / V) / 30.0)[c]
+    w = s["OpenPoints3D"][c] == 1
+    w[K - 1] = False
+    assert np.abs(lhs - net)[w].max() / np.abs(tot["X"]).max() < 1e-12
