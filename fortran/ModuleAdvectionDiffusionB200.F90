@@ -25,7 +25,7 @@ module ModuleAdvectionDiffusionB200
     private
 
     public :: T_AdtParams, T_AdtOptions, T_AdtSize3D
-    public :: B200_Start, B200_Kill, B200_SetGrid2D, B200_SetStep, B200_AdvectBatch, B200_LastError
+    public :: B200_Start, B200_Kill, B200_SetGrid2D, B200_SetStep, B200_SetNoFlux, B200_AdvectBatch, B200_LastError
 
     ! mohid_adt_size3d == T_Size3D (ModuleGlobalData.F90:2041-2052)
     type, bind(c) :: T_AdtSize3D
@@ -75,6 +75,11 @@ module ModuleAdvectionDiffusionB200
             integer(c_int), dimension(*) :: OpenPoints3D, LandPoints3D, WaterPoints3D
             integer(c_int), dimension(*) :: ComputeFacesU3D, ComputeFacesV3D, ComputeFacesW3D
             type(c_ptr), value           :: SmallDepths          ! c_null_ptr when not present (AD:1297-1302)
+        end function
+        integer(c_int) function mohid_adt_set_noflux(handle, NoFluxU, NoFluxV, NoFluxW) bind(c, name="mohid_adt_set_noflux")
+            import :: c_int, c_ptr
+            integer(c_int)     :: handle
+            type(c_ptr), value :: NoFluxU, NoFluxV, NoFluxW   ! c_loc(NoFlux?(0,0,0)) or c_null_ptr (all three)
         end function
         integer(c_int) function mohid_adt_advect_batch(handle, nprop, prop, reference_prop, params) &
                 bind(c, name="mohid_adt_advect_batch")
@@ -145,6 +150,18 @@ contains
                                   AreaU, AreaV, OpenPoints3D, LandPoints3D, WaterPoints3D, ComputeFacesU3D,          &
                                   ComputeFacesV3D, ComputeFacesW3D, sd)
     end subroutine B200_SetStep
+
+    ! The optional NoFluxU/V/W dummies (AD:1143-1146); not associated = not present.
+    subroutine B200_SetNoFlux(Handle, NoFluxU, NoFluxV, NoFluxW, STAT)
+        integer(c_int)                            :: Handle
+        integer(c_int), dimension(:,:,:), pointer :: NoFluxU, NoFluxV, NoFluxW
+        integer, intent(OUT)                      :: STAT
+        if (associated(NoFluxU) .and. associated(NoFluxV) .and. associated(NoFluxW)) then
+            STAT = mohid_adt_set_noflux(Handle, c_loc(NoFluxU(0,0,0)), c_loc(NoFluxV(0,0,0)), c_loc(NoFluxW(0,0,0)))
+        else
+            STAT = mohid_adt_set_noflux(Handle, c_null_ptr, c_null_ptr, c_null_ptr)
+        endif
+    end subroutine B200_SetNoFlux
 
     ! The batched replacement of the per-property call loop (WP:14603-15143 -> AD:1108).
     ! PropPtr(n) = c_loc(Property%Concentration(0,0,0)); RefPtr(n) = c_loc(Property%Assimilation%Field(0,0,0))

@@ -80,7 +80,7 @@ typedef struct mohid_adt_params {
     int    NullDif;                /* logical */
     int    BoundaryCondition;      /* MOHID_BC_*; MOHID_BC_None when ReferenceProp is absent */
     double DecayTime;              /* seconds */
-    int    NoAdvFlux;              /* logical; needs NoFluxU/V/W (set_noflux) */
+    int    NoAdvFlux;              /* logical; needs NoFluxU/V/W (mohid_adt_set_noflux) */
     int    NoDifFlux;              /* logical */
     int    CellFluxes;             /* logical: also produce the six cell-face fluxes (AD:1457-1470, 3356-3954) */
     int    reserved1;
@@ -123,6 +123,11 @@ int mohid_adt_set_step(const int *handle,
                        const int *OpenPoints3D, const int *LandPoints3D, const int *WaterPoints3D,
                        const int *ComputeFacesU3D, const int *ComputeFacesV3D,
                        const int *ComputeFacesW3D, const int *SmallDepths);
+
+/* The optional NoFluxU / NoFluxV / NoFluxW dummies of AdvectionDiffusion (AD:1146, 1332-1334; int32 3-D):
+ * faces whose advective (NoAdvFlux) or diffusive (NoDifFlux) coefficients are zeroed for the properties that
+ * set those flags.  All three NULL = not present. */
+int mohid_adt_set_noflux(const int *handle, const int *NoFluxU, const int *NoFluxV, const int *NoFluxW);
 
 /* SetDischarges / UnSetDischarges (AD:978-1095), same arguments as the reference plus the position
  * `prop_index` (0-based) of the property in the next advect batch: the caller invokes SetDischarges

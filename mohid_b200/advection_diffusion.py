@@ -100,6 +100,11 @@ class TransportStep:
         args.append(_ptr(SmallDepths, "i4", self.n2, "SmallDepths"))
         self._check(self.lib.mohid_adt_set_step(C.byref(self.h), *args))
 
+    def set_noflux(self, NoFluxU=None, NoFluxV=None, NoFluxW=None):
+        """The optional NoFluxU/V/W dummies (AD:1146); all None = not present."""
+        self._check(self.lib.mohid_adt_set_noflux(C.byref(self.h), _ptr(NoFluxU, "i4", self.n3, "NoFluxU"),
+                                                  _ptr(NoFluxV, "i4", self.n3, "NoFluxV"), _ptr(NoFluxW, "i4", self.n3, "NoFluxW")))
+
     def set_discharges(self, prop_index: int, d: Dict[str, object]):
         """SetDischarges (AD:978-1034) for the property at position ``prop_index`` of the next batch.
         ``d`` holds the reference's argument names: DischFlow, DischConc, DischI, DischJ, DischK, DischKmin,
@@ -237,7 +242,7 @@ def AdvectionDiffusion(AdvectionDiffusionID: int, PROP, schmidt_H, SchmidtCoef_V
                        OpenPoints3D, LandPoints3D, ComputeFacesU3D, ComputeFacesV3D, ComputeFacesW3D, Visc_H, Diff_V,
                        *, DWZ, DZZ, AreaU, AreaV, CellFluxes: bool = False, WaterPoints3D=None, ReferenceProp=None,
                        BoundaryCondition: Optional[int] = None, DecayTime: float = 0.0, SmallDepths=None,
-                       NoAdvFlux: bool = False, NoDifFlux: bool = False) -> int:
+                       NoAdvFlux: bool = False, NoDifFlux: bool = False, NoFluxU=None, NoFluxV=None, NoFluxW=None) -> int:
     """Same dummy arguments as AD:1108-1147 (DWZ, DZZ, AreaU, AreaV are what the reference fetches from
     ModuleGeometry inside the call, AD:1386-1401).  ``PROP`` is updated in place.  Returns STAT."""
     obj = _get(AdvectionDiffusionID)
@@ -250,6 +255,7 @@ def AdvectionDiffusion(AdvectionDiffusionID: int, PROP, schmidt_H, SchmidtCoef_V
                 LandPoints3D=LandPoints3D, WaterPoints3D=WaterPoints3D, ComputeFacesU3D=ComputeFacesU3D,
                 ComputeFacesV3D=ComputeFacesV3D, ComputeFacesW3D=ComputeFacesW3D)
     obj.set_step(step, SmallDepths)
+    obj.set_noflux(NoFluxU, NoFluxV, NoFluxW)
     p = dict(Schmidt_H=schmidt_H, SchmidtCoef_V=SchmidtCoef_V, SchmidtBackground_V=SchmidtBackground_V,
              AdvMethodH=AdvMethodH, TVDLimitationH=TVDLimitationH, AdvMethodV=AdvMethodV, TVDLimitationV=TVDLimitationV,
              Upwind2H=int(Upwind2H), Upwind2V=int(Upwind2V), VolumeRelMax=VolumeRelMax, DTProp=DTProp,

@@ -36,6 +36,9 @@ struct Handle {
     int *KFloorZ = nullptr, *Bnd = nullptr, *SmallDepths = nullptr;
     bool have_small = false;
     int *bnd_cols = nullptr;
+    int *noflux[3] = {nullptr, nullptr, nullptr};       // NoFluxU/V/W mirrors (allocated by set_noflux)
+    bool have_noflux = false;
+    unsigned char *nfmask = nullptr;                    // NF_* bits, rebuilt by K1 every step
     int n_bnd_cols = 0;
     // raw per-step inputs
     double *raw_d[11] = {nullptr};
@@ -150,6 +153,8 @@ void free_all(Handle *h) {
     auto F = [](void *p) { if (p) cudaFree(p); };
     F(h->DUX); F(h->DVY); F(h->DZX); F(h->DZY); F(h->rdx); F(h->rdy); F(h->KFloorZ); F(h->Bnd); F(h->SmallDepths);
     F(h->bnd_cols);
+    for (auto p : h->noflux) F(p);
+    F(h->nfmask);
     for (auto p : h->raw_d) F(p);
     for (auto p : h->raw_i) F(p);
     F(h->dtv); F(h->vr); F(h->dhu); F(h->dhv); F(h->dvz); F(h->rdz); F(h->mask);
@@ -181,11 +186,61 @@ int upload_bnd_cols(Handle *h) {
     return 0;
 }
 
+// What the reference's module state makes of a property's own flags.  AdvectionDiffusion is called once per
+// property and Set_Internal_State (AD:5746-5835) decides per call which coefficient arrays are rebuilt; arrays that
+// are not rebuilt keep what the PREVIOUS property of the time step left in them, including its NullDif / NoDifFlux /
+// NoAdvFlux zeroing.  The batch reproduces that by resolving, in caller order, which flags each property really sees.
+struct PropEff {
+    double schmidt_h = 0., coef_v = 0., bg_v = 0.;   // Schmidt numbers behind DifX/DifY and DifZ
+    int nulldif_h = 0, nulldif_v = 0;                // NullDif zeroing present in DifX/DifY, in DifZ
+    int nodif_h = 0;                                 // NoDifFlux zeroing present in DifX/DifY (AD:2497-2501, 2524-2528)
+    int nodif_w = 0;                                 // NoDifFlux on AuxK: always the property's own (AD:2737-2741)
+    unsigned nfsel = 0;                              // NF_* bits of the advective coefficients the property uses
+    bool same_dif(const PropEff &o) const {
+        return schmidt_h == o.schmidt_h && coef_v == o.coef_v && bg_v == o.bg_v && nulldif_h == o.nulldif_h &&
+               nulldif_v == o.nulldif_v && nodif_h == o.nodif_h && nodif_w == o.nodif_w;
+    }
+};
+
 struct Batch {          // validated view of one advect call
     int nprop = 0;
     bool optimize = false;
     const mohid_adt_params *p = nullptr;
+    std::vector<PropEff> eff;
 };
+
+// Set_Internal_State (AD:5746-5835) + the rebuild conditions of AD:1423-1456, 4280-4300, replayed over the batch.
+// The first property of a batch sees LastCalc /= Now (a batch is one time step), so everything is rebuilt for it.
+void resolve_effective_flags(const Handle *h, Batch &b) {
+    b.eff.assign(b.nprop, PropEff{});
+    bool xz_u = false, xz_v = false, vz_w = false;      // zeroed cell lists sitting in COEF3_HorAdvXX / COEF3_VertAdv
+    for (int n = 0; n < b.nprop; ++n) {
+        const mohid_adt_params &q = b.p[n];
+        PropEff &e = b.eff[n];
+        const bool first = n == 0;
+        const mohid_adt_params &pv = b.p[first ? 0 : n - 1];
+        // State%HorDif / VertDif ON -> Convert_* runs (non-Optimize: every time; Optimize: first property only)
+        const bool hdif_on = first || ((pv.Schmidt_H != q.Schmidt_H || q.NullDif) && !b.optimize);
+        const bool vdif_on = first || ((pv.SchmidtCoef_V != q.SchmidtCoef_V ||
+                                        pv.SchmidtBackground_V != q.SchmidtBackground_V || q.NullDif) && !b.optimize);
+        if (hdif_on) { e.schmidt_h = q.Schmidt_H; e.nulldif_h = q.NullDif; e.nodif_h = q.NoDifFlux && h->have_noflux; }
+        else { e.schmidt_h = b.eff[n - 1].schmidt_h; e.nulldif_h = b.eff[n - 1].nulldif_h; e.nodif_h = b.eff[n - 1].nodif_h; }
+        if (vdif_on) { e.coef_v = q.SchmidtCoef_V; e.bg_v = q.SchmidtBackground_V; e.nulldif_v = q.NullDif; }
+        else { e.coef_v = b.eff[n - 1].coef_v; e.bg_v = b.eff[n - 1].bg_v; e.nulldif_v = b.eff[n - 1].nulldif_v; }
+        e.nodif_w = q.NoDifFlux && h->have_noflux;
+        // State%HorAdv / VertAdv: methods are uniform over the batch, so only P2_TVD coefficients are rebuilt
+        const bool noadv = q.NoAdvFlux && h->have_noflux;
+        if (first || q.AdvMethodH == MOHID_P2_TVD) {
+            e.nfsel |= noadv ? (NF_UW | NF_UE) : 0u;                    // XX pass (AD:4434-4443)
+            xz_u = noadv;
+            xz_v = noadv && !h->opt.XZFlow;                             // YY pass, after the XX use (AD:4804-4813)
+        } else {
+            e.nfsel |= (xz_u ? (NF_UW | NF_UE) : 0u) | (xz_v ? (NF_VW | NF_VE) : 0u);
+        }
+        if (first || q.AdvMethodV == MOHID_P2_TVD) vz_w = noadv;        // AD:3004-3013
+        e.nfsel |= vz_w ? NF_WT : 0u;
+    }
+}
 
 // The reference's argument checks (AD:1229-1237, 1340-1349, 3124, 4525; MF:10869-10873) plus the
 // limits of the GPU path.
@@ -232,8 +287,8 @@ int validate(Handle *h, int nprop, const mohid_adt_params *p, Batch &b) {
             bc != MOHID_BC_NullGradient && bc != MOHID_BC_SubModel && bc != MOHID_BC_MassConservNullGrad &&
             bc != MOHID_BC_CyclicBoundary)
             return fail(h, MOHID_ADT_ERR_ARG, "Set_Internal_State - ModuleAdvectionDiffusion - ERR01");
-        if (q.NoAdvFlux || q.NoDifFlux)
-            return fail(h, MOHID_ADT_ERR_UNSUPPORTED, "NoAdvFlux / NoDifFlux cells are not available on the GPU path");
+        if ((q.NoAdvFlux || q.NoDifFlux) && !h->have_noflux)
+            return fail(h, MOHID_ADT_ERR_ARG, "NoAdvFlux / NoDifFlux need the NoFluxU/V/W arrays (mohid_adt_set_noflux)");
         if (!(q.DTProp > 0.0)) return fail(h, MOHID_ADT_ERR_ARG, "DTProp must be positive");
         // one kernel variant per batch: these keywords are read FromFile in the reference (WP:9580-9632)
         if (q.AdvMethodH != f.AdvMethodH || q.AdvMethodV != f.AdvMethodV || q.TVDLimitationH != f.TVDLimitationH ||
@@ -243,19 +298,20 @@ int validate(Handle *h, int nprop, const mohid_adt_params *p, Batch &b) {
                         "properties of one batch must share DTProp, advection methods, limiters and VolumeRelMax");
         // OptimizeFlag (WP:14580-14598)
         if (q.Schmidt_H != f.Schmidt_H || q.NullDif || q.AdvMethodH != MOHID_P2_TVD || q.AdvMethodV != MOHID_P2_TVD ||
-            q.TVDLimitationH != MOHID_SuperBee || q.TVDLimitationV != MOHID_SuperBee)
+            q.TVDLimitationH != MOHID_SuperBee || q.TVDLimitationV != MOHID_SuperBee || q.NoAdvFlux || q.NoDifFlux)
             optimize = false;
     }
     b.nprop = nprop; b.optimize = optimize; b.p = p;
+    resolve_effective_flags(h, b);
     return 0;
 }
 
-int launch_coef(Handle *h, const mohid_adt_params &q, bool geom, bool diff) {
+int launch_coef(Handle *h, const mohid_adt_params &q, const PropEff &e, bool geom, bool diff) {
     CoefArgs a{};
     a.ni = h->ni; a.nj = h->nj; a.nk = h->nk; a.ld = h->ld; a.I = h->I; a.J = h->J; a.K = h->K;
     a.sj = h->sj; a.sk = h->sk;
-    a.dt = q.DTProp; a.schmidt_h = q.Schmidt_H; a.schmidt_coef_v = q.SchmidtCoef_V; a.schmidt_bg_v = q.SchmidtBackground_V;
-    a.nulldif = q.NullDif;
+    a.dt = q.DTProp; a.schmidt_h = e.schmidt_h; a.schmidt_coef_v = e.coef_v; a.schmidt_bg_v = e.bg_v;
+    a.nulldif = e.nulldif_h; a.nulldif_v = e.nulldif_v; a.nodif_h = e.nodif_h; a.nodif_w = e.nodif_w;
     a.Wflux_X = h->raw_d[0]; a.Wflux_Y = h->raw_d[1]; a.Wflux_Z = h->raw_d[2]; a.VolumeZOld = h->raw_d[3];
     a.VolumeZ = h->raw_d[4]; a.Visc_H = h->raw_d[5]; a.Diff_V = h->raw_d[6]; a.DWZ = h->raw_d[7]; a.DZZ = h->raw_d[8];
     a.AreaU = h->raw_d[9]; a.AreaV = h->raw_d[10];
@@ -263,6 +319,8 @@ int launch_coef(Handle *h, const mohid_adt_params &q, bool geom, bool diff) {
     a.CFW = h->raw_i[5]; a.SmallDepths = h->have_small ? h->SmallDepths : nullptr;
     a.DUX = h->DUX; a.DVY = h->DVY; a.DZX = h->DZX; a.DZY = h->DZY; a.Bnd = h->Bnd;
     a.dtv = h->dtv; a.vr = h->vr; a.dhu = h->dhu; a.dhv = h->dhv; a.dvz = h->dvz; a.rdz = h->rdz; a.mask = h->mask;
+    a.NoFluxU = h->have_noflux ? h->noflux[0] : nullptr; a.NoFluxV = h->have_noflux ? h->noflux[1] : nullptr;
+    a.NoFluxW = h->have_noflux ? h->noflux[2] : nullptr; a.nfmask = h->nfmask;
     a.do_geom = geom; a.do_diff = diff;
     const dim3 grid((unsigned)((h->ld + 127) / 128), (unsigned)h->nj, (unsigned)h->nk);
     adt_coef_kernel<<<grid, 128, 0, h->stream>>>(a);
@@ -287,6 +345,7 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
     s.rdx = h->rdx; s.rdy = h->rdy; s.DUX = h->DUX; s.DVY = h->DVY; s.DWZ = h->raw_d[7];
     s.VolumeZ = h->raw_d[4]; s.VolumeZOld = h->raw_d[3];
     s.zero_pivots = h->d_zero_piv;
+    s.nfmask = h->have_noflux ? h->nfmask : nullptr;
     s.disch.ncell = h->d_ncell; s.disch.K = h->K; s.disch.ci = h->d_ci; s.disch.cj = h->d_cj;
     s.disch.kmin_eff = h->d_kmin_eff; s.disch.kmax_eff = h->d_kmax_eff; s.disch.cbypass = h->d_cbypass;
     s.disch.flow_k = h->d_flow_k;
@@ -301,6 +360,7 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
         pa.tdec = 1.0 / (1.0 + q.DecayTime / q.DTProp);
         pa.bc = h->has_ref[n] ? q.BoundaryCondition : MOHID_BC_None;                    // AD:5816-5830
         pa.advv_implicit = (q.ImpExp_AdvV == 1.0) ? 1 : 0;
+        pa.nfsel = b.eff[n].nfsel;
         const bool hd = h->d_ncell > 0 && n < (int)h->d_conc.size() && h->d_conc[n];
         pa.dconc = hd ? h->d_conc[n] : nullptr;
         pa.dconcmf = hd ? h->d_concmf[n] : nullptr;
@@ -310,6 +370,7 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
     for (int m = 0; m < s.nprop; ++m) {
         any_disch = any_disch || s.p[m].dconc != nullptr;
         all_impv = all_impv && s.p[m].advv_implicit;
+        any_disch = any_disch || s.p[m].nfsel != 0;     // NoAdvFlux rides on the DISCH variants
     }
     // FULL: 3-D, both horizontal directions, implicit vertical advection for every property of the launch
     const bool full = !s.vertical1d && !s.xzflow && s.K > 1 && all_impv;
@@ -405,6 +466,7 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
         fa.method_h = q.AdvMethodH; fa.limiter_h = q.TVDLimitationH; fa.method_v = q.AdvMethodV; fa.limiter_v = q.TVDLimitationV;
         fa.upwind2_h = q.Upwind2H; fa.upwind2_v = q.Upwind2V; fa.vertical1d = h->opt.Vertical1D; fa.xzflow = h->opt.XZFlow;
         fa.vrelmax = q.VolumeRelMax; fa.w_advv = q.ImpExp_AdvV; fa.theta = q.ImpExp_DifV;
+        fa.nfmask = s.nfmask; fa.nfsel = b.eff[n].nfsel;
         fa.pold = s.p[m].pin; fa.pnew = s.p[m].pout;
         fa.qx = s.qx; fa.qy = s.qy; fa.qz = s.qz; fa.dtv = s.dtv; fa.dhu = s.dhu; fa.dhv = s.dhv; fa.dvz = s.dvz;
         fa.rdz = s.rdz; fa.rdx = s.rdx; fa.rdy = s.rdy; fa.DUX = s.DUX; fa.DVY = s.DVY; fa.DWZ = s.DWZ; fa.mask = s.mask;
@@ -429,14 +491,12 @@ int step_once(Handle *h, const Batch &b) {
         std::vector<int> idx;
         for (int m = n; m < b.nprop; ++m) {
             if (done[m]) continue;
-            const auto &x = b.p[n], &y = b.p[m];
-            if (x.Schmidt_H == y.Schmidt_H && x.SchmidtCoef_V == y.SchmidtCoef_V &&
-                x.SchmidtBackground_V == y.SchmidtBackground_V && x.NullDif == y.NullDif) {
+            if (b.eff[n].same_dif(b.eff[m])) {
                 idx.push_back(m);
                 done[m] = 1;
             }
         }
-        if (int rc = launch_coef(h, b.p[n], !geom_done, true)) return rc;
+        if (int rc = launch_coef(h, b.p[n], b.eff[n], !geom_done, true)) return rc;
         if (!geom_done && h->d_ncell > 0) {               // flag the receiving cells, per-layer flows (AD:4063-4077)
             DischArgs d{};
             d.ncell = h->d_ncell; d.K = h->K; d.ld = h->ld; d.sj = h->sj; d.sk = h->sk;
@@ -850,6 +910,26 @@ int mohid_adt_pack_columns(const int *handle, const int *nprop, const int *j0, c
 int mohid_adt_unpack_columns(const int *handle, const int *nprop, const int *j0, const int *width,
                              const void *device_buffer) {
     return pack_common(handle, nprop, j0, width, (double *)device_buffer, 1);
+}
+
+int mohid_adt_set_noflux(const int *handle, const int *NoFluxU, const int *NoFluxV, const int *NoFluxW) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    CU(h, cudaSetDevice(h->dev));
+    if (!NoFluxU && !NoFluxV && !NoFluxW) { h->have_noflux = false; return 0; }
+    if (!NoFluxU || !NoFluxV || !NoFluxW) return fail(h, MOHID_ADT_ERR_ARG, "NoFluxU, NoFluxV and NoFluxW must be given together");
+    const int *src[3] = {NoFluxU, NoFluxV, NoFluxW};
+    for (int a = 0; a < 3; ++a) {
+        if (!h->noflux[a]) {
+            if (int rc = dalloc(h, &h->noflux[a], h->n3)) return rc;
+            CU(h, cudaMemsetAsync(h->noflux[a], 0, h->n3 * sizeof(int), h->stream));
+        }
+        if (int rc = h2d3(h, h->noflux[a], src[a], 4)) return rc;
+    }
+    if (!h->nfmask) if (int rc = dalloc(h, &h->nfmask, h->n3)) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->have_noflux = true;
+    return 0;
 }
 
 int mohid_adt_get_cell_fluxes(const int *handle, const int *prop_index, double *AdvFluxX, double *AdvFluxY,

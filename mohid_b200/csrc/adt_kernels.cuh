@@ -59,6 +59,20 @@ enum : unsigned {
     M_DISCH = 1u << 26     // a point discharge feeds this cell (set by adt_discharge_prep_kernel after K1)
 };
 
+// NoFluxU/V/W cell lists (AD:1146) live in their own byte per cell, written by K1 only when the caller supplied the
+// arrays and read only by the DISCH kernel variants.  A property honours the bits selected by its PropArgs::nfsel:
+//   NF_U*: NoAdvFlux zeroes the XX coefficients of the face in the XX pass (AD:4434-4443).
+//   NF_V*: the YY pass zeroes the XX coefficient arrays again, at the NoFluxV cells (copy-paste quirk A.4-7,
+//          AD:4804-4813) -- after their last use for that property.  They only act on a LATER property of the same
+//          time step whose coefficients are not rebuilt (Set_Internal_State, AD:5768-5785: non-TVD methods).
+//   NF_WT: NoFluxW zeroes the vertical coefficients of the face (AD:3004-3013).
+enum : unsigned {
+    NF_UW = 1u, NF_UE = 2u,     // NoFluxU of this cell (west face) / of cell j+1 (east face)
+    NF_VW = 4u, NF_VE = 8u,     // NoFluxV of this cell / of cell j+1, acting on the same U faces
+    NF_WT = 16u,                // NoFluxW of cell k+1 (top face)
+    NF_WEST = NF_UW | NF_VW, NF_EAST = NF_UE | NF_VE
+};
+
 struct CoefArgs {
     int ni, nj, nk, ld;              // allocated extents (I+2, J+2, K+2) and leading dimension
     int sj, sk;                      // element strides of j and k in the 3-D device arrays
@@ -68,6 +82,10 @@ struct CoefArgs {
     // raw interface arrays (device copies)
     const double *Wflux_X, *Wflux_Y, *Wflux_Z, *VolumeZOld, *VolumeZ, *Visc_H, *Diff_V, *DWZ, *DZZ, *AreaU, *AreaV;
     const int *Open, *Land, *Water, *CFU, *CFV, *CFW, *SmallDepths;
+    const int *NoFluxU, *NoFluxV, *NoFluxW;   // optional (nullptr): NoAdvFlux / NoDifFlux cell lists
+    unsigned char *nfmask;                    // NF_* bits per cell (with the cell lists only)
+    int nulldif_v;                            // NullDif as it applies to DifZ (nulldif: to DifX / DifY), see PropEff
+    int nodif_h, nodif_w;                     // NoDifFlux on DifX / DifY (AD:2497-2501, 2524-2528) and on AuxK (AD:2737-2741)
     const double *DUX, *DVY, *DZX, *DZY;
     const int *Bnd;
     // outputs
@@ -123,7 +141,7 @@ __global__ void __launch_bounds__(128) adt_coef_kernel(const CoefArgs a) {
         areau = a.AreaU[q]; areav = a.AreaV[q]; diffv = a.Diff_V[q]; dzz_m = a.DZZ[q + okm1];
         dux = a.DUX[q2]; dux_w = a.DUX[q2 - (jm1 ? sj2 : 0)]; dvy = a.DVY[q2]; dvy_s = a.DVY[q2 + oim1];
         dzx_w = a.DZX[q2 - (jm1 ? sj2 : 0)]; dzy_s = a.DZY[q2 + oim1];
-        if (a.nulldif) { wx = a.Wflux_X[q]; wy = a.Wflux_Y[q]; wz = a.Wflux_Z[q]; }
+        if (a.nulldif || a.nulldif_v) { wx = a.Wflux_X[q]; wy = a.Wflux_Y[q]; wz = a.Wflux_Z[q]; }
         if (a.SmallDepths) small = a.SmallDepths[q2];
     }
 
@@ -160,6 +178,15 @@ __global__ void __launch_bounds__(128) adt_coef_kernel(const CoefArgs a) {
             if (ojp1b && a.Bnd[q2 + sj2] != 1) m |= M_A_JP1;
             if (ojm1b && a.Bnd[q2 - sj2] != 1) m |= M_A_JM1;
         }
+        if (a.NoFluxU) {
+            unsigned nf = 0;
+            if (a.NoFluxU[q] == 1) nf |= NF_UW;
+            if (a.NoFluxV[q] == 1) nf |= NF_VW;
+            if (jp1 && a.NoFluxU[q + ojp1] == 1) nf |= NF_UE;
+            if (jp1 && a.NoFluxV[q + ojp1] == 1) nf |= NF_VE;
+            if (kp1 && a.NoFluxW[q + okp1] == 1) nf |= NF_WT;
+            a.nfmask[q] = (unsigned char)nf;
+        }
         a.mask[q] = m;
         const bool inwork = (i >= 1 && i <= a.I && j >= 1 && j <= a.J && k >= 1 && k <= a.K);
         a.dtv[q] = (inwork && V != 0.) ? a.dt / V : 0.;
@@ -173,19 +200,22 @@ __global__ void __launch_bounds__(128) adt_coef_kernel(const CoefArgs a) {
             // DifX (AD:2486-2495) then Diff_H_Const_U (AD:1549-1553), same operation order
             double difx = a.schmidt_h * (visc * dux_w + visc_w * dux) / (dux + dux_w);
             if (a.nulldif && wx == 0.) difx = 0.;
+            if (a.nodif_h && a.NoFluxU && a.NoFluxU[q] == 1) difx = 0.;
             hu = difx * areau / dzx_w;
         }
         if (cfv && im1) {
             double dify = a.schmidt_h * (visc * dvy_s + visc_s * dvy) / (dvy + dvy_s);
             if (a.nulldif && wy == 0.) dify = 0.;
+            if (a.nodif_h && a.NoFluxV && a.NoFluxV[q] == 1) dify = 0.;
             hv = dify * areav / dzy_s;
         }
         if (cfw && km1 && small == 0) {
             // DifZ (AD:2397-2405) then Diff_V_Const (AD:1591-1597)
             double difz = (a.schmidt_coef_v * diffv + a.schmidt_bg_v);
-            if (a.nulldif && wz == 0.) difz = 0.;
+            if (a.nulldif_v && wz == 0.) difz = 0.;
             const double auxk = difz * dux * dvy;
             vz = auxk / dzz_m;
+            if (a.nodif_w && a.NoFluxW && a.NoFluxW[q] == 1) vz = 0.;
         }
         a.dhu[q] = hu; a.dhv[q] = hv; a.dvz[q] = vz;
     }
@@ -261,6 +291,8 @@ struct PropArgs {
     double tdec;            // 1/(1+DecayTime/DT) (AD:5418-5419)
     int bc;                 // MOHID_BC_*
     int advv_implicit;      // ImpExp_AdvV == ImplicitScheme (AD:3087)
+    unsigned nfsel;         // NF_* bits this property honours (0 = none), see PropEff in adt_api.cu
+    int pad0;
     const double *dconc;    // DischConc of this property per listed discharge cell, or nullptr (no discharges)
     const double *dconcmf;  // DischConcMF
 };
@@ -277,6 +309,7 @@ struct StepArgs {
     const uint32_t *mask;
     const double *rdx, *rdy, *DUX, *DVY, *DWZ;
     const double *VolumeZ, *VolumeZOld;         // open-boundary flux only (AD:5718-5727)
+    const unsigned char *nfmask;      // NF_* bits (nullptr without NoFlux cell lists)
     unsigned long long *zero_pivots;
     DischView disch;
     PropArgs p[NPMAX];
@@ -488,7 +521,8 @@ struct Level {
 //   warps of a block read the same shared coefficients (L1 hits).
 //   blockDim.x = 32 * WPB; dynamic shared memory = 2 * K * WPB * 32 doubles.
 //   MH/LH/MV/LV > 0 fix the advection method / limiter at compile time; 0 = read from StepArgs.
-//   DISCH = the batch has point discharges (keeps the rare out-of-line call out of the common kernels).
+//   DISCH = the batch has point discharges or NoAdvFlux cell lists (keeps the rare out-of-line call and the extra
+//           face predicates out of the common kernels).
 //   PF    = 0 no look-ahead, 1 next level fetched into registers, 2 next two levels staged in shared memory
 //           with cp.async (in-flight loads hold no registers; needs FULL and a non-QUICK scheme).
 //   GGLOB = G of the column solve is parked in the output array instead of shared memory.
@@ -553,6 +587,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
     // vertical advection acts on a top face iff both cells are open, the face is a compute face, the column's
     // surface cell is open and the run is not Vertical1D (AD:2966, 3041; MF:10559); bit 31 is never set in a mask
     const unsigned top_req = (do_h && colopen) ? (M_OPEN | M_O_KP1 | M_CFWT) : (1u << 31);
+    // NoAdvFlux: a selected NF_* bit switches the advective part of that face off
+    const unsigned nfsel = DISCH ? pa.nfsel : 0u;
     const double theta = pa.theta_difv, omt = 1. - pa.theta_difv;
     const bool advv_imp = FULL || pa.advv_implicit != 0;
     // halo lanes of the strip: lanes 0,1 fetch cell i-2, lane 31 fetches cell i+1
@@ -629,6 +665,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
         const Level &cur = (PF == 1) ? cur_ : nxt;
 
         const unsigned m = cur.m;
+        const unsigned nf = (DISCH && nfsel) ? (s.nfmask[q] & nfsel) : 0u;
         const bool open_c = (m & M_OPEN) != 0;
         // ---------------- VolumeVariation (AD:3966-4021) ----------------
         Row row;
@@ -645,10 +682,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
         // ---------------- horizontal faces (explicit) ----------------
         if (do_h) {
             const bool o_w1 = (m & M_O_JM1) != 0, o_e1 = (m & M_O_JP1) != 0;
-            const double fw = hface_flux<MH, LH>(s, all_set(m, M_CFU | M_O_JM1 | M_OPEN), cur.qxw, cur.dhw, cur.Pw2, cur.Pw1,
+            const double fw = hface_flux<MH, LH>(s, all_set(m, M_CFU | M_O_JM1 | M_OPEN) && !(nf & NF_WEST), cur.qxw, cur.dhw, cur.Pw2, cur.Pw1,
                                                  Pc, cur.Pe1, (m & M_O_JM2) != 0, o_e1, cur.t_w2, cur.t_w, dtv_c,
                                                  cur.t_e, rho_wp, rdx_c, rho_wn, dux_m, dux_c);
-            const double fe = hface_flux<MH, LH>(s, all_set(m, M_CFUE | M_O_JP1 | M_OPEN), cur.qxe, cur.dhe, cur.Pw1, Pc,
+            const double fe = hface_flux<MH, LH>(s, all_set(m, M_CFUE | M_O_JP1 | M_OPEN) && !(nf & NF_EAST), cur.qxe, cur.dhe, cur.Pw1, Pc,
                                                  cur.Pe1, cur.Pe2, o_w1, (m & M_O_JP2) != 0, cur.t_w, dtv_c, cur.t_e,
                                                  cur.t_e2, rho_ep, rdx_p, rho_en, dux_c, dux_p);
             double fsum = fw - fe;
@@ -686,7 +723,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
             En_b = aux2 * theta;
             TIn_b = -aux2 * dP * omt;
             // advection (AD:2941-3144); weights exist iff both cells are open (MF:10559), applied on compute faces
-            const bool adv_on = all_set(m, top_req);
+            const bool adv_on = all_set(m, top_req) && !(nf & NF_WT);
             const bool pos = qz_p > 0.;
             const double Puu = sel(pos, Pm1, Pp2), Pu = sel(pos, Pc, Pp1), Pd = sel(pos, Pp1, Pc);
             double du_u = 0., du_d = 0.;
@@ -876,6 +913,7 @@ __global__ void adt_cyclic_kernel(const BndArgs b, int phase) {
 struct FluxArgs {
     int I, J, K, ld, sj, sk;
     int method_h, limiter_h, method_v, limiter_v, upwind2_h, upwind2_v, vertical1d, xzflow;
+    const unsigned char *nfmask; unsigned nfsel;   // as in StepArgs / PropArgs
     double vrelmax, w_advv, theta;                 // ImpExp_AdvV (0 or 1), ImpExp_DifV as passed by the caller
     const double *pold, *pnew;
     const double *qx, *qy, *qz, *dtv, *dhu, *dhv, *dvz, *rdz, *rdx, *rdy, *DUX, *DVY, *DWZ;
@@ -904,6 +942,7 @@ __global__ void __launch_bounds__(128) adt_cell_flux_kernel(const FluxArgs a) {
     const int sj = a.sj, sk = a.sk, sj2 = a.ld;
     const int q = i + sj * j + sk * k, q2 = i + sj2 * j;
     const unsigned m = a.mask[q];
+    const unsigned nf = a.nfsel ? (a.nfmask[q] & a.nfsel) : 0u;
     const double *__restrict__ P = a.pold;
     const double *__restrict__ N = a.pnew;
     const int jw2 = (j >= 2) ? 2 * sj : sj;
@@ -912,7 +951,7 @@ __global__ void __launch_bounds__(128) adt_cell_flux_kernel(const FluxArgs a) {
         if (m & M_CFU) {
             const double Pw[4] = {P[q - jw2], P[q - sj], P[q], P[q + sj]};
             double adv = 0.;
-            if (all_set(m, M_O_JM1 | M_OPEN)) {
+            if (all_set(m, M_O_JM1 | M_OPEN) && !(nf & NF_WEST)) {
                 const double t[4] = {a.dtv[q - jw2], a.dtv[q - sj], a.dtv[q], a.dtv[q + sj]};
                 adv = adv_face_flux(a.method_h, a.limiter_h, a.upwind2_h != 0, a.vrelmax, a.qx[q], Pw, Pw,
                                     (m & M_O_JM2) != 0, (m & M_O_JP1) != 0, t, a.rdx[q2 - sj2], a.rdx[q2],
@@ -947,7 +986,7 @@ __global__ void __launch_bounds__(128) adt_cell_flux_kernel(const FluxArgs a) {
         a.dz[qt] = dif;
         double adv = 0.;
         const unsigned mtop = a.mask[i + sj * j + sk * a.K];
-        if (!a.vertical1d && (mtop & M_COLOPEN) && all_set(m, M_OPEN | M_O_KP1)) {
+        if (!a.vertical1d && (mtop & M_COLOPEN) && all_set(m, M_OPEN | M_O_KP1) && !(nf & NF_WT)) {
             const double t[4] = {a.dtv[q - sk], a.dtv[q], a.dtv[qt], a.dtv[q2k]};
             double du2 = 0., du3 = 0.;
             if (a.method_v == MOHID_CentralDif || a.method_v == MOHID_LeapFrog) { du2 = a.DWZ[q]; du3 = a.DWZ[qt]; }

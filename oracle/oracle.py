@@ -128,6 +128,10 @@ class OracleAdvectionDiffusion:
                       _ip(s["LandPoints3D"]), _ip(s["WaterPoints3D"]), _ip(s["ComputeFacesU3D"]),
                       _ip(s["ComputeFacesV3D"]), _ip(s["ComputeFacesW3D"]), _ip(small_depths)))
 
+    def set_noflux(self, u, v, w):
+        self._keep["noflux"] = (u, v, w)
+        self._check(lib().mohid_oracle_set_noflux(C.byref(self.h), _ip(u), _ip(v), _ip(w)))
+
     def set_discharges(self, d: dict):
         nd, nc = len(d["DischnCells"]), len(d["DischFlow"])
         a = {k: np.ascontiguousarray(v, dtype=(np.float64 if k in ("DischFlow", "DischConc", "DischConcMF") else np.int32))

@@ -308,3 +308,90 @@ def test_cell_fluxes_match_oracle_and_close_the_budget(oracle_lib, cfg):
     w[K - 1] = False                                   # the surface layer also exchanges through its free surface
     assert np.abs(lhs - net)[w].max() / np.abs(tot["X"]).max() < 1e-11
     ts.close()
+
+
+@pytest.mark.parametrize("noadv,nodif", [(1, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("mh", [1, 4])
+def test_noflux_cells(oracle_lib, noadv, nodif, mh):
+    """NoAdvFlux / NoDifFlux with the NoFluxU/V/W cell lists (AD:4438-4447, 4804-4813, 3003-3012, 2497-2501,
+    2524-2528, 2737-2741): one property with the flags and one without, in the same batch."""
+    case = make_case(52, 37, 9, nprop=2, stepped_bottom=True)
+    o, g, s, props, refs = oracle_for(case)
+    rng = np.random.default_rng(5)
+    nf = [np.asfortranarray((rng.random(s["OpenPoints3D"].shape) < 0.15).astype(np.int32)).reshape(s["OpenPoints3D"].shape)
+          for _ in range(3)]
+    nf = [np.ascontiguousarray(a) for a in nf]
+    prm = [default_params(mh, 4, mh, 4, impexp_advv=0.0, theta_difv=0.5), default_params(mh, 4, mh, 4)]
+    prm[0]["NoAdvFlux"], prm[0]["NoDifFlux"] = noadv, nodif
+    ts = gpu_for(case, g, s)
+    ts.set_noflux(*nf)
+    o.set_noflux(*nf)
+    gpu, cpu = [p.copy() for p in props], [p.copy() for p in props]
+    for _ in range(2):
+        ts.advect_batch(gpu, prm)
+        o.advect_batch(cpu, prm)
+    compare(gpu, cpu, s, 2 * TOL_STEP)
+    # the cell lists did change property 0 and left property 1 alone
+    ts2 = gpu_for(case, g, s)
+    ref = [p.copy() for p in props]
+    prm0 = [dict(prm[0], NoAdvFlux=0, NoDifFlux=0), prm[1]]
+    for _ in range(2):
+        ts2.advect_batch(ref, prm0)
+    assert np.abs(ref[0] - gpu[0]).max() > 0
+    # P2_TVD coefficients are rebuilt for every property; the upwind ones are not (Set_Internal_State, AD:5768-5785),
+    # so there the unflagged second property inherits the zeroed coefficients of the first; DifX / DifY are only
+    # rebuilt when Schmidt_H changes, so their NoDifFlux zeroing is inherited with every method
+    inherits = (mh != 4 and noadv) or nodif
+    assert np.array_equal(ref[1], gpu[1]) != bool(inherits)
+    ts.close(); ts2.close()
+
+
+@pytest.mark.parametrize("case_id", ["nulldif_first", "nulldif_second", "optimize_schmidt_v", "schmidt_h_aba",
+                                     "nodif_first", "noadv_second_upwind", "noadv_quick_vertical"])
+def test_state_carried_between_properties(oracle_lib, case_id):
+    """Coefficient arrays that Set_Internal_State (AD:5746-5835) does not rebuild keep what the previous property of
+    the time step left in them (NullDif / NoDifFlux / NoAdvFlux zeroing, Optimize: first property's DifZ)."""
+    case = make_case(48, 33, 8, nprop=3, stepped_bottom=True)
+    o, g, s, props, refs = oracle_for(case)
+    # faces without flow, so that NullDif has something to zero
+    s = dict(s)
+    rng = np.random.default_rng(11)
+    for name in ("Wflux_X", "Wflux_Y", "Wflux_Z"):
+        a = s[name].copy(); a[rng.random(a.shape) < 0.2] = 0.0; s[name] = a
+    o.set_step(s)
+    nf = [np.ascontiguousarray((rng.random(s["OpenPoints3D"].shape) < 0.15).astype(np.int32)) for _ in range(3)]
+    up = lambda **kw: dict(default_params(1, 4, 1, 4), **kw)
+    tvd = lambda **kw: dict(default_params(4, 4, 4, 4), **kw)
+    prm = {
+        "nulldif_first": [up(NullDif=1), up(), up(SchmidtCoef_V=2.0)],
+        "nulldif_second": [up(), up(NullDif=1), up()],
+        "optimize_schmidt_v": [tvd(), tvd(SchmidtCoef_V=3.0), tvd(SchmidtBackground_V=1e-3)],
+        "schmidt_h_aba": [tvd(Schmidt_H=1.0), tvd(Schmidt_H=2.0), tvd(Schmidt_H=1.0)],
+        "nodif_first": [up(NoDifFlux=1), up(), up(Schmidt_H=0.5)],
+        "noadv_second_upwind": [up(), up(NoAdvFlux=1), up()],
+        "noadv_quick_vertical": [dict(default_params(4, 4, 2, 4, impexp_advv=0.0), NoAdvFlux=1),
+                                 dict(default_params(4, 4, 2, 4, impexp_advv=0.0)),
+                                 dict(default_params(4, 4, 2, 4, impexp_advv=0.0), NoAdvFlux=1)],
+    }[case_id]
+    ts = gpu_for(case, g, s)
+    ts.set_noflux(*nf)
+    o.set_noflux(*nf)
+    gpu, cpu = [p.copy() for p in props], [p.copy() for p in props]
+    for _ in range(2):
+        ts.advect_batch(gpu, prm)
+        o.advect_batch(cpu, prm)
+    compare(gpu, cpu, s, 2 * TOL_STEP)
+    ts.close()
+
+
+def test_noflux_flags_need_the_arrays():
+    from mohid_b200.capi import AdtError
+    case = make_case(20, 20, 5, nprop=1)
+    o, g, s, props, refs = oracle_for(case)
+    ts = gpu_for(case, g, s)
+    prm = [default_params(1, 4, 1, 4)]
+    prm[0]["NoAdvFlux"] = 1
+    with pytest.raises(AdtError) as e:
+        ts.advect_batch([props[0].copy()], prm)
+    assert "NoFlux" in str(e.value)
+    ts.close()

@@ -155,3 +155,34 @@ def test_cell_fluxes_close_the_cell_budget(oracle_lib, optimize):
     w = s["OpenPoints3D"][c] == 1
     w[K - 1] = False
     assert np.abs(lhs - net)[w].max() / np.abs(tot["X"]).max() < 1e-12
+
+
+def test_noflux_cells_block_fluxes_and_carry_over(oracle_lib):
+    """NoAdvFlux / NoDifFlux (AD:4434-4443, 4804-4813, 3004-3013, 2497-2501): with every face listed and closed
+    boundaries a flagged property only feels the volume change; NoFluxV alone changes nothing for the flagged
+    property itself (its zeroing hits the XX arrays after their use) but is inherited by the next upwind property."""
+    case = make_case(30, 26, 6, nprop=2, closed=True, volume_change=False)
+    o, g, s, props, refs = oracle_for(case)
+    ones = np.ones(s["OpenPoints3D"].shape, np.int32)
+    zero = np.zeros_like(ones)
+    up = lambda **kw: dict(default_params(1, 4, 1, 4), **kw)
+    w = water_mask(s)
+    o.set_noflux(ones, ones, ones)
+    a = [props[0].copy()]
+    o.advect_batch(a, [up(NoAdvFlux=1, NoDifFlux=1)])
+    assert np.abs(a[0] - props[0])[w].max() > 1e-3           # YY advection is never switched off (quirk A.4-7)
+    s0 = dict(s); s0["Wflux_Y"] = np.zeros_like(s["Wflux_Y"])
+    o.set_step(s0)
+    a = [props[0].copy()]
+    o.advect_batch(a, [up(NoAdvFlux=1, NoDifFlux=1)])
+    o.set_step(s)
+    want = props[0] * s["VolumeZOld"] / np.where(w, s["VolumeZ"], 1.0)       # VolumeVariation only (AD:3966-4021)
+    assert np.abs(a[0] - want)[w].max() < 1e-12
+    o.set_noflux(zero, ones, zero)
+    b = [props[0].copy()]; c = [props[0].copy()]
+    o.advect_batch(b, [up(NoAdvFlux=1)])
+    o.advect_batch(c, [up()])
+    assert np.array_equal(b[0], c[0])                         # NoFluxV never reaches the YY coefficients
+    d = [props[0].copy(), props[0].copy()]
+    o.advect_batch(d, [up(NoAdvFlux=1), up()])
+    assert np.array_equal(d[0], c[0]) and not np.array_equal(d[1], c[0])   # ... but the next property inherits it
