@@ -55,7 +55,8 @@ def load(build_if_missing: bool = False) -> C.CDLL:
     if not os.path.exists(_build.LIB):
         raise ImportError(f"{_build.LIB} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(the CUDA extension is the only compute path; there is no fallback)")
-    _lib = C.CDLL(_build.LIB)
+    # MOHID_ADT_LIB: load another build of the same library (A/B experiments with compile-time switches)
+    _lib = C.CDLL(os.environ.get("MOHID_ADT_LIB") or _build.LIB)
     return _lib
 
 

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "adt_kernels.cuh"
+#include "adt_ring_kernel.cuh"
 
 using namespace adt;
 
@@ -103,8 +104,9 @@ Handle *get(const int *handle) {
 
 template <typename T>
 int dalloc(Handle *h, T **p, size_t n) {
-    CU(h, cudaMalloc((void **)p, n * sizeof(T)));
-    h->bytes += (long long)(n * sizeof(T));
+    // 64 elements of slack: the staged row windows of adt_transport_ring_kernel run up to 36 elements past a row end
+    CU(h, cudaMalloc((void **)p, (n + 64) * sizeof(T)));
+    h->bytes += (long long)((n + 64) * sizeof(T));
     return 0;
 }
 
@@ -384,7 +386,22 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
     // 12 warps 168.  The two headline variants fit 168 registers once G of the column solve is parked in the
     // output array instead of shared memory (W needs K*32 doubles per warp, W+G twice that).
     const size_t w_bytes = (size_t)h->K * 32 * sizeof(double);
-    if (full && !any_disch && (tvd_sb || upw) && 12 * w_bytes <= (size_t)h->smem_optin) {
+    // Ring variant (adt_ring_kernel.cuh): one block per strip, one consumer warp per property, inputs staged through
+    // cp.async / mbarrier rings.  Bit-identical to the plain kernel and measured at the same speed on C3 (40-42 ms
+    // against 37.7 ms: with 10 properties two SM sub-partitions carry 3 consumer warps and two carry 2, and the block
+    // runs at the pace of the loaded ones), so it stays opt-in (MOHID_ADT_RING=1) until that imbalance is solved.
+    constexpr int RING_NCW = 10, RING_MIN_PROPS = 4;
+    const bool ring_ok = full && !any_disch && (tvd_sb || upw) && s.nprop >= RING_MIN_PROPS && s.nprop <= RING_NCW &&
+                         h->ld % 4 == 0 && ring_smem_bytes(s.nprop, h->K) <= (size_t)h->smem_optin &&
+                         getenv("MOHID_ADT_RING") && atoi(getenv("MOHID_ADT_RING")) != 0;
+    long grid_override = 0;
+    if (ring_ok) {
+        kern = tvd_sb ? adt_transport_ring_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, RING_NCW>
+                      : adt_transport_ring_kernel<MOHID_UpwindOrder1, MOHID_SuperBee, MOHID_UpwindOrder1, MOHID_SuperBee, RING_NCW>;
+        wpb = s.nprop + 1;
+        smem = ring_smem_bytes(s.nprop, h->K);
+        grid_override = std::min<long>((long)s.ntile_i * h->j_count, (long)h->num_sms);
+    } else if (full && !any_disch && (tvd_sb || upw) && 12 * w_bytes <= (size_t)h->smem_optin) {
         kern = tvd_sb ? adt_transport_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, false, true, 12, 1, true>
                       : adt_transport_kernel<MOHID_UpwindOrder1, MOHID_SuperBee, MOHID_UpwindOrder1, MOHID_SuperBee, false, true, 12, 1, true>;
         wpb = 12;
@@ -408,7 +425,7 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
     if (wpb < 1)
         return fail(h, MOHID_ADT_ERR_UNSUPPORTED, "K = %d layers need more shared memory than one SM has", h->K);
     const long nunits = (long)s.nprop * s.ntile_i * h->j_count;
-    const long blocks = (nunits + wpb - 1) / wpb;
+    const long blocks = grid_override ? grid_override : (nunits + wpb - 1) / wpb;
     if (blocks > 2147483647L) return fail(h, MOHID_ADT_ERR_ARG, "grid too large");
     CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -426,6 +443,16 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
     kern<<<(unsigned)blocks, wpb * 32, smem, h->stream>>>(s);
     CU(h, cudaGetLastError());
     if (timed) CU(h, cudaEventRecord(e1, h->stream));
+#ifdef ADT_EXPERIMENT
+    if (getenv("MOHID_ADT_DEBUG")) {
+        unsigned long long c[4];
+        cudaStreamSynchronize(h->stream);
+        cudaMemcpy(c, h->d_zero_piv, sizeof(c), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[ring] producer wait-empty cycles/plane %.0f  consumer0 wait-full cycles/level %.0f (planes %llu)\n",
+                (double)c[1] / (double)std::max(1ull, c[3]), (double)c[2] / (double)std::max(1ull, c[3]), c[3]);
+        cudaMemset(h->d_zero_piv + 1, 0, 3 * sizeof(unsigned long long));
+    }
+#endif
     h->launches++;
 
     // post-solve boundary passes (AD:1874-1882)

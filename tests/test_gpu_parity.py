@@ -395,3 +395,34 @@ def test_noflux_flags_need_the_arrays():
         ts.advect_batch([props[0].copy()], prm)
     assert "NoFlux" in str(e.value)
     ts.close()
+
+
+@pytest.mark.parametrize("shape", [(70, 45, 9, 4), (130, 37, 12, 10), (31, 20, 5, 7), (64, 33, 40, 10)])
+@pytest.mark.parametrize("method", [4, 1])
+@pytest.mark.parametrize("bc", [0, 4, 1])
+def test_ring_kernel_matches_plain_kernel_and_oracle(oracle_lib, shape, method, bc, monkeypatch):
+    """adt_transport_ring_kernel (inputs staged through cp.async / mbarrier rings, one consumer warp per property;
+    opt-in with MOHID_ADT_RING=1) against adt_transport_kernel (bitwise: same arithmetic) and against the oracle."""
+    I, J, K, N = shape
+    case = make_case(I, J, K, nprop=N, stepped_bottom=True)
+    o, g, s, props, refs = oracle_for(case)
+    prm = [default_params(method, 4, method, 4, bc=bc, decay_time=600.0) for _ in range(N)]
+    out = {}
+    for mode in ("ring", "plain"):
+        if mode == "ring":
+            monkeypatch.setenv("MOHID_ADT_RING", "1")
+        else:
+            monkeypatch.delenv("MOHID_ADT_RING", raising=False)
+        ts = gpu_for(case, g, s)
+        a = [p.copy() for p in props]
+        for _ in range(3):
+            ts.advect_batch(a, prm, refs)
+        out[mode] = a
+        assert ts.counters()["zero_pivots"] == 0
+        ts.close()
+    for a, b in zip(out["ring"], out["plain"]):
+        assert np.array_equal(a, b)
+    cpu = [p.copy() for p in props]
+    for _ in range(3):
+        o.advect_batch(cpu, prm, refs)
+    compare(out["ring"], cpu, s, 3 * TOL_STEP)
