@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
@@ -26,6 +27,8 @@ struct Handle {
     int id = 0, dev = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t s_up = nullptr, s_down = nullptr;      // copy streams of the pipelined host path (advect_batch)
+    std::vector<cudaEvent_t> pipe_ev;
     mohid_adt_options opt{};
     int I = 0, J = 0, K = 0, ni = 0, nj = 0, nk = 0, ld_h = 0, ld = 0;
     long n2 = 0, n3 = 0;
@@ -119,18 +122,28 @@ int h2d2(Handle *h, void *dst, const void *src, size_t es) {
 }
 // 3-D arrays: the caller's layout is Fortran (i, j, k); the device mirror is (i, k, j) when kmid, so each k-plane
 // of the caller is one strided 2-D copy (row pitch sj on the device).
-int h2d3(Handle *h, void *dst, const void *src, size_t es) {
+int h2d3(Handle *h, void *dst, const void *src, size_t es, cudaStream_t st = nullptr) {
+    if (!st) st = h->stream;
+    if (h->ld == h->ld_h && h->sj == h->ld && h->sk == h->ld * h->nj) {      // same layout on both sides: one copy
+        CU(h, cudaMemcpyAsync(dst, src, es * h->n3, cudaMemcpyDefault, st));
+        return 0;
+    }
     for (int k = 0; k < h->nk; ++k)
         CU(h, cudaMemcpy2DAsync((char *)dst + es * (size_t)h->sk * k, es * h->sj,
                                 (const char *)src + es * (size_t)h->ld_h * h->nj * k, es * h->ld_h,
-                                es * std::min(h->ld, h->ld_h), h->nj, cudaMemcpyDefault, h->stream));
+                                es * std::min(h->ld, h->ld_h), h->nj, cudaMemcpyDefault, st));
     return 0;
 }
-int d2h3(Handle *h, void *dst, const void *src, size_t es) {
+int d2h3(Handle *h, void *dst, const void *src, size_t es, cudaStream_t st = nullptr) {
+    if (!st) st = h->stream;
+    if (h->ld == h->ld_h && h->sj == h->ld && h->sk == h->ld * h->nj) {
+        CU(h, cudaMemcpyAsync(dst, src, es * h->n3, cudaMemcpyDefault, st));
+        return 0;
+    }
     for (int k = 0; k < h->nk; ++k)
         CU(h, cudaMemcpy2DAsync((char *)dst + es * (size_t)h->ld_h * h->nj * k, es * h->ld_h,
                                 (const char *)src + es * (size_t)h->sk * k, es * h->sj,
-                                es * std::min(h->ld, h->ld_h), h->nj, cudaMemcpyDefault, h->stream));
+                                es * std::min(h->ld, h->ld_h), h->nj, cudaMemcpyDefault, st));
     return 0;
 }
 
@@ -169,6 +182,10 @@ void free_all(Handle *h) {
     for (auto p : h->d_concmf) F(p);
     for (auto &v : h->flux) for (auto p : v) F(p);
     for (auto &e : h->ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    if (h->s_up) cudaStreamDestroy(h->s_up);
+    if (h->s_down) cudaStreamDestroy(h->s_down);
+    for (auto e : h->pipe_ev) cudaEventDestroy(e);
+    h->s_up = h->s_down = nullptr; h->pipe_ev.clear();
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
 }
 
@@ -509,8 +526,11 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
 }
 
 // One transport step of all properties of the batch: per-step coefficient pass + fused kernel,
-// one (K1 diff part + K2) group per distinct set of Schmidt numbers.
-int step_once(Handle *h, const Batch &b) {
+// one (K1 diff part + K2) group per distinct set of effective diffusion flags.  With chunk > 0 a group is launched in
+// pieces of at most `chunk` properties, `before` / `after` being called around each piece (the pipelined host path
+// uses them to wait for the piece's upload and to start its download).
+using ChunkHook = std::function<int(const std::vector<int> &)>;
+int step_once(Handle *h, const Batch &b, int chunk = 0, const ChunkHook &before = nullptr, const ChunkHook &after = nullptr) {
     std::vector<char> done(b.nprop, 0);
     bool geom_done = false;
     for (int n = 0; n < b.nprop; ++n) {
@@ -536,7 +556,13 @@ int step_once(Handle *h, const Batch &b) {
             h->launches++;
         }
         geom_done = true;
-        if (int rc = launch_step(h, b, idx, true)) return rc;
+        const size_t step = chunk > 0 ? (size_t)chunk : idx.size();
+        for (size_t c0 = 0; c0 < idx.size(); c0 += step) {
+            const std::vector<int> part(idx.begin() + c0, idx.begin() + std::min(idx.size(), c0 + step));
+            if (before) if (int rc = before(part)) return rc;
+            if (int rc = launch_step(h, b, part, true)) return rc;
+            if (after) if (int rc = after(part)) return rc;
+        }
     }
     return 0;
 }
@@ -806,6 +832,26 @@ int mohid_adt_unset_discharges(const int *handle) {
     return 0;
 }
 
+// caller -> device copy of one property (and its reference field) on stream `st`
+static int upload_one(Handle *h, int n, const double *prop, const double *r, cudaStream_t st) {
+    if (!prop) return fail(h, MOHID_ADT_ERR_ARG, "prop[%d] is null", n);
+    double *a = h->prop[0][n], *b = h->prop[1][n];
+    if (h->ld != h->ld_h) CU(h, cudaMemsetAsync(a, 0, h->n3 * sizeof(double), st));   // ld padding reads as zero
+    if (int rc = h2d3(h, a, prop, 8, st)) return rc;
+    // both ping-pong buffers start identical: halos, dry columns and closed cells are never rewritten
+    CU(h, cudaMemcpyAsync(b, a, h->n3 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    h->cur[n] = 0;
+    h->has_ref[n] = r != nullptr;
+    if (r) {
+        if (!h->ref[n]) {
+            if (int rc = dalloc(h, &h->ref[n], h->n3)) return rc;
+            CU(h, cudaMemsetAsync(h->ref[n], 0, h->n3 * sizeof(double), st));
+        }
+        if (int rc = h2d3(h, h->ref[n], r, 8, st)) return rc;
+    }
+    return 0;
+}
+
 int mohid_adt_upload_props(const int *handle, const int *nprop, const double *const *prop,
                            const double *const *reference_prop) {
     Handle *h = get(handle);
@@ -813,24 +859,8 @@ int mohid_adt_upload_props(const int *handle, const int *nprop, const double *co
     if (!nprop || !prop) return fail(h, MOHID_ADT_ERR_ARG, "null argument");
     CU(h, cudaSetDevice(h->dev));
     if (int rc = ensure_props(h, *nprop, reference_prop != nullptr)) return rc;
-    for (int n = 0; n < *nprop; ++n) {
-        if (!prop[n]) return fail(h, MOHID_ADT_ERR_ARG, "prop[%d] is null", n);
-        double *a = h->prop[0][n], *b = h->prop[1][n];
-        if (h->ld != h->ld_h) CU(h, cudaMemsetAsync(a, 0, h->n3 * sizeof(double), h->stream));   // ld padding reads as zero
-        if (int rc = h2d3(h, a, prop[n], 8)) return rc;
-        // both ping-pong buffers start identical: halos, dry columns and closed cells are never rewritten
-        CU(h, cudaMemcpyAsync(b, a, h->n3 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-        h->cur[n] = 0;
-        const double *r = reference_prop ? reference_prop[n] : nullptr;
-        h->has_ref[n] = r != nullptr;
-        if (r) {
-            if (!h->ref[n]) {
-                if (int rc = dalloc(h, &h->ref[n], h->n3)) return rc;
-                CU(h, cudaMemsetAsync(h->ref[n], 0, h->n3 * sizeof(double), h->stream));
-            }
-            if (int rc = h2d3(h, h->ref[n], r, 8)) return rc;
-        }
-    }
+    for (int n = 0; n < *nprop; ++n)
+        if (int rc = upload_one(h, n, prop[n], reference_prop ? reference_prop[n] : nullptr, h->stream)) return rc;
     CU(h, cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -870,10 +900,64 @@ int mohid_adt_advect_batch(const int *handle, const int *nprop, double *const *p
     if (!h->have_grid || !h->have_step) return fail(h, MOHID_ADT_ERR_STATE, "set_grid2d / set_step must precede advect");
     Batch b;
     if (int rc = validate(h, *nprop, params, b)) return rc;        // fail before moving any data
-    if (int rc = mohid_adt_upload_props(handle, nprop, prop, reference_prop)) return rc;
-    const int one = 1;
-    if (int rc = mohid_adt_advect_device(handle, nprop, params, &one)) return rc;
-    return mohid_adt_download_props(handle, nprop, prop);
+    for (int n = 0; n < *nprop; ++n) if (!prop[n]) return fail(h, MOHID_ADT_ERR_ARG, "prop[%d] is null", n);
+    CU(h, cudaSetDevice(h->dev));
+    if (int rc = ensure_props(h, *nprop, reference_prop != nullptr)) return rc;
+    // Pipelined host path: the properties go up on one copy stream, are advanced in pieces of PIPE_CHUNK on the
+    // compute stream and come down on a second copy stream, so that on a full-duplex link the download of the first
+    // pieces overlaps the upload of the later ones (pinned host arrays; pageable ones are staged by the driver).
+    int chunk = 1;      // measured on C3 (PCIe gen5): 1 -> 722 ms, 2 -> 750 ms, 5 -> 835 ms, unpipelined 974 ms per call
+    if (const char *e = getenv("MOHID_ADT_PIPE_CHUNK")) chunk = atoi(e);
+    if (chunk <= 0 || *nprop <= chunk) {
+        for (int n = 0; n < *nprop; ++n)
+            if (int rc = upload_one(h, n, prop[n], reference_prop ? reference_prop[n] : nullptr, h->stream)) return rc;
+        if (int rc = step_once(h, b)) return rc;
+        for (int n = 0; n < *nprop; ++n)
+            if (int rc = d2h3(h, prop[n], h->prop[h->cur[n]][n], 8)) return rc;
+        CU(h, cudaStreamSynchronize(h->stream));
+        return 0;
+    }
+    if (!h->s_up) {
+        CU(h, cudaStreamCreateWithFlags(&h->s_up, cudaStreamNonBlocking));
+        CU(h, cudaStreamCreateWithFlags(&h->s_down, cudaStreamNonBlocking));
+    }
+    size_t ev_used = 0;
+    auto next_event = [&](cudaEvent_t *e) -> int {
+        if (ev_used == h->pipe_ev.size()) {
+            cudaEvent_t x;
+            CU(h, cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
+            h->pipe_ev.push_back(x);
+        }
+        *e = h->pipe_ev[ev_used++];
+        return 0;
+    };
+    // everything queued earlier on the compute stream (set_step precompute, ...) precedes the uploads
+    cudaEvent_t e0;
+    if (int rc = next_event(&e0)) return rc;
+    CU(h, cudaEventRecord(e0, h->stream));
+    CU(h, cudaStreamWaitEvent(h->s_up, e0, 0));
+    auto before = [&](const std::vector<int> &part) -> int {
+        for (int n : part)
+            if (int rc = upload_one(h, n, prop[n], reference_prop ? reference_prop[n] : nullptr, h->s_up)) return rc;
+        cudaEvent_t e;
+        if (int rc = next_event(&e)) return rc;
+        CU(h, cudaEventRecord(e, h->s_up));
+        CU(h, cudaStreamWaitEvent(h->stream, e, 0));
+        return 0;
+    };
+    auto after = [&](const std::vector<int> &part) -> int {
+        cudaEvent_t e;
+        if (int rc = next_event(&e)) return rc;
+        CU(h, cudaEventRecord(e, h->stream));
+        CU(h, cudaStreamWaitEvent(h->s_down, e, 0));
+        for (int n : part)
+            if (int rc = d2h3(h, prop[n], h->prop[h->cur[n]][n], 8, h->s_down)) return rc;
+        return 0;
+    };
+    if (int rc = step_once(h, b, chunk, before, after)) return rc;
+    CU(h, cudaStreamSynchronize(h->s_down));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return 0;
 }
 
 int mohid_adt_prop_device_ptr(const int *handle, const int *n, void **dptr, int *ld, int *nj, int *nk) {
