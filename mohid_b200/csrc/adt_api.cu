@@ -18,6 +18,7 @@
 
 #include "adt_kernels.cuh"
 #include "adt_ring_kernel.cuh"
+#include "adt_hsolve_kernel.cuh"
 
 using namespace adt;
 
@@ -42,6 +43,7 @@ struct Handle {
     int *bnd_cols = nullptr;
     int *noflux[3] = {nullptr, nullptr, nullptr};       // NoFluxU/V/W mirrors (allocated by set_noflux)
     bool have_noflux = false;
+    std::vector<double *> wline;                        // W of the line recurrence (horizontally implicit advection)
     unsigned char *nfmask = nullptr;                    // NF_* bits, rebuilt by K1 every step
     int n_bnd_cols = 0;
     // raw per-step inputs
@@ -170,6 +172,7 @@ void free_all(Handle *h) {
     F(h->bnd_cols);
     for (auto p : h->noflux) F(p);
     F(h->nfmask);
+    for (auto p : h->wline) F(p);
     for (auto p : h->raw_d) F(p);
     for (auto p : h->raw_i) F(p);
     F(h->dtv); F(h->vr); F(h->dhu); F(h->dhv); F(h->dvz); F(h->rdz); F(h->mask);
@@ -285,9 +288,16 @@ int validate(Handle *h, int nprop, const mohid_adt_params *p, Batch &b) {
             return fail(h, MOHID_ADT_ERR_ARG, "sub. HorizontalAdvectionYY - ModuleAdvectionDiffusion - ERR01");
         if (q.ImpExp_AdvV != 0.0 && q.ImpExp_AdvV != 1.0)
             return fail(h, MOHID_ADT_ERR_ARG, "sub. VerticalAdvection - ModuleAdvectionDiffusion - ERR01");
-        if (q.ImpExp_AdvXX == 1.0 || q.ImpExp_AdvYY == 1.0)
-            return fail(h, MOHID_ADT_ERR_UNSUPPORTED,
-                        "horizontally implicit advection (AD:4167-4258) is not available on the GPU path");
+        if ((q.ImpExp_AdvXX == 1.0 || q.ImpExp_AdvYY == 1.0) && !h->opt.Vertical1D) {
+            if (h->K == 1)
+                return fail(h, MOHID_ADT_ERR_UNSUPPORTED,
+                            "horizontally implicit advection of a 2-D domain (AD:1758-1841) is not available on the GPU path");
+            if (h->j_begin != 1 || h->j_count != h->J)
+                return fail(h, MOHID_ADT_ERR_UNSUPPORTED,
+                            "horizontally implicit advection couples whole rows: not available on a column slab (AD:4200-4244)");
+            if (q.CellFluxes)
+                return fail(h, MOHID_ADT_ERR_UNSUPPORTED, "CellFluxes with horizontally implicit advection are not available");
+        }
         for (int m : {q.AdvMethodH, q.AdvMethodV})
             if (m < MOHID_UpwindOrder1 || m > MOHID_LeapFrog)
                 return fail(h, MOHID_ADT_ERR_ARG, "This method is not valid to compute Advection1D");
@@ -348,8 +358,11 @@ int launch_coef(Handle *h, const mohid_adt_params &q, const PropEff &e, bool geo
     return 0;
 }
 
-int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool timed) {
+// hdir: 0 = the whole step; 1 / 2 = horizontally implicit along j / i: adt_hsolve_kernel (stage 1) and then the
+// vertical half of the step from the intermediate field (stage 2)
+int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool timed, int hdir = 0, bool stage2 = false) {
     StepArgs s{};
+    s.stage2 = stage2 ? 1 : 0;
     s.I = h->I; s.J = h->J; s.K = h->K; s.ld = h->ld; s.nj = h->nj; s.sj = h->sj; s.sk = h->sk;
     s.nprop = (int)idx.size();
     s.ntile_i = (h->I + 30) / 31;
@@ -384,6 +397,26 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
         pa.dconc = hd ? h->d_conc[n] : nullptr;
         pa.dconcmf = hd ? h->d_concmf[n] : nullptr;
     }
+    if (hdir) {
+        // ---- stage 1: implicit horizontal direction (adt_hsolve_kernel.cuh), then the vertical half ----
+        HSolveArgs hs{};
+        if ((int)h->wline.size() < (int)h->prop[0].size()) h->wline.resize(h->prop[0].size(), nullptr);
+        for (int m = 0; m < s.nprop; ++m) {
+            const int n = idx[m];
+            if (!h->wline[n]) if (int rc = dalloc(h, &h->wline[n], h->n3)) return rc;
+            hs.wline[m] = h->wline[n];
+        }
+        const int nc = hdir == 1 ? h->I : h->J;
+        const long nunits = (long)s.nprop * ((nc + 30) / 31) * h->K;
+        const long blocks = (nunits + 7) / 8;
+        if (blocks > 2147483647L) return fail(h, MOHID_ADT_ERR_ARG, "grid too large");
+        if (hdir == 1) adt_hsolve_kernel<0><<<(unsigned)blocks, 256, 0, h->stream>>>(s, hs);
+        else adt_hsolve_kernel<1><<<(unsigned)blocks, 256, 0, h->stream>>>(s, hs);
+        CU(h, cudaGetLastError());
+        h->launches++;
+        for (int n : idx) h->cur[n] ^= 1;
+        return launch_step(h, b, idx, timed, 0, true);
+    }
     // ---- kernel variant and launch shape ----
     bool any_disch = false, all_impv = true;
     for (int m = 0; m < s.nprop; ++m) {
@@ -392,7 +425,7 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
         any_disch = any_disch || s.p[m].nfsel != 0;     // NoAdvFlux rides on the DISCH variants
     }
     // FULL: 3-D, both horizontal directions, implicit vertical advection for every property of the launch
-    const bool full = !s.vertical1d && !s.xzflow && s.K > 1 && all_impv;
+    const bool full = !s.vertical1d && !s.xzflow && s.K > 1 && all_impv && !stage2;
     const bool tvd_sb = s.method_h == MOHID_P2_TVD && s.method_v == MOHID_P2_TVD && s.limiter_h == MOHID_SuperBee &&
                         s.limiter_v == MOHID_SuperBee;
     const bool upw = s.method_h == MOHID_UpwindOrder1 && s.method_v == MOHID_UpwindOrder1;
@@ -560,7 +593,16 @@ int step_once(Handle *h, const Batch &b, int chunk = 0, const ChunkHook &before 
         for (size_t c0 = 0; c0 < idx.size(); c0 += step) {
             const std::vector<int> part(idx.begin() + c0, idx.begin() + std::min(idx.size(), c0 + step));
             if (before) if (int rc = before(part)) return rc;
-            if (int rc = launch_step(h, b, part, true)) return rc;
+            // horizontally implicit properties take the split path, per direction (WP:14676-14700 alternates it)
+            for (int hdir = 0; hdir <= 2; ++hdir) {
+                std::vector<int> sub;
+                for (int m : part) {
+                    const mohid_adt_params &q = b.p[m];
+                    const int d = h->opt.Vertical1D ? 0 : (q.ImpExp_AdvXX == 1.0 ? 1 : q.ImpExp_AdvYY == 1.0 ? 2 : 0);
+                    if (d == hdir) sub.push_back(m);
+                }
+                if (!sub.empty()) if (int rc = launch_step(h, b, sub, true, hdir)) return rc;
+            }
             if (after) if (int rc = after(part)) return rc;
         }
     }

@@ -304,6 +304,7 @@ struct StepArgs {
     int j_begin, j_count;                       // columns j_begin .. j_begin+j_count-1 are advanced
     int method_h, limiter_h, method_v, limiter_v, upwind2_h, upwind2_v;
     int vertical1d, xzflow;
+    int stage2, pad1;                           // see adt_transport_kernel
     double vrelmax, dt;
     const double *qx, *qy, *qz, *dtv, *vr, *dhu, *dhv, *dvz, *rdz;
     const uint32_t *mask;
@@ -561,7 +562,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
     const bool central_v = (method_v == MOHID_CentralDif || method_v == MOHID_LeapFrog);
     const bool far_h = (method_h == MOHID_UpwindOrder2 || method_h == MOHID_UpwindOrder3);
     const bool far_v = (method_v == MOHID_UpwindOrder2 || method_v == MOHID_UpwindOrder3);
-    const bool do_h = FULL || !s.vertical1d, do_y = FULL || (do_h && !s.xzflow);
+    // stage2: second half of a horizontally implicit step (adt_hsolve_kernel.cuh): the row restarts from the
+    // intermediate field (TI = PROP, E = 1, AD:4250-4253) and only the vertical terms and the boundary rows remain
+    const bool stage2 = !FULL && s.stage2 != 0;
+    const bool do_h = FULL || (!s.vertical1d && !stage2), do_y = FULL || (do_h && !s.xzflow);
+    const bool do_vadv = FULL || !s.vertical1d;
 
     // ---- 2-D metrics of the column ----
     const double rdx_m = s.rdx[c2 - sj2], rdx_c = s.rdx[c2], rdx_p = s.rdx[c2 + sj2], rdx_pp = s.rdx[c2 + je2_2];
@@ -586,7 +591,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
     const bool obc = (mtop & M_BND) != 0 && pa.bc != MOHID_BC_None;
     // vertical advection acts on a top face iff both cells are open, the face is a compute face, the column's
     // surface cell is open and the run is not Vertical1D (AD:2966, 3041; MF:10559); bit 31 is never set in a mask
-    const unsigned top_req = (do_h && colopen) ? (M_OPEN | M_O_KP1 | M_CFWT) : (1u << 31);
+    const unsigned top_req = (do_vadv && colopen) ? (M_OPEN | M_O_KP1 | M_CFWT) : (1u << 31);
     // NoAdvFlux: a selected NF_* bit switches the advective part of that face off
     const unsigned nfsel = DISCH ? pa.nfsel : 0u;
     const double theta = pa.theta_difv, omt = 1. - pa.theta_difv;
@@ -669,10 +674,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
         const bool open_c = (m & M_OPEN) != 0;
         // ---------------- VolumeVariation (AD:3966-4021) ----------------
         Row row;
-        double ti0 = sel(open_c, Pc * cur.vr, Pc);
-        double e0 = sel(open_c && k == s.K, 1.0 + dtv_c * qz_p, 1.0);
+        double ti0 = sel(open_c && !stage2, Pc * cur.vr, Pc);
+        double e0 = sel(open_c && k == s.K && !stage2, 1.0 + dtv_c * qz_p, 1.0);
         // ---------------- Discharges (AD:4025-4128); rare ----------------
-        if (DISCH && (m & M_DISCH) && pa.dconc)
+        if (DISCH && (m & M_DISCH) && pa.dconc && !stage2)
             apply_discharges(s.disch, pa.dconc, pa.dconcmf, ic, j, k, open_c, Pc, cur.vr, dtv_c, ti0, e0);
         row.TI = ti0 + TIk_b;
         row.E = e0 + Ek_b;

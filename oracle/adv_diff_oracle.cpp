@@ -720,9 +720,25 @@ int HorizontalAdvectionXX(Oracle &o) {
                         }
                     }
         }
+    } else if (o.P.ImpExp_AdvXX == ImplicitScheme) {
+        // AD:4483-4509: only D_flux / E_flux enter the tridiagonal system ("C and G not computed")
+#pragma omp parallel for schedule(dynamic, CH) num_threads(o.nthreads)
+        for (int k = W.KLB; k <= W.KUB; ++k)
+            for (int j = W.JLB; j <= W.JUB; ++j)
+                for (int i = W.ILB; i <= W.IUB; ++i) {
+                    long q = o.i3(i, j, k);
+                    if (o.ComputeFacesU3D[q] == 1) {
+                        long qm = o.i3(i, j - 1, k);
+                        double DT2 = DT / o.VolumeZ[q], DT1 = DT / o.VolumeZ[qm];
+                        o.D[q]  = o.D[q]  - o.XD[q] * DT2;
+                        o.E[q]  = o.E[q]  - o.XE[q] * DT2;
+                        o.E[qm] = o.E[qm] + o.XD[q] * DT1;
+                        o.F[qm] = o.F[qm] + o.XE[q] * DT1;
+                    }
+                }
     } else {
-        o.err = "horizontally implicit advection (AD:4497-4506, 4167-4258) is not restated in the oracle";
-        return ORACLE_ERR_UNSUPPORTED;
+        o.err = "sub. HorizontalAdvectionXX - ModuleAdvectionDiffusion - ERR01";
+        return ORACLE_ERR_ARG;
     }
     return 0;
 }
@@ -801,10 +817,72 @@ int HorizontalAdvectionYY(Oracle &o) {
                     }
             }
         }
+    } else if (o.P.ImpExp_AdvYY == ImplicitScheme) {
+        // AD:4862-4893
+        const int CH = chunk_of(W.JLB, W.JUB);
+#pragma omp parallel num_threads(o.nthreads)
+        for (int k = W.KLB; k <= W.KUB; ++k) {
+#pragma omp for schedule(dynamic, CH) nowait
+            for (int j = W.JLB; j <= W.JUB; ++j)
+                for (int i = W.ILB; i <= W.IUB; ++i) {
+                    long q = o.i3(i, j, k);
+                    if (o.ComputeFacesV3D[q] == 1) {
+                        long qm = o.i3(i - 1, j, k);
+                        double DT2 = DT / o.VolumeZ[q], DT1 = DT / o.VolumeZ[qm];
+                        o.D[q]  = o.D[q]  - o.YD[q] * DT2;
+                        o.E[q]  = o.E[q]  - o.YE[q] * DT2;
+                        o.E[qm] = o.E[qm] + o.YD[q] * DT1;
+                        o.F[qm] = o.F[qm] + o.YE[q] * DT1;
+                    }
+                }
+        }
     } else {
-        o.err = "horizontally implicit advection (AD:4873-4893, 4167-4258) is not restated in the oracle";
-        return ORACLE_ERR_UNSUPPORTED;
+        o.err = "sub. HorizontalAdvectionYY - ModuleAdvectionDiffusion - ERR01";
+        return ORACLE_ERR_ARG;
     }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// THOMAS_3D_i0_j1_NewType / _i1_j0_NewType (MF:3751-3875): the recurrence along j (dj = 1) or i (di = 1) for every
+// work level; the line runs to the halo cell UB+1, whose row is the identity with TI = 0.
+// ---------------------------------------------------------------------------------------
+int THOMAS_3D(Oracle &o, int di, int dj) {
+    const auto &Wk = o.W;
+    const int CH = chunk_of(Wk.KLB, Wk.KUB);
+    const int IJmin = dj ? Wk.ILB : Wk.JLB, IJmax = dj ? Wk.IUB : Wk.JUB;      // lines
+    const int JImin = dj ? Wk.JLB : Wk.ILB, JImax = dj ? Wk.JUB : Wk.IUB;      // along a line
+    int bad = 0;
+    (void)di;
+#pragma omp parallel num_threads(o.nthreads)
+    {
+        std::vector<double> Wv(JImax + 3), Gv(JImax + 3);
+#pragma omp for schedule(dynamic, CH) nowait
+        for (int K = Wk.KLB; K <= Wk.KUB; ++K)
+            for (int IJ = IJmin; IJ <= IJmax; ++IJ) {
+                auto at = [&](int JI) { return dj ? o.i3(IJ, JI, K) : o.i3(JI, IJ, K); };
+                Wv[JImin] = -o.F[at(JImin)] / o.E[at(JImin)];
+                Gv[JImin] = o.TI[at(JImin)] / o.E[at(JImin)];
+                for (int JI = JImin + 1; JI <= JImax + 1; ++JI) {
+                    const long q = at(JI);
+                    double AUX = o.E[q] + o.D[q] * Wv[JI - 1];
+                    if (std::fabs(AUX) > 0) {
+                        Wv[JI] = -o.F[q] / AUX;
+                        Gv[JI] = (o.TI[q] - o.D[q] * Gv[JI - 1]) / AUX;
+                    } else {
+#pragma omp atomic write
+                        bad = 1;                                       // 'Instability in THOMAS3D' (MF:3799)
+                        Wv[JI] = 0.; Gv[JI] = 0.;
+                    }
+                }
+                o.PROP[at(JImax + 1)] = Gv[JImax + 1];
+                for (int II = JImin + 1; II <= JImax + 1; ++II) {
+                    const int MM = JImax + JImin + 1 - II;
+                    o.PROP[at(MM)] = Wv[MM] * o.PROP[at(MM + 1)] + Gv[MM];
+                }
+            }
+    }
+    if (bad) { o.err = "Error: Instability in THOMAS3D - ModuleFunctions - ERR10"; return ORACLE_ERR_ARG; }
     return 0;
 }
 
@@ -1382,6 +1460,16 @@ int AdvectionDiffusionIteration(Oracle &o) {
         if (!o.opt.XZFlow) {
             if ((rc = HorizontalAdvectionYY(o))) return rc;
             if (o.st_CellFluxes && o.P.ImpExp_AdvYY == ExplicitScheme) CalcHorizontalAdvFluxYY(o, 1. - o.P.ImpExp_AdvYY);   // AD:4902-4908
+        }
+        // direction splitting (AD:4193-4258): solve the implicit horizontal direction, then restart the system from
+        // the intermediate field for the vertical terms
+        if ((o.P.ImpExp_AdvXX == ImplicitScheme || o.P.ImpExp_AdvYY == ImplicitScheme) && o.W.KUB > 1) {
+            if (o.P.ImpExp_AdvXX == ImplicitScheme) { if ((rc = THOMAS_3D(o, 0, 1))) return rc; }
+            else if ((rc = THOMAS_3D(o, 1, 0))) return rc;
+            SetMatrixValue(o, o.D, 0.0);
+            SetMatrixValue(o, o.E, 1.0);
+            SetMatrixValue(o, o.F, 0.0);
+            for (long q = 0; q < o.n3; ++q) o.TI[q] = o.PROP[q];          // SetMatrixValue(TICOEF3, Size, PROP), AD:4253
         }
     }
 

@@ -426,3 +426,37 @@ def test_ring_kernel_matches_plain_kernel_and_oracle(oracle_lib, shape, method, 
     for _ in range(3):
         o.advect_batch(cpu, prm, refs)
     compare(out["ring"], cpu, s, 3 * TOL_STEP)
+
+
+@pytest.mark.parametrize("method", [(1, 4), (4, 4), (4, 2), (5, 4)])
+@pytest.mark.parametrize("bc", [0, 4, 1])
+def test_horizontally_implicit_advection(oracle_lib, method, bc):
+    """ImpExp_AdvXX / ImpExp_AdvYY = 1 (AD:4132-4265): implicit D/E fluxes of one horizontal direction, THOMAS_3D along
+    it, then the vertical half of the step from the intermediate field.  One batch mixes an XX-implicit, a
+    YY-implicit and an explicit property, as the alternating ImplicitH_Direction of WP:14676-14700 does."""
+    mh, lim = method
+    case = make_case(45, 38, 7, nprop=3, stepped_bottom=True)
+    o, g, s, props, refs = oracle_for(case)
+    mv = 1 if mh == 5 else mh
+    base = default_params(mh, lim, mv, lim, bc=bc, decay_time=600.0)
+    prm = [dict(base, ImpExp_AdvXX=1.0), dict(base, ImpExp_AdvYY=1.0), dict(base)]
+    ts = gpu_for(case, g, s)
+    gpu, cpu = [p.copy() for p in props], [p.copy() for p in props]
+    for step in range(3):
+        ts.advect_batch(gpu, prm, refs)
+        o.advect_batch(cpu, prm, refs)
+        prm[0], prm[1] = dict(prm[1]), dict(prm[0])          # the direction alternates from step to step
+    compare(gpu, cpu, s, 3 * TOL_STEP)
+    assert ts.counters()["zero_pivots"] == 0
+    ts.close()
+
+
+def test_horizontally_implicit_limits():
+    from mohid_b200.capi import AdtError
+    case = make_case(20, 20, 1, nprop=1)
+    o, g, s, props, refs = oracle_for(case)
+    ts = gpu_for(case, g, s)
+    with pytest.raises(AdtError) as e:
+        ts.advect_batch([props[0].copy()], [dict(default_params(1, 4, 1, 4), ImpExp_AdvXX=1.0)])
+    assert e.value.code == 21
+    ts.close()
