@@ -37,6 +37,7 @@ WORKLOADS = {
     "small": (256, 256, 20, 4, 4, 4),
     "c3q": (1024, 1024, 40, 10, 4, 4),      # quarter of C3 (size-sensitivity checks)
     "c3s": (512, 512, 40, 10, 4, 4),
+    "c3n8": (2048, 2048, 40, 8, 4, 4),      # 8 properties (ring-variant balance probe)
     "strip": (62, 16384, 40, 10, 4, 4),     # narrow in i: a k-plane is only 1 MB (TLB / page-locality probe)
 }
 

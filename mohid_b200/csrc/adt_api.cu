@@ -438,8 +438,7 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
     const size_t w_bytes = (size_t)h->K * 32 * sizeof(double);
     // Ring variant (adt_ring_kernel.cuh): one block per strip, one consumer warp per property, inputs staged through
     // cp.async / mbarrier rings.  Bit-identical to the plain kernel and measured at the same speed on C3 (40-42 ms
-    // against 37.7 ms: with 10 properties two SM sub-partitions carry 3 consumer warps and two carry 2, and the block
-    // runs at the pace of the loaded ones), so it stays opt-in (MOHID_ADT_RING=1) until that imbalance is solved.
+    // against 37.7 ms), so it stays opt-in (MOHID_ADT_RING=1).
     constexpr int RING_NCW = 10, RING_MIN_PROPS = 4;
     const bool ring_ok = full && !any_disch && (tvd_sb || upw) && s.nprop >= RING_MIN_PROPS && s.nprop <= RING_NCW &&
                          h->ld % 4 == 0 && ring_smem_bytes(s.nprop, h->K) <= (size_t)h->smem_optin &&
