@@ -81,6 +81,18 @@ module ModuleAdvectionDiffusionB200
             integer(c_int)     :: handle
             type(c_ptr), value :: NoFluxU, NoFluxV, NoFluxW   ! c_loc(NoFlux?(0,0,0)) or c_null_ptr (all three)
         end function
+        integer(c_int) function mohid_adt_set_premix(handle, Density, WaterColumnZ, SmallDepthsLimit) &
+                bind(c, name="mohid_adt_set_premix")
+            import :: c_int, c_ptr, c_double
+            integer(c_int)     :: handle
+            type(c_ptr), value :: Density, WaterColumnZ          ! c_loc(...(0,0,0)) / c_loc(...(0,0)) or c_null_ptr
+            real(c_double)     :: SmallDepthsLimit
+        end function
+        integer(c_int) function mohid_adt_set_offsets(handle, nprop, OffSet) bind(c, name="mohid_adt_set_offsets")
+            import :: c_int, c_double
+            integer(c_int)               :: handle, nprop
+            real(c_double), dimension(*) :: OffSet
+        end function
         integer(c_int) function mohid_adt_advect_batch(handle, nprop, prop, reference_prop, params) &
                 bind(c, name="mohid_adt_advect_batch")
             import :: c_int, c_ptr, T_AdtParams

@@ -129,6 +129,21 @@ int mohid_adt_set_step(const int *handle,
  * set those flags.  All three NULL = not present. */
 int mohid_adt_set_noflux(const int *handle, const int *NoFluxU, const int *NoFluxV, const int *NoFluxW);
 
+/* Caller-side steps of ModuleWaterProperties::Advection_Diffusion_Processes that run on each property right before
+ * its AdvectionDiffusion call, done on the device-resident fields inside advect_batch /
+ * advect_device:
+ *   Density       /= NULL: FreeConvection (WP:13017-13074) with Me%Density%Field (fp64 3-D);
+ *   WaterColumnZ  /= NULL: SmallDepthsMixing_Processes (WP:12939-13012) with the water column (fp64 2-D) and
+ *                          Me%SmallDepths%Limit; the library then builds Me%SmallDepths%ON itself and uses it as the
+ *                          SmallDepths dummy of AdvectionDiffusion (mohid_adt_get_small_depths returns it, int32 2-D).
+ * Both NULL switches the steps off.  The arrays are copied during the call. */
+int mohid_adt_set_premix(const int *handle, const double *Density, const double *WaterColumnZ,
+                         const double *SmallDepthsLimit);
+int mohid_adt_get_small_depths(const int *handle, int *SmallDepthsOn);
+/* Property%AddOffSet / Property%OffSet (WP:14724-14746, 14833-14858): the water points of property n, of its
+ * reference field and its DischConc are shifted by OffSet[n] before the step and shifted back after it. */
+int mohid_adt_set_offsets(const int *handle, const int *nprop, const double *OffSet);
+
 /* SetDischarges / UnSetDischarges (AD:978-1095), same arguments as the reference plus the position
  * `prop_index` (0-based) of the property in the next advect batch: the caller invokes SetDischarges
  * once per property with that property's DischConc / DischConcMF (WP:14761-14773); the discharge

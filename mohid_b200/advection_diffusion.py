@@ -105,6 +105,24 @@ class TransportStep:
         self._check(self.lib.mohid_adt_set_noflux(C.byref(self.h), _ptr(NoFluxU, "i4", self.n3, "NoFluxU"),
                                                   _ptr(NoFluxV, "i4", self.n3, "NoFluxV"), _ptr(NoFluxW, "i4", self.n3, "NoFluxW")))
 
+    def set_premix(self, Density=None, WaterColumnZ=None, SmallDepthsLimit: float = 0.0):
+        """FreeConvection / SmallDepthsMixing_Processes before each transport call (WP:13017-13074, 12939-13012)."""
+        self._check(self.lib.mohid_adt_set_premix(C.byref(self.h), _ptr(Density, "f8", self.n3, "Density"),
+                                                  _ptr(WaterColumnZ, "f8", self.n2, "WaterColumnZ"),
+                                                  C.byref(C.c_double(SmallDepthsLimit))))
+
+    def set_offsets(self, offsets):
+        """Property%OffSet per property of the batch (WP:14724-14746); [] clears them."""
+        arr = (C.c_double * max(1, len(offsets)))(*[float(x) for x in offsets])
+        self._check(self.lib.mohid_adt_set_offsets(C.byref(self.h), C.byref(C.c_int(len(offsets))), arr))
+
+    def get_small_depths(self):
+        """Me%SmallDepths%ON as built by the library (int32, (J+2, ld))."""
+        import numpy as np
+        out = np.zeros((self.J + 2, self.ld), np.int32)
+        self._check(self.lib.mohid_adt_get_small_depths(C.byref(self.h), out.ctypes.data_as(C.POINTER(C.c_int))))
+        return out
+
     def set_discharges(self, prop_index: int, d: Dict[str, object]):
         """SetDischarges (AD:978-1034) for the property at position ``prop_index`` of the next batch.
         ``d`` holds the reference's argument names: DischFlow, DischConc, DischI, DischJ, DischK, DischKmin,

@@ -43,6 +43,10 @@ struct Handle {
     int *bnd_cols = nullptr;
     int *noflux[3] = {nullptr, nullptr, nullptr};       // NoFluxU/V/W mirrors (allocated by set_noflux)
     bool have_noflux = false;
+    double *density = nullptr, *wcol = nullptr;         // caller-side pre-steps (mohid_adt_set_premix)
+    bool premix_fc = false, premix_sd = false;
+    double sd_limit = 0.;
+    std::vector<double> offsets;                        // AddOffSet per property (mohid_adt_set_offsets)
     std::vector<double *> wline;                        // W of the line recurrence (horizontally implicit advection)
     unsigned char *nfmask = nullptr;                    // NF_* bits, rebuilt by K1 every step
     int n_bnd_cols = 0;
@@ -173,6 +177,7 @@ void free_all(Handle *h) {
     for (auto p : h->noflux) F(p);
     F(h->nfmask);
     for (auto p : h->wline) F(p);
+    F(h->density); F(h->wcol);
     for (auto p : h->raw_d) F(p);
     for (auto p : h->raw_i) F(p);
     F(h->dtv); F(h->vr); F(h->dhu); F(h->dhv); F(h->dvz); F(h->rdz); F(h->mask);
@@ -358,9 +363,41 @@ int launch_coef(Handle *h, const mohid_adt_params &q, const PropEff &e, bool geo
     return 0;
 }
 
+// Caller-side column steps (K7) for the properties `idx`: sign = +1 before the transport call (mixing + OffSet),
+// -1 after it (OffSet taken out again).
+int launch_premix(Handle *h, const std::vector<int> &idx, int sign) {
+    bool any_off = false;
+    for (int n : idx) any_off = any_off || (n < (int)h->offsets.size() && h->offsets[n] != 0.);
+    if (sign > 0 ? !(h->premix_fc || h->premix_sd || any_off) : !any_off) return 0;
+    PremixArgs a{};
+    a.I = h->I; a.J = h->J; a.K = h->K; a.ld = h->ld; a.sj = h->sj; a.sk = h->sk; a.nprop = (int)idx.size();
+    a.Open = h->raw_i[0]; a.Water = h->raw_i[2]; a.KFloorZ = h->KFloorZ; a.VolumeZ = h->raw_d[4];
+    a.Density = (sign > 0 && h->premix_fc) ? h->density : nullptr;
+    a.WaterColumnZ = (sign > 0 && h->premix_sd) ? h->wcol : nullptr;
+    a.limit = h->sd_limit;
+    for (int m = 0; m < a.nprop; ++m) {
+        const int n = idx[m];
+        a.pa[m] = h->prop[h->cur[n]][n]; a.pb[m] = h->prop[h->cur[n] ^ 1][n];
+        a.pref[m] = h->has_ref[n] ? h->ref[n] : nullptr;
+        a.off[m] = (n < (int)h->offsets.size()) ? sign * h->offsets[n] : 0.;
+        // Property%DischConc(:) is shifted with the field (WP:14725-14727, 14834-14836)
+        if (a.off[m] != 0. && h->d_ncell > 0 && n < (int)h->d_conc.size() && h->d_conc[n]) {
+            adt_shift_kernel<<<(h->d_ncell + 127) / 128, 128, 0, h->stream>>>(h->d_conc[n], h->d_ncell, a.off[m]);
+            h->launches++;
+        }
+    }
+    const dim3 grid((unsigned)((h->I + 127) / 128), (unsigned)h->J, (unsigned)a.nprop);
+    if (sign > 0) adt_premix_kernel<<<grid, 128, 0, h->stream>>>(a);
+    else adt_offset_kernel<<<grid, 128, 0, h->stream>>>(a);
+    CU(h, cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
 // hdir: 0 = the whole step; 1 / 2 = horizontally implicit along j / i: adt_hsolve_kernel (stage 1) and then the
 // vertical half of the step from the intermediate field (stage 2)
 int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool timed, int hdir = 0, bool stage2 = false) {
+    if (!stage2) if (int rc = launch_premix(h, idx, +1)) return rc;
     StepArgs s{};
     s.stage2 = stage2 ? 1 : 0;
     s.I = h->I; s.J = h->J; s.K = h->K; s.ld = h->ld; s.nj = h->nj; s.sj = h->sj; s.sk = h->sk;
@@ -554,7 +591,7 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
         h->launches++;
     }
     for (int n : idx) h->cur[n] ^= 1;
-    return 0;
+    return launch_premix(h, idx, -1);
 }
 
 // One transport step of all properties of the batch: per-step coefficient pass + fused kernel,
@@ -565,6 +602,15 @@ using ChunkHook = std::function<int(const std::vector<int> &)>;
 int step_once(Handle *h, const Batch &b, int chunk = 0, const ChunkHook &before = nullptr, const ChunkHook &after = nullptr) {
     std::vector<char> done(b.nprop, 0);
     bool geom_done = false;
+    if (h->premix_sd) {                                   // Me%SmallDepths%ON (WP:12975-12980), consumed by K1
+        PremixArgs a{};
+        a.I = h->I; a.J = h->J; a.K = h->K; a.ld = h->ld; a.sj = h->sj; a.sk = h->sk;
+        a.Open = h->raw_i[0]; a.WaterColumnZ = h->wcol; a.limit = h->sd_limit; a.SmallDepths = h->SmallDepths;
+        adt_small_depths_kernel<<<dim3((unsigned)((h->ld + 127) / 128), (unsigned)h->nj), 128, 0, h->stream>>>(a);
+        CU(h, cudaGetLastError());
+        h->launches++;
+        h->have_small = true;
+    }
     for (int n = 0; n < b.nprop; ++n) {
         if (done[n]) continue;
         std::vector<int> idx;
@@ -1081,6 +1127,46 @@ int mohid_adt_set_noflux(const int *handle, const int *NoFluxU, const int *NoFlu
     if (!h->nfmask) if (int rc = dalloc(h, &h->nfmask, h->n3)) return rc;
     CU(h, cudaStreamSynchronize(h->stream));
     h->have_noflux = true;
+    return 0;
+}
+
+int mohid_adt_set_premix(const int *handle, const double *Density, const double *WaterColumnZ, const double *SmallDepthsLimit) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    CU(h, cudaSetDevice(h->dev));
+    if (WaterColumnZ && !SmallDepthsLimit) return fail(h, MOHID_ADT_ERR_ARG, "WaterColumnZ needs SmallDepthsLimit");
+    if (h->premix_sd && !WaterColumnZ) h->have_small = false;       // the flag array was ours
+    h->premix_fc = Density != nullptr;
+    h->premix_sd = WaterColumnZ != nullptr;
+    if (Density) {
+        if (!h->density) if (int rc = dalloc(h, &h->density, h->n3)) return rc;
+        if (int rc = h2d3(h, h->density, Density, 8)) return rc;
+    }
+    if (WaterColumnZ) {
+        if (!h->wcol) if (int rc = dalloc(h, &h->wcol, h->n2)) return rc;
+        if (int rc = h2d2(h, h->wcol, WaterColumnZ, 8)) return rc;
+        h->sd_limit = *SmallDepthsLimit;
+    }
+    CU(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int mohid_adt_set_offsets(const int *handle, const int *nprop, const double *OffSet) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    if (!nprop || *nprop < 0 || *nprop > NPMAX || (*nprop > 0 && !OffSet)) return fail(h, MOHID_ADT_ERR_ARG, "bad offsets");
+    h->offsets.assign(OffSet, OffSet + *nprop);
+    return 0;
+}
+
+int mohid_adt_get_small_depths(const int *handle, int *SmallDepthsOn) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    if (!SmallDepthsOn) return fail(h, MOHID_ADT_ERR_ARG, "null argument");
+    CU(h, cudaSetDevice(h->dev));
+    CU(h, cudaMemcpy2DAsync(SmallDepthsOn, 4 * (size_t)h->ld_h, h->SmallDepths, 4 * (size_t)h->ld,
+                            4 * (size_t)std::min(h->ld, h->ld_h), h->nj, cudaMemcpyDefault, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
     return 0;
 }
 

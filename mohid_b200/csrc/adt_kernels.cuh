@@ -844,6 +844,105 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
 }
 
 // -------------------------------------------------------------------------------------
+// K7: the caller-side column steps of ModuleWaterProperties::Advection_Diffusion_Processes that run on a property
+// right before its transport call (WP:14716-14759), on the device-resident fields:
+//   FreeConvection (WP:13017-13074): from the first level whose upper neighbour is denser, the column is replaced by
+//     its volume-weighted mean up to the surface;
+//   SmallDepthsMixing_Processes (WP:12939-13012): columns thinner than the limit are mixed from KFloorZ to the surface
+//     (Me%SmallDepths%ON itself is produced by adt_small_depths_kernel before the coefficient pass);
+//   AddOffSet (WP:14724-14746): water points of the property and of its reference field are shifted by OffSet.
+// One thread per (i, j, property), k serial in the reference's summation order; both ping-pong buffers are written so
+// that cells the transport kernel never rewrites stay identical in the two.
+// -------------------------------------------------------------------------------------
+struct PremixArgs {
+    int I, J, K, ld, sj, sk, nprop;
+    const int *Open, *Water, *KFloorZ;
+    const double *VolumeZ, *Density, *WaterColumnZ;      // Density / WaterColumnZ: nullptr = step not requested
+    double limit;
+    int *SmallDepths;                                     // adt_small_depths_kernel only
+    double *pa[NPMAX], *pb[NPMAX], *pref[NPMAX];
+    double off[NPMAX];
+};
+
+__global__ void adt_small_depths_kernel(const PremixArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= a.ld) return;
+    const bool work = i >= 1 && i <= a.I && j >= 1 && j <= a.J;
+    const int q2 = i + a.ld * j;
+    a.SmallDepths[q2] = (work && a.Open[i + a.sj * j + a.sk * a.K] == 1 && a.WaterColumnZ[q2] < a.limit) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(128) adt_premix_kernel(const PremixArgs a) {
+    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y, n = blockIdx.z;
+    if (i > a.I) return;
+    double *__restrict__ A = a.pa[n], *__restrict__ B = a.pb[n];
+    const int c = i + a.sj * j, sk = a.sk;
+    if (a.Density) {
+        int ki = 0;
+        for (int k = 1; k <= a.K; ++k) {
+            const int q = c + sk * k;
+            if (a.Open[q] == 1 && a.Open[q + sk] == 1 && (a.Density[q + sk] - a.Density[q]) > 0.) { ki = k; break; }
+        }
+        if (ki) {
+            double Msum = 0., Vsum = 0.;
+            for (int k = ki; k <= a.K; ++k) {
+                const int q = c + sk * k;
+                Msum = Msum + a.VolumeZ[q] * A[q];
+                Vsum = Vsum + a.VolumeZ[q];
+            }
+            const double Cnew = Msum / Vsum;
+            for (int k = ki; k <= a.K; ++k) { A[c + sk * k] = Cnew; B[c + sk * k] = Cnew; }
+        }
+    }
+    if (a.WaterColumnZ && a.Open[c + sk * a.K] == 1 && a.WaterColumnZ[i + a.ld * j] < a.limit) {
+        double MassSum = 0., VolSum = 0.;
+        const int kb = a.KFloorZ[i + a.ld * j];
+        for (int k = kb; k <= a.K; ++k) {
+            const int q = c + sk * k;
+            MassSum = MassSum + a.VolumeZ[q] * A[q];
+            VolSum = VolSum + a.VolumeZ[q];
+        }
+        const double Cnew = MassSum / VolSum;
+        for (int k = kb; k <= a.K; ++k) { A[c + sk * k] = Cnew; B[c + sk * k] = Cnew; }
+    }
+    const double off = a.off[n];
+    if (off != 0.) {
+        double *__restrict__ R = a.pref[n];
+        for (int k = 1; k <= a.K; ++k) {
+            const int q = c + sk * k;
+            if (a.Water[q] == 1) {
+                const double v = A[q] + off;
+                A[q] = v; B[q] = v;
+                if (R) R[q] = R[q] + off;
+            }
+        }
+    }
+}
+
+// after the transport call: the shift is taken out again (WP:14833-14858); off[] holds -OffSet
+__global__ void __launch_bounds__(128) adt_offset_kernel(const PremixArgs a) {
+    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y, n = blockIdx.z;
+    if (i > a.I) return;
+    const double off = a.off[n];
+    if (off == 0.) return;
+    double *__restrict__ A = a.pa[n], *__restrict__ B = a.pb[n], *__restrict__ R = a.pref[n];
+    const int c = i + a.sj * j;
+    for (int k = 1; k <= a.K; ++k) {
+        const int q = c + a.sk * k;
+        if (a.Water[q] == 1) {
+            A[q] = A[q] + off;
+            B[q] = B[q] + off;
+            if (R) R[q] = R[q] + off;
+        }
+    }
+}
+
+__global__ void adt_shift_kernel(double *x, int n, double off) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) x[t] = x[t] + off;
+}
+
+// -------------------------------------------------------------------------------------
 // K3a: ImposeNullGradient (AD:1926-1987): boundary cells take the compute-face-weighted mean of
 // their (new) neighbours.  One thread per (boundary column, k).  Neighbours reached through a
 // compute face are never boundary points themselves (HM:939-942), so the pass is order-free.

@@ -1677,6 +1677,65 @@ int mohid_oracle_set_noflux(const int *handle, const int *NoFluxU, const int *No
     return 0;
 }
 
+// Caller-side steps that ModuleWaterProperties::Advection_Diffusion_Processes runs on a property right before the
+// transport call (WP:14716-14759): FreeConvection (WP:13017-13074, when Density is given), SmallDepthsMixing_Processes
+// (WP:12939-13012, when WaterColumnZ is given; SmallDepthsOn(i,j) receives Me%SmallDepths%ON as 0/1) and the
+// AddOffSet shift of the water points (WP:14724-14735).  Pass Offset = -x afterwards to undo the shift (WP:14833-14846).
+int mohid_oracle_caller_premix(const int *handle, double *PROP, const double *Density, const double *WaterColumnZ,
+                               const double *SmallDepthsLimit, int *SmallDepthsOn, const double *Offset) {
+    Oracle *op = get(handle);
+    if (!op) return MOHID_ADT_ERR_HANDLE;
+    Oracle &o = *op;
+    const auto &W = o.W;
+    if (!o.OpenPoints3D || !o.VolumeZ || !o.KFloorZ) { o.err = "set_grid2d / set_step not called"; return MOHID_ADT_ERR_STATE; }
+    if (Density) {
+        for (int j = W.JLB; j <= W.JUB; ++j)
+            for (int i = W.ILB; i <= W.IUB; ++i) {
+                bool ProfileInstable = false;
+                int ki = 0;
+                for (int k = W.KLB; k <= W.KUB; ++k) {
+                    if (o.OpenPoints3D[o.i3(i, j, k)] == 1 && o.OpenPoints3D[o.i3(i, j, k + 1)] == 1) {
+                        if ((Density[o.i3(i, j, k + 1)] - Density[o.i3(i, j, k)]) > 0.) {
+                            ki = k; ProfileInstable = true; break;
+                        }
+                    }
+                }
+                if (ProfileInstable) {
+                    double Msum = 0., Vsum = 0.;
+                    for (int k = ki; k <= W.KUB; ++k) {
+                        Msum = Msum + o.VolumeZ[o.i3(i, j, k)] * PROP[o.i3(i, j, k)];
+                        Vsum = Vsum + o.VolumeZ[o.i3(i, j, k)];
+                    }
+                    const double Cnew = Msum / Vsum;
+                    for (int k = ki; k <= W.KUB; ++k) PROP[o.i3(i, j, k)] = Cnew;
+                }
+            }
+    }
+    if (WaterColumnZ) {
+        for (int j = W.JLB; j <= W.JUB; ++j)
+            for (int i = W.ILB; i <= W.IUB; ++i) {
+                if (SmallDepthsOn) SmallDepthsOn[o.i2(i, j)] = 0;
+                if (o.OpenPoints3D[o.i3(i, j, W.KUB)] == 1 && WaterColumnZ[o.i2(i, j)] < *SmallDepthsLimit) {
+                    if (SmallDepthsOn) SmallDepthsOn[o.i2(i, j)] = 1;
+                    double MassSum = 0., VolSum = 0.;
+                    const int kbottom = o.KFloorZ[o.i2(i, j)];
+                    for (int k = kbottom; k <= W.KUB; ++k) {
+                        MassSum = MassSum + o.VolumeZ[o.i3(i, j, k)] * PROP[o.i3(i, j, k)];
+                        VolSum = VolSum + o.VolumeZ[o.i3(i, j, k)];
+                    }
+                    for (int k = kbottom; k <= W.KUB; ++k) PROP[o.i3(i, j, k)] = MassSum / VolSum;
+                }
+            }
+    }
+    if (Offset && *Offset != 0.) {
+        for (int k = W.KLB; k <= W.KUB; ++k)
+            for (int j = W.JLB; j <= W.JUB; ++j)
+                for (int i = W.ILB; i <= W.IUB; ++i)
+                    if (o.WaterPoints3D[o.i3(i, j, k)] == 1) PROP[o.i3(i, j, k)] = PROP[o.i3(i, j, k)] + *Offset;
+    }
+    return 0;
+}
+
 int mohid_oracle_set_discharges(const int *handle, const int *DischNumber, const int *n_cells,
                                 const double *DischFlow, const double *DischConc, const int *DischI,
                                 const int *DischJ, const int *DischK, const int *DischKmin, const int *DischKmax,

@@ -132,6 +132,14 @@ class OracleAdvectionDiffusion:
         self._keep["noflux"] = (u, v, w)
         self._check(lib().mohid_oracle_set_noflux(C.byref(self.h), _ip(u), _ip(v), _ip(w)))
 
+    def caller_premix(self, prop, density=None, water_column=None, limit=0.0, offset=0.0):
+        """FreeConvection + SmallDepthsMixing_Processes + AddOffSet of WP:14716-14759 on one property (in place);
+        returns Me%SmallDepths%ON as an int32 2-D array (None when water_column is None)."""
+        on = np.zeros((self.J + 2, self.ld), np.int32) if water_column is not None else None
+        self._check(lib().mohid_oracle_caller_premix(C.byref(self.h), _dp(prop), _dp(density), _dp(water_column),
+                                                     C.byref(C.c_double(limit)), _ip(on), C.byref(C.c_double(offset))))
+        return on
+
     def set_discharges(self, d: dict):
         nd, nc = len(d["DischnCells"]), len(d["DischFlow"])
         a = {k: np.ascontiguousarray(v, dtype=(np.float64 if k in ("DischFlow", "DischConc", "DischConcMF") else np.int32))

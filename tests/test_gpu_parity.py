@@ -460,3 +460,47 @@ def test_horizontally_implicit_limits():
         ts.advect_batch([props[0].copy()], [dict(default_params(1, 4, 1, 4), ImpExp_AdvXX=1.0)])
     assert e.value.code == 21
     ts.close()
+
+
+@pytest.mark.parametrize("use", ["free_convection", "small_depths", "offsets", "all"])
+def test_caller_side_pre_steps(oracle_lib, use):
+    """FreeConvection, SmallDepthsMixing_Processes and AddOffSet of WP:14716-14759 / 14833-14858, done by the library
+    on the device-resident fields, against the oracle's restatement of the caller loop."""
+    I, J, K, N = 41, 33, 8, 3
+    case = make_case(I, J, K, nprop=N, stepped_bottom=True)
+    o, g, s, props, refs = oracle_for(case)
+    rng = np.random.default_rng(3)
+    shape3 = s["OpenPoints3D"].shape
+    density = np.ascontiguousarray(1025.0 + rng.standard_normal(shape3) * 0.05 - 0.02 * np.arange(shape3[0])[:, None, None])
+    wcol = np.ascontiguousarray(5.0 + 40.0 * rng.random(shape3[1:]))
+    limit = 12.0
+    offs = [0.0, 273.15, -3.0]
+    fc = use in ("free_convection", "all")
+    sd = use in ("small_depths", "all")
+    of = use in ("offsets", "all")
+    prm = [default_params(4, 4, 4, 4, bc=4, theta_difv=0.5) for _ in range(N)]
+    ts = gpu_for(case, g, s)
+    ts.set_premix(density if fc else None, wcol if sd else None, limit)
+    if of:
+        ts.set_offsets(offs)
+    gpu, cpu = [p.copy() for p in props], [p.copy() for p in props]
+    water = np.zeros(shape3, bool)
+    water[1:K + 1, 1:J + 1, 1:I + 1] = s["WaterPoints3D"][1:K + 1, 1:J + 1, 1:I + 1] == 1
+    for _ in range(2):
+        ts.advect_batch(gpu, prm, refs)
+        shifted_refs, on = [], None
+        for n in range(N):
+            off = offs[n] if of else 0.0
+            on = o.caller_premix(cpu[n], density if fc else None, wcol if sd else None, limit, off)
+            r = refs[n].copy()
+            r[water] += off
+            shifted_refs.append(r)
+        o.set_step(s, small_depths=on)
+        o.advect_batch(cpu, prm, shifted_refs)
+        for n in range(N):
+            if of and offs[n] != 0.0:
+                o.caller_premix(cpu[n], offset=-offs[n])
+    if sd:
+        assert np.array_equal(ts.get_small_depths(), on) and on.sum() > 0
+    compare(gpu, cpu, s, 1e-11)
+    ts.close()

@@ -208,3 +208,34 @@ def test_horizontally_implicit_conserves_mass(oracle_lib, mh, direction):
     assert abs((a[0] * V)[w].sum() - m0) <= 1e-12 * abs(m0)
     assert np.abs(a[0] - b[0])[w].max() < 0.5 and not np.array_equal(a[0], b[0])    # fields span ~7 units
     assert np.array_equal(a[0] == NULL_REAL, props[0] == NULL_REAL)
+
+
+def test_caller_premix_conserves_mass_and_flags_shallow_columns(oracle_lib):
+    """FreeConvection / SmallDepthsMixing_Processes (WP:13017-13074, 12939-13012) replace part of a column by its
+    volume-weighted mean: the column mass is unchanged, mixed cells are uniform, the ON flag marks thin open columns."""
+    case = make_case(30, 24, 8, nprop=1, stepped_bottom=True)
+    o, g, s, props, refs = oracle_for(case)
+    rng = np.random.default_rng(1)
+    shape3 = s["OpenPoints3D"].shape
+    density = np.ascontiguousarray(1025.0 + rng.standard_normal(shape3) * 0.05)
+    wcol = np.ascontiguousarray(5.0 + 40.0 * rng.random(shape3[1:]))
+    p = props[0].copy()
+    V = s["VolumeZ"]
+    K = case.K
+    cols = (s["OpenPoints3D"][K] == 1)
+    m0 = (p * V)[1:K + 1][:, cols].sum(axis=0)
+    on = o.caller_premix(p, density, wcol, 15.0, 0.0)
+    m1 = (p * V)[1:K + 1][:, cols].sum(axis=0)
+    assert np.allclose(m0, m1, rtol=1e-13)
+    assert not np.array_equal(p, props[0])
+    want = (s["OpenPoints3D"][K] == 1) & (wcol < 15.0)
+    want[0] = want[-1] = False; want[:, 0] = False; want[:, case.I + 1:] = False
+    assert np.array_equal(on == 1, want)
+    jj, ii = np.argwhere(on == 1)[0]
+    kb = g["KFloorZ"][jj, ii]
+    assert np.ptp(p[kb:K + 1, jj, ii]) == 0.0
+    q = props[0].copy()
+    o.caller_premix(q, offset=2.5)
+    w = water_mask(s)
+    work = np.zeros_like(w); work[1:K + 1, 1:case.J + 1, 1:case.I + 1] = True
+    assert np.array_equal(q[w & work], props[0][w & work] + 2.5) and np.array_equal(q[~(w & work)], props[0][~(w & work)])
