@@ -482,9 +482,14 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
                          getenv("MOHID_ADT_RING") && atoi(getenv("MOHID_ADT_RING")) != 0;
     long grid_override = 0;
     if (ring_ok) {
-        kern = tvd_sb ? adt_transport_ring_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, RING_NCW>
-                      : adt_transport_ring_kernel<MOHID_UpwindOrder1, MOHID_SuperBee, MOHID_UpwindOrder1, MOHID_SuperBee, RING_NCW>;
-        wpb = s.nprop + 1;
+        const int npt = atoi(getenv("MOHID_ADT_RING")) >= 2 ? 2 : 1;          // properties per consumer warp
+        if (npt == 2)
+            kern = tvd_sb ? adt_transport_ring_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, RING_NCW / 2, 2>
+                          : adt_transport_ring_kernel<MOHID_UpwindOrder1, MOHID_SuperBee, MOHID_UpwindOrder1, MOHID_SuperBee, RING_NCW / 2, 2>;
+        else
+            kern = tvd_sb ? adt_transport_ring_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, RING_NCW>
+                          : adt_transport_ring_kernel<MOHID_UpwindOrder1, MOHID_SuperBee, MOHID_UpwindOrder1, MOHID_SuperBee, RING_NCW>;
+        wpb = (s.nprop + npt - 1) / npt + 1;
         smem = ring_smem_bytes(s.nprop, h->K);
         grid_override = std::min<long>((long)s.ntile_i * h->j_count, (long)h->num_sms);
     } else if (full && !any_disch && (tvd_sb || upw) && 12 * w_bytes <= (size_t)h->smem_optin) {

@@ -82,7 +82,7 @@ __device__ __forceinline__ void cp_async_arrive(uint64_t *bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int MH, int LH, int MV, int LV, int NCW>
+template <int MH, int LH, int MV, int LV, int NCW, int NPT = 1>
 __global__ void __launch_bounds__((NCW + 1) * 32, 1) adt_transport_ring_kernel(const __grid_constant__ StepArgs s) {
     extern __shared__ __align__(128) unsigned char ring_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) adt_transport_ring_kernel(c
     uint64_t *const full = reinterpret_cast<uint64_t *>(pring + (size_t)np * RING_PS * RING_P_BYTES);
     uint64_t *const empty = full + RING_SS;
     if (threadIdx.x == 0) {
-        for (int t = 0; t < RING_SS; ++t) { mbar_init(full + t, 32); mbar_init(empty + t, (unsigned)np); }
+        for (int t = 0; t < RING_SS; ++t) { mbar_init(full + t, 32); mbar_init(empty + t, (unsigned)((np + NPT - 1) / NPT)); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) adt_transport_ring_kernel(c
     const long nsu = (long)s.ntile_i * s.j_count;
     const int planes = K + 1;                               // planes 1 .. K+1 of a column pass through the rings
 
-    if (warp == np) {
+    if (warp == (np + NPT - 1) / NPT) {
         // =========================== producer of the shared rows ===========================
         // chunk id = lane + 32 t: row = id / 20, piece = id % 20 for the 13 double rows, ids 260..269 = the mask row
         unsigned g = 0;                                     // running plane counter: stage = g % SS, phase = (g / SS) & 1
@@ -165,18 +165,30 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) adt_transport_ring_kernel(c
         cp_async_wait<0>();
         return;
     }
-    if (warp > np) return;
-
     // =========================== consumers ===========================
-    const int n = warp;
-    const PropArgs pa = s.p[n];
-    const double *__restrict__ P = pa.pin;
-    double *__restrict__ Wsm = Wbase + warp * 32 + lane;
+    // consumer warp w advances properties NPT*w .. NPT*w + NPT-1 together: the mask logic, the flow-direction selects
+    // and the shared-row loads of a level are common to them (the compiler merges the common subexpressions of the
+    // unrolled property loop), and two independent dependency chains run through the level
+    const int ncons = (np + NPT - 1) / NPT;
+    if (warp >= ncons) return;
+    int pn[NPT];
+    bool live[NPT];
+    const double *__restrict__ P[NPT];
+    double *__restrict__ Wsm[NPT];
+    double *myring[NPT];
+    double theta[NPT], omt[NPT];
+#pragma unroll
+    for (int u = 0; u < NPT; ++u) {
+        live[u] = NPT * warp + u < np;
+        pn[u] = live[u] ? NPT * warp + u : NPT * warp;    // an odd last property is shadowed by its neighbour
+        P[u] = s.p[pn[u]].pin;
+        Wsm[u] = Wbase + pn[u] * 32 + lane;
+        myring[u] = reinterpret_cast<double *>(pring + (size_t)pn[u] * RING_PS * RING_P_BYTES);
+        theta[u] = s.p[pn[u]].theta_difv; omt[u] = 1. - theta[u];
+    }
     const int wstride = np * 32;
-    double *const myring = reinterpret_cast<double *>(pring + (size_t)n * RING_PS * RING_P_BYTES);
     constexpr int PSTG = RING_P_BYTES / 8;                // doubles per private stage
     constexpr bool FAST_H = (MH == MOHID_P2_TVD && LH == MOHID_SuperBee);
-    const double theta = pa.theta_difv, omt = 1. - pa.theta_difv;
 
     // ---- private prefetch stream: the five property rows of every plane, continuous over the units of the block ----
     // piece id = lane + 32 t (16 bytes each): row = id / 20 (j-2 .. j+2), piece = id % 20; ids 96..99 only on lanes 0..3
@@ -200,12 +212,16 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) adt_transport_ring_kernel(c
     if (isu < nsu) set_psrc(isu);
     auto issue_next = [&]() {
         if (isu < nsu) {
-            unsigned char *dst = reinterpret_cast<unsigned char *>(myring + ist * PSTG) + 16 * lane;
-            const double *src = P + (size_t)sk * ip;
 #pragma unroll
-            for (int t = 0; t < RING_P_PER_LANE; ++t)
-                if (t < RING_P_PER_LANE - 1 || lane < RING_P_CHUNKS - 32 * (RING_P_PER_LANE - 1))
-                    cp_async16(dst + 512 * t, src + psrc[t]);
+            for (int u = 0; u < NPT; ++u) {
+                if (u > 0 && !live[u]) continue;
+                unsigned char *dst = reinterpret_cast<unsigned char *>(myring[u] + ist * PSTG) + 16 * lane;
+                const double *src = P[u] + (size_t)sk * ip;
+#pragma unroll
+                for (int t = 0; t < RING_P_PER_LANE; ++t)
+                    if (t < RING_P_PER_LANE - 1 || lane < RING_P_CHUNKS - 32 * (RING_P_PER_LANE - 1))
+                        cp_async16(dst + 512 * t, src + psrc[t]);
+            }
             if (++ip > planes) {
                 ip = 1;
                 isu += gridDim.x;
@@ -247,7 +263,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) adt_transport_ring_kernel(c
 
         const unsigned mtop = s.mask[c2d + sk * K];
         const bool colwet = (mtop & M_COLWET) != 0, colopen = (mtop & M_COLOPEN) != 0;
-        const bool obc = (mtop & M_BND) != 0 && pa.bc != MOHID_BC_None;
+        const bool bnd = (mtop & M_BND) != 0;
         const unsigned top_req = colopen ? (M_OPEN | M_O_KP1 | M_CFWT) : (1u << 31);
 
         auto shrow = [&](const unsigned char *st, int row) { return reinterpret_cast<const double *>(st) + row * RING_W + wi; };
@@ -258,13 +274,17 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) adt_transport_ring_kernel(c
         wait_full(gsh);
         wait_full(gsh + 1);                                 // shared rows of planes 1 and 2 (K + 1 >= 2)
         int q = c2d + sk;                                   // cell (i,j,1)
-        double Pm1 = P[c2d];
-        double Pc = myring[pst * PSTG + 2 * RING_W + wi], Pp1 = myring[pnext(pst) * PSTG + 2 * RING_W + wi];
+        double Pm1[NPT], Pc[NPT], Pp1[NPT], Dk[NPT], Ek_b[NPT], TIk_b[NPT], Wprev[NPT], Gprev[NPT];
+#pragma unroll
+        for (int u = 0; u < NPT; ++u) {
+            Pm1[u] = P[u][c2d];
+            Pc[u] = myring[u][pst * PSTG + 2 * RING_W + wi];
+            Pp1[u] = myring[u][pnext(pst) * PSTG + 2 * RING_W + wi];
+            Dk[u] = 0.; Ek_b[u] = 0.; TIk_b[u] = 0.; Wprev[u] = 0.; Gprev[u] = 0.;
+        }
         double dtv_m = 0., dtv_c = *shrow(sh_stage(gsh), RR_TC);
         double rdz_c = *shrow(sh_stage(gsh), RR_RDZ), rdz_p = *shrow(sh_stage(gsh + 1), RR_RDZ);
         double qz_c = *shrow(sh_stage(gsh), RR_QZ);
-        double Dk = 0., Ek_b = 0., TIk_b = 0.;
-        double Wprev = 0., Gprev = 0.;
         unsigned zp = 0;
 
         for (int k = 1; k <= K; ++k, ++gsh) {
@@ -284,99 +304,101 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) adt_transport_ring_kernel(c
             const unsigned char *A = sh_stage(gsh), *B = sh_stage(gsh + 1), *C = sh_stage(has_c ? gsh + 2 : gsh + 1);
             const unsigned m = *(reinterpret_cast<const uint32_t *>(A + RING_MASK_OFF) + wi);
             const double vr = *shrow(A, RR_VR);
-            const double *PA = myring + pst * PSTG + wi;
-            const double Pw2 = PA[0], Pw1 = PA[RING_W], Pe1 = PA[3 * RING_W], Pe2 = PA[4 * RING_W];
-            const double Ps2 = PA[2 * RING_W - 2], Ps1 = PA[2 * RING_W - 1], Pn1 = PA[2 * RING_W + 1];
             const double t_w = *shrow(A, RR_TW), t_e = *shrow(A, RR_TE), t_s = shrow(A, RR_TC)[-1];
             const double qxw = *shrow(A, RR_QXW), qxe = *shrow(A, RR_QXE), dhw = *shrow(A, RR_DHW), dhe = *shrow(A, RR_DHE);
             const double qys = *shrow(A, RR_QY), dhs = *shrow(A, RR_DHV);
             const double dtv_p = *shrow(B, RR_TC), qz_p = *shrow(B, RR_QZ), dvz_p = *shrow(B, RR_DVZ);
-            const double Pp2 = myring[pstC * PSTG + 2 * RING_W + wi], rdz_pp = *shrow(C, RR_RDZ), dtv_pp = *shrow(C, RR_TC);
-
+            const double rdz_pp = *shrow(C, RR_RDZ), dtv_pp = *shrow(C, RR_TC);
             const bool open_c = (m & M_OPEN) != 0;
-            // ---------------- VolumeVariation (AD:3966-4021) ----------------
-            Row row;
-            row.TI = sel(open_c, Pc * vr, Pc) + TIk_b;
-            row.E = sel(open_c && k == K, 1.0 + dtv_c * qz_p, 1.0) + Ek_b;
-            row.D = Dk;
-            row.F = 0.;
 
-            // ---------------- horizontal faces (explicit) ----------------
-            {
-                const bool o_w1 = (m & M_O_JM1) != 0, o_e1 = (m & M_O_JP1) != 0;
-                const double fw = hface_flux<MH, LH>(s, all_set(m, M_CFU | M_O_JM1 | M_OPEN), qxw, dhw, Pw2, Pw1, Pc, Pe1,
-                                                     (m & M_O_JM2) != 0, o_e1, 0., t_w, dtv_c, t_e, rho_wp, rdx_c, rho_wn, 0., 0.);
-                const double fe = hface_flux<MH, LH>(s, all_set(m, M_CFUE | M_O_JP1 | M_OPEN), qxe, dhe, Pw1, Pc, Pe1, Pe2,
-                                                     o_w1, (m & M_O_JP2) != 0, t_w, dtv_c, t_e, 0., rho_ep, rdx_p, rho_en, 0., 0.);
-                // each lane builds its south face; the north face is the south face of lane+1
-                const double fs = hface_flux<MH, LH>(s, all_set(m, M_CFV | M_O_IM1 | M_OPEN), qys, dhs, Ps2, Ps1, Pc, Pn1,
-                                                     (m & M_O_IM2) != 0, (m & M_O_IP1) != 0, 0., t_s, dtv_c, 0., rho_sp, rdy_c,
-                                                     rho_sn, 0., 0.);
-                const double fsum = (fw - fe) + (fs - shfl_dn_d(fs, 1));
-                row.TI += fsum * dtv_c;
-            }
-
-            // ---------------- vertical face k+1 (top of this cell) ----------------
-            double Dn, En_b, TIn_b;
-            {
-                const double aux1 = dvz_p * dtv_c, aux2 = dvz_p * dtv_p;
-                const double dP = Pp1 - Pc;
-                row.E += aux1 * theta;
-                row.F -= aux1 * theta;
-                row.TI += aux1 * dP * omt;
-                Dn = -aux2 * theta;
-                En_b = aux2 * theta;
-                TIn_b = -aux2 * dP * omt;
-                const bool adv_on = all_set(m, top_req);
-                const bool pos = qz_p > 0.;
-                const double Puu = sel(pos, Pm1, Pp2), Pu = sel(pos, Pc, Pp1), Pd = sel(pos, Pp1, Pc);
-                double wuu, wu, wd;
-                oriented_weights<MV, LV>(s.method_v, s.limiter_v, s.upwind2_v != 0, s.vrelmax, qz_p, Puu, Pu, Pd,
-                                         pos ? !(m & M_O_KM1) : !(m & M_O_KP2), sel(pos, dtv_m, dtv_pp), sel(pos, dtv_c, dtv_p),
-                                         sel(pos, dtv_p, dtv_c), sel(pos, rdz_c, rdz_pp), rdz_p, 0., 0., wuu, wu, wd);
-                const double qa = sel(adv_on, qz_p, 0.);
-                const double dfl = qa * sel(pos, wu, wd), efl = qa * sel(pos, wd, wu);   // D_flux, E_flux (MF:10583-10586)
-                row.E += dfl * dtv_c;
-                row.F += efl * dtv_c;
-                Dn -= dfl * dtv_p;
-                En_b -= efl * dtv_p;
-            }
-
-            // ---------------- land fill (AD:1753) ----------------
-            row.TI = sel((m & M_LAND) != 0, NULL_REAL, row.TI);
-
-            // ---------------- Thomas forward elimination, row k (MF:4087-4099) ----------------
-            const double Wp0 = Wprev, Gp0 = Gprev;
-            {
-                const double aux = row.E + row.D * Wp0;
-                const bool ok = aux != 0.;
-                const double ra = fast_rcp(aux);
-                Wprev = sel(ok, -row.F * ra, Wp0);
-                Gprev = sel(ok, (row.TI - row.D * Gp0) * ra, Gp0);
-                zp += ok ? 0u : 1u;
-            }
-            // ---------------- open boundary rows (AD:5369-5672); rare ----------------
-            if (obc && open_c) {
-                open_boundary_row(s, pa, q, m, Pc, qz_c, qz_p, dtv_c, row);
-                const double aux = row.E + row.D * Wp0;
-                if (aux != 0.) {
-                    const double ra = 1.0 / aux;
-                    Wprev = -row.F * ra;
-                    Gprev = (row.TI - row.D * Gp0) * ra;
-                } else {
-                    Wprev = Wp0; Gprev = Gp0;
+#pragma unroll
+            for (int u = 0; u < NPT; ++u) {
+                const double *PA = myring[u] + pst * PSTG + wi;
+                const double Pw2 = PA[0], Pw1 = PA[RING_W], Pe1 = PA[3 * RING_W], Pe2 = PA[4 * RING_W];
+                const double Ps2 = PA[2 * RING_W - 2], Ps1 = PA[2 * RING_W - 1], Pn1 = PA[2 * RING_W + 1];
+                const double Pp2 = myring[u][pstC * PSTG + 2 * RING_W + wi];
+                const double Pcu = Pc[u];
+                // ---------------- VolumeVariation (AD:3966-4021) ----------------
+                Row row;
+                row.TI = sel(open_c, Pcu * vr, Pcu) + TIk_b[u];
+                row.E = sel(open_c && k == K, 1.0 + dtv_c * qz_p, 1.0) + Ek_b[u];
+                row.D = Dk[u];
+                row.F = 0.;
+                // ---------------- horizontal faces (explicit) ----------------
+                {
+                    const bool o_w1 = (m & M_O_JM1) != 0, o_e1 = (m & M_O_JP1) != 0;
+                    const double fw = hface_flux<MH, LH>(s, all_set(m, M_CFU | M_O_JM1 | M_OPEN), qxw, dhw, Pw2, Pw1, Pcu, Pe1,
+                                                         (m & M_O_JM2) != 0, o_e1, 0., t_w, dtv_c, t_e, rho_wp, rdx_c, rho_wn, 0., 0.);
+                    const double fe = hface_flux<MH, LH>(s, all_set(m, M_CFUE | M_O_JP1 | M_OPEN), qxe, dhe, Pw1, Pcu, Pe1, Pe2,
+                                                         o_w1, (m & M_O_JP2) != 0, t_w, dtv_c, t_e, 0., rho_ep, rdx_p, rho_en, 0., 0.);
+                    // each lane builds its south face; the north face is the south face of lane+1
+                    const double fs = hface_flux<MH, LH>(s, all_set(m, M_CFV | M_O_IM1 | M_OPEN), qys, dhs, Ps2, Ps1, Pcu, Pn1,
+                                                         (m & M_O_IM2) != 0, (m & M_O_IP1) != 0, 0., t_s, dtv_c, 0., rho_sp, rdy_c,
+                                                         rho_sn, 0., 0.);
+                    const double fsum = (fw - fe) + (fs - shfl_dn_d(fs, 1));
+                    row.TI += fsum * dtv_c;
                 }
+                // ---------------- vertical face k+1 (top of this cell) ----------------
+                double Dn, En_b, TIn_b;
+                {
+                    const double aux1 = dvz_p * dtv_c, aux2 = dvz_p * dtv_p;
+                    const double dP = Pp1[u] - Pcu;
+                    row.E += aux1 * theta[u];
+                    row.F -= aux1 * theta[u];
+                    row.TI += aux1 * dP * omt[u];
+                    Dn = -aux2 * theta[u];
+                    En_b = aux2 * theta[u];
+                    TIn_b = -aux2 * dP * omt[u];
+                    const bool adv_on = all_set(m, top_req);
+                    const bool pos = qz_p > 0.;
+                    const double Puu = sel(pos, Pm1[u], Pp2), Pu = sel(pos, Pcu, Pp1[u]), Pd = sel(pos, Pp1[u], Pcu);
+                    double wuu, wu, wd;
+                    oriented_weights<MV, LV>(s.method_v, s.limiter_v, s.upwind2_v != 0, s.vrelmax, qz_p, Puu, Pu, Pd,
+                                             pos ? !(m & M_O_KM1) : !(m & M_O_KP2), sel(pos, dtv_m, dtv_pp), sel(pos, dtv_c, dtv_p),
+                                             sel(pos, dtv_p, dtv_c), sel(pos, rdz_c, rdz_pp), rdz_p, 0., 0., wuu, wu, wd);
+                    const double qa = sel(adv_on, qz_p, 0.);
+                    const double dfl = qa * sel(pos, wu, wd), efl = qa * sel(pos, wd, wu);   // D_flux, E_flux (MF:10583-10586)
+                    row.E += dfl * dtv_c;
+                    row.F += efl * dtv_c;
+                    Dn -= dfl * dtv_p;
+                    En_b -= efl * dtv_p;
+                }
+                // ---------------- land fill (AD:1753) ----------------
+                row.TI = sel((m & M_LAND) != 0, NULL_REAL, row.TI);
+                // ---------------- Thomas forward elimination, row k (MF:4087-4099) ----------------
+                const double Wp0 = Wprev[u], Gp0 = Gprev[u];
+                {
+                    const double aux = row.E + row.D * Wp0;
+                    const bool ok = aux != 0.;
+                    const double ra = fast_rcp(aux);
+                    Wprev[u] = sel(ok, -row.F * ra, Wp0);
+                    Gprev[u] = sel(ok, (row.TI - row.D * Gp0) * ra, Gp0);
+                    zp += (ok || !live[u]) ? 0u : 1u;
+                }
+                // ---------------- open boundary rows (AD:5369-5672); rare ----------------
+                if (bnd && open_c && s.p[pn[u]].bc != MOHID_BC_None) {
+                    open_boundary_row(s, s.p[pn[u]], q, m, Pcu, qz_c, qz_p, dtv_c, row);
+                    const double aux = row.E + row.D * Wp0;
+                    if (aux != 0.) {
+                        const double ra = 1.0 / aux;
+                        Wprev[u] = -row.F * ra;
+                        Gprev[u] = (row.TI - row.D * Gp0) * ra;
+                    } else {
+                        Wprev[u] = Wp0; Gprev[u] = Gp0;
+                    }
+                }
+                if (live[u]) {
+                    Wsm[u][(size_t)(k - 1) * wstride] = Wprev[u];
+                    if (writer && colwet) s.p[pn[u]].pout[q] = Gprev[u];      // G parked in the output array
+                }
+                // ---------------- roll ----------------
+                Dk[u] = Dn; Ek_b[u] = En_b; TIk_b[u] = TIn_b;
+                Pm1[u] = Pcu; Pc[u] = Pp1[u]; Pp1[u] = Pp2;
             }
-            Wsm[(size_t)(k - 1) * wstride] = Wprev;
-            if (writer && colwet) pa.pout[q] = Gprev;      // G parked in the output array
 
-            // ---- this property is done with the shared rows of plane k ----
+            // ---- these properties are done with the shared rows of plane k ----
             __syncwarp();
             if (lane == 0) mbar_arrive(empty + (gsh % RING_SS));
-
-            // ---------------- roll ----------------
-            Dk = Dn; Ek_b = En_b; TIk_b = TIn_b;
-            Pm1 = Pc; Pc = Pp1; Pp1 = Pp2;
             dtv_m = dtv_c; dtv_c = dtv_p;
             rdz_c = rdz_p; rdz_p = rdz_pp;
             qz_c = qz_p;
@@ -391,26 +413,30 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) adt_transport_ring_kernel(c
 
         // ---------------- back substitution (MF:4100-4105) ----------------
         if (writer && colwet) {
-            double *__restrict__ O = pa.pout;
-            int qo = c2d + sk * (K + 1);
-            double x = 0.0;                                   // RES(KUB+1) = G(KUB+1) = 0 (halo row is the identity)
-            O[qo] = x;
-            int k = K;
-            for (; k >= 8; k -= 8) {
-                double gq[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) gq[u] = O[qo - (u + 1) * sk];
+            for (int u = 0; u < NPT; ++u) {
+                if (!live[u]) continue;
+                double *__restrict__ O = s.p[pn[u]].pout;
+                int qo = c2d + sk * (K + 1);
+                double x = 0.0;                               // RES(KUB+1) = G(KUB+1) = 0 (halo row is the identity)
+                O[qo] = x;
+                int k = K;
+                for (; k >= 8; k -= 8) {
+                    double gq[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                    for (int v = 0; v < 8; ++v) gq[v] = O[qo - (v + 1) * sk];
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) {
+                        qo -= sk;
+                        x = Wsm[u][(size_t)(k - 1 - v) * wstride] * x + gq[v];
+                        O[qo] = x;
+                    }
+                }
+                for (; k >= 1; --k) {
                     qo -= sk;
-                    x = Wsm[(size_t)(k - 1 - u) * wstride] * x + gq[u];
+                    x = Wsm[u][(size_t)(k - 1) * wstride] * x + O[qo];
                     O[qo] = x;
                 }
-            }
-            for (; k >= 1; --k) {
-                qo -= sk;
-                x = Wsm[(size_t)(k - 1) * wstride] * x + O[qo];
-                O[qo] = x;
             }
             if (zp) atomicAdd(s.zero_pivots, (unsigned long long)zp);
         }

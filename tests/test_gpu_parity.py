@@ -408,9 +408,9 @@ def test_ring_kernel_matches_plain_kernel_and_oracle(oracle_lib, shape, method, 
     o, g, s, props, refs = oracle_for(case)
     prm = [default_params(method, 4, method, 4, bc=bc, decay_time=600.0) for _ in range(N)]
     out = {}
-    for mode in ("ring", "plain"):
-        if mode == "ring":
-            monkeypatch.setenv("MOHID_ADT_RING", "1")
+    for mode in ("ring", "ring2", "plain"):
+        if mode != "plain":
+            monkeypatch.setenv("MOHID_ADT_RING", "2" if mode == "ring2" else "1")     # 2: two properties per warp
         else:
             monkeypatch.delenv("MOHID_ADT_RING", raising=False)
         ts = gpu_for(case, g, s)
@@ -420,8 +420,9 @@ def test_ring_kernel_matches_plain_kernel_and_oracle(oracle_lib, shape, method, 
         out[mode] = a
         assert ts.counters()["zero_pivots"] == 0
         ts.close()
-    for a, b in zip(out["ring"], out["plain"]):
-        assert np.array_equal(a, b)
+    for mode in ("ring", "ring2"):
+        for a, b in zip(out[mode], out["plain"]):
+            assert np.array_equal(a, b)
     cpu = [p.copy() for p in props]
     for _ in range(3):
         o.advect_batch(cpu, prm, refs)
