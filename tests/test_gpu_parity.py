@@ -199,10 +199,16 @@ def test_reference_stop_conditions_become_errors(oracle_lib):
     bad = default_params(1, 4, 1, 4); bad["ImpExp_AdvV"] = 0.5
     with pytest.raises(AdtError, match="VerticalAdvection"):
         ts.advect_batch([p0], [bad])
-    bad = default_params(1, 4, 1, 4); bad["ImpExp_AdvXX"] = 1.0
-    with pytest.raises(AdtError) as e:
+    bad = default_params(1, 4, 1, 4); bad["ImpExp_AdvXX"] = 1.0; bad["ImpExp_AdvYY"] = 1.0
+    with pytest.raises(AdtError, match="ERR03"):
         ts.advect_batch([p0], [bad])
-    assert e.value.code == 21                          # exists in the reference, not on the GPU path
+    bad = default_params(2, 4, 1, 4); bad["ImpExp_AdvXX"] = 1.0
+    with pytest.raises(AdtError, match="ERR100"):
+        ts.advect_batch([p0], [bad])
+    bad = default_params(1, 4, 1, 4, bc=6)
+    with pytest.raises(AdtError) as e:
+        ts.advect_batch([p0], [bad], [props[0].copy()])
+    assert e.value.code == 21                          # Orlanski: exists in the reference, not on the GPU path
     assert np.array_equal(p0, props[0])                # nothing was touched
     ts.close()
 
