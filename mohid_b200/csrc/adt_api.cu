@@ -50,6 +50,7 @@ struct Handle {
     std::vector<double *> wline;                        // W of the line recurrence (horizontally implicit advection)
     unsigned char *nfmask = nullptr;                    // NF_* bits, rebuilt by K1 every step
     int n_bnd_cols = 0;
+    bool bnd_off_ring = false;                          // a boundary point away from the outer ring (Orlanski stops on it)
     // raw per-step inputs
     double *raw_d[11] = {nullptr};
     int *raw_i[6] = {nullptr};
@@ -200,8 +201,10 @@ void free_all(Handle *h) {
 // boundary columns inside the active j-range -> device list used by the post-solve passes
 int upload_bnd_cols(Handle *h) {
     std::vector<int> cols;
+    h->bnd_off_ring = false;
     for (size_t c = 0; c + 1 < h->bnd_host.size(); c += 2) {
-        const int j = h->bnd_host[c + 1];
+        const int j = h->bnd_host[c + 1], i = h->bnd_host[c];
+        if (!(i == 1 || i == h->I || j == 1 || j == h->J)) h->bnd_off_ring = true;
         if (j >= h->j_begin && j < h->j_begin + h->j_count) { cols.push_back(h->bnd_host[c]); cols.push_back(j); }
     }
     if (h->bnd_cols) { cudaFree(h->bnd_cols); h->bnd_cols = nullptr; }
@@ -314,12 +317,16 @@ int validate(Handle *h, int nprop, const mohid_adt_params *p, Batch &b) {
         if ((q.AdvMethodH >= MOHID_UpwindOrder2 && q.AdvMethodH <= MOHID_P2_TVD && !q.Upwind2H) ||
             (q.AdvMethodV >= MOHID_UpwindOrder2 && q.AdvMethodV <= MOHID_P2_TVD && !q.Upwind2V))
             return fail(h, MOHID_ADT_ERR_ARG, "This method is not valid to compute Advection1D (Upwind2 must be set, WP:9638-9652)");
-        if (q.BoundaryCondition == MOHID_BC_Orlanski)
-            return fail(h, MOHID_ADT_ERR_UNSUPPORTED, "Orlanski boundary (AD:5504-5570) is not available on the GPU path");
         const int bc = q.BoundaryCondition;
+        if (bc == MOHID_BC_Orlanski) {
+            if (h->bnd_off_ring)
+                return fail(h, MOHID_ADT_ERR_ARG, "Orlanski Advection 2 (a boundary point is not on the outer ring, AD:5518)");
+            if (h->j_begin != 1 || h->j_count != h->J)
+                return fail(h, MOHID_ADT_ERR_UNSUPPORTED, "Orlanski boundary is not available on a column slab");
+        }
         if (bc != MOHID_BC_None && bc != MOHID_BC_MassConservation && bc != MOHID_BC_ImposedValue &&
             bc != MOHID_BC_NullGradient && bc != MOHID_BC_SubModel && bc != MOHID_BC_MassConservNullGrad &&
-            bc != MOHID_BC_CyclicBoundary)
+            bc != MOHID_BC_CyclicBoundary && bc != MOHID_BC_Orlanski)
             return fail(h, MOHID_ADT_ERR_ARG, "Set_Internal_State - ModuleAdvectionDiffusion - ERR01");
         if ((q.NoAdvFlux || q.NoDifFlux) && !h->have_noflux)
             return fail(h, MOHID_ADT_ERR_ARG, "NoAdvFlux / NoDifFlux need the NoFluxU/V/W arrays (mohid_adt_set_noflux)");
@@ -460,6 +467,7 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
         any_disch = any_disch || s.p[m].dconc != nullptr;
         all_impv = all_impv && s.p[m].advv_implicit;
         any_disch = any_disch || s.p[m].nfsel != 0;     // NoAdvFlux rides on the DISCH variants
+        any_disch = any_disch || s.p[m].bc == MOHID_BC_Orlanski;      // ... and so does the Orlanski boundary
     }
     // FULL: 3-D, both horizontal directions, implicit vertical advection for every property of the launch
     const bool full = !s.vertical1d && !s.xzflow && s.K > 1 && all_impv && !stage2;
@@ -550,6 +558,16 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
     for (int m = 0; m < s.nprop; ++m) {
         const int n = idx[m];
         const int bc = b.p[n].BoundaryCondition;
+        if (bc == MOHID_BC_Orlanski && h->has_ref[n] && h->n_bnd_cols > 0) {
+            BndArgs ba{};
+            ba.I = h->I; ba.J = h->J; ba.K = h->K; ba.ld = h->ld; ba.nj = h->nj; ba.ncols = h->n_bnd_cols;
+            ba.sj = s.sj; ba.sk = s.sk; ba.cols = h->bnd_cols;
+            const long tot = (long)h->n_bnd_cols * h->K;
+            adt_orlanski_halo_sync_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(ba, s.p[m].pout,
+                                                                                             const_cast<double *>(s.p[m].pin));
+            CU(h, cudaGetLastError());
+            h->launches++;
+        }
         if ((bc == MOHID_BC_NullGradient || (bc == MOHID_BC_CyclicBoundary && h->has_ref[n])) && h->n_bnd_cols > 0) {
             BndArgs ba{};
             ba.I = h->I; ba.J = h->J; ba.K = h->K; ba.ld = h->ld; ba.nj = h->nj; ba.ncols = h->n_bnd_cols;

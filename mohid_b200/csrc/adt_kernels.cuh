@@ -459,8 +459,41 @@ __device__ __noinline__ void apply_discharges(const DischView &d, const double *
 
 // Rows of open-boundary cells (AD:5369-5672); rare (boundary ring only): a predicated-off branch elsewhere.
 struct Row { double D, E, F, TI; };
+// Orlanski (bc 6, AD:5504-5570 + MF:4129-4490): the reference overwrites the "old" field with the current one right
+// before the radiation routine looks at it (AD:5428-5429), so the wave celerity it derives is zero and only the boundary
+// flow FlowVelX = Q_b DT/V remains: outflow -> implicit upstream extrapolation of the exterior value from three
+// interior cells, inflow -> relaxation to the reference value, both with the default 300-day relaxation time.  The
+// exterior (halo) cell of the property receives the new exterior value (written to the output buffer only: the other
+// threads of the step still read the old halo).
+__device__ __forceinline__ double orlanski_exterior(const StepArgs &s, const PropArgs &pa, int q, int i, int j, double vel) {
+    const double *__restrict__ P = pa.pin;
+    const bool iedge = (i == 1 || i == s.I);
+    const int d = iedge ? 1 : s.sj;                               // stride along the boundary normal
+    const bool low = (i == 1 || j == 1);                          // AD:5522: tested before the upper edges
+    const int qe = low ? q - d : q + d;                           // "exterior" cell handed to OrlanskiCelerity2D
+    const int sg = low ? d : -d;                                  // towards the interior
+    int q3 = qe + 3 * sg;
+    // corner i = IUB, j = JLB: the lower-edge rule wins, the "exterior" cell is the interior cell IUB-1 and the third
+    // point is element IUB+2 of the row = element 0 of row j+1 in the reference's unpadded array
+    const bool corner = iedge && i == s.I && j == 1 && s.I > 1;
+    if (corner) q3 = q - i + s.sj;
+    const double I1 = P[qe + sg], I2 = P[qe + 2 * sg], I3 = P[q3];
+    const double ref = pa.pref[qe], old = P[qe];
+    const double trelax = 86400 * 300;
+    double wc = 0., adj = ref;
+    if (vel > 0) { wc = 4 * vel; adj = 0.0546875 * I3 - 0.2578125 * I2 + 0.6015625 * I1; }
+    const double auxint = wc * adj;
+    const double auxbound = 1 + wc * (1 - 0.6015625) + s.dt / trelax;
+    const double ext = (old + auxint + ref * s.dt / trelax) / auxbound;
+    if (!corner) pa.pout[qe] = ext;
+    return ext;
+}
+
+// RARE: compiled with the Orlanski branch (only the DISCH kernel variants, which the host selects for it)
+template <bool RARE = false>
 __device__ __forceinline__ void open_boundary_row(const StepArgs &s, const PropArgs &pa, int q, unsigned m, double Pc,
-                                               double qz_c, double qz_p, double dtv_c, Row &row) {
+                                               double qz_c, double qz_p, double dtv_c, Row &row, int i = 0, int j = 0,
+                                               bool writer = true) {
     const double *__restrict__ P = pa.pin;
     const int sj = s.sj;
     const int bc = pa.bc;
@@ -484,9 +517,11 @@ __device__ __forceinline__ void open_boundary_row(const StepArgs &s, const PropA
                           s.qy[q] * ((m & M_CFV) ? 1. : 0.) - s.qy[q + 1] * ((m & M_CFVN) ? 1. : 0.) +
                           qz_c * ((m & M_CFW) ? 1. : 0.) - qz_p * ((m & M_CFWT) ? 1. : 0.) -
                           (s.VolumeZ[q] - s.VolumeZOld[q]) / s.dt;
+        double ext_orl = 0.;
+        if constexpr (RARE) { if (bc == MOHID_BC_Orlanski && writer) ext_orl = orlanski_exterior(s, pa, q, i, j, qb * dtv_c); }
         if (qb < 0.) {
-            if (bc == MOHID_BC_MassConservation) {
-                const double ext = Pc * (1.0 - pa.tdec) + pa.pref[q] * pa.tdec;
+            if (bc == MOHID_BC_MassConservation || (RARE && bc == MOHID_BC_Orlanski)) {
+                const double ext = (RARE && bc == MOHID_BC_Orlanski) ? ext_orl : Pc * (1.0 - pa.tdec) + pa.pref[q] * pa.tdec;
                 row.TI -= qb * ext * dtv_c;
             } else {                               // MassConservNullGrad: NullGradProp of the old field
                 const int cVn = (m & M_CFVN) ? 1 : 0, cVs = (m & M_CFV) ? 1 : 0;
@@ -771,7 +806,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
         // Rare (boundary ring only): the row is amended and eliminated again, so the common path stays one
         // basic block.  Open boundary cells are never land.
         if (obc && open_c) {
-            open_boundary_row(s, pa, q, m, Pc, qz_c, qz_p, dtv_c, row);
+            open_boundary_row<DISCH>(s, pa, q, m, Pc, qz_c, qz_p, dtv_c, row, ic, j, writer);
             const double aux = row.E + row.D * Wp0;
             if (aux != 0.) {
                 const double ra = 1.0 / aux;
@@ -956,6 +991,23 @@ struct BndArgs {
     double *prop;             // new field (in place)
     const double *pref;
 };
+
+// Orlanski: the exterior cells written into the new buffer are copied to the other one, so that halo cells, which
+// no later step may rewrite, stay identical in the two ping-pong buffers
+__global__ void adt_orlanski_halo_sync_kernel(const BndArgs b, const double *newbuf, double *oldbuf) {
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long)b.ncols * b.K) return;
+    const int c = (int)(t / b.K), k = (int)(t % b.K) + 1;
+    const int i = b.cols[2 * c], j = b.cols[2 * c + 1];
+    const bool iedge = (i == 1 || i == b.I);
+    if (!iedge && !(j == 1 || j == b.J)) return;
+    if (iedge && i == b.I && j == 1 && b.I > 1) return;           // the corner whose "exterior" cell is interior
+    const long d = iedge ? 1 : b.sj;
+    const long q = (long)i + (long)b.sj * j + (long)b.sk * k;
+    const long qe = (i == 1 || j == 1) ? q - d : q + d;
+    oldbuf[qe] = newbuf[qe];
+}
+
 
 __global__ void adt_nullgrad_kernel(const BndArgs b) {
     const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;

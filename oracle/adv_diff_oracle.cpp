@@ -1159,18 +1159,104 @@ void FluxAtOpenBoundary(Oracle &o) {
 // ---------------------------------------------------------------------------------------
 // OpenBoundaryCondition (AD:5369-5672) -- serial in the reference (OpenMP commented out)
 // ---------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------
+// OrlanskiCelerity2D (MF:4129-4490) as called from AD:5549-5566: implicit, oblique radiation, celerity from the
+// fields, reference field present, default relaxation times, FlowVelX given; returns NewValue.
+// Index reads past the allocated upper bound (the corner i = IUB, j = JLB passes an interior cell as "exterior" and
+// then reads IUB+2) follow the memory order of the reference's unpadded (0:IUB+1, 0:JUB+1) array: element IUB+2 of a
+// row is element 0 of the next one.
+// ---------------------------------------------------------------------------------------
+double OrlanskiCelerity2D(Oracle &o, double *NewField, double *OldField, int IMin, int IMax, int JMin, int JMax, int di,
+                          int dj, int i, int j, int k, double LimitMax, bool EastNorthBoundary, double DT, double FlowVelX) {
+    auto at = [&](int ii, int jj) {
+        if (ii > o.S.IUB) { ii -= (o.S.IUB - o.S.ILB + 1); jj += 1; }          // unpadded memory order
+        if (ii < o.S.ILB) { ii += (o.S.IUB - o.S.ILB + 1); jj -= 1; }
+        return o.i3(ii, jj, k);
+    };
+    const int *ComputePoints = o.OpenPoints3D;
+    bool NoSouthWest = false, NoNorthEast = false;
+    const int sg = EastNorthBoundary ? -1 : 1;
+    const double Interior1New = NewField[at(i + sg * di, j + sg * dj)], Interior1Old = OldField[at(i + sg * di, j + sg * dj)];
+    const double Interior2New = NewField[at(i + sg * 2 * di, j + sg * 2 * dj)];
+    const double Interior3New = NewField[at(i + sg * 3 * di, j + sg * 3 * dj)];
+    const double Interior6Old = OldField[at(i + sg * di + dj, j + sg * dj + di)];
+    const double Interior7Old = OldField[at(i + sg * di - dj, j + sg * dj - di)];
+    const int bi = i + sg * di, bj = j + sg * dj;
+    if ((bi + 3 * dj) > IMax || (bj + 3 * di) > JMax) NoNorthEast = true;
+    else if (ComputePoints[at(bi + dj, bj + di)] * ComputePoints[at(bi + 2 * dj, bj + 2 * di)] *
+             ComputePoints[at(bi + 3 * dj, bj + 3 * di)] == 0) NoNorthEast = true;
+    if ((bi - 3 * dj) < IMin || (bj - 3 * di) < JMin) NoSouthWest = true;
+    else if (ComputePoints[at(bi - dj, bj - di)] * ComputePoints[at(bi - 2 * dj, bj - 2 * di)] *
+             ComputePoints[at(bi - 3 * dj, bj - 3 * di)] == 0) NoSouthWest = true;
+    double Boundary3Old = 0., Boundary32Old = 0., Boundary33Old = 0., Boundary4Old = 0., Boundary42Old = 0., Boundary43Old = 0.;
+    if (!NoNorthEast) {
+        Boundary3Old = OldField[at(i + dj, j + di)]; Boundary32Old = OldField[at(i + 2 * dj, j + 2 * di)];
+        Boundary33Old = OldField[at(i + 3 * dj, j + 3 * di)];
+    }
+    if (!NoSouthWest) {
+        Boundary4Old = OldField[at(i - dj, j - di)]; Boundary42Old = OldField[at(i - 2 * dj, j - 2 * di)];
+        Boundary43Old = OldField[at(i - 3 * dj, j - 3 * di)];
+    }
+    const double Boundary5Old = OldField[at(i, j)];
+    double WaveCelerityX_, WaveCelerityY_;
+    {   // .not. ConstantCelerity_
+        const double TimeVariability = Interior1New - Interior1Old;
+        const double SpaceVariabilityX = Interior1New - Interior2New;
+        const double AuxIntY = Interior6Old - Interior7Old;
+        double SpaceVariabilityY;
+        if ((AuxIntY * TimeVariability) > 0) { SpaceVariabilityY = Interior1Old - Interior7Old; if (NoSouthWest) SpaceVariabilityY = 0.; }
+        else { SpaceVariabilityY = Interior6Old - Interior1Old; if (NoNorthEast) SpaceVariabilityY = 0.; }
+        const double SpaceSquare = SpaceVariabilityX * SpaceVariabilityX + SpaceVariabilityY * SpaceVariabilityY;
+        if (SpaceSquare > 0.) {
+            WaveCelerityX_ = -(TimeVariability * SpaceVariabilityX) / SpaceSquare;
+            WaveCelerityY_ = -(TimeVariability * SpaceVariabilityY) / SpaceSquare;
+            if (std::fabs(WaveCelerityX_) > LimitMax) WaveCelerityX_ = LimitMax * WaveCelerityX_ / std::fabs(WaveCelerityX_);
+            if (std::fabs(WaveCelerityY_) > LimitMax) WaveCelerityY_ = LimitMax * WaveCelerityY_ / std::fabs(WaveCelerityY_);
+        } else {
+            WaveCelerityX_ = 0.; WaveCelerityY_ = 0.;
+        }
+    }
+    const double ReferenceValue = o.ReferenceProp[at(i, j)];
+    const double TrelaxOut_ = 86400 * 300, TrelaxIn_ = 86400 * 300;
+    WaveCelerityX_ = WaveCelerityX_ + FlowVelX;
+    double AdjacentPropX, Trelax;
+    if (WaveCelerityX_ > 0) {
+        WaveCelerityX_ = 4 * WaveCelerityX_;
+        AdjacentPropX = 0.0546875 * Interior3New - 0.2578125 * Interior2New + 0.6015625 * Interior1New;
+        Trelax = TrelaxOut_;
+    } else {
+        AdjacentPropX = ReferenceValue;
+        WaveCelerityX_ = 0.; WaveCelerityY_ = 0.;
+        Trelax = TrelaxIn_;
+    }
+    double AuxInt = WaveCelerityX_ * AdjacentPropX;
+    if (WaveCelerityY_ >= 0 && !NoSouthWest) {
+        const double AdjacentPropY = 0.0546875 * Boundary43Old - 0.2578125 * Boundary42Old + 0.6015625 * Boundary4Old + 0.6015625 * Boundary5Old;
+        AuxInt = AuxInt - 4 * WaveCelerityY_ * (Boundary5Old - AdjacentPropY);
+    } else if (WaveCelerityY_ < 0 && !NoNorthEast) {
+        const double AdjacentPropY = 0.0546875 * Boundary33Old - 0.2578125 * Boundary32Old + 0.6015625 * Boundary3Old + 0.6015625 * Boundary5Old;
+        AuxInt = AuxInt - 4 * WaveCelerityY_ * (AdjacentPropY - Boundary5Old);
+    }
+    OldField[at(i, j)] = NewField[at(i, j)];
+    double AuxBound = 1;
+    AuxBound = AuxBound + WaveCelerityX_ * (1 - 0.6015625) + DT / Trelax;
+    NewField[at(i, j)] = (OldField[at(i, j)] + AuxInt + ReferenceValue * DT / Trelax) / AuxBound;
+    return NewField[at(i, j)];
+}
+
 int OpenBoundaryCondition(Oracle &o) {
     const auto &W = o.W;
     const int BoundaryCondition = o.P.BoundaryCondition;
     const double DTPropDouble = o.P.DTProp;
     const double TdecAux = 1.0 / (1.0 + o.P.DecayTime / o.P.DTProp);
 
-    if (BoundaryCondition == MOHID_BC_Orlanski) {
-        o.err = "Orlanski boundary (AD:5504-5570, MF:4129) is not restated in the oracle";
-        return ORACLE_ERR_UNSUPPORTED;
-    }
-    if (BoundaryCondition == MOHID_BC_MassConservation || BoundaryCondition == MOHID_BC_MassConservNullGrad)
+    if (BoundaryCondition == MOHID_BC_MassConservation || BoundaryCondition == MOHID_BC_Orlanski ||
+        BoundaryCondition == MOHID_BC_MassConservNullGrad)
         FluxAtOpenBoundary(o);
+    // AD:5428-5429: the "old" field of the radiation condition is overwritten with the current one before it is used,
+    // so the time variability seen by OrlanskiCelerity2D is zero and the celerity is the boundary flow alone (kept)
+    std::vector<double> PROPOld;
+    if (BoundaryCondition == MOHID_BC_Orlanski) PROPOld.assign(o.PROP, o.PROP + o.n3);
 
     for (int j = W.JLB; j <= W.JUB; ++j)
         for (int i = W.ILB; i <= W.IUB; ++i) {
@@ -1198,7 +1284,22 @@ int OpenBoundaryCondition(Oracle &o) {
                     }
                 }
 
-                if (BoundaryCondition == MOHID_BC_MassConservation ||
+                if (BoundaryCondition == MOHID_BC_Orlanski) {
+                    // AD:5504-5570
+                    const double VelBound = o.QB[q] * DT_V;
+                    int di, dj, iext, jext;
+                    bool EastNorthBoundary;
+                    if (i == W.ILB || i == W.IUB) { di = 1; dj = 0; }
+                    else if (j == W.JLB || j == W.JUB) { di = 0; dj = 1; }
+                    else { o.err = "Orlanski Advection 2"; return ORACLE_ERR_ARG; }
+                    if (i == W.ILB || j == W.JLB) { EastNorthBoundary = false; iext = i - di; jext = j - dj; }
+                    else if (i == W.IUB || j == W.JUB) { EastNorthBoundary = true; iext = i + di; jext = j + dj; }
+                    else { o.err = "Orlanski Advection 1"; return ORACLE_ERR_ARG; }
+                    const double LimitMax = 10. * o.P.DTProp / (o.DUX[o.i2(i, j)] + o.DVY[o.i2(i, j)]) * 2;
+                    ExteriorProp = OrlanskiCelerity2D(o, o.PROP, PROPOld.data(), W.ILB, W.IUB, W.JLB, W.JUB, di, dj, iext, jext,
+                                                      k, LimitMax, EastNorthBoundary, o.P.DTProp, VelBound);
+                }
+                if (BoundaryCondition == MOHID_BC_MassConservation || BoundaryCondition == MOHID_BC_Orlanski ||
                     BoundaryCondition == MOHID_BC_MassConservNullGrad) {
                     if (BoundaryCondition == MOHID_BC_MassConservation) {
                         InteriorProp = o.PROP[q];

@@ -205,10 +205,9 @@ def test_reference_stop_conditions_become_errors(oracle_lib):
     bad = default_params(2, 4, 1, 4); bad["ImpExp_AdvXX"] = 1.0
     with pytest.raises(AdtError, match="ERR100"):
         ts.advect_batch([p0], [bad])
-    bad = default_params(1, 4, 1, 4, bc=6)
-    with pytest.raises(AdtError) as e:
+    bad = default_params(1, 4, 1, 4, bc=3)
+    with pytest.raises(AdtError, match="ERR01"):       # not a boundary condition of the reference (AD:5816-5830)
         ts.advect_batch([p0], [bad], [props[0].copy()])
-    assert e.value.code == 21                          # Orlanski: exists in the reference, not on the GPU path
     assert np.array_equal(p0, props[0])                # nothing was touched
     ts.close()
 
@@ -510,4 +509,26 @@ def test_caller_side_pre_steps(oracle_lib, use):
     if sd:
         assert np.array_equal(ts.get_small_depths(), on) and on.sum() > 0
     compare(gpu, cpu, s, 1e-11)
+    ts.close()
+
+
+@pytest.mark.parametrize("method", [1, 4])
+def test_orlanski_boundary(oracle_lib, method):
+    """BoundaryCondition 6 (AD:5504-5570, OrlanskiCelerity2D MF:4129-4490): boundary rows and the exterior (halo) cells
+    the reference writes into the property.  Halo values go through Q_b DT/V, so they agree to round-off, not bitwise."""
+    case = make_case(44, 37, 7, nprop=2, stepped_bottom=True)
+    o, g, s, props, refs = oracle_for(case)
+    prm = [default_params(method, 4, method, 4, bc=6) for _ in range(2)]
+    ts = gpu_for(case, g, s)
+    gpu, cpu = [p.copy() for p in props], [p.copy() for p in props]
+    for _ in range(3):
+        ts.advect_batch(gpu, prm, refs)
+        o.advect_batch(cpu, prm, refs)
+    w = water_mask(s)
+    for a, b, p0 in zip(gpu, cpu, props):
+        assert rel_err(a, b, w) <= 3 * TOL_STEP
+        changed = (b != p0) & ~w                                       # exterior cells written by the radiation routine
+        assert changed.sum() > 0
+        assert np.array_equal(a[~w & ~changed], b[~w & ~changed])
+        assert np.allclose(a[changed], b[changed], rtol=1e-13, atol=0)
     ts.close()

@@ -239,3 +239,25 @@ def test_caller_premix_conserves_mass_and_flags_shallow_columns(oracle_lib):
     w = water_mask(s)
     work = np.zeros_like(w); work[1:K + 1, 1:case.J + 1, 1:case.I + 1] = True
     assert np.array_equal(q[w & work], props[0][w & work] + 2.5) and np.array_equal(q[~(w & work)], props[0][~(w & work)])
+
+
+def test_orlanski_keeps_a_constant_and_writes_the_exterior_cells(oracle_lib):
+    """BC 6 (AD:5504-5570, MF:4129-4490): with the exterior cells and the reference at the same constant the field
+    stays constant; the exterior (halo) cells next to open boundary cells are rewritten by the routine."""
+    case = make_case(36, 30, 6, nprop=1, stepped_bottom=True)
+    o, g, s, props, refs = oracle_for(case)
+    p = np.where(s["LandPoints3D"] == 1, NULL_REAL, 7.0)
+    p[0] = p[-1] = 0
+    p = np.ascontiguousarray(p)
+    ref = np.full_like(p, 7.0)
+    a = [p.copy()]
+    for _ in range(3):
+        o.advect_batch(a, [default_params(4, 4, 4, 4, bc=6)], [ref])
+    w = water_mask(s)
+    assert np.abs(a[0][w] - 7.0).max() < 1e-12
+    b = [props[0].copy()]
+    o.advect_batch(b, [default_params(1, 4, 1, 4, bc=6)], [refs[0]])
+    changed = (b[0] != props[0]) & ~w
+    K, J, I = case.K, case.J, case.I
+    ring = np.zeros_like(w); ring[1:K + 1, 0, :] = ring[1:K + 1, J + 1, :] = ring[1:K + 1, :, 0] = ring[1:K + 1, :, I + 1] = True
+    assert changed.sum() > 0 and not (changed & ~ring).any()
