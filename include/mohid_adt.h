@@ -144,6 +144,13 @@ int mohid_adt_get_small_depths(const int *handle, int *SmallDepthsOn);
  * reference field and its DischConc are shifted by OffSet[n] before the step and shifted back after it. */
 int mohid_adt_set_offsets(const int *handle, const int *nprop, const double *OffSet);
 
+/* SetLimitsProperty (WP:20594-20720; SetLimitsConcentration(PhysicalProcesses) at WP:12711-12714): after every step
+ * property n is clamped to MinValue[n] (if MinOn[n]) and MaxValue[n] (if MaxOn[n]); the mass added / removed is
+ * accumulated in Mass_created / Mass_Destroid (fp64 3-D), which mohid_adt_get_limit_mass copies out.  nprop = 0 clears. */
+int mohid_adt_set_limits(const int *handle, const int *nprop, const int *MinOn, const double *MinValue,
+                         const int *MaxOn, const double *MaxValue);
+int mohid_adt_get_limit_mass(const int *handle, const int *prop_index, double *Mass_Created, double *Mass_Destroid);
+
 /* SetDischarges / UnSetDischarges (AD:978-1095), same arguments as the reference plus the position
  * `prop_index` (0-based) of the property in the next advect batch: the caller invokes SetDischarges
  * once per property with that property's DischConc / DischConcMF (WP:14761-14773); the discharge

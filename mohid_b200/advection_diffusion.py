@@ -116,6 +116,25 @@ class TransportStep:
         arr = (C.c_double * max(1, len(offsets)))(*[float(x) for x in offsets])
         self._check(self.lib.mohid_adt_set_offsets(C.byref(self.h), C.byref(C.c_int(len(offsets))), arr))
 
+    def set_limits(self, min_values, max_values):
+        """SetLimitsProperty after every step (WP:20594-20720); None entries = no limit; two empty lists clear."""
+        n = len(min_values)
+        assert len(max_values) == n
+        mo = (C.c_int * max(1, n))(*[int(v is not None) for v in min_values])
+        xo = (C.c_int * max(1, n))(*[int(v is not None) for v in max_values])
+        mv = (C.c_double * max(1, n))(*[float(v or 0.0) for v in min_values])
+        xv = (C.c_double * max(1, n))(*[float(v or 0.0) for v in max_values])
+        self._check(self.lib.mohid_adt_set_limits(C.byref(self.h), C.byref(C.c_int(n)), mo, mv, xo, xv))
+
+    def get_limit_mass(self, prop_index: int):
+        """(Mass_created, Mass_Destroid) accumulated for one property."""
+        import numpy as np
+        mc = np.zeros((self.K + 2, self.J + 2, self.ld)); md = np.zeros_like(mc)
+        self._check(self.lib.mohid_adt_get_limit_mass(C.byref(self.h), C.byref(C.c_int(prop_index)),
+                                                      mc.ctypes.data_as(C.POINTER(C.c_double)),
+                                                      md.ctypes.data_as(C.POINTER(C.c_double))))
+        return mc, md
+
     def get_small_depths(self):
         """Me%SmallDepths%ON as built by the library (int32, (J+2, ld))."""
         import numpy as np

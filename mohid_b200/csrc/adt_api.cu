@@ -47,6 +47,9 @@ struct Handle {
     bool premix_fc = false, premix_sd = false;
     double sd_limit = 0.;
     std::vector<double> offsets;                        // AddOffSet per property (mohid_adt_set_offsets)
+    std::vector<int> lim_min_on, lim_max_on;            // SetLimitsProperty per property (mohid_adt_set_limits)
+    std::vector<double> lim_min, lim_max;
+    std::vector<double *> mass_created, mass_destroyed;
     std::vector<double *> wline;                        // W of the line recurrence (horizontally implicit advection)
     unsigned char *nfmask = nullptr;                    // NF_* bits, rebuilt by K1 every step
     int n_bnd_cols = 0;
@@ -179,6 +182,8 @@ void free_all(Handle *h) {
     F(h->nfmask);
     for (auto p : h->wline) F(p);
     F(h->density); F(h->wcol);
+    for (auto p : h->mass_created) F(p);
+    for (auto p : h->mass_destroyed) F(p);
     for (auto p : h->raw_d) F(p);
     for (auto p : h->raw_i) F(p);
     F(h->dtv); F(h->vr); F(h->dhu); F(h->dhv); F(h->dvz); F(h->rdz); F(h->mask);
@@ -401,6 +406,37 @@ int launch_premix(Handle *h, const std::vector<int> &idx, int sign) {
     return 0;
 }
 
+// SetLimitsProperty (WP:20594-20720) for the properties `idx`, after the step and the OffSet removal
+int launch_limits(Handle *h, const std::vector<int> &idx) {
+    bool any = false;
+    for (int n : idx) any = any || (n < (int)h->lim_min_on.size() && (h->lim_min_on[n] || h->lim_max_on[n]));
+    if (!any) return 0;
+    LimitArgs a{};
+    a.I = h->I; a.J = h->J; a.K = h->K; a.ld = h->ld; a.sj = h->sj; a.sk = h->sk; a.docycle = h->opt.Docycle_method;
+    a.Water = h->raw_i[2]; a.KFloorZ = h->KFloorZ; a.VolumeZ = h->raw_d[4];
+    if (h->mass_created.size() < h->prop[0].size()) { h->mass_created.resize(h->prop[0].size(), nullptr); h->mass_destroyed.resize(h->prop[0].size(), nullptr); }
+    for (int m = 0; m < (int)idx.size(); ++m) {
+        const int n = idx[m];
+        const bool on = n < (int)h->lim_min_on.size() && (h->lim_min_on[n] || h->lim_max_on[n]);
+        a.min_on[m] = on ? h->lim_min_on[n] : 0; a.max_on[m] = on ? h->lim_max_on[n] : 0;
+        a.vmin[m] = on ? h->lim_min[n] : 0.; a.vmax[m] = on ? h->lim_max[n] : 0.;
+        a.pa[m] = h->prop[h->cur[n]][n]; a.pb[m] = h->prop[h->cur[n] ^ 1][n];
+        if (on) {
+            for (auto *v : {&h->mass_created, &h->mass_destroyed})
+                if (!(*v)[n]) {
+                    if (int rc = dalloc(h, &(*v)[n], h->n3)) return rc;
+                    CU(h, cudaMemsetAsync((*v)[n], 0, h->n3 * sizeof(double), h->stream));
+                }
+            a.created[m] = h->mass_created[n]; a.destroyed[m] = h->mass_destroyed[n];
+        }
+    }
+    const dim3 grid((unsigned)((h->I + 127) / 128), (unsigned)h->J, (unsigned)idx.size());
+    adt_limits_kernel<<<grid, 128, 0, h->stream>>>(a);
+    CU(h, cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
 // hdir: 0 = the whole step; 1 / 2 = horizontally implicit along j / i: adt_hsolve_kernel (stage 1) and then the
 // vertical half of the step from the intermediate field (stage 2)
 int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool timed, int hdir = 0, bool stage2 = false) {
@@ -614,7 +650,8 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
         h->launches++;
     }
     for (int n : idx) h->cur[n] ^= 1;
-    return launch_premix(h, idx, -1);
+    if (int rc = launch_premix(h, idx, -1)) return rc;
+    return launch_limits(h, idx);
 }
 
 // One transport step of all properties of the batch: per-step coefficient pass + fused kernel,
@@ -1179,6 +1216,35 @@ int mohid_adt_set_offsets(const int *handle, const int *nprop, const double *Off
     if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
     if (!nprop || *nprop < 0 || *nprop > NPMAX || (*nprop > 0 && !OffSet)) return fail(h, MOHID_ADT_ERR_ARG, "bad offsets");
     h->offsets.assign(OffSet, OffSet + *nprop);
+    return 0;
+}
+
+int mohid_adt_set_limits(const int *handle, const int *nprop, const int *MinOn, const double *MinValue, const int *MaxOn,
+                         const double *MaxValue) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    if (!nprop || *nprop < 0 || *nprop > NPMAX || (*nprop > 0 && (!MinOn || !MinValue || !MaxOn || !MaxValue)))
+        return fail(h, MOHID_ADT_ERR_ARG, "bad limits");
+    h->lim_min_on.assign(MinOn, MinOn + *nprop); h->lim_max_on.assign(MaxOn, MaxOn + *nprop);
+    h->lim_min.assign(MinValue, MinValue + *nprop); h->lim_max.assign(MaxValue, MaxValue + *nprop);
+    return 0;
+}
+
+int mohid_adt_get_limit_mass(const int *handle, const int *prop_index, double *Mass_Created, double *Mass_Destroid) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    if (!prop_index || *prop_index < 0) return fail(h, MOHID_ADT_ERR_ARG, "bad property index");
+    CU(h, cudaSetDevice(h->dev));
+    const int n = *prop_index;
+    double *src[2] = {n < (int)h->mass_created.size() ? h->mass_created[n] : nullptr,
+                      n < (int)h->mass_destroyed.size() ? h->mass_destroyed[n] : nullptr};
+    double *dst[2] = {Mass_Created, Mass_Destroid};
+    for (int t = 0; t < 2; ++t) {
+        if (!dst[t]) continue;
+        if (!src[t]) return fail(h, MOHID_ADT_ERR_STATE, "no limits were applied to property %d", n);
+        if (int rc = d2h3(h, dst[t], src[t], 8)) return rc;
+    }
+    CU(h, cudaStreamSynchronize(h->stream));
     return 0;
 }
 

@@ -972,6 +972,42 @@ __global__ void __launch_bounds__(128) adt_offset_kernel(const PremixArgs a) {
     }
 }
 
+// SetLimitsProperty (WP:20594-20720) after the transport call: clamp to MinValue / MaxValue and book the mass
+// difference in Mass_created / Mass_Destroid (fp64 3-D accumulators); column form for Docycle_method 1, cell form else.
+struct LimitArgs {
+    int I, J, K, ld, sj, sk, docycle;
+    const int *Water, *KFloorZ;
+    const double *VolumeZ;
+    double *pa[NPMAX], *pb[NPMAX], *created[NPMAX], *destroyed[NPMAX];
+    double vmin[NPMAX], vmax[NPMAX];
+    int min_on[NPMAX], max_on[NPMAX];
+};
+__global__ void __launch_bounds__(128) adt_limits_kernel(const LimitArgs a) {
+    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y, n = blockIdx.z;
+    if (i > a.I || !(a.min_on[n] || a.max_on[n])) return;
+    double *__restrict__ A = a.pa[n], *__restrict__ B = a.pb[n];
+    const int c = i + a.sj * j;
+    int k0 = 1;
+    if (a.docycle == 1) {
+        if (a.Water[c + a.sk * a.K] != 1) return;
+        k0 = a.KFloorZ[i + a.ld * j];
+    }
+    for (int k = k0; k <= a.K; ++k) {
+        const int q = c + a.sk * k;
+        if (a.docycle != 1 && a.Water[q] != 1) continue;
+        double v = A[q];
+        if (a.min_on[n] && v < a.vmin[n]) {
+            a.created[n][q] = a.created[n][q] + (a.vmin[n] - v) * a.VolumeZ[q];
+            v = a.vmin[n];
+        }
+        if (a.max_on[n] && v > a.vmax[n]) {
+            a.destroyed[n][q] = a.destroyed[n][q] + (a.vmax[n] - v) * a.VolumeZ[q];
+            v = a.vmax[n];
+        }
+        A[q] = v; B[q] = v;
+    }
+}
+
 __global__ void adt_shift_kernel(double *x, int n, double off) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) x[t] = x[t] + off;

@@ -1837,6 +1837,39 @@ int mohid_oracle_caller_premix(const int *handle, double *PROP, const double *De
     return 0;
 }
 
+// SetLimitsProperty (WP:20594-20720), the per-property body of SetLimitsConcentration(PhysicalProcesses = .true.)
+// that follows the transport step (WP:12711-12714): clamp to MinValue / MaxValue and book the mass difference.
+int mohid_oracle_set_limits(const int *handle, double *PROP, const int *MinOn, const double *MinValue, const int *MaxOn,
+                            const double *MaxValue, double *Mass_Created, double *Mass_Destroid) {
+    Oracle *op = get(handle);
+    if (!op) return MOHID_ADT_ERR_HANDLE;
+    Oracle &o = *op;
+    const auto &W = o.W;
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 0 ? !*MinOn : !*MaxOn) continue;
+        double *Mass = pass == 0 ? Mass_Created : Mass_Destroid;
+        const double lim = pass == 0 ? *MinValue : *MaxValue;
+        auto cell = [&](long q) {
+            if (pass == 0 ? (PROP[q] < lim) : (PROP[q] > lim)) {
+                Mass[q] = Mass[q] + (lim - PROP[q]) * o.VolumeZ[q];
+                PROP[q] = lim;
+            }
+        };
+        if (o.opt.Docycle_method == 1) {
+            for (int j = W.JLB; j <= W.JUB; ++j)
+                for (int i = W.ILB; i <= W.IUB; ++i)
+                    if (o.WaterPoints3D[o.i3(i, j, W.KUB)] == 1)
+                        for (int k = o.KFloorZ[o.i2(i, j)]; k <= W.KUB; ++k) cell(o.i3(i, j, k));
+        } else {
+            for (int k = W.KLB; k <= W.KUB; ++k)
+                for (int j = W.JLB; j <= W.JUB; ++j)
+                    for (int i = W.ILB; i <= W.IUB; ++i)
+                        if (o.WaterPoints3D[o.i3(i, j, k)] == 1) cell(o.i3(i, j, k));
+        }
+    }
+    return 0;
+}
+
 int mohid_oracle_set_discharges(const int *handle, const int *DischNumber, const int *n_cells,
                                 const double *DischFlow, const double *DischConc, const int *DischI,
                                 const int *DischJ, const int *DischK, const int *DischKmin, const int *DischKmax,

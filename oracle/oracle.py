@@ -140,6 +140,16 @@ class OracleAdvectionDiffusion:
                                                      C.byref(C.c_double(limit)), _ip(on), C.byref(C.c_double(offset))))
         return on
 
+    def set_limits(self, prop, min_value=None, max_value=None, mass_created=None, mass_destroyed=None):
+        """SetLimitsProperty (WP:20594-20720) on one property, in place; the mass arrays accumulate."""
+        shape = prop.shape
+        mc = mass_created if mass_created is not None else np.zeros(shape)
+        md = mass_destroyed if mass_destroyed is not None else np.zeros(shape)
+        self._check(lib().mohid_oracle_set_limits(
+            C.byref(self.h), _dp(prop), C.byref(C.c_int(min_value is not None)), C.byref(C.c_double(min_value or 0.0)),
+            C.byref(C.c_int(max_value is not None)), C.byref(C.c_double(max_value or 0.0)), _dp(mc), _dp(md)))
+        return mc, md
+
     def set_discharges(self, d: dict):
         nd, nc = len(d["DischnCells"]), len(d["DischFlow"])
         a = {k: np.ascontiguousarray(v, dtype=(np.float64 if k in ("DischFlow", "DischConc", "DischConcMF") else np.int32))

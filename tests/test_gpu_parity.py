@@ -532,3 +532,28 @@ def test_orlanski_boundary(oracle_lib, method):
         assert np.array_equal(a[~w & ~changed], b[~w & ~changed])
         assert np.allclose(a[changed], b[changed], rtol=1e-13, atol=0)
     ts.close()
+
+
+@pytest.mark.parametrize("docycle", [1, 2])
+def test_set_limits_after_the_step(oracle_lib, docycle):
+    """SetLimitsProperty (WP:20594-20720) applied by the library after every step, with Mass_created / Mass_Destroid."""
+    case = make_case(40, 31, 7, nprop=2, stepped_bottom=True)
+    o, g, s, props, refs = oracle_for(case, docycle_method=docycle)
+    ts = gpu_for(case, g, s, docycle_method=docycle)
+    w = water_mask(s)
+    lo, hi = np.percentile(props[0][w], [20, 80])
+    ts.set_limits([float(lo), None], [float(hi), None])
+    prm = [default_params(4, 4, 4, 4, bc=4) for _ in range(2)]
+    gpu, cpu = [p.copy() for p in props], [p.copy() for p in props]
+    mc, md = np.zeros_like(props[0]), np.zeros_like(props[0])
+    for _ in range(2):
+        ts.advect_batch(gpu, prm, refs)
+        o.advect_batch(cpu, prm, refs)
+        o.set_limits(cpu[0], float(lo), float(hi), mc, md)
+    compare(gpu, cpu, s, 2 * TOL_STEP)
+    gmc, gmd = ts.get_limit_mass(0)
+    assert mc.max() > 0 and md.min() < 0
+    scale = np.abs(mc).max() + np.abs(md).max()
+    assert np.abs(gmc - mc).max() <= 1e-11 * scale and np.abs(gmd - md).max() <= 1e-11 * scale
+    assert gpu[0][w].min() >= lo and gpu[0][w].max() <= hi
+    ts.close()
