@@ -221,7 +221,7 @@ def run_ours(args):
     ts.set_grid2d(**case.grid2d)
     ts.set_step(case.step)
     ts.upload(case.props)
-    halo = HaloExchanger(ts, dec, rank, nprop, dev) if world > 1 else None
+    halo = HaloExchanger(ts, dec, rank, nprop, dev, overlap=not os.environ.get("MOHID_ADT_NO_OVERLAP")) if world > 1 else None
 
     # pinned host copies for the end-to-end leg (what a Fortran host would own)
     e2e_steps = max(1, min(args.steps, 3))
@@ -258,6 +258,8 @@ def run_ours(args):
     e0.record(stream)
     for _ in range(args.steps):
         one_step()
+    if halo is not None:
+        ts.join_halo()                        # the last exchange runs on the communication stream
     e1.record(stream)
     barrier()
     sampler.mark_timed(w0, time.time())

@@ -144,6 +144,14 @@ int mohid_adt_get_small_depths(const int *handle, int *SmallDepthsOn);
  * reference field and its DischConc are shifted by OffSet[n] before the step and shifted back after it. */
 int mohid_adt_set_offsets(const int *handle, const int *nprop, const double *OffSet);
 
+/* Halo overlap for a column slab: with ghost > 0 and a communication stream, advect_device advances
+ * the first / last `ghost` owned columns first, pack_columns / unpack_columns run on the communication stream as
+ * soon as those are final (while the interior is still being advanced), and the next step -- or
+ * mohid_adt_join_halo / download_props / synchronize -- waits for the exchange.  The caller issues its NCCL
+ * send/recv between pack and unpack on the same communication stream.  ghost = 0 switches it off. */
+int mohid_adt_set_overlap(const int *handle, const int *ghost, void *comm_stream);
+int mohid_adt_join_halo(const int *handle);
+
 /* SetLimitsProperty (WP:20594-20720; SetLimitsConcentration(PhysicalProcesses) at WP:12711-12714): after every step
  * property n is clamped to MinValue[n] (if MinOn[n]) and MaxValue[n] (if MaxOn[n]); the mass added / removed is
  * accumulated in Mass_created / Mass_Destroid (fp64 3-D), which mohid_adt_get_limit_mass copies out.  nprop = 0 clears. */

@@ -217,6 +217,14 @@ class TransportStep:
         self._check(self.lib.mohid_adt_set_active_columns(C.byref(self.h), C.byref(C.c_int(j_begin)),
                                                           C.byref(C.c_int(j_count))))
 
+    def set_overlap(self, ghost: int, comm_stream: int = 0):
+        """Edge-first stepping + pack/unpack on `comm_stream`; ghost = 0 switches it off."""
+        self._check(self.lib.mohid_adt_set_overlap(C.byref(self.h), C.byref(C.c_int(ghost)), C.c_void_p(comm_stream)))
+
+    def join_halo(self):
+        """The compute stream waits for a halo exchange still running on the communication stream."""
+        self._check(self.lib.mohid_adt_join_halo(C.byref(self.h)))
+
     def halo_buffer_elems(self, nprop: int, width: int) -> int:
         return nprop * (self.K + 2) * width * self.device_ld
 

@@ -29,6 +29,12 @@ struct Handle {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t s_up = nullptr, s_down = nullptr;      // copy streams of the pipelined host path (advect_batch)
+    // halo overlap (mohid_adt_set_overlap): the edge columns of a slab are advanced first, ev_edges is recorded, and
+    // pack / unpack run on the caller's communication stream while the interior columns are still being advanced
+    cudaStream_t comm = nullptr;
+    cudaEvent_t ev_edges = nullptr, ev_halo = nullptr;
+    int overlap_ghost = 0;
+    bool halo_pending = false, allow_edge_first = false;
     std::vector<cudaEvent_t> pipe_ev;
     mohid_adt_options opt{};
     int I = 0, J = 0, K = 0, ni = 0, nj = 0, nk = 0, ld_h = 0, ld = 0;
@@ -196,6 +202,9 @@ void free_all(Handle *h) {
     for (auto p : h->d_concmf) F(p);
     for (auto &v : h->flux) for (auto p : v) F(p);
     for (auto &e : h->ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    if (h->ev_edges) cudaEventDestroy(h->ev_edges);
+    if (h->ev_halo) cudaEventDestroy(h->ev_halo);
+    h->ev_edges = h->ev_halo = nullptr;
     if (h->s_up) cudaStreamDestroy(h->s_up);
     if (h->s_down) cudaStreamDestroy(h->s_down);
     for (auto e : h->pipe_ev) cudaEventDestroy(e);
@@ -575,8 +584,56 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
         h->ev_used++;
         CU(h, cudaEventRecord(e0, h->stream));
     }
-    kern<<<(unsigned)blocks, wpb * 32, smem, h->stream>>>(s);
-    CU(h, cudaGetLastError());
+    // NullGradient post-pass of the boundary columns jmin..jmax (AD:1874-1882, 1926-1987)
+    auto nullgrad_pass = [&](int jmin, int jmax) -> int {
+        for (int m = 0; m < s.nprop; ++m) {
+            if (b.p[idx[m]].BoundaryCondition != MOHID_BC_NullGradient || h->n_bnd_cols == 0) continue;
+            BndArgs ba{};
+            ba.I = h->I; ba.J = h->J; ba.K = h->K; ba.ld = h->ld; ba.nj = h->nj; ba.ncols = h->n_bnd_cols;
+            ba.sj = s.sj; ba.sk = s.sk; ba.cols = h->bnd_cols; ba.kfloor = h->KFloorZ; ba.mask = h->mask;
+            ba.prop = s.p[m].pout; ba.pref = s.p[m].pref; ba.jmin = jmin; ba.jmax = jmax;
+            const long tot = (long)h->n_bnd_cols * h->K;
+            adt_nullgrad_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(ba);
+            CU(h, cudaGetLastError());
+            h->launches++;
+        }
+        return 0;
+    };
+    // Edge-first order for the halo overlap: the first / last `g` owned columns (the ones the neighbours need) are
+    // advanced and post-processed before the interior; eligible when nothing else touches the new field afterwards.
+    const int g = h->overlap_ghost;
+    bool edge_first = g > 0 && h->comm && h->allow_edge_first && !grid_override && !hdir && !stage2 && h->j_count >= 4 * g;
+    for (int m = 0; m < s.nprop && edge_first; ++m) {
+        const int n = idx[m];
+        const int bc = b.p[n].BoundaryCondition;
+        if (b.p[n].CellFluxes || (bc == MOHID_BC_CyclicBoundary && h->has_ref[n]) || bc == MOHID_BC_Orlanski ||
+            (n < (int)h->offsets.size() && h->offsets[n] != 0.) ||
+            (n < (int)h->lim_min_on.size() && (h->lim_min_on[n] || h->lim_max_on[n])))
+            edge_first = false;
+    }
+    auto launch_range = [&](int jb, int jc) -> int {
+        s.j_begin = jb; s.j_count = jc;
+        const long nu = (long)s.nprop * s.ntile_i * jc;
+        kern<<<(unsigned)((nu + wpb - 1) / wpb), wpb * 32, smem, h->stream>>>(s);
+        CU(h, cudaGetLastError());
+        h->launches++;
+        return 0;
+    };
+    if (edge_first) {
+        const int jb = h->j_begin, je = h->j_begin + h->j_count - 1;
+        if (int rc = launch_range(jb, g)) return rc;
+        if (int rc = launch_range(je - g + 1, g)) return rc;
+        if (int rc = nullgrad_pass(jb, jb + g - 1)) return rc;
+        if (int rc = nullgrad_pass(je - g + 1, je)) return rc;
+        CU(h, cudaEventRecord(h->ev_edges, h->stream));
+        if (int rc = launch_range(jb + g, h->j_count - 2 * g)) return rc;
+        if (int rc = nullgrad_pass(jb + g, je - g)) return rc;
+        s.j_begin = h->j_begin; s.j_count = h->j_count;
+        h->launches--;                                   // (counted once below, as in the single-launch order)
+    } else {
+        kern<<<(unsigned)blocks, wpb * 32, smem, h->stream>>>(s);
+        CU(h, cudaGetLastError());
+    }
     if (timed) CU(h, cudaEventRecord(e1, h->stream));
 #ifdef ADT_EXPERIMENT
     if (getenv("MOHID_ADT_DEBUG")) {
@@ -591,6 +648,7 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
     h->launches++;
 
     // post-solve boundary passes (AD:1874-1882)
+    if (!edge_first) if (int rc = nullgrad_pass(0, 2147483647)) return rc;
     for (int m = 0; m < s.nprop; ++m) {
         const int n = idx[m];
         const int bc = b.p[n].BoundaryCondition;
@@ -604,16 +662,13 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
             CU(h, cudaGetLastError());
             h->launches++;
         }
-        if ((bc == MOHID_BC_NullGradient || (bc == MOHID_BC_CyclicBoundary && h->has_ref[n])) && h->n_bnd_cols > 0) {
+        if ((bc == MOHID_BC_CyclicBoundary && h->has_ref[n]) && h->n_bnd_cols > 0) {
             BndArgs ba{};
             ba.I = h->I; ba.J = h->J; ba.K = h->K; ba.ld = h->ld; ba.nj = h->nj; ba.ncols = h->n_bnd_cols;
             ba.sj = s.sj; ba.sk = s.sk; ba.cols = h->bnd_cols; ba.kfloor = h->KFloorZ; ba.mask = h->mask;
-            ba.prop = s.p[m].pout; ba.pref = s.p[m].pref;
+            ba.prop = s.p[m].pout; ba.pref = s.p[m].pref; ba.jmin = 0; ba.jmax = 2147483647;
             const long tot = (long)h->n_bnd_cols * h->K;
-            if (bc == MOHID_BC_NullGradient) {
-                adt_nullgrad_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(ba);
-                h->launches++;
-            } else {
+            {
                 adt_cyclic_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(ba, 0);
                 const long t1 = (long)std::max(h->I - 2, 0) * h->K, t2 = (long)std::max(h->J - 2, 0) * h->K;
                 if (t1 > 0) adt_cyclic_kernel<<<(unsigned)((t1 + 255) / 256), 256, 0, h->stream>>>(ba, 1);
@@ -651,7 +706,9 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
     }
     for (int n : idx) h->cur[n] ^= 1;
     if (int rc = launch_premix(h, idx, -1)) return rc;
-    return launch_limits(h, idx);
+    if (int rc = launch_limits(h, idx)) return rc;
+    if (h->comm && !edge_first) CU(h, cudaEventRecord(h->ev_edges, h->stream));     // nothing to overlap: halo after the step
+    return 0;
 }
 
 // One transport step of all properties of the batch: per-step coefficient pass + fused kernel,
@@ -662,6 +719,13 @@ using ChunkHook = std::function<int(const std::vector<int> &)>;
 int step_once(Handle *h, const Batch &b, int chunk = 0, const ChunkHook &before = nullptr, const ChunkHook &after = nullptr) {
     std::vector<char> done(b.nprop, 0);
     bool geom_done = false;
+    if (h->halo_pending) { CU(h, cudaStreamWaitEvent(h->stream, h->ev_halo, 0)); h->halo_pending = false; }
+    {   // edge-first needs the whole batch in one launch group
+        bool one = chunk == 0;
+        for (int n = 1; n < b.nprop && one; ++n) one = b.eff[0].same_dif(b.eff[n]);
+        for (int n = 0; n < b.nprop && one; ++n) one = !(b.p[n].ImpExp_AdvXX == 1.0 || b.p[n].ImpExp_AdvYY == 1.0);
+        h->allow_edge_first = one && !(h->premix_fc || h->premix_sd);
+    }
     if (h->premix_sd) {                                   // Me%SmallDepths%ON (WP:12975-12980), consumed by K1
         PremixArgs a{};
         a.I = h->I; a.J = h->J; a.K = h->K; a.ld = h->ld; a.sj = h->sj; a.sk = h->sk;
@@ -1018,6 +1082,7 @@ int mohid_adt_download_props(const int *handle, const int *nprop, double *const 
     if (!nprop || !prop) return fail(h, MOHID_ADT_ERR_ARG, "null argument");
     if (*nprop > (int)h->prop[0].size()) return fail(h, MOHID_ADT_ERR_STATE, "properties were never uploaded");
     CU(h, cudaSetDevice(h->dev));
+    if (h->halo_pending) { CU(h, cudaStreamWaitEvent(h->stream, h->ev_halo, 0)); h->halo_pending = false; }
     for (int n = 0; n < *nprop; ++n)
         if (int rc = d2h3(h, prop[n], h->prop[h->cur[n]][n], 8)) return rc;
     CU(h, cudaStreamSynchronize(h->stream));
@@ -1157,8 +1222,11 @@ static int pack_common(const int *handle, const int *nprop, const int *j0, const
     for (int n = 0; n < *nprop; ++n) a.prop[n] = h->prop[h->cur[n]][n];
     const long tot = (long)a.nk * a.width * a.ld * a.nprop;
     const int blocks = (int)std::min<long>((tot + 255) / 256, (long)h->num_sms * 16);
-    adt_pack_columns_kernel<<<blocks, 256, 0, h->stream>>>(a, buf, unpack);
+    cudaStream_t st = h->comm ? h->comm : h->stream;
+    if (h->comm && !unpack) CU(h, cudaStreamWaitEvent(h->comm, h->ev_edges, 0));     // the packed columns are final
+    adt_pack_columns_kernel<<<blocks, 256, 0, st>>>(a, buf, unpack);
     CU(h, cudaGetLastError());
+    if (h->comm && unpack) { CU(h, cudaEventRecord(h->ev_halo, h->comm)); h->halo_pending = true; }
     h->launches++;
     return 0;
 }
@@ -1286,10 +1354,39 @@ int mohid_adt_set_active_columns(const int *handle, const int *j_begin, const in
     return upload_bnd_cols(h);
 }
 
+int mohid_adt_set_overlap(const int *handle, const int *ghost, void *comm_stream) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    if (!ghost || *ghost < 0) return fail(h, MOHID_ADT_ERR_ARG, "bad ghost width");
+    CU(h, cudaSetDevice(h->dev));
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (h->comm) CU(h, cudaStreamSynchronize(h->comm));
+    h->halo_pending = false;
+    h->overlap_ghost = *ghost;
+    h->comm = (*ghost > 0) ? (cudaStream_t)comm_stream : nullptr;
+    if (h->comm && !h->ev_edges) {
+        CU(h, cudaEventCreateWithFlags(&h->ev_edges, cudaEventDisableTiming));
+        CU(h, cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming));
+        CU(h, cudaEventRecord(h->ev_edges, h->stream));
+    }
+    return 0;
+}
+
+// the compute stream waits for a halo exchange still running on the communication stream
+int mohid_adt_join_halo(const int *handle) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    CU(h, cudaSetDevice(h->dev));
+    if (h->halo_pending) { CU(h, cudaStreamWaitEvent(h->stream, h->ev_halo, 0)); h->halo_pending = false; }
+    return 0;
+}
+
 int mohid_adt_synchronize(const int *handle) {
     Handle *h = get(handle);
     if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
     CU(h, cudaSetDevice(h->dev));
+    if (h->comm) CU(h, cudaStreamSynchronize(h->comm));
+    h->halo_pending = false;
     CU(h, cudaStreamSynchronize(h->stream));
     return 0;
 }

@@ -1026,6 +1026,7 @@ struct BndArgs {
     const uint32_t *mask;
     double *prop;             // new field (in place)
     const double *pref;
+    int jmin, jmax;           // only boundary columns with jmin <= j <= jmax are processed (edge-first launches)
 };
 
 // Orlanski: the exterior cells written into the new buffer are copied to the other one, so that halo cells, which
@@ -1050,6 +1051,7 @@ __global__ void adt_nullgrad_kernel(const BndArgs b) {
     if (t >= (long)b.ncols * b.K) return;
     const int c = (int)(t / b.K), k = (int)(t % b.K) + 1;
     const int i = b.cols[2 * c], j = b.cols[2 * c + 1];
+    if (j < b.jmin || j > b.jmax) return;
     const long q2 = (long)i + (long)b.ld * j;
     int kf = b.kfloor[q2];
     kf = kf < 0 ? -kf : kf;

@@ -94,7 +94,9 @@ def _p2p_exchange(dist, send_left, recv_left, send_right, recv_right, rank: int,
 class HaloExchanger:
     """Device-resident halo exchange of all properties of a :class:`TransportStep` (NCCL)."""
 
-    def __init__(self, ts, dec: SlabDecomposition, rank: int, nprop: int, device):
+    def __init__(self, ts, dec: SlabDecomposition, rank: int, nprop: int, device, overlap: bool = True):
+        """overlap: the library advances the edge columns first and the exchange runs on its own stream while the
+        interior columns are still being advanced (the next step, or ``ts.join_halo()``, waits for it)."""
         import torch
         self.ts, self.dec, self.rank, self.nprop = ts, dec, rank, nprop
         self.sl = dec.slab(rank)
@@ -104,8 +106,18 @@ class HaloExchanger:
         self.send_l, self.recv_l, self.send_r, self.recv_r = mk(), mk(), mk(), mk()
         self.launches = 0
         ts.set_active_columns(self.sl.j_begin, self.sl.n_owned)
+        self.comm = torch.cuda.Stream(device=device) if overlap else None
+        if self.comm is not None:
+            ts.set_overlap(g, self.comm.cuda_stream)
 
     def exchange(self):
+        import torch
+        if self.comm is None:
+            return self._exchange()
+        with torch.cuda.stream(self.comm):               # NCCL work is ordered after the pack on this stream
+            self._exchange()
+
+    def _exchange(self):
         import torch.distributed as dist
         sl, g, ts = self.sl, self.dec.ghost, self.ts
         if sl.ghost_left:
