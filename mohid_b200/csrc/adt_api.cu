@@ -377,7 +377,7 @@ int launch_coef(Handle *h, const mohid_adt_params &q, const PropEff &e, bool geo
     a.NoFluxU = h->have_noflux ? h->noflux[0] : nullptr; a.NoFluxV = h->have_noflux ? h->noflux[1] : nullptr;
     a.NoFluxW = h->have_noflux ? h->noflux[2] : nullptr; a.nfmask = h->nfmask;
     a.do_geom = geom; a.do_diff = diff;
-    const dim3 grid((unsigned)((h->ld + 127) / 128), (unsigned)h->nj, (unsigned)h->nk);
+    const dim3 grid((unsigned)((h->ld + 127) / 128), (unsigned)h->nk, (unsigned)h->nj);
     adt_coef_kernel<<<grid, 128, 0, h->stream>>>(a);
     CU(h, cudaGetLastError());
     h->launches++;

@@ -95,12 +95,14 @@ struct CoefArgs {
 };
 
 // -------------------------------------------------------------------------------------
-// K1: one thread per allocated cell; grid = (ceil(ld/128), nj, nk) so no index divisions are needed,
+// K1: one thread per allocated cell; grid = (ceil(ld/128), nk, nj) so no index divisions are needed,
 // i fastest (coalesced).  Memory bound: 112 B in, 52 B out per cell.
 // -------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) adt_coef_kernel(const CoefArgs a) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y, k = blockIdx.z;
+    // blocks run i fastest, then k, then j: the k+-1/2 and j+-1/2 neighbour reads of a cell are then issued within a
+    // few MB of traffic of the cell itself and hit L2 (with k slowest, a whole plane of all 17 inputs lies in between)
+    const int k = blockIdx.y, j = blockIdx.z;
     if (i >= a.ld) return;
     const int sj = a.sj, sk = a.sk, sj2 = a.ld;          // 3-D strides; 2-D arrays are (i + ld*j)
     const int q2 = i + sj2 * j;
