@@ -1,0 +1,108 @@
+"""An independent, equation-level restatement of the default transport step in plain numpy (first-order upwind,
+explicit horizontal terms, theta-weighted vertical diffusion, implicit vertical advection, dense column solve with
+numpy.linalg.solve) checked against the C++ oracle.
+
+It shares no code and no structure with oracle/adv_diff_oracle.cpp: it is written from the discrete equations of
+SURVEY.md A.3 / A.5 (cell-wise assembly of one matrix per column instead of the reference's pass-by-pass scatter into
+D/E/F/TI arrays), so an error in the oracle's bookkeeping (pass order, index shifts, sign conventions) shows up here.
+"""
+import numpy as np
+import pytest
+
+from mohid_b200.synthetic import make_case, default_params
+from helpers import oracle_for, water_mask, NULL_REAL
+
+
+def numpy_step(g, s, P, dt, theta, schmidt_h=1.0, coef_v=1.0, bg_v=1.0e-8):
+    """One step of one property; arrays are (K+2, J+2, ld) / (J+2, ld), index order [k, j, i]."""
+    K, J, I = P.shape[0] - 2, P.shape[1] - 2, g["_I"]         # the i extent may be padded: the work size comes along
+    Open, Water, Land = s["OpenPoints3D"], s["WaterPoints3D"], s["LandPoints3D"]
+    CFU, CFV, CFW = s["ComputeFacesU3D"], s["ComputeFacesV3D"], s["ComputeFacesW3D"]
+    V, Vold = s["VolumeZ"], s["VolumeZOld"]
+    Qx, Qy, Qz = s["Wflux_X"], s["Wflux_Y"], s["Wflux_Z"]
+    DUX, DVY, DZX, DZY = g["DUX"], g["DVY"], g["DZX"], g["DZY"]
+    out = P.copy()
+
+    def hflux(k, j, i, dj, di):
+        """Flux of property through the low face of cell (k,j,i) in direction (dj,di), positive towards the cell,
+        split as (advective, diffusive)."""
+        jm, im = j - dj, i - di
+        if dj:
+            if CFU[k, j, i] != 1:
+                return 0.0, 0.0
+            q, area, dz = Qx[k, j, i], s["AreaU"][k, j, i], DZX[jm, im]
+            dif = schmidt_h * (s["Visc_H"][k, j, i] * DUX[jm, im] + s["Visc_H"][k, jm, im] * DUX[j, i]) / (DUX[j, i] + DUX[jm, im])
+        else:
+            if CFV[k, j, i] != 1:
+                return 0.0, 0.0
+            q, area, dz = Qy[k, j, i], s["AreaV"][k, j, i], DZY[jm, im]
+            dif = schmidt_h * (s["Visc_H"][k, j, i] * DVY[jm, im] + s["Visc_H"][k, jm, im] * DVY[j, i]) / (DVY[j, i] + DVY[jm, im])
+        adv = 0.0
+        if Open[k, jm, im] == 1 and Open[k, j, i] == 1:
+            adv = q * (P[k, jm, im] if q > 0 else P[k, j, i])
+        difflux = -dif * area / dz * (P[k, j, i] - P[k, jm, im])
+        return adv, difflux
+
+    for j in range(1, J + 1):
+        for i in range(1, I + 1):
+            if Water[K, j, i] != 1:
+                continue
+            n = K + 1                                   # unknowns k = 1 .. K+1 (the last one is the identity halo row)
+            A = np.zeros((n, n))
+            b = np.zeros(n)
+            for k in range(1, K + 1):
+                r = k - 1
+                dtv = dt / V[k, j, i]
+                is_open = Open[k, j, i] == 1
+                b[r] = P[k, j, i] * (Vold[k, j, i] / V[k, j, i]) if is_open else P[k, j, i]
+                A[r, r] = 1.0
+                if is_open and k == K:
+                    A[r, r] += dtv * Qz[K + 1, j, i]
+                # horizontal: inflow through the low faces, outflow through the high faces of the cell
+                for dj, di in ((1, 0), (0, 1)):
+                    a_lo, d_lo = hflux(k, j, i, dj, di)
+                    a_hi, d_hi = hflux(k, j + dj, i + di, dj, di) if (j + dj <= J + 1 and i + di <= I + 1) else (0.0, 0.0)
+                    if dj and j + 1 > J:
+                        a_hi, d_hi = 0.0, 0.0            # face loops of the reference end at JUB / IUB
+                    if di and i + 1 > I:
+                        a_hi, d_hi = 0.0, 0.0
+                    b[r] += (a_lo - a_hi) * dtv + (d_lo - d_hi) * dtv
+                # vertical faces: bottom (k) and top (k+1)
+                for kf, sign in ((k, +1.0), (k + 1, -1.0)):
+                    if kf < 2 or kf > K or CFW[kf, j, i] != 1:
+                        continue
+                    lo, hi = kf - 1, kf                    # cells below / above the face
+                    if True:
+                        difz = coef_v * s["Diff_V"][kf, j, i] + bg_v
+                        auxk = difz * DUX[j, i] * DVY[j, i] / s["DZZ"][lo, j, i]
+                        # flux upwards through the face = -auxk (P_hi - P_lo); implicit share theta
+                        other = lo if k == hi else hi
+                        A[r, r] += theta * auxk * dtv
+                        A[r, other - 1] -= theta * auxk * dtv
+                        b[r] += (1.0 - theta) * auxk * dtv * (P[other, j, i] - P[k, j, i])
+                    if Open[lo, j, i] == 1 and Open[hi, j, i] == 1 and Open[K, j, i] == 1:
+                        q = Qz[kf, j, i]
+                        up = lo if q > 0 else hi           # implicit first-order upwind: flux = q P_up^{n+1}
+                        A[r, up - 1] -= sign * q * dtv
+                if Land[k, j, i] == 1:
+                    A[r, :] = 0.0; A[r, r] = 1.0; b[r] = NULL_REAL
+            A[n - 1, n - 1] = 1.0
+            x = np.linalg.solve(A, b)
+            out[1:K + 2, j, i] = x
+    return out
+
+
+@pytest.mark.parametrize("theta", [1.0, 0.4])
+def test_oracle_matches_equation_level_numpy(oracle_lib, theta):
+    case = make_case(13, 11, 5, nprop=1, stepped_bottom=True)
+    o, g, s, props, refs = oracle_for(case)
+    g = dict(g); g["_I"] = case.I
+    prm = [default_params(1, 4, 1, 4, theta_difv=theta)]
+    a = [props[0].copy()]
+    o.advect_batch(a, prm)
+    want = numpy_step(g, s, props[0], case.dt, theta)
+    w = water_mask(s)
+    assert np.array_equal(a[0] == NULL_REAL, want == NULL_REAL)
+    scale = np.abs(props[0][w]).max()
+    assert np.abs(a[0] - want)[w].max() <= 1e-11 * scale
+    assert np.array_equal(a[0][~w], want[~w])
