@@ -1,5 +1,5 @@
-"""An independent, equation-level restatement of the default transport step in plain numpy (first-order upwind,
-explicit horizontal terms, theta-weighted vertical diffusion, implicit vertical advection, dense column solve with
+"""An independent, equation-level restatement of the default transport step in plain numpy (first-order upwind and
+P2_TVD with the SuperBee limiter, explicit horizontal terms, theta-weighted vertical diffusion, implicit vertical advection, dense column solve with
 numpy.linalg.solve) checked against the C++ oracle.
 
 It shares no code and no structure with oracle/adv_diff_oracle.cpp: it is written from the discrete equations of
@@ -13,7 +13,22 @@ from mohid_b200.synthetic import make_case, default_params
 from helpers import oracle_for, water_mask, NULL_REAL
 
 
-def numpy_step(g, s, P, dt, theta, schmidt_h=1.0, coef_v=1.0, bg_v=1.0e-8):
+def superbee_theta(q, Puu, Pu, Pd, du_uu, du_u, du_d, dt_over_vu, second_upwind_open):
+    """Weight of the downwind value in the face value, theta = psi(r) (1 - Cr) / 2 (MF:10785-10858): r compares the
+    upwind gradient with the face gradient (distance-weighted), Cr = Q DT / V_upwind keeps the sign of Q (quirk A.4),
+    faces whose second upwind cell is not an open point fall back to first order (Upwind2)."""
+    if not second_upwind_open:
+        return 0.0
+    dc = (Pd - Pu) / (du_u + du_d)
+    if abs(dc) < 1e-16:
+        dc = 1e-16 if dc >= 0 else -1e-16
+    r = ((Pu - Puu) / (du_u + du_uu)) / dc
+    psi = max(0.0, min(2.0 * r, 1.0), min(r, 2.0))
+    cr = q * dt_over_vu
+    return 0.5 * psi * (1.0 - cr)
+
+
+def numpy_step(g, s, P, dt, theta, schmidt_h=1.0, coef_v=1.0, bg_v=1.0e-8, tvd=False):
     """One step of one property; arrays are (K+2, J+2, ld) / (J+2, ld), index order [k, j, i]."""
     K, J, I = P.shape[0] - 2, P.shape[1] - 2, g["_I"]         # the i extent may be padded: the work size comes along
     Open, Water, Land = s["OpenPoints3D"], s["WaterPoints3D"], s["LandPoints3D"]
@@ -40,6 +55,17 @@ def numpy_step(g, s, P, dt, theta, schmidt_h=1.0, coef_v=1.0, bg_v=1.0e-8):
         adv = 0.0
         if Open[k, jm, im] == 1 and Open[k, j, i] == 1:
             adv = q * (P[k, jm, im] if q > 0 else P[k, j, i])
+            if tvd:
+                du = DUX if dj else DVY
+                # cells along the direction: a-2, a-1 | a, a+1 around the face
+                c = [(j - 2 * dj, i - 2 * di), (jm, im), (j, i), (j + dj, i + di)]
+                c[0] = (max(c[0][0], 0), max(c[0][1], 0))
+                if q > 0:
+                    uu, u, d = c[0], c[1], c[2]
+                else:
+                    uu, u, d = c[3], c[2], c[1]
+                th = superbee_theta(q, P[k][uu], P[k][u], P[k][d], du[uu], du[u], du[d], dt / V[k][u], Open[k][uu] == 1)
+                adv = q * ((1.0 - th) * P[k][u] + th * P[k][d])
         difflux = -dif * area / dz * (P[k, j, i] - P[k, jm, im])
         return adv, difflux
 
@@ -82,8 +108,15 @@ def numpy_step(g, s, P, dt, theta, schmidt_h=1.0, coef_v=1.0, bg_v=1.0e-8):
                         b[r] += (1.0 - theta) * auxk * dtv * (P[other, j, i] - P[k, j, i])
                     if Open[lo, j, i] == 1 and Open[hi, j, i] == 1 and Open[K, j, i] == 1:
                         q = Qz[kf, j, i]
-                        up = lo if q > 0 else hi           # implicit first-order upwind: flux = q P_up^{n+1}
-                        A[r, up - 1] -= sign * q * dtv
+                        up, dn = (lo, hi) if q > 0 else (hi, lo)   # implicit: flux = q ((1-th) P_up + th P_dn)^{n+1}
+                        th = 0.0
+                        if tvd:
+                            uu = min(max(up + (up - dn), 0), K + 1)
+                            dwz = s["DWZ"]
+                            th = superbee_theta(q, P[uu, j, i], P[up, j, i], P[dn, j, i], dwz[uu, j, i], dwz[up, j, i],
+                                                dwz[dn, j, i], dt / V[up, j, i], Open[uu, j, i] == 1)
+                        A[r, up - 1] -= sign * q * dtv * (1.0 - th)
+                        A[r, dn - 1] -= sign * q * dtv * th
                 if Land[k, j, i] == 1:
                     A[r, :] = 0.0; A[r, r] = 1.0; b[r] = NULL_REAL
             A[n - 1, n - 1] = 1.0
@@ -93,14 +126,16 @@ def numpy_step(g, s, P, dt, theta, schmidt_h=1.0, coef_v=1.0, bg_v=1.0e-8):
 
 
 @pytest.mark.parametrize("theta", [1.0, 0.4])
-def test_oracle_matches_equation_level_numpy(oracle_lib, theta):
+@pytest.mark.parametrize("tvd", [False, True])
+def test_oracle_matches_equation_level_numpy(oracle_lib, theta, tvd):
     case = make_case(13, 11, 5, nprop=1, stepped_bottom=True)
     o, g, s, props, refs = oracle_for(case)
     g = dict(g); g["_I"] = case.I
-    prm = [default_params(1, 4, 1, 4, theta_difv=theta)]
+    m = 4 if tvd else 1
+    prm = [default_params(m, 4, m, 4, theta_difv=theta)]
     a = [props[0].copy()]
     o.advect_batch(a, prm)
-    want = numpy_step(g, s, props[0], case.dt, theta)
+    want = numpy_step(g, s, props[0], case.dt, theta, tvd=tvd)
     w = water_mask(s)
     assert np.array_equal(a[0] == NULL_REAL, want == NULL_REAL)
     scale = np.abs(props[0][w]).max()
