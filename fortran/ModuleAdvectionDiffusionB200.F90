@@ -93,6 +93,19 @@ module ModuleAdvectionDiffusionB200
             integer(c_int)               :: handle, nprop
             real(c_double), dimension(*) :: OffSet
         end function
+        integer(c_int) function mohid_adt_set_limits(handle, nprop, MinOn, MinValue, MaxOn, MaxValue) &
+                bind(c, name="mohid_adt_set_limits")
+            import :: c_int, c_double
+            integer(c_int)               :: handle, nprop
+            integer(c_int), dimension(*) :: MinOn, MaxOn            ! Property%Evolution%MinConcentration / MaxConcentration as 0/1
+            real(c_double), dimension(*) :: MinValue, MaxValue
+        end function
+        integer(c_int) function mohid_adt_get_limit_mass(handle, prop_index, Mass_Created, Mass_Destroid) &
+                bind(c, name="mohid_adt_get_limit_mass")
+            import :: c_int, c_ptr
+            integer(c_int)     :: handle, prop_index
+            type(c_ptr), value :: Mass_Created, Mass_Destroid       ! c_loc(Property%Mass_created(0,0,0)) or c_null_ptr
+        end function
         integer(c_int) function mohid_adt_advect_batch(handle, nprop, prop, reference_prop, params) &
                 bind(c, name="mohid_adt_advect_batch")
             import :: c_int, c_ptr, T_AdtParams
