@@ -1166,9 +1166,12 @@ int mohid_adt_advect_batch(const int *handle, const int *nprop, double *const *p
             if (int rc = d2h3(h, prop[n], h->prop[h->cur[n]][n], 8, h->s_down)) return rc;
         return 0;
     };
-    if (int rc = step_once(h, b, chunk, before, after)) return rc;
-    CU(h, cudaStreamSynchronize(h->s_down));
-    CU(h, cudaStreamSynchronize(h->stream));
+    const int rc = step_once(h, b, chunk, before, after);
+    // the caller's arrays are only borrowed for the call: drain all three streams, also when a launch failed midway
+    const cudaError_t e1 = cudaStreamSynchronize(h->s_up), e2 = cudaStreamSynchronize(h->s_down),
+                      e3 = cudaStreamSynchronize(h->stream);
+    if (rc) return rc;
+    CU(h, e1); CU(h, e2); CU(h, e3);
     return 0;
 }
 
