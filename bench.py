@@ -150,7 +150,8 @@ def cpu_reference_run(workload: str, steps: int, warmup: int, budget_s: float = 
     si, sj = min(I, 384), min(J, 384)
     case = make_case(si, sj, K, nprop=nprop)
     g, s, props, refs = case_to_numpy(case)
-    o = OracleAdvectionDiffusion(si, sj, K)
+    # all the host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which is not the machine's limit)
+    o = OracleAdvectionDiffusion(si, sj, K, nthreads=len(os.sched_getaffinity(0)))
     o.set_grid2d(g)
     o.set_step(s)
     prm = params_for(nprop, method, limiter, case.dt)

@@ -113,7 +113,9 @@ int mohid_adt_set_grid2d(const int *handle, const double *DUX, const double *DVY
 /* Per-time-step shared inputs = array dummies of AdvectionDiffusion that are common to all
  * properties of a step (AD:1132-1141) plus the Geometry getters (AD:1386-1401).
  * HOST pointers; copied to the device inside the call.  SmallDepths may be NULL
- * (SmallDepthsPresent = .false., AD:1297-1302); it is int32 0/1 (0:I+1,0:J+1). */
+ * (SmallDepthsPresent = .false., AD:1297-1302); it is int32 0/1 (0:I+1,0:J+1).
+ * After a first complete call, a NULL 3-D array means "unchanged since the last step" (its device copy is kept):
+ * LandPoints3D / WaterPoints3D never change, the other maps only with wetting and drying. */
 int mohid_adt_set_step(const int *handle,
                        const double *Wflux_X, const double *Wflux_Y, const double *Wflux_Z,
                        const double *VolumeZOld, const double *VolumeZ,

@@ -944,10 +944,14 @@ int mohid_adt_set_step(const int *handle, const double *Wflux_X, const double *W
     CU(h, cudaSetDevice(h->dev));
     const double *d[11] = {Wflux_X, Wflux_Y, Wflux_Z, VolumeZOld, VolumeZ, Visc_H, Diff_V, DWZ, DZZ, AreaU, AreaV};
     const int *m[6] = {OpenPoints3D, LandPoints3D, WaterPoints3D, ComputeFacesU3D, ComputeFacesV3D, ComputeFacesW3D};
-    for (auto p : d) if (!p) return fail(h, MOHID_ADT_ERR_ARG, "null array");
-    for (auto p : m) if (!p) return fail(h, MOHID_ADT_ERR_ARG, "null mask (WaterPoints3D is required: THOMASZ_NewType2 reads it, MF:4086)");
-    for (int a = 0; a < 11; ++a) if (int rc = h2d3(h, h->raw_d[a], d[a], 8)) return rc;
-    for (int a = 0; a < 6; ++a) if (int rc = h2d3(h, h->raw_i[a], m[a], 4)) return rc;
+    // after a first complete call a NULL array means "unchanged since the last step": its device mirror is kept
+    // (the land / water maps never change, the others only with wetting and drying)
+    if (!h->have_step) {
+        for (auto p : d) if (!p) return fail(h, MOHID_ADT_ERR_ARG, "null array");
+        for (auto p : m) if (!p) return fail(h, MOHID_ADT_ERR_ARG, "null mask (WaterPoints3D is required: THOMASZ_NewType2 reads it, MF:4086)");
+    }
+    for (int a = 0; a < 11; ++a) if (d[a]) if (int rc = h2d3(h, h->raw_d[a], d[a], 8)) return rc;
+    for (int a = 0; a < 6; ++a) if (m[a]) if (int rc = h2d3(h, h->raw_i[a], m[a], 4)) return rc;
     h->have_small = SmallDepths != nullptr;
     if (SmallDepths) if (int rc = h2d2(h, h->SmallDepths, SmallDepths, 4)) return rc;
     CU(h, cudaStreamSynchronize(h->stream));     // the host arrays are only borrowed for the call (AD:2229-2349)

@@ -557,3 +557,21 @@ def test_set_limits_after_the_step(oracle_lib, docycle):
     assert np.abs(gmc - mc).max() <= 1e-11 * scale and np.abs(gmd - md).max() <= 1e-11 * scale
     assert gpu[0][w].min() >= lo and gpu[0][w].max() <= hi
     ts.close()
+
+
+def test_set_step_keeps_arrays_passed_as_none(oracle_lib):
+    """A NULL 3-D array in a later mohid_adt_set_step call keeps the device copy of the previous step."""
+    case = make_case(30, 26, 6, nprop=1)
+    o, g, s, props, refs = oracle_for(case)
+    ts = gpu_for(case, g, s)
+    s2 = dict(s)
+    s2["Wflux_X"] = np.ascontiguousarray(s["Wflux_X"] * 0.5)
+    partial = {k: (v if k == "Wflux_X" else None) for k, v in s2.items()}
+    ts.set_step(partial)
+    o.set_step(s2)
+    prm = [default_params(4, 4, 4, 4)]
+    a, b = [props[0].copy()], [props[0].copy()]
+    ts.advect_batch(a, prm)
+    o.advect_batch(b, prm)
+    compare(a, b, s2, TOL_STEP)
+    ts.close()
