@@ -66,3 +66,32 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.lower() or f == "synthetic.py" and "oracle" not in txt, (dirpath, f)
+
+
+def _build_c_driver(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "c_driver")
+    libdir = os.path.join(ROOT, "mohid_b200")
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "c_driver.c"), "-L", libdir, "-lmohid_adt", f"-Wl,-rpath,{libdir}", "-lm", "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_header_is_plain_c_and_a_c_host_links(lib, tmp_path):
+    """include/mohid_adt.h compiles as C99 and a C program links against the library (the Fortran shim's position);
+    without a CUDA device the program stops on the library's error, not on a fallback."""
+    import subprocess
+    import torch
+    exe = _build_c_driver(tmp_path)
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 1 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_c_host_runs_a_step(lib, tmp_path):
+    import subprocess
+    r = subprocess.run([_build_c_driver(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
