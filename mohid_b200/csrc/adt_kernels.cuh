@@ -639,18 +639,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
 
     // fetch the horizontal data of level k at cell offset q (all loads independent of computed values)
     auto fetch = [&](int q, Level &L) {
-        L.m = s.mask[q];
-        L.vr = s.vr[q];
+        L.m = __ldg(s.mask + (q));
+        L.vr = __ldg(s.vr + (q));
         if (do_h) {
-            L.Pw2 = P[q - jw2]; L.Pw1 = P[q - sj]; L.Pe1 = P[q + sj]; L.Pe2 = P[q + je2];
-            L.t_w = s.dtv[q - sj]; L.t_e = s.dtv[q + sj];
-            L.qxw = s.qx[q]; L.qxe = s.qx[q + sj]; L.dhw = s.dhu[q]; L.dhe = s.dhu[q + sj];
-            if (far_h) { L.t_w2 = s.dtv[q - jw2]; L.t_e2 = s.dtv[q + je2]; }
+            L.Pw2 = __ldg(P + (q - jw2)); L.Pw1 = __ldg(P + (q - sj)); L.Pe1 = __ldg(P + (q + sj)); L.Pe2 = __ldg(P + (q + je2));
+            L.t_w = __ldg(s.dtv + (q - sj)); L.t_e = __ldg(s.dtv + (q + sj));
+            L.qxw = __ldg(s.qx + (q)); L.qxe = __ldg(s.qx + (q + sj)); L.dhw = __ldg(s.dhu + (q)); L.dhe = __ldg(s.dhu + (q + sj));
+            if (far_h) { L.t_w2 = __ldg(s.dtv + (q - jw2)); L.t_e2 = __ldg(s.dtv + (q + je2)); }
             if (do_y) {
-                L.qys = s.qy[q]; L.dhs = s.dhv[q];
-                L.hP = halo_lane ? P[q + halo_off] : 0.;
-                L.t_h = (lane == 0) ? s.dtv[q - 1] : 0.;
-                if (far_h) L.t_h2 = halo_lane ? s.dtv[q + halo_off] : 0.;
+                L.qys = __ldg(s.qy + (q)); L.dhs = __ldg(s.dhv + (q));
+                L.hP = halo_lane ? __ldg(P + (q + halo_off)) : 0.;
+                L.t_h = (lane == 0) ? __ldg(s.dtv + (q - 1)) : 0.;
+                if (far_h) L.t_h2 = halo_lane ? __ldg(s.dtv + (q + halo_off)) : 0.;
             }
         }
     };
@@ -699,8 +699,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
         // were loaded one level ago; here plane k+3 is requested for the next level (clamped to plane K+1)
         const int q2 = (k + 2 <= s.K + 1) ? q + 2 * sk : q + sk;
         const int q3 = (k + 3 <= s.K + 1) ? q + 3 * sk : q2;
-        const double Pp3 = P[q3], rdz_p3 = s.rdz[q3];
-        const double dtv_pp = s.dtv[q2], qz_pp = s.qz[q2], dvz_pp = s.dvz[q2];
+        const double Pp3 = __ldg(P + q3), rdz_p3 = __ldg(s.rdz + q3);
+        const double dtv_pp = __ldg(s.dtv + q2), qz_pp = __ldg(s.qz + q2), dvz_pp = __ldg(s.dvz + q2);
         if (PF == 1) fetch(q + sk, nxt);                  // plane K+1 exists, so the look-ahead is always in bounds
         else if (PF == 0) fetch(q, nxt);
         else { __pipeline_wait_prior(NSTAGE - 1); load_stage((k - 1) & 1, nxt); }
