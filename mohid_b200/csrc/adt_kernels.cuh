@@ -98,24 +98,17 @@ struct CoefArgs {
 // K1: one thread per allocated cell; grid = (ceil(ld/128), nk, nj) so no index divisions are needed,
 // i fastest (coalesced).  Memory bound: 112 B in, 52 B out per cell.
 // -------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) adt_coef_kernel(const CoefArgs a) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    // blocks run i fastest, then k, then j: the k+-1/2 and j+-1/2 neighbour reads of a cell are then issued within a
-    // few MB of traffic of the cell itself and hit L2 (with k slowest, a whole plane of all 17 inputs lies in between)
-    const int k = blockIdx.y, j = blockIdx.z;
-    if (i >= a.ld) return;
+// EDGE = false: the cell is at least two cells away from every side of the allocation, so all neighbour probes are
+// in range and their offsets are constants (immediate-offset loads, no clamping logic); EDGE = true: the general form.
+template <bool EDGE>
+__device__ __forceinline__ void adt_coef_cell(const CoefArgs &a, const int i, const int j, const int k) {
     const int sj = a.sj, sk = a.sk, sj2 = a.ld;          // 3-D strides; 2-D arrays are (i + ld*j)
     const int q2 = i + sj2 * j;
     const int q = i + sj * j + sk * k;
-    if (i >= a.ni) {                                  // leading-dimension padding
-        if (a.do_geom) { a.mask[q] = 0; a.dtv[q] = 0.; a.vr[q] = 1.; a.rdz[q] = 0.; }
-        if (a.do_diff) { a.dhu[q] = 0.; a.dhv[q] = 0.; a.dvz[q] = 0.; }
-        return;
-    }
     // ---- neighbour offsets, clamped to the allocation (a clamped probe is masked out below) ----
-    const bool im1 = i >= 1, im2 = i >= 2, ip1 = i + 1 < a.ni, ip2 = i + 2 < a.ni;
-    const bool jm1 = j >= 1, jm2 = j >= 2, jp1 = j + 1 < a.nj, jp2 = j + 2 < a.nj;
-    const bool km1 = k >= 1, kp1 = k + 1 < a.nk, kp2 = k + 2 < a.nk;
+    const bool im1 = !EDGE || i >= 1, im2 = !EDGE || i >= 2, ip1 = !EDGE || i + 1 < a.ni, ip2 = !EDGE || i + 2 < a.ni;
+    const bool jm1 = !EDGE || j >= 1, jm2 = !EDGE || j >= 2, jp1 = !EDGE || j + 1 < a.nj, jp2 = !EDGE || j + 2 < a.nj;
+    const bool km1 = !EDGE || k >= 1, kp1 = !EDGE || k + 1 < a.nk, kp2 = !EDGE || k + 2 < a.nk;
     const int oim1 = im1 ? -1 : 0, oim2 = im2 ? -2 : 0, oip1 = ip1 ? 1 : 0, oip2 = ip2 ? 2 : 0;
     const int ojm1 = jm1 ? -sj : 0, ojm2 = jm2 ? -2 * sj : 0, ojp1 = jp1 ? sj : 0, ojp2 = jp2 ? 2 * sj : 0;
     const int okm1 = km1 ? -sk : 0, okp1 = kp1 ? sk : 0, okp2 = kp2 ? 2 * sk : 0;
@@ -221,6 +214,23 @@ __global__ void __launch_bounds__(128) adt_coef_kernel(const CoefArgs a) {
         }
         a.dhu[q] = hu; a.dhv[q] = hv; a.dvz[q] = vz;
     }
+}
+
+__global__ void __launch_bounds__(128) adt_coef_kernel(const CoefArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // blocks run i fastest, then k, then j: the k+-1/2 and j+-1/2 neighbour reads of a cell are then issued within a
+    // few MB of traffic of the cell itself and hit L2 (with k slowest, a whole plane of all 17 inputs lies in between)
+    const int k = blockIdx.y, j = blockIdx.z;
+    if (i >= a.ld) return;
+    if (i >= a.ni) {                                  // leading-dimension padding
+        const int q = i + a.sj * j + a.sk * k;
+        if (a.do_geom) { a.mask[q] = 0; a.dtv[q] = 0.; a.vr[q] = 1.; a.rdz[q] = 0.; }
+        if (a.do_diff) { a.dhu[q] = 0.; a.dhv[q] = 0.; a.dvz[q] = 0.; }
+        return;
+    }
+    const bool interior = i >= 2 && i + 2 < a.ni && j >= 2 && j + 2 < a.nj && k >= 1 && k + 2 < a.nk;
+    if (interior) adt_coef_cell<false>(a, i, j, k);
+    else adt_coef_cell<true>(a, i, j, k);
 }
 
 // 2-D reciprocal metric sums: rdx(i,j) = 1/(DUX(i,j)+DUX(i,j-1)), rdy(i,j) = 1/(DVY(i,j)+DVY(i-1,j))
