@@ -19,6 +19,7 @@
 #include "adt_kernels.cuh"
 #include "adt_ring_kernel.cuh"
 #include "adt_hsolve_kernel.cuh"
+#include "adt_hflux_kernel.cuh"
 
 using namespace adt;
 
@@ -56,6 +57,7 @@ struct Handle {
     std::vector<int> lim_min_on, lim_max_on;            // SetLimitsProperty per property (mohid_adt_set_limits)
     std::vector<double> lim_min, lim_max;
     std::vector<double *> mass_created, mass_destroyed;
+    std::vector<double *> tih;                          // net horizontal flux per cell (adt_hflux_kernel -> HSPLIT K2)
     std::vector<double *> wline;                        // W of the line recurrence (horizontally implicit advection)
     unsigned char *nfmask = nullptr;                    // NF_* bits, rebuilt by K1 every step
     int n_bnd_cols = 0;
@@ -187,6 +189,7 @@ void free_all(Handle *h) {
     for (auto p : h->noflux) F(p);
     F(h->nfmask);
     for (auto p : h->wline) F(p);
+    for (auto p : h->tih) F(p);
     F(h->density); F(h->wcol);
     for (auto p : h->mass_created) F(p);
     for (auto p : h->mass_destroyed) F(p);
@@ -552,6 +555,31 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
                       : adt_transport_kernel<MOHID_UpwindOrder1, MOHID_SuperBee, MOHID_UpwindOrder1, MOHID_SuperBee, false, true, 12, 1, true>;
         wpb = 12;
         smem = wpb * w_bytes;
+        if (const char *e = getenv("MOHID_ADT_HSPLIT")) {
+            // opt-in split: the explicit horizontal fluxes in their own kernel (adt_hflux_kernel.cuh), the column part
+            // in the HSPLIT variant of K2 with 12 or 16 warps per block
+            const int vw = atoi(e) == 16 && 16 * w_bytes <= (size_t)h->smem_optin ? 16 : 12;
+            if ((int)h->tih.size() < (int)h->prop[0].size()) h->tih.resize(h->prop[0].size(), nullptr);
+            for (int m = 0; m < s.nprop; ++m) {
+                const int n = idx[m];
+                if (!h->tih[n]) if (int rc = dalloc(h, &h->tih[n], h->n3)) return rc;
+                s.p[m].tih = h->tih[n];
+            }
+            constexpr int TJ = 7;
+            const long hblocks = (long)s.nprop * s.ntile_i * ((h->j_count + TJ - 1) / TJ);
+            if (tvd_sb) adt_hflux_kernel<MOHID_P2_TVD, MOHID_SuperBee, TJ><<<(unsigned)hblocks, (TJ + 1) * 32, 0, h->stream>>>(s);
+            else adt_hflux_kernel<MOHID_UpwindOrder1, MOHID_SuperBee, TJ><<<(unsigned)hblocks, (TJ + 1) * 32, 0, h->stream>>>(s);
+            CU(h, cudaGetLastError());
+            h->launches++;
+            if (vw == 16)
+                kern = tvd_sb ? adt_transport_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, false, true, 16, 1, true, true>
+                              : adt_transport_kernel<MOHID_UpwindOrder1, MOHID_SuperBee, MOHID_UpwindOrder1, MOHID_SuperBee, false, true, 16, 1, true, true>;
+            else
+                kern = tvd_sb ? adt_transport_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, false, true, 12, 1, true, true>
+                              : adt_transport_kernel<MOHID_UpwindOrder1, MOHID_SuperBee, MOHID_UpwindOrder1, MOHID_SuperBee, false, true, 12, 1, true, true>;
+            wpb = vw;
+            smem = wpb * w_bytes;
+        }
         if (getenv("MOHID_ADT_PF2") && tvd_sb && wpb * (w_bytes + 2 * 16 * 32 * sizeof(double)) <= (size_t)h->smem_optin) {
             kern = adt_transport_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, false, true, 12, 2, true>;
             smem = wpb * (w_bytes + 2 * 16 * 32 * sizeof(double));

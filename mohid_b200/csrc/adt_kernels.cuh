@@ -305,6 +305,7 @@ struct PropArgs {
     int advv_implicit;      // ImpExp_AdvV == ImplicitScheme (AD:3087)
     unsigned nfsel;         // NF_* bits this property honours (0 = none), see PropEff in adt_api.cu
     int pad0;
+    double *tih;            // net horizontal flux into each cell: written by adt_hflux_kernel, read by the HSPLIT variants
     const double *dconc;    // DischConc of this property per listed discharge cell, or nullptr (no discharges)
     const double *dconcmf;  // DischConcMF
 };
@@ -557,6 +558,7 @@ struct Level {
     double t_w, t_e, t_h;               // DT/V at j-1, j+1 and of the south neighbour of lane 0
     double t_w2, t_e2, t_h2;            // DT/V at j-2, j+2, strip halo (QUICK / QUICKEST only)
     double qxw, qxe, qys, dhw, dhe, dhs, vr;
+    double tih;                         // HSPLIT: net horizontal flux into the cell, from adt_hflux_kernel
     unsigned m;
 };
 
@@ -574,10 +576,12 @@ struct Level {
 //   PF    = 0 no look-ahead, 1 next level fetched into registers, 2 next two levels staged in shared memory
 //           with cp.async (in-flight loads hold no registers; needs FULL and a non-QUICK scheme).
 //   GGLOB = G of the column solve is parked in the output array instead of shared memory.
+//   HSPLIT = the explicit horizontal terms were computed by adt_hflux_kernel (every face once, high occupancy) and
+//           arrive as one increment per cell; this kernel keeps the column part (needs PF <= 1).
 //   FULL  = 3-D run with both horizontal directions and implicit vertical advection for every property:
 //           the level body becomes one basic block (no uniform branches), which lets ptxas interleave the faces.
 // -------------------------------------------------------------------------------------
-template <int MH, int LH, int MV, int LV, bool DISCH, bool FULL, int WARPS = 8, int PF = 1, bool GGLOB = false>
+template <int MH, int LH, int MV, int LV, bool DISCH, bool FULL, int WARPS = 8, int PF = 1, bool GGLOB = false, bool HSPLIT = false>
 __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __grid_constant__ StepArgs s) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, WPB = blockDim.x >> 5;
@@ -612,7 +616,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
     // stage2: second half of a horizontally implicit step (adt_hsolve_kernel.cuh): the row restarts from the
     // intermediate field (TI = PROP, E = 1, AD:4250-4253) and only the vertical terms and the boundary rows remain
     const bool stage2 = !FULL && s.stage2 != 0;
-    const bool do_h = FULL || (!s.vertical1d && !stage2), do_y = FULL || (do_h && !s.xzflow);
+    const bool do_h = !HSPLIT && (FULL || (!s.vertical1d && !stage2)), do_y = !HSPLIT && (FULL || (do_h && !s.xzflow));
     const bool do_vadv = FULL || !s.vertical1d;
 
     // ---- 2-D metrics of the column ----
@@ -651,6 +655,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
     auto fetch = [&](int q, Level &L) {
         L.m = __ldg(s.mask + (q));
         L.vr = __ldg(s.vr + (q));
+        if (HSPLIT) L.tih = __ldg(pa.tih + (q));
         if (do_h) {
             L.Pw2 = __ldg(P + (q - jw2)); L.Pw1 = __ldg(P + (q - sj)); L.Pe1 = __ldg(P + (q + sj)); L.Pe2 = __ldg(P + (q + je2));
             L.t_w = __ldg(s.dtv + (q - sj)); L.t_e = __ldg(s.dtv + (q + sj));
@@ -732,6 +737,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
         row.F = 0.;
 
         // ---------------- horizontal faces (explicit) ----------------
+        if (HSPLIT) row.TI += cur.tih * dtv_c;           // tih = net horizontal flux into the cell (adt_hflux_kernel)
         if (do_h) {
             const bool o_w1 = (m & M_O_JM1) != 0, o_e1 = (m & M_O_JP1) != 0;
             const double fw = hface_flux<MH, LH>(s, all_set(m, M_CFU | M_O_JM1 | M_OPEN) && !(nf & NF_WEST), cur.qxw, cur.dhw, cur.Pw2, cur.Pw1,

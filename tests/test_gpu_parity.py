@@ -413,11 +413,13 @@ def test_ring_kernel_matches_plain_kernel_and_oracle(oracle_lib, shape, method, 
     o, g, s, props, refs = oracle_for(case)
     prm = [default_params(method, 4, method, 4, bc=bc, decay_time=600.0) for _ in range(N)]
     out = {}
-    for mode in ("ring", "ring2", "plain"):
-        if mode != "plain":
+    for mode in ("ring", "ring2", "hsplit", "hsplit16", "plain"):
+        monkeypatch.delenv("MOHID_ADT_RING", raising=False)
+        monkeypatch.delenv("MOHID_ADT_HSPLIT", raising=False)
+        if mode.startswith("ring"):
             monkeypatch.setenv("MOHID_ADT_RING", "2" if mode == "ring2" else "1")     # 2: two properties per warp
-        else:
-            monkeypatch.delenv("MOHID_ADT_RING", raising=False)
+        elif mode.startswith("hsplit"):
+            monkeypatch.setenv("MOHID_ADT_HSPLIT", "16" if mode == "hsplit16" else "12")   # warps of the column kernel
         ts = gpu_for(case, g, s)
         a = [p.copy() for p in props]
         for _ in range(3):
@@ -425,9 +427,9 @@ def test_ring_kernel_matches_plain_kernel_and_oracle(oracle_lib, shape, method, 
         out[mode] = a
         assert ts.counters()["zero_pivots"] == 0
         ts.close()
-    for mode in ("ring", "ring2"):
+    for mode in ("ring", "ring2", "hsplit", "hsplit16"):
         for a, b in zip(out[mode], out["plain"]):
-            assert np.array_equal(a, b)
+            assert np.array_equal(a, b), mode
     cpu = [p.copy() for p in props]
     for _ in range(3):
         o.advect_batch(cpu, prm, refs)
