@@ -550,6 +550,17 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
         wpb = (s.nprop + npt - 1) / npt + 1;
         smem = ring_smem_bytes(s.nprop, h->K);
         grid_override = std::min<long>((long)s.ntile_i * h->j_count, (long)h->num_sms);
+    } else if (full && !any_disch && s.method_h == MOHID_P2_TVD && s.method_v == MOHID_P2_TVD && !tvd_sb &&
+               s.limiter_h == s.limiter_v && 12 * w_bytes <= (size_t)h->smem_optin) {
+        // P2_TVD with one of the other limiters (MinMod, VanLeer, Muscl, PDM) in both directions: same 12-warp form
+        switch (s.limiter_h) {
+            case MOHID_MinMod: kern = adt_transport_kernel<MOHID_P2_TVD, MOHID_MinMod, MOHID_P2_TVD, MOHID_MinMod, false, true, 12, 1, true>; break;
+            case MOHID_VanLeer: kern = adt_transport_kernel<MOHID_P2_TVD, MOHID_VanLeer, MOHID_P2_TVD, MOHID_VanLeer, false, true, 12, 1, true>; break;
+            case MOHID_Muscl: kern = adt_transport_kernel<MOHID_P2_TVD, MOHID_Muscl, MOHID_P2_TVD, MOHID_Muscl, false, true, 12, 1, true>; break;
+            default: kern = adt_transport_kernel<MOHID_P2_TVD, MOHID_PDM, MOHID_P2_TVD, MOHID_PDM, false, true, 12, 1, true>; break;
+        }
+        wpb = 12;
+        smem = wpb * w_bytes;
     } else if (full && !any_disch && (tvd_sb || upw) && 12 * w_bytes <= (size_t)h->smem_optin) {
         kern = tvd_sb ? adt_transport_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, false, true, 12, 1, true>
                       : adt_transport_kernel<MOHID_UpwindOrder1, MOHID_SuperBee, MOHID_UpwindOrder1, MOHID_SuperBee, false, true, 12, 1, true>;
