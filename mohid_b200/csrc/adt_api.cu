@@ -30,6 +30,7 @@ struct Handle {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t s_up = nullptr, s_down = nullptr;      // copy streams of the pipelined host path (advect_batch)
+    void *stage[3] = {nullptr, nullptr, nullptr};       // one field in the caller's pitch per stream (short padded rows)
     // halo overlap (mohid_adt_set_overlap): the edge columns of a slab are advanced first, ev_edges is recorded, and
     // pack / unpack run on the caller's communication stream while the interior columns are still being advanced
     cudaStream_t comm = nullptr, s_edge = nullptr;      // s_edge: the edge columns run beside the interior ones
@@ -140,10 +141,33 @@ int h2d2(Handle *h, void *dst, const void *src, size_t es) {
 }
 // 3-D arrays: the caller's layout is Fortran (i, j, k); the device mirror is (i, k, j) when kmid, so each k-plane
 // of the caller is one strided 2-D copy (row pitch sj on the device).
+// Staging buffer of the stream (one field in the caller's pitch), or nullptr when the rows are long enough for the
+// copy engine to move them pitched at link speed.  When ld_h > ld the caller's padding columns travel too; the
+// D2H direction then leaves them untouched on the host only in the direct path, so staging is limited to ld_h <= ld.
+void *staging(Handle *h, cudaStream_t st, size_t es) {
+    if (h->ld_h > h->ld || es * (size_t)h->ld_h >= 8192) return nullptr;
+    const int w = (st == h->s_up && h->s_up) ? 1 : (st == h->s_down && h->s_down) ? 2 : 0;
+    if (!h->stage[w]) {
+        if (cudaMalloc(&h->stage[w], 8 * (size_t)h->ld_h * h->nj * h->nk) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        h->bytes += 8LL * h->ld_h * h->nj * h->nk;
+    }
+    return h->stage[w];
+}
+
 int h2d3(Handle *h, void *dst, const void *src, size_t es, cudaStream_t st = nullptr) {
     if (!st) st = h->stream;
     if (h->ld == h->ld_h && h->sj == h->ld && h->sk == h->ld * h->nj) {      // same layout on both sides: one copy
         CU(h, cudaMemcpyAsync(dst, src, es * h->n3, cudaMemcpyDefault, st));
+        return 0;
+    }
+    if (h->sj == h->ld && h->sk == h->ld * h->nj) {      // rows of all planes are equally spaced on both sides: one 2-D copy
+        void *stg = staging(h, st, es);
+        if (stg) {      // short rows: cross the link contiguously, change the pitch on the device
+            CU(h, cudaMemcpyAsync(stg, src, es * (size_t)h->ld_h * h->nj * h->nk, cudaMemcpyDefault, st));
+            src = stg;
+        }
+        CU(h, cudaMemcpy2DAsync(dst, es * h->ld, src, es * h->ld_h, es * std::min(h->ld, h->ld_h), (size_t)h->nj * h->nk,
+                                cudaMemcpyDefault, st));
         return 0;
     }
     for (int k = 0; k < h->nk; ++k)
@@ -156,6 +180,18 @@ int d2h3(Handle *h, void *dst, const void *src, size_t es, cudaStream_t st = nul
     if (!st) st = h->stream;
     if (h->ld == h->ld_h && h->sj == h->ld && h->sk == h->ld * h->nj) {
         CU(h, cudaMemcpyAsync(dst, src, es * h->n3, cudaMemcpyDefault, st));
+        return 0;
+    }
+    if (h->sj == h->ld && h->sk == h->ld * h->nj) {
+        void *stg = staging(h, st, es);
+        if (stg) {
+            CU(h, cudaMemcpy2DAsync(stg, es * h->ld_h, src, es * h->ld, es * std::min(h->ld, h->ld_h), (size_t)h->nj * h->nk,
+                                    cudaMemcpyDeviceToDevice, st));
+            CU(h, cudaMemcpyAsync(dst, stg, es * (size_t)h->ld_h * h->nj * h->nk, cudaMemcpyDefault, st));
+            return 0;
+        }
+        CU(h, cudaMemcpy2DAsync(dst, es * h->ld_h, src, es * h->ld, es * std::min(h->ld, h->ld_h), (size_t)h->nj * h->nk,
+                                cudaMemcpyDefault, st));
         return 0;
     }
     for (int k = 0; k < h->nk; ++k)
@@ -210,6 +246,7 @@ void free_all(Handle *h) {
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->s_edge) cudaStreamDestroy(h->s_edge);
     h->ev_edges = h->ev_halo = h->ev_fork = nullptr; h->s_edge = nullptr;
+    for (auto &p : h->stage) { if (p) cudaFree(p); p = nullptr; }
     if (h->s_up) cudaStreamDestroy(h->s_up);
     if (h->s_down) cudaStreamDestroy(h->s_down);
     for (auto e : h->pipe_ev) cudaEventDestroy(e);
