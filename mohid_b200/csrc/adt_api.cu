@@ -145,7 +145,8 @@ int h2d2(Handle *h, void *dst, const void *src, size_t es) {
 // copy engine to move them pitched at link speed.  When ld_h > ld the caller's padding columns travel too; the
 // D2H direction then leaves them untouched on the host only in the direct path, so staging is limited to ld_h <= ld.
 void *staging(Handle *h, cudaStream_t st, size_t es) {
-    if (h->ld_h > h->ld || es * (size_t)h->ld_h >= 8192) return nullptr;
+    static const size_t row_limit = getenv("MOHID_ADT_STAGE_ROW") ? (size_t)atol(getenv("MOHID_ADT_STAGE_ROW")) : 8192;
+    if (h->ld_h > h->ld || es * (size_t)h->ld_h >= row_limit) return nullptr;
     const int w = (st == h->s_up && h->s_up) ? 1 : (st == h->s_down && h->s_down) ? 2 : 0;
     if (!h->stage[w]) {
         if (cudaMalloc(&h->stage[w], 8 * (size_t)h->ld_h * h->nj * h->nk) != cudaSuccess) { cudaGetLastError(); return nullptr; }
