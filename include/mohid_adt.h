@@ -239,6 +239,36 @@ int mohid_adt_unpack_columns(const int *handle, const int *nprop, const int *j0,
 /* Use the caller's CUDA stream (cudaStream_t passed as void*) for all work of this handle. */
 int mohid_adt_set_stream(const int *handle, void *cuda_stream);
 
+/* ---- NCCL halo exchange (one handle = one rank = one GPU) ---------------------------- */
+/* Replaces the MPI halo exchange of the property fields, ReceiveSendProperitiesMPI (ModuleWaterProperties.F90:
+ * 15034-15045) -> ReceiveSendProperities3DMPIr8 (ModuleHorizontalGrid.F90:8479-8658), for hosts that keep the
+ * properties resident on the GPUs.  libnccl.so.2 is loaded at run time by the first of these calls.
+ *   comm_get_unique_id : rank 0 obtains the 128-byte NCCL id and hands it to the other ranks with the host's own
+ *                        means (MPI_Bcast in a MOHID MPI run, the torch store in bench.py);
+ *   comm_init          : collective over the ranks; the handle must already be restricted to its owned columns
+ *                        (mohid_adt_set_active_columns) with `ghost` (= 2, the reach of the advection stencil,
+ *                        ModuleFunctions.F90:10572-10574) columns left on every interior side; overlap != 0 lets
+ *                        the next steps advance the edge columns first so the exchange overlaps the interior;
+ *   exchange_halos     : after a step: first / last `ghost` owned columns of properties 0..nprop-1 -> neighbours'
+ *                        ghost columns (pack -> ncclSend/ncclRecv -> unpack on the handle's communication stream;
+ *                        the next step, a download or mohid_adt_synchronize waits for it);
+ *   comm_destroy       : collective. */
+int mohid_adt_comm_get_unique_id(void *unique_id, const int *nbytes);
+int mohid_adt_comm_init(const int *handle, const int *nranks, const int *rank, const void *unique_id, const int *ghost,
+                        const int *overlap);
+int mohid_adt_exchange_halos(const int *handle, const int *nprop);
+int mohid_adt_comm_destroy(const int *handle);
+
+/* ---- stand-alone column solve ------------------------------------------------------ */
+/* THOMASZ_NewType2 (ModuleFunctions.F90:4026-4123) on caller-supplied coefficient fields: for every column with
+ * WaterPoints3D(i,j,KUB) == 1 (all columns when WaterPoints3D is NULL) eliminates rows 1 .. KUB+1 of
+ * D(k) x(k-1) + E(k) x(k) + F(k) x(k+1) = TI(k) and back-substitutes into Res (in/out: cells outside solved columns
+ * are kept).  This is the entry the reference's legacy GPU path binds as SolveThomas_C(cudaObjID, bounds, D, E, F, TI,
+ * Res, dimension = Z) (ModuleCuda.F90:103-111, CudaThomas/Thomas.cu:24-52, kernel DevThomasIK :62-131); the arrays
+ * may be host or device pointers, shaped like every 3-D array of the handle. */
+int mohid_adt_solve_thomas_z(const int *handle, const double *D, const double *E, const double *F, const double *TI,
+                             const int *WaterPoints3D, double *Res);
+
 /* ---- diagnostics ------------------------------------------------------------------ */
 /* Copies the last error message of the handle (or of the library when handle is NULL). */
 int mohid_adt_last_error(const int *handle, char *buf, const int *buflen);

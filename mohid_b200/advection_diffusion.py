@@ -221,6 +221,26 @@ class TransportStep:
         """Edge-first stepping + pack/unpack on `comm_stream`; ghost = 0 switches it off."""
         self._check(self.lib.mohid_adt_set_overlap(C.byref(self.h), C.byref(C.c_int(ghost)), C.c_void_p(comm_stream)))
 
+    # ---- NCCL halo exchange inside the library (mohid_adt_comm_*) -------------------
+    def comm_unique_id(self) -> bytes:
+        """128-byte NCCL id (rank 0 obtains it; the host hands it to the other ranks)."""
+        buf = C.create_string_buffer(128)
+        self._check(self.lib.mohid_adt_comm_get_unique_id(buf, C.byref(C.c_int(128))))
+        return buf.raw
+
+    def comm_init(self, nranks: int, rank: int, unique_id: bytes, ghost: int = 2, overlap: bool = True):
+        """Collective: one communicator over the j-slabs; needs set_active_columns first."""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(self.lib.mohid_adt_comm_init(C.byref(self.h), C.byref(C.c_int(nranks)), C.byref(C.c_int(rank)), buf,
+                                                 C.byref(C.c_int(ghost)), C.byref(C.c_int(int(overlap)))))
+
+    def exchange_halos(self, nprop: int):
+        """Edge columns of properties 0..nprop-1 -> the neighbours' ghost columns (replaces HG:8479-8658)."""
+        self._check(self.lib.mohid_adt_exchange_halos(C.byref(self.h), C.byref(C.c_int(nprop))))
+
+    def comm_destroy(self):
+        self._check(self.lib.mohid_adt_comm_destroy(C.byref(self.h)))
+
     def join_halo(self):
         """The compute stream waits for a halo exchange still running on the communication stream."""
         self._check(self.lib.mohid_adt_join_halo(C.byref(self.h)))
@@ -237,6 +257,14 @@ class TransportStep:
 
     def synchronize(self):
         self._check(self.lib.mohid_adt_synchronize(C.byref(self.h)))
+
+    # ---- stand-alone column solve ---------------------------------------------------
+    def solve_thomas_z(self, D, E, F, TI, res, water=None):
+        """THOMASZ_NewType2 (MF:4026-4123) / SolveThomas_C (ModuleCuda.F90:103-111) on caller-supplied fields;
+        ``res`` is updated in place."""
+        self._check(self.lib.mohid_adt_solve_thomas_z(
+            C.byref(self.h), _ptr(D, "f8", self.n3, "D"), _ptr(E, "f8", self.n3, "E"), _ptr(F, "f8", self.n3, "F"),
+            _ptr(TI, "f8", self.n3, "TI"), _ptr(water, "i4", self.n3, "WaterPoints3D"), _ptr(res, "f8", self.n3, "Res")))
 
     # ---- diagnostics ----------------------------------------------------------------
     def counters(self) -> Dict[str, int]:

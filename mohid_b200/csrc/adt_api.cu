@@ -16,10 +16,14 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nccl.h>      // types only: the library is dlopen'ed by mohid_adt_comm_init, never linked
+
 #include "adt_kernels.cuh"
 #include "adt_ring_kernel.cuh"
 #include "adt_hsolve_kernel.cuh"
 #include "adt_hflux_kernel.cuh"
+#include "adt_lean_kernel.cuh"
 
 using namespace adt;
 
@@ -90,7 +94,57 @@ struct Handle {
     std::vector<double *> d_conc, d_concmf;             // per property (nullptr = no discharges)
     std::vector<double *> flux[6];                      // per property: AdvFluxX/Y/Z, DifFluxX/Y/Z (allocated on demand)
     std::vector<int> bnd_host;                          // (i,j) of all boundary columns
+    // lean path (adt_lean_kernel.cuh): face packs U, V, W, C of the columns pk_jc0 .. pk_jc0+pk_ncol-1, 2-D metric ratios
+    Pack4 *pk[4] = {nullptr, nullptr, nullptr, nullptr};
+    int pk_ncol = 0, pk_jc0 = 0;
+    double *rho2d[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool rho_valid = false, lean_now = false;
+    // NCCL halo exchange behind the C-ABI (mohid_adt_comm_init): communicator, neighbour buffers, own comm stream
+    ncclComm_t nccl = nullptr;
+    int nranks = 1, rank = 0, halo_ghost = 0;
+    cudaStream_t s_comm_own = nullptr;
+    double *halo_buf[4] = {nullptr, nullptr, nullptr, nullptr};     // send left, recv left, send right, recv right
+    size_t halo_cap = 0;
 };
+
+// ---- NCCL, loaded at run time (single-GPU users never need it) ----
+struct NcclApi {
+    void *dl = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+
+// a copy already loaded by the host process (torch ships its own) is reused; else the system library
+const char *load_nccl() {
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    if (g_nccl.dl) return nullptr;
+    void *dl = nullptr;
+    const char *env = getenv("MOHID_ADT_NCCL_LIB");
+    if (env) dl = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+    if (!dl) dl = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!dl) dl = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!dl) dl = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!dl) return "libnccl.so.2 not found (set MOHID_ADT_NCCL_LIB)";
+    NcclApi a;
+    a.dl = dl;
+#define ADT_SYM(field, name)                                   \
+    *(void **)(&a.field) = dlsym(dl, name);                    \
+    if (!a.field) return "symbol " name " missing in libnccl";
+    ADT_SYM(GetUniqueId, "ncclGetUniqueId") ADT_SYM(CommInitRank, "ncclCommInitRank") ADT_SYM(CommDestroy, "ncclCommDestroy")
+    ADT_SYM(Send, "ncclSend") ADT_SYM(Recv, "ncclRecv") ADT_SYM(GroupStart, "ncclGroupStart")
+    ADT_SYM(GroupEnd, "ncclGroupEnd") ADT_SYM(GetErrorString, "ncclGetErrorString")
+#undef ADT_SYM
+    g_nccl = a;
+    return nullptr;
+}
 
 std::mutex g_mu;
 std::map<int, Handle *> g_h;
@@ -236,6 +290,11 @@ void free_all(Handle *h) {
     for (int b = 0; b < 2; ++b) for (auto p : h->prop[b]) F(p);
     for (auto p : h->ref) F(p);
     F(h->d_zero_piv);
+    for (auto p : h->pk) F(p);
+    for (auto p : h->rho2d) F(p);
+    for (auto p : h->halo_buf) F(p);
+    if (h->nccl && g_nccl.CommDestroy) { g_nccl.CommDestroy(h->nccl); h->nccl = nullptr; }
+    if (h->s_comm_own) { cudaStreamDestroy(h->s_comm_own); h->s_comm_own = nullptr; }
     F(h->d_ci); F(h->d_cj); F(h->d_ck); F(h->d_ckmin); F(h->d_ckmax); F(h->d_cvert); F(h->d_cbypass);
     F(h->d_kmin_eff); F(h->d_kmax_eff); F(h->d_cflow); F(h->d_flow_k);
     for (auto p : h->d_conc) F(p);
@@ -427,6 +486,72 @@ int launch_coef(Handle *h, const mohid_adt_params &q, const PropEff &e, bool geo
     return 0;
 }
 
+// ---- lean path (adt_lean_kernel.cuh) ----
+// The batch takes the lean kernels when every property runs the headline form: 3-D, both horizontal directions
+// explicit, implicit vertical advection, P2_TVD + SuperBee or first-order upwind in both directions, and none of the
+// rare options (discharges, NoFlux cell lists, Orlanski, CellFluxes).
+bool lean_eligible(const Handle *h, const Batch &b) {
+    if (getenv("MOHID_ADT_NOLEAN")) return false;
+    if (h->opt.Vertical1D || h->opt.XZFlow || h->K < 2 || h->have_noflux || h->kmid) return false;
+    const mohid_adt_params &f = b.p[0];
+    const bool tvd_sb = f.AdvMethodH == MOHID_P2_TVD && f.AdvMethodV == MOHID_P2_TVD &&
+                        f.TVDLimitationH == MOHID_SuperBee && f.TVDLimitationV == MOHID_SuperBee;
+    const bool upw = f.AdvMethodH == MOHID_UpwindOrder1 && f.AdvMethodV == MOHID_UpwindOrder1;
+    if (!tvd_sb && !upw) return false;
+    for (int n = 0; n < b.nprop; ++n) {
+        const mohid_adt_params &q = b.p[n];
+        if (q.ImpExp_AdvV != 1.0 || q.ImpExp_AdvXX == 1.0 || q.ImpExp_AdvYY == 1.0 || q.CellFluxes) return false;
+        if (q.BoundaryCondition == MOHID_BC_Orlanski && h->has_ref[n]) return false;
+        if (h->d_ncell > 0 && n < (int)h->d_conc.size() && h->d_conc[n]) return false;
+        if (b.eff[n].nfsel || b.eff[n].nodif_h || b.eff[n].nodif_w) return false;
+    }
+    return (size_t)h->K * 32 * sizeof(double) * 8 <= (size_t)h->smem_optin;
+}
+
+int ensure_lean(Handle *h, int ncol) {
+    for (auto &p : h->rho2d) if (!p) { if (int rc = dalloc(h, &p, h->n2)) return rc; h->rho_valid = false; }
+    if (!h->rho_valid) {
+        adt_grid2d_rho_kernel<<<std::max(1, (int)std::min<long>((h->n2 + 255) / 256, 4096)), 256, 0, h->stream>>>(
+            h->ni, h->nj, h->ld, h->I, h->J, h->rdx, h->rdy, h->rho2d[0], h->rho2d[1], h->rho2d[2], h->rho2d[3]);
+        CU(h, cudaGetLastError());
+        h->launches++;
+        h->rho_valid = true;
+    }
+    if (h->pk_ncol < ncol) {
+        CU(h, cudaStreamSynchronize(h->stream));
+        for (auto &p : h->pk) { if (p) cudaFree(p); p = nullptr; }
+        for (auto &p : h->pk) if (int rc = dalloc(h, &p, (size_t)h->ld * ncol * h->nk)) return rc;
+        h->pk_ncol = ncol;
+    }
+    return 0;
+}
+
+// packs of the columns jc0 .. jc0+ncol-1 for the diffusion flags `e`
+int launch_lean_coef(Handle *h, const mohid_adt_params &q, const PropEff &e, int jc0, int ncol) {
+    LeanCoefArgs A{};
+    CoefArgs &a = A.c;
+    a.ni = h->ni; a.nj = h->nj; a.nk = h->nk; a.ld = h->ld; a.I = h->I; a.J = h->J; a.K = h->K;
+    a.sj = h->sj; a.sk = h->sk;
+    a.dt = q.DTProp; a.schmidt_h = e.schmidt_h; a.schmidt_coef_v = e.coef_v; a.schmidt_bg_v = e.bg_v;
+    a.nulldif = e.nulldif_h; a.nulldif_v = e.nulldif_v;
+    a.Wflux_X = h->raw_d[0]; a.Wflux_Y = h->raw_d[1]; a.Wflux_Z = h->raw_d[2]; a.VolumeZOld = h->raw_d[3];
+    a.VolumeZ = h->raw_d[4]; a.Visc_H = h->raw_d[5]; a.Diff_V = h->raw_d[6]; a.DWZ = h->raw_d[7]; a.DZZ = h->raw_d[8];
+    a.AreaU = h->raw_d[9]; a.AreaV = h->raw_d[10];
+    a.Open = h->raw_i[0]; a.Land = h->raw_i[1]; a.Water = h->raw_i[2]; a.CFU = h->raw_i[3]; a.CFV = h->raw_i[4];
+    a.CFW = h->raw_i[5]; a.SmallDepths = h->have_small ? h->SmallDepths : nullptr;
+    a.DUX = h->DUX; a.DVY = h->DVY; a.DZX = h->DZX; a.DZY = h->DZY; a.Bnd = h->Bnd;
+    A.pkU = h->pk[0]; A.pkV = h->pk[1]; A.pkW = h->pk[2]; A.pkC = h->pk[3];
+    A.jc0 = jc0; A.ncol = ncol; A.skc = h->ld * h->pk_ncol;
+    A.tvd = q.AdvMethodH == MOHID_P2_TVD; A.upwind2_h = q.Upwind2H; A.upwind2_v = q.Upwind2V;
+    A.rhoUp = h->rho2d[0]; A.rhoUn = h->rho2d[1]; A.rhoVp = h->rho2d[2]; A.rhoVn = h->rho2d[3];
+    const dim3 grid((unsigned)((h->ld + 127) / 128), (unsigned)h->nk, (unsigned)ncol);
+    adt_lean_coef_kernel<<<grid, 128, 0, h->stream>>>(A);
+    CU(h, cudaGetLastError());
+    h->launches++;
+    h->pk_jc0 = jc0;
+    return 0;
+}
+
 // Caller-side column steps (K7) for the properties `idx`: sign = +1 before the transport call (mixing + OffSet),
 // -1 after it (OffSet taken out again).
 int launch_premix(Handle *h, const std::vector<int> &idx, int sign) {
@@ -562,7 +687,9 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
     const bool tvd_sb = s.method_h == MOHID_P2_TVD && s.method_v == MOHID_P2_TVD && s.limiter_h == MOHID_SuperBee &&
                         s.limiter_v == MOHID_SuperBee;
     const bool upw = s.method_h == MOHID_UpwindOrder1 && s.method_v == MOHID_UpwindOrder1;
-    void (*kern)(const StepArgs);
+    void (*kern)(const StepArgs) = nullptr;
+    void (*lkern)(const LeanArgs) = nullptr;      // lean path: the step kernel takes the packs
+    LeanArgs la{};
     int wpb;
     size_t smem;
     // Occupancy is bounded by registers (16K per SM sub-partition): 8 warps allow 255 registers per thread,
@@ -577,7 +704,27 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
                          h->ld % 4 == 0 && ring_smem_bytes(s.nprop, h->K) <= (size_t)h->smem_optin &&
                          getenv("MOHID_ADT_RING") && atoi(getenv("MOHID_ADT_RING")) != 0;
     long grid_override = 0;
-    if (ring_ok) {
+    if (h->lean_now) {
+        // warps per block: MOHID_ADT_LEAN_WARPS (8, 12, 16 or 20; experiments) or the measured best that fits
+        int want = getenv("MOHID_ADT_LEAN_WARPS") ? atoi(getenv("MOHID_ADT_LEAN_WARPS")) : 16;
+        while (want > 8 && (size_t)want * w_bytes > (size_t)h->smem_optin) want -= 4;
+#define ADT_LEAN(M)                                                                            \
+    (want >= 20   ? adt_transport_lean_kernel<M, 20>                                           \
+     : want >= 16 ? adt_transport_lean_kernel<M, 16>                                           \
+     : want >= 12 ? adt_transport_lean_kernel<M, 12>                                           \
+                  : adt_transport_lean_kernel<M, 8>)
+        lkern = tvd_sb ? ADT_LEAN(MOHID_P2_TVD) : ADT_LEAN(MOHID_UpwindOrder1);
+#undef ADT_LEAN
+        wpb = want >= 20 ? 20 : want >= 16 ? 16 : want >= 12 ? 12 : 8;
+        smem = wpb * w_bytes;
+        la.I = s.I; la.J = s.J; la.K = s.K; la.ld = s.ld; la.sj = s.sj; la.sk = s.sk;
+        la.nprop = s.nprop; la.ntile_i = s.ntile_i; la.j_begin = s.j_begin; la.j_count = s.j_count;
+        la.jc0 = h->pk_jc0; la.skc = h->ld * h->pk_ncol; la.dt = s.dt;
+        la.pkU = h->pk[0]; la.pkV = h->pk[1]; la.pkW = h->pk[2]; la.pkC = h->pk[3];
+        la.qx = s.qx; la.qy = s.qy; la.qz = s.qz; la.VolumeZ = s.VolumeZ; la.VolumeZOld = s.VolumeZOld;
+        la.zero_pivots = s.zero_pivots;
+        for (int m = 0; m < s.nprop; ++m) la.p[m] = s.p[m];
+    } else if (ring_ok) {
         const int npt = atoi(getenv("MOHID_ADT_RING")) >= 2 ? 2 : 1;          // properties per consumer warp
         if (npt == 2)
             kern = tvd_sb ? adt_transport_ring_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, RING_NCW / 2, 2>
@@ -650,7 +797,8 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
     const long nunits = (long)s.nprop * s.ntile_i * h->j_count;
     const long blocks = grid_override ? grid_override : (nunits + wpb - 1) / wpb;
     if (blocks > 2147483647L) return fail(h, MOHID_ADT_ERR_ARG, "grid too large");
-    CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (lkern) CU(h, cudaFuncSetAttribute(lkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (timed) {
         if (h->ev_used == h->ev.size()) {
@@ -670,7 +818,7 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
             if (b.p[idx[m]].BoundaryCondition != MOHID_BC_NullGradient || h->n_bnd_cols == 0) continue;
             BndArgs ba{};
             ba.I = h->I; ba.J = h->J; ba.K = h->K; ba.ld = h->ld; ba.nj = h->nj; ba.ncols = h->n_bnd_cols;
-            ba.sj = s.sj; ba.sk = s.sk; ba.cols = h->bnd_cols; ba.kfloor = h->KFloorZ; ba.mask = h->mask;
+            ba.sj = s.sj; ba.sk = s.sk; ba.cols = h->bnd_cols; ba.kfloor = h->KFloorZ; ba.CFU = h->raw_i[3]; ba.CFV = h->raw_i[4]; ba.Bnd = h->Bnd;
             ba.prop = s.p[m].pout; ba.pref = s.p[m].pref; ba.jmin = jmin; ba.jmax = jmax;
             const long tot = (long)h->n_bnd_cols * h->K;
             adt_nullgrad_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, lst>>>(ba);
@@ -693,8 +841,10 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
     }
     auto launch_range = [&](int jb, int jc) -> int {
         s.j_begin = jb; s.j_count = jc;
+        la.j_begin = jb; la.j_count = jc;
         const long nu = (long)s.nprop * s.ntile_i * jc;
-        kern<<<(unsigned)((nu + wpb - 1) / wpb), wpb * 32, smem, lst>>>(s);
+        if (lkern) lkern<<<(unsigned)((nu + wpb - 1) / wpb), wpb * 32, smem, lst>>>(la);
+        else kern<<<(unsigned)((nu + wpb - 1) / wpb), wpb * 32, smem, lst>>>(s);
         CU(h, cudaGetLastError());
         h->launches++;
         return 0;
@@ -717,7 +867,8 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
         s.j_begin = h->j_begin; s.j_count = h->j_count;
         h->launches--;                                   // (counted once below, as in the single-launch order)
     } else {
-        kern<<<(unsigned)blocks, wpb * 32, smem, h->stream>>>(s);
+        if (lkern) lkern<<<(unsigned)blocks, wpb * 32, smem, h->stream>>>(la);
+        else kern<<<(unsigned)blocks, wpb * 32, smem, h->stream>>>(s);
         CU(h, cudaGetLastError());
     }
     if (timed) CU(h, cudaEventRecord(e1, h->stream));
@@ -751,7 +902,7 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
         if ((bc == MOHID_BC_CyclicBoundary && h->has_ref[n]) && h->n_bnd_cols > 0) {
             BndArgs ba{};
             ba.I = h->I; ba.J = h->J; ba.K = h->K; ba.ld = h->ld; ba.nj = h->nj; ba.ncols = h->n_bnd_cols;
-            ba.sj = s.sj; ba.sk = s.sk; ba.cols = h->bnd_cols; ba.kfloor = h->KFloorZ; ba.mask = h->mask;
+            ba.sj = s.sj; ba.sk = s.sk; ba.cols = h->bnd_cols; ba.kfloor = h->KFloorZ; ba.CFU = h->raw_i[3]; ba.CFV = h->raw_i[4]; ba.Bnd = h->Bnd;
             ba.prop = s.p[m].pout; ba.pref = s.p[m].pref; ba.jmin = 0; ba.jmax = 2147483647;
             const long tot = (long)h->n_bnd_cols * h->K;
             {
@@ -812,6 +963,8 @@ int step_once(Handle *h, const Batch &b, int chunk = 0, const ChunkHook &before 
         for (int n = 0; n < b.nprop && one; ++n) one = !(b.p[n].ImpExp_AdvXX == 1.0 || b.p[n].ImpExp_AdvYY == 1.0);
         h->allow_edge_first = one && !(h->premix_fc || h->premix_sd);
     }
+    h->lean_now = lean_eligible(h, b);
+    if (h->lean_now) if (int rc = ensure_lean(h, h->nj)) return rc;
     if (h->premix_sd) {                                   // Me%SmallDepths%ON (WP:12975-12980), consumed by K1
         PremixArgs a{};
         a.I = h->I; a.J = h->J; a.K = h->K; a.ld = h->ld; a.sj = h->sj; a.sk = h->sk;
@@ -831,7 +984,8 @@ int step_once(Handle *h, const Batch &b, int chunk = 0, const ChunkHook &before 
                 done[m] = 1;
             }
         }
-        if (int rc = launch_coef(h, b.p[n], b.eff[n], !geom_done, true)) return rc;
+        if (h->lean_now) { if (int rc = launch_lean_coef(h, b.p[n], b.eff[n], 0, h->nj)) return rc; }
+        else if (int rc = launch_coef(h, b.p[n], b.eff[n], !geom_done, true)) return rc;
         if (!geom_done && h->d_ncell > 0) {               // flag the receiving cells, per-layer flows (AD:4063-4077)
             DischArgs d{};
             d.ncell = h->d_ncell; d.K = h->K; d.ld = h->ld; d.sj = h->sj; d.sk = h->sk;
@@ -962,6 +1116,12 @@ int mohid_adt_destroy(int *handle) {
         g_h.erase(it);
     }
     cudaSetDevice(h->dev);
+    // work queued on the communication / edge / copy streams may still touch the buffers freed below
+    if (h->comm) cudaStreamSynchronize(h->comm);
+    if (h->s_comm_own) cudaStreamSynchronize(h->s_comm_own);
+    if (h->s_edge) cudaStreamSynchronize(h->s_edge);
+    if (h->s_up) cudaStreamSynchronize(h->s_up);
+    if (h->s_down) cudaStreamSynchronize(h->s_down);
     cudaStreamSynchronize(h->stream);
     free_all(h);
     delete h;
@@ -1476,13 +1636,166 @@ int mohid_adt_join_halo(const int *handle) {
     return 0;
 }
 
+// ---- NCCL halo exchange behind the C-ABI (replaces ReceiveSendProperitiesMPI, WP:15034-15045 -> HG:8479-8658) ----
+int mohid_adt_comm_get_unique_id(void *unique_id, const int *nbytes) {
+    if (!unique_id || !nbytes || *nbytes < (int)sizeof(ncclUniqueId))
+        return fail(nullptr, MOHID_ADT_ERR_ARG, "unique_id buffer must hold %d bytes", (int)sizeof(ncclUniqueId));
+    if (const char *e = load_nccl()) return fail(nullptr, MOHID_ADT_ERR_UNSUPPORTED, "NCCL: %s", e);
+    ncclUniqueId id;
+    const ncclResult_t r = g_nccl.GetUniqueId(&id);
+    if (r != ncclSuccess) return fail(nullptr, MOHID_ADT_ERR_CUDA, "ncclGetUniqueId: %s", g_nccl.GetErrorString(r));
+    memcpy(unique_id, &id, sizeof id);
+    return 0;
+}
+
+int mohid_adt_comm_init(const int *handle, const int *nranks, const int *rank, const void *unique_id, const int *ghost,
+                        const int *overlap) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    if (!nranks || !rank || !unique_id || !ghost || *nranks < 1 || *rank < 0 || *rank >= *nranks || *ghost < 1)
+        return fail(h, MOHID_ADT_ERR_ARG, "bad communicator arguments");
+    if (h->nccl) return fail(h, MOHID_ADT_ERR_STATE, "the handle already has a communicator");
+    if (const char *e = load_nccl()) return fail(h, MOHID_ADT_ERR_UNSUPPORTED, "NCCL: %s", e);
+    CU(h, cudaSetDevice(h->dev));
+    // the slab must carry `ghost` columns on every interior side (set_active_columns)
+    const int left = h->j_begin - 1, right = h->J - (h->j_begin + h->j_count - 1);
+    if ((*rank > 0 && left != *ghost) || (*rank == 0 && left != 0) ||
+        (*rank < *nranks - 1 && right != *ghost) || (*rank == *nranks - 1 && right != 0) || h->j_count < *ghost)
+        return fail(h, MOHID_ADT_ERR_STATE,
+                    "active columns %d..%d of 1..%d do not leave %d ghost columns on the interior sides of rank %d/%d",
+                    h->j_begin, h->j_begin + h->j_count - 1, h->J, *ghost, *rank, *nranks);
+    ncclUniqueId id;
+    memcpy(&id, unique_id, sizeof id);
+    const ncclResult_t r = g_nccl.CommInitRank(&h->nccl, *nranks, id, *rank);
+    if (r != ncclSuccess) { h->nccl = nullptr; return fail(h, MOHID_ADT_ERR_CUDA, "ncclCommInitRank: %s", g_nccl.GetErrorString(r)); }
+    h->nranks = *nranks; h->rank = *rank; h->halo_ghost = *ghost;
+    CU(h, cudaStreamCreateWithFlags(&h->s_comm_own, cudaStreamNonBlocking));
+    const int ov = (overlap && *overlap) ? *ghost : 0;
+    int rc = mohid_adt_set_overlap(handle, &ov, h->s_comm_own);
+    if (rc) return rc;
+    return 0;
+}
+
+int mohid_adt_exchange_halos(const int *handle, const int *nprop) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    if (!h->nccl) return fail(h, MOHID_ADT_ERR_STATE, "mohid_adt_comm_init must precede exchange_halos");
+    if (!nprop || *nprop < 1 || *nprop > (int)h->prop[0].size() || *nprop > NPMAX)
+        return fail(h, MOHID_ADT_ERR_ARG, "bad property count");
+    CU(h, cudaSetDevice(h->dev));
+    const int g = h->halo_ghost;
+    const size_t n = (size_t)h->ld * g * h->nk * (size_t)*nprop;
+    if (h->halo_cap < n) {
+        CU(h, cudaStreamSynchronize(h->s_comm_own));
+        CU(h, cudaStreamSynchronize(h->stream));
+        for (auto &p : h->halo_buf) { if (p) cudaFree(p); p = nullptr; }
+        for (auto &p : h->halo_buf) if (int rc = dalloc(h, &p, n)) return rc;
+        h->halo_cap = n;
+    }
+    const bool has_l = h->rank > 0, has_r = h->rank < h->nranks - 1;
+    // without overlap the exchange is stream-ordered after the step: the communication stream waits for it
+    cudaStream_t cs = h->comm ? h->comm : h->s_comm_own;
+    if (!h->comm) {
+        if (!h->ev_edges) CU(h, cudaEventCreateWithFlags(&h->ev_edges, cudaEventDisableTiming));
+        if (!h->ev_halo) CU(h, cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming));
+        CU(h, cudaEventRecord(h->ev_edges, h->stream));
+        CU(h, cudaStreamWaitEvent(cs, h->ev_edges, 0));
+    }
+    auto pack = [&](int j0, double *buf, int unpack) -> int {
+        if (h->comm) return unpack ? mohid_adt_unpack_columns(handle, nprop, &j0, &g, buf)
+                                   : mohid_adt_pack_columns(handle, nprop, &j0, &g, buf);
+        PackArgs a{};
+        a.ld = h->ld; a.nj = h->nj; a.nk = h->nk; a.nprop = *nprop; a.j0 = j0; a.width = g; a.sj = h->sj; a.sk = h->sk;
+        for (int m = 0; m < *nprop; ++m) a.prop[m] = h->prop[h->cur[m]][m];
+        const int blocks = (int)std::min<long>(((long)n + 255) / 256, (long)h->num_sms * 16);
+        adt_pack_columns_kernel<<<blocks, 256, 0, cs>>>(a, buf, unpack);
+        CU(h, cudaGetLastError());
+        h->launches++;
+        return 0;
+    };
+    if (has_l) if (int rc = pack(h->j_begin, h->halo_buf[0], 0)) return rc;
+    if (has_r) if (int rc = pack(h->j_begin + h->j_count - g, h->halo_buf[2], 0)) return rc;
+    ncclResult_t r = g_nccl.GroupStart();
+    if (r == ncclSuccess && has_l) r = g_nccl.Send(h->halo_buf[0], n, ncclDouble, h->rank - 1, h->nccl, cs);
+    if (r == ncclSuccess && has_l) r = g_nccl.Recv(h->halo_buf[1], n, ncclDouble, h->rank - 1, h->nccl, cs);
+    if (r == ncclSuccess && has_r) r = g_nccl.Send(h->halo_buf[2], n, ncclDouble, h->rank + 1, h->nccl, cs);
+    if (r == ncclSuccess && has_r) r = g_nccl.Recv(h->halo_buf[3], n, ncclDouble, h->rank + 1, h->nccl, cs);
+    const ncclResult_t r2 = g_nccl.GroupEnd();
+    if (r != ncclSuccess || r2 != ncclSuccess)
+        return fail(h, MOHID_ADT_ERR_CUDA, "NCCL halo exchange: %s", g_nccl.GetErrorString(r != ncclSuccess ? r : r2));
+    if (has_l) if (int rc = pack(h->j_begin - g, h->halo_buf[1], 1)) return rc;
+    if (has_r) if (int rc = pack(h->j_begin + h->j_count, h->halo_buf[3], 1)) return rc;
+    if (!h->comm) {                                     // the next step (or a download) waits for the ghost columns
+        CU(h, cudaEventRecord(h->ev_halo, cs));
+        h->halo_pending = true;
+    }
+    return 0;
+}
+
+int mohid_adt_comm_destroy(const int *handle) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    if (!h->nccl) return 0;
+    CU(h, cudaSetDevice(h->dev));
+    if (h->s_comm_own) CU(h, cudaStreamSynchronize(h->s_comm_own));
+    CU(h, cudaStreamSynchronize(h->stream));
+    const int zero = 0;
+    mohid_adt_set_overlap(handle, &zero, nullptr);
+    g_nccl.CommDestroy(h->nccl);
+    h->nccl = nullptr;
+    h->halo_pending = false;
+    return 0;
+}
+
 int mohid_adt_synchronize(const int *handle) {
     Handle *h = get(handle);
     if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
     CU(h, cudaSetDevice(h->dev));
     if (h->comm) CU(h, cudaStreamSynchronize(h->comm));
+    if (h->s_comm_own) CU(h, cudaStreamSynchronize(h->s_comm_own));
+    if (h->s_edge) CU(h, cudaStreamSynchronize(h->s_edge));
     h->halo_pending = false;
     CU(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int mohid_adt_solve_thomas_z(const int *handle, const double *D, const double *E, const double *F, const double *TI,
+                             const int *WaterPoints3D, double *Res) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    if (!D || !E || !F || !TI || !Res) return fail(h, MOHID_ADT_ERR_ARG, "null array");
+    if (h->kmid) return fail(h, MOHID_ADT_ERR_UNSUPPORTED, "not available with MOHID_ADT_LAYOUT=1");
+    CU(h, cudaSetDevice(h->dev));
+    double *d[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};      // D, E, F, TI, Res, W
+    int *wat = nullptr;
+    auto cleanup = [&]() { for (auto p : d) if (p) cudaFree(p); if (wat) cudaFree(wat); };
+    const double *src[5] = {D, E, F, TI, Res};
+    int rc = 0;
+    for (int a = 0; a < 6 && !rc; ++a) {
+        if (cudaMalloc((void **)&d[a], (size_t)(h->n3 + 64) * sizeof(double)) != cudaSuccess) {
+            rc = fail(h, MOHID_ADT_ERR_CUDA, "out of device memory (solve_thomas_z)");
+            break;
+        }
+        if (a < 5) rc = h2d3(h, d[a], src[a], 8);
+    }
+    if (!rc && WaterPoints3D) {
+        if (cudaMalloc((void **)&wat, (size_t)(h->n3 + 64) * sizeof(int)) != cudaSuccess)
+            rc = fail(h, MOHID_ADT_ERR_CUDA, "out of device memory (solve_thomas_z)");
+        else rc = h2d3(h, wat, WaterPoints3D, 4);
+    }
+    if (!rc) {
+        cudaMemsetAsync(h->d_zero_piv, 0, sizeof(unsigned long long), h->stream);
+        const dim3 grid((unsigned)((h->I + 127) / 128), (unsigned)h->J);
+        adt_thomas_z_kernel<<<grid, 128, 0, h->stream>>>(h->I, h->J, h->K, h->sj, h->sk, d[0], d[1], d[2], d[3], wat, d[4],
+                                                       d[5], h->d_zero_piv);
+        h->launches++;
+        if (cudaGetLastError() != cudaSuccess) rc = fail(h, MOHID_ADT_ERR_CUDA, "adt_thomas_z_kernel launch failed");
+    }
+    if (!rc) rc = d2h3(h, Res, d[4], 8);
+    const cudaError_t e = cudaStreamSynchronize(h->stream);
+    cleanup();
+    if (rc) return rc;
+    CU(h, e);
     return 0;
 }
 

@@ -33,6 +33,8 @@
 
 namespace adt {
 
+struct __align__(32) Pack4 { double a, b, c, d; };   // one 256-bit load (adt_lean_kernel.cuh)
+
 constexpr int NPMAX = 32;                 // max properties per launch (kernel-parameter arrays)
 constexpr double NULL_REAL = MOHID_NULL_REAL;
 constexpr double MIN_VALUE = 1.e-16;      // MGD:1812
@@ -503,8 +505,8 @@ __device__ __forceinline__ double orlanski_exterior(const StepArgs &s, const Pro
 }
 
 // RARE: compiled with the Orlanski branch (only the DISCH kernel variants, which the host selects for it)
-template <bool RARE = false>
-__device__ __forceinline__ void open_boundary_row(const StepArgs &s, const PropArgs &pa, int q, unsigned m, double Pc,
+template <bool RARE = false, class Args = StepArgs>
+__device__ __forceinline__ void open_boundary_row(const Args &s, const PropArgs &pa, int q, unsigned m, double Pc,
                                                double qz_c, double qz_p, double dtv_c, Row &row, int i = 0, int j = 0,
                                                bool writer = true) {
     const double *__restrict__ P = pa.pin;
@@ -1041,7 +1043,7 @@ struct BndArgs {
     int sj, sk;               // element strides of j and k in the 3-D device arrays
     const int *cols;          // packed (i,j) of boundary columns
     const int *kfloor;
-    const uint32_t *mask;
+    const int *CFU, *CFV, *Bnd;   // ComputeFacesU3D / V3D (device mirrors), BoundaryPoints2D
     double *prop;             // new field (in place)
     const double *pref;
     int jmin, jmax;           // only boundary columns with jmin <= j <= jmax are processed (edge-first launches)
@@ -1075,9 +1077,8 @@ __global__ void adt_nullgrad_kernel(const BndArgs b) {
     kf = kf < 0 ? -kf : kf;
     if (k < kf) return;
     const long q = (long)i + (long)b.sj * j + (long)b.sk * k;
-    const unsigned m = b.mask[q];
-    const int cVn = (m & M_CFVN) ? 1 : 0, cVs = (m & M_CFV) ? 1 : 0;
-    const int cUe = (m & M_CFUE) ? 1 : 0, cUw = (m & M_CFU) ? 1 : 0;
+    const int cVn = b.CFV[q + 1] == 1 ? 1 : 0, cVs = b.CFV[q] == 1 ? 1 : 0;
+    const int cUe = b.CFU[q + b.sj] == 1 ? 1 : 0, cUw = b.CFU[q] == 1 ? 1 : 0;
     const int aux = cVn + cVs + cUe + cUw;
     if (aux > 0)
         b.prop[q] = (b.prop[q + 1] * cVn + b.prop[q - 1] * cVs + b.prop[q + b.sj] * cUe + b.prop[q - b.sj] * cUw) /
@@ -1099,7 +1100,7 @@ __global__ void adt_cyclic_kernel(const BndArgs b, int phase) {
         const int i = (int)(t / b.K) + 2, k = (int)(t % b.K) + 1;
         const long r1 = (long)i + sj * 1, rJ = (long)i + sj * b.J;                 // 3-D column bases of (i,1), (i,J)
         const long f1 = (long)i + (long)b.ld * 1, fJ = (long)i + (long)b.ld * b.J;   // the same columns in 2-D arrays
-        if ((b.mask[r1 + sk * b.K] & M_BND) && (b.mask[rJ + sk * b.K] & M_BND)) {
+        if (b.Bnd[f1] == 1 && b.Bnd[fJ] == 1) {
             if (k >= b.kfloor[fJ - b.ld]) b.prop[r1 + sk * k] = b.prop[rJ - sj + sk * k];
             if (k >= b.kfloor[f1 + b.ld]) b.prop[rJ + sk * k] = b.prop[r1 + sj + sk * k];
         }
@@ -1108,7 +1109,7 @@ __global__ void adt_cyclic_kernel(const BndArgs b, int phase) {
         const int j = (int)(t / b.K) + 2, k = (int)(t % b.K) + 1;
         const long r1 = 1 + sj * j, rI = (long)b.I + sj * j;
         const long f1 = 1 + (long)b.ld * j, fI = (long)b.I + (long)b.ld * j;
-        if ((b.mask[r1 + sk * b.K] & M_BND) && (b.mask[rI + sk * b.K] & M_BND)) {
+        if (b.Bnd[f1] == 1 && b.Bnd[fI] == 1) {
             if (k >= b.kfloor[fI - 1]) b.prop[r1 + sk * k] = b.prop[rI - 1 + sk * k];
             if (k >= b.kfloor[f1 + 1]) b.prop[rI + sk * k] = b.prop[r1 + 1 + sk * k];
         }
@@ -1212,6 +1213,42 @@ __global__ void __launch_bounds__(128) adt_cell_flux_kernel(const FluxArgs a) {
         }
         a.az[qt] = adv;
     }
+}
+
+// -------------------------------------------------------------------------------------
+// Stand-alone column solve: THOMASZ_NewType2 (MF:4026-4123) on caller-supplied D, E, F, TI -- the drop-in for the
+// reference's own GPU entry SolveThomas_C / DevThomasIK (ModuleCuda.F90:103-111, CudaThomas/Thomas.cu:62-131).
+// Same elimination as K2 (branch-free reciprocal pivot, a zero pivot keeps the previous W, G and is counted), rows
+// 1 .. K+1, one thread per column, i fastest; W in a scratch field, G parked in Res.
+// -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) adt_thomas_z_kernel(int I, int J, int K, int sj, int sk, const double *D,
+                                                           const double *E, const double *F, const double *TI,
+                                                           const int *Water, double *Res, double *Wg,
+                                                           unsigned long long *zero_pivots) {
+    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y;
+    if (i > I) return;
+    const int c = i + sj * j;
+    if (Water && Water[c + sk * K] != 1) return;                      // MF:4086
+    double Wp = 0., Gp = 0.;
+    unsigned zp = 0;
+    for (int k = 1; k <= K + 1; ++k) {
+        const int q = c + sk * k;
+        const double d = k == 1 ? 0. : D[q];                          // the first row ignores D (MF:4087-4088)
+        const double aux = E[q] + d * Wp;
+        const bool ok = aux != 0.;
+        const double ra = fast_rcp(aux);
+        const double w = -F[q] * ra, g = (TI[q] - d * Gp) * ra;
+        Wp = ok ? w : Wp; Gp = ok ? g : Gp;
+        zp += ok ? 0u : 1u;
+        Wg[q] = Wp; Res[q] = Gp;
+    }
+    double x = Gp;                                                    // RES(KUB+1) = G(KUB+1)
+    for (int k = K; k >= 1; --k) {
+        const int q = c + sk * k;
+        x = Wg[q] * x + Res[q];
+        Res[q] = x;
+    }
+    if (zp) atomicAdd(zero_pivots, (unsigned long long)zp);
 }
 
 // -------------------------------------------------------------------------------------

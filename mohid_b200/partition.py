@@ -92,47 +92,35 @@ def _p2p_exchange(dist, send_left, recv_left, send_right, recv_right, rank: int,
 
 
 class HaloExchanger:
-    """Device-resident halo exchange of all properties of a :class:`TransportStep` (NCCL)."""
+    """Device-resident halo exchange of all properties of a :class:`TransportStep`.
+
+    The exchange itself lives in the library (``mohid_adt_comm_init`` / ``mohid_adt_exchange_halos``: pack ->
+    ncclSend/ncclRecv -> unpack on the handle's communication stream), exactly as a Fortran/MPI host reaches it; this
+    class only restricts the handle to its owned columns and carries the NCCL id from rank 0 to the other ranks
+    through the ``torch.distributed`` process group the launcher already set up.
+    """
 
     def __init__(self, ts, dec: SlabDecomposition, rank: int, nprop: int, device, overlap: bool = True):
-        """overlap: the library advances the edge columns first and the exchange runs on its own stream while the
-        interior columns are still being advanced (the next step, or ``ts.join_halo()``, waits for it)."""
+        """overlap: the library advances the edge columns first and the exchange runs while the interior columns are
+        still being advanced (the next step, or ``ts.join_halo()``, waits for it)."""
         import torch
+        import torch.distributed as dist
         self.ts, self.dec, self.rank, self.nprop = ts, dec, rank, nprop
         self.sl = dec.slab(rank)
-        g = dec.ghost
-        n = ts.halo_buffer_elems(nprop, g)
-        mk = lambda: torch.empty(n, dtype=torch.float64, device=device)
-        self.send_l, self.recv_l, self.send_r, self.recv_r = mk(), mk(), mk(), mk()
-        self.launches = 0
+        self.launches = 0                    # pack / unpack launches are counted by the library itself
         ts.set_active_columns(self.sl.j_begin, self.sl.n_owned)
-        self.comm = torch.cuda.Stream(device=device) if overlap else None
-        if self.comm is not None:
-            ts.set_overlap(g, self.comm.cuda_stream)
+        on_gpu = dist.get_backend() == "nccl"
+        idt = torch.zeros(128, dtype=torch.uint8, device=device if on_gpu else "cpu")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(ts.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        ts.comm_init(dec.world, rank, bytes(idt.cpu().numpy().tobytes()), dec.ghost, overlap)
 
     def exchange(self):
-        import torch
-        if self.comm is None:
-            return self._exchange()
-        with torch.cuda.stream(self.comm):               # NCCL work is ordered after the pack on this stream
-            self._exchange()
+        self.ts.exchange_halos(self.nprop)
 
-    def _exchange(self):
-        import torch.distributed as dist
-        sl, g, ts = self.sl, self.dec.ghost, self.ts
-        if sl.ghost_left:
-            ts.pack_columns(self.nprop, sl.j_begin, g, self.send_l)
-            self.launches += 1
-        if sl.ghost_right:
-            ts.pack_columns(self.nprop, sl.j_begin + sl.n_owned - g, g, self.send_r)
-            self.launches += 1
-        _p2p_exchange(dist, self.send_l, self.recv_l, self.send_r, self.recv_r, self.rank, self.dec.world)
-        if sl.ghost_left:
-            ts.unpack_columns(self.nprop, sl.j_begin - g, g, self.recv_l)
-            self.launches += 1
-        if sl.ghost_right:
-            ts.unpack_columns(self.nprop, sl.j_begin + sl.n_owned, g, self.recv_r)
-            self.launches += 1
+    def close(self):
+        self.ts.comm_destroy()
 
 
 def exchange_host_arrays(props: Sequence, dec: SlabDecomposition, rank: int):

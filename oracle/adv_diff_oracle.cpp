@@ -7,10 +7,12 @@
 //  build with -ffp-contract=off).  The reference's OpenMP loop structure is mirrored so
 //  the same file doubles as the "CPU restatement of the reference path" timing baseline.
 //
-//  PARITY UNPINNED: the reference ships no golden vectors / known-answer tests for this
-//  path and cannot be compiled here (no Fortran compiler, HDF5, MPI),
-//  so this oracle is pinned only by (a) line-by-line citation of the source below and
-//  (b) the self-consistency properties in tests/test_oracle_*.py.
+//  PARITY UNPINNED except for the column solve: the reference ships no golden vectors /
+//  known-answer tests for this path and its Fortran cannot be compiled
+//  here (no Fortran compiler, HDF5, MPI), so this oracle is pinned by (a) line-by-line
+//  citation of the source below, (b) the self-consistency properties in tests/test_oracle_*.py
+//  and (c) for THOMASZ_NewType2 only, the reference's own CUDA solver (CudaThomas/Thomas.cu,
+//  compiled unmodified into oracle/_ref by oracle/Makefile; tests/test_gpu_ref_thomas.py).
 //
 //  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
 //  legs may load this file's shared library.
@@ -21,9 +23,10 @@
 //     MGD = MOHIDBase1/ModuleGlobalData.F90
 //     WP  = MOHIDWater/ModuleWaterProperties.F90
 //
-//  Not restated (returns ORACLE_ERR_UNSUPPORTED): horizontally implicit advection
-//  (AD:4167-4258, THOMAS_3D MF:3667-3875), AdvectionNudging (AD:1989-2068), Orlanski
-//  boundary (MF:4129-4500).
+//  Not restated (returns ORACLE_ERR_UNSUPPORTED): AdvectionNudging (AD:1989-2068; it reads
+//  uninitialised indices in the reference) and the 2-D (K = 1) / decomposed forms of the
+//  horizontally implicit solve (AD:1758-1841, HG:8245-8478).  Horizontally implicit advection
+//  in 3-D (AD:4167-4258, THOMAS_3D MF:3667-3875) and the Orlanski boundary (MF:4129-4500) are.
 // =====================================================================================
 #include <algorithm>
 #include <cmath>
@@ -1969,6 +1972,23 @@ int mohid_oracle_zero_pivots(const int *handle, long long *n) {
 int mohid_oracle_num_threads(const int *handle) {
     Oracle *o = get(handle);
     return o ? o->nthreads : 0;
+}
+
+// THOMASZ_NewType2 (MF:4026-4123) on caller-supplied coefficients: D, E, F, TI, WaterPoints3D as in the reference's
+// argument bundle, RES updated in place.  Used to pin the column solve against the reference's own CUDA solver
+// (Software/CudaThomas/Thomas.cu, built as oracle/_ref by oracle/Makefile).
+int mohid_oracle_thomasz(const int *handle, const double *D, const double *E, const double *F, const double *TI,
+                         const int *WaterPoints3D, double *RES) {
+    Oracle *o = get(handle);
+    if (!o) return MOHID_ADT_ERR_HANDLE;
+    if (!D || !E || !F || !TI || !WaterPoints3D || !RES) return ORACLE_ERR_ARG;
+    o->D.assign(D, D + o->n3); o->E.assign(E, E + o->n3); o->F.assign(F, F + o->n3); o->TI.assign(TI, TI + o->n3);
+    o->WaterPoints3D = WaterPoints3D;
+    o->PROP = RES;
+    THOMASZ_NewType2(*o);
+    o->WaterPoints3D = nullptr;
+    o->PROP = nullptr;
+    return 0;
 }
 
 // Face-weight function exposed for unit tests of A.5 (MF:10702-10894).

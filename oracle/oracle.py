@@ -196,6 +196,10 @@ class OracleAdvectionDiffusion:
             out[name] = a
         return out
 
+    def thomasz(self, D, E, F, TI, water, res):
+        """THOMASZ_NewType2 (MF:4026-4123) on caller-supplied coefficient fields; ``res`` is updated in place."""
+        self._check(lib().mohid_oracle_thomasz(C.byref(self.h), _dp(D), _dp(E), _dp(F), _dp(TI), _ip(water), _dp(res)))
+
     def zero_pivots(self) -> int:
         n = C.c_longlong(0)
         lib().mohid_oracle_zero_pivots(C.byref(self.h), C.byref(n))
