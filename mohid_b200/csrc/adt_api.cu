@@ -95,8 +95,8 @@ struct Handle {
     std::vector<double *> flux[6];                      // per property: AdvFluxX/Y/Z, DifFluxX/Y/Z (allocated on demand)
     std::vector<int> bnd_host;                          // (i,j) of all boundary columns
     // lean path (adt_lean_kernel.cuh): face packs U, V, W, C of the columns pk_jc0 .. pk_jc0+pk_ncol-1, 2-D metric ratios
-    Pack4 *pk[4] = {nullptr, nullptr, nullptr, nullptr};
-    int pk_ncol = 0, pk_jc0 = 0;
+    Pack4 *pk = nullptr;                               // layout: adt_lean_kernel.cuh (LeanCoefArgs)
+    int pk_ncol = 0, pk_jc0 = 0, pk_nt32 = 0;
     double *rho2d[4] = {nullptr, nullptr, nullptr, nullptr};
     bool rho_valid = false, lean_now = false;
     // NCCL halo exchange behind the C-ABI (mohid_adt_comm_init): communicator, neighbour buffers, own comm stream
@@ -290,7 +290,7 @@ void free_all(Handle *h) {
     for (int b = 0; b < 2; ++b) for (auto p : h->prop[b]) F(p);
     for (auto p : h->ref) F(p);
     F(h->d_zero_piv);
-    for (auto p : h->pk) F(p);
+    F(h->pk);
     for (auto p : h->rho2d) F(p);
     for (auto p : h->halo_buf) F(p);
     if (h->nccl && g_nccl.CommDestroy) { g_nccl.CommDestroy(h->nccl); h->nccl = nullptr; }
@@ -492,6 +492,8 @@ int launch_coef(Handle *h, const mohid_adt_params &q, const PropEff &e, bool geo
 // rare options (discharges, NoFlux cell lists, Orlanski, CellFluxes).
 bool lean_eligible(const Handle *h, const Batch &b) {
     if (getenv("MOHID_ADT_NOLEAN")) return false;
+    // the packs cost 128 B per cell to write and to read: they pay once they are shared by a few properties
+    if (b.nprop < 3 && !getenv("MOHID_ADT_LEAN_ALWAYS")) return false;
     if (h->opt.Vertical1D || h->opt.XZFlow || h->K < 2 || h->have_noflux || h->kmid) return false;
     const mohid_adt_params &f = b.p[0];
     const bool tvd_sb = f.AdvMethodH == MOHID_P2_TVD && f.AdvMethodV == MOHID_P2_TVD &&
@@ -519,8 +521,9 @@ int ensure_lean(Handle *h, int ncol) {
     }
     if (h->pk_ncol < ncol) {
         CU(h, cudaStreamSynchronize(h->stream));
-        for (auto &p : h->pk) { if (p) cudaFree(p); p = nullptr; }
-        for (auto &p : h->pk) if (int rc = dalloc(h, &p, (size_t)h->ld * ncol * h->nk)) return rc;
+        if (h->pk) { cudaFree(h->pk); h->pk = nullptr; }
+        h->pk_nt32 = (h->ni + 31) / 32;
+        if (int rc = dalloc(h, &h->pk, (size_t)h->pk_nt32 * 128 * ncol * h->nk)) return rc;
         h->pk_ncol = ncol;
     }
     return 0;
@@ -540,12 +543,14 @@ int launch_lean_coef(Handle *h, const mohid_adt_params &q, const PropEff &e, int
     a.Open = h->raw_i[0]; a.Land = h->raw_i[1]; a.Water = h->raw_i[2]; a.CFU = h->raw_i[3]; a.CFV = h->raw_i[4];
     a.CFW = h->raw_i[5]; a.SmallDepths = h->have_small ? h->SmallDepths : nullptr;
     a.DUX = h->DUX; a.DVY = h->DVY; a.DZX = h->DZX; a.DZY = h->DZY; a.Bnd = h->Bnd;
-    A.pkU = h->pk[0]; A.pkV = h->pk[1]; A.pkW = h->pk[2]; A.pkC = h->pk[3];
-    A.jc0 = jc0; A.ncol = ncol; A.skc = h->ld * h->pk_ncol;
+    A.pk = h->pk; A.jc0 = jc0; A.ncol = h->pk_ncol; A.nt32 = h->pk_nt32;
     A.tvd = q.AdvMethodH == MOHID_P2_TVD; A.upwind2_h = q.Upwind2H; A.upwind2_v = q.Upwind2V;
     A.rhoUp = h->rho2d[0]; A.rhoUn = h->rho2d[1]; A.rhoVp = h->rho2d[2]; A.rhoVn = h->rho2d[3];
-    const dim3 grid((unsigned)((h->ld + 127) / 128), (unsigned)h->nk, (unsigned)ncol);
-    adt_lean_coef_kernel<<<grid, 128, 0, h->stream>>>(A);
+    const dim3 grid((unsigned)((h->pk_nt32 * 32 + 127) / 128), (unsigned)h->nk, (unsigned)ncol);
+    const int minb = getenv("MOHID_ADT_COEF_MINB") ? atoi(getenv("MOHID_ADT_COEF_MINB")) : 4;
+    if (minb >= 8) adt_lean_coef_kernel<8><<<grid, 128, 0, h->stream>>>(A);
+    else if (minb >= 6) adt_lean_coef_kernel<6><<<grid, 128, 0, h->stream>>>(A);
+    else adt_lean_coef_kernel<4><<<grid, 128, 0, h->stream>>>(A);
     CU(h, cudaGetLastError());
     h->launches++;
     h->pk_jc0 = jc0;
@@ -705,22 +710,23 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
                          getenv("MOHID_ADT_RING") && atoi(getenv("MOHID_ADT_RING")) != 0;
     long grid_override = 0;
     if (h->lean_now) {
-        // warps per block: MOHID_ADT_LEAN_WARPS (8, 12, 16 or 20; experiments) or the measured best that fits
-        int want = getenv("MOHID_ADT_LEAN_WARPS") ? atoi(getenv("MOHID_ADT_LEAN_WARPS")) : 16;
+        // warps per block / L2 prefetch distance: MOHID_ADT_LEAN_WARPS (12 or 16), MOHID_ADT_LEAN_PFD (0, 2, 3, 4)
+        // measured on C3 (profiles/r02_*): 12 warps at 168 registers without spills beat 16 at 128 with; prefetch
+        // distance 3: 29.4 ms against 33.8 ms without
+        int want = getenv("MOHID_ADT_LEAN_WARPS") ? atoi(getenv("MOHID_ADT_LEAN_WARPS")) : 12;
+        const int pfd = getenv("MOHID_ADT_LEAN_PFD") ? atoi(getenv("MOHID_ADT_LEAN_PFD")) : 3;
         while (want > 8 && (size_t)want * w_bytes > (size_t)h->smem_optin) want -= 4;
-#define ADT_LEAN(M)                                                                            \
-    (want >= 20   ? adt_transport_lean_kernel<M, 20>                                           \
-     : want >= 16 ? adt_transport_lean_kernel<M, 16>                                           \
-     : want >= 12 ? adt_transport_lean_kernel<M, 12>                                           \
-                  : adt_transport_lean_kernel<M, 8>)
+#define ADT_LEAN_W(M, P) (want >= 16 ? adt_transport_lean_kernel<M, 16, P> : want >= 12 ? adt_transport_lean_kernel<M, 12, P> : adt_transport_lean_kernel<M, 8, P>)
+#define ADT_LEAN(M) (pfd >= 4 ? ADT_LEAN_W(M, 4) : pfd == 3 ? ADT_LEAN_W(M, 3) : pfd == 2 ? ADT_LEAN_W(M, 2) : ADT_LEAN_W(M, 0))
         lkern = tvd_sb ? ADT_LEAN(MOHID_P2_TVD) : ADT_LEAN(MOHID_UpwindOrder1);
 #undef ADT_LEAN
-        wpb = want >= 20 ? 20 : want >= 16 ? 16 : want >= 12 ? 12 : 8;
+#undef ADT_LEAN_W
+        wpb = want >= 16 ? 16 : want >= 12 ? 12 : 8;
         smem = wpb * w_bytes;
         la.I = s.I; la.J = s.J; la.K = s.K; la.ld = s.ld; la.sj = s.sj; la.sk = s.sk;
         la.nprop = s.nprop; la.ntile_i = s.ntile_i; la.j_begin = s.j_begin; la.j_count = s.j_count;
-        la.jc0 = h->pk_jc0; la.skc = h->ld * h->pk_ncol; la.dt = s.dt;
-        la.pkU = h->pk[0]; la.pkV = h->pk[1]; la.pkW = h->pk[2]; la.pkC = h->pk[3];
+        la.jc0 = h->pk_jc0; la.ncol = h->pk_ncol; la.nt32 = h->pk_nt32; la.dt = s.dt;
+        la.pk = h->pk;
         la.qx = s.qx; la.qy = s.qy; la.qz = s.qz; la.VolumeZ = s.VolumeZ; la.VolumeZOld = s.VolumeZOld;
         la.zero_pivots = s.zero_pivots;
         for (int m = 0; m < s.nprop; ++m) la.p[m] = s.p[m];
@@ -749,6 +755,11 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
     } else if (full && !any_disch && (tvd_sb || upw) && 12 * w_bytes <= (size_t)h->smem_optin) {
         kern = tvd_sb ? adt_transport_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, false, true, 12, 1, true>
                       : adt_transport_kernel<MOHID_UpwindOrder1, MOHID_SuperBee, MOHID_UpwindOrder1, MOHID_SuperBee, false, true, 12, 1, true>;
+        if (tvd_sb && getenv("MOHID_ADT_PFD")) {          // experiment: selective L2 prefetch in the round-1 kernel
+            const int d = atoi(getenv("MOHID_ADT_PFD"));
+            if (d >= 4) kern = adt_transport_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, false, true, 12, 1, true, false, 4>;
+            else if (d >= 2) kern = adt_transport_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, false, true, 12, 1, true, false, 2>;
+        }
         wpb = 12;
         smem = wpb * w_bytes;
         if (const char *e = getenv("MOHID_ADT_HSPLIT")) {

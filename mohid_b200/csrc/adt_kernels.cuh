@@ -583,7 +583,7 @@ struct Level {
 //   FULL  = 3-D run with both horizontal directions and implicit vertical advection for every property:
 //           the level body becomes one basic block (no uniform branches), which lets ptxas interleave the faces.
 // -------------------------------------------------------------------------------------
-template <int MH, int LH, int MV, int LV, bool DISCH, bool FULL, int WARPS = 8, int PF = 1, bool GGLOB = false, bool HSPLIT = false>
+template <int MH, int LH, int MV, int LV, bool DISCH, bool FULL, int WARPS = 8, int PF = 1, bool GGLOB = false, bool HSPLIT = false, int PFD = 0>
 __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __grid_constant__ StepArgs s) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, WPB = blockDim.x >> 5;
@@ -718,6 +718,25 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
         const int q3 = (k + 3 <= s.K + 1) ? q + 3 * sk : q2;
         const double Pp3 = __ldg(P + q3), rdz_p3 = __ldg(s.rdz + q3);
         const double dtv_pp = __ldg(s.dtv + q2), qz_pp = __ldg(s.qz + q2), dvz_pp = __ldg(s.dvz + q2);
+        if constexpr (PFD > 0) {
+            // L2 prefetch, PFD levels ahead, of the streams no earlier block has touched: the east-most property row
+            // (every warp) and the shared coefficients of this column and of column j+1 (first property's warp)
+            const int kk = min(k + PFD, s.K + 1) - k;
+            const int qf = q + kk * sk;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(P + (qf + je2)));
+            if (n == 0) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(s.qx + (qf + sj)));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(s.dhu + (qf + sj)));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(s.dtv + (qf + sj)));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(s.qy + qf));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(s.dhv + qf));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(s.vr + qf));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(s.mask + qf));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(s.qz + qf));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(s.dvz + qf));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(s.rdz + qf));
+            }
+        }
         if (PF == 1) fetch(q + sk, nxt);                  // plane K+1 exists, so the look-ahead is always in bounds
         else if (PF == 0) fetch(q, nxt);
         else { __pipeline_wait_prior(NSTAGE - 1); load_stage((k - 1) & 1, nxt); }

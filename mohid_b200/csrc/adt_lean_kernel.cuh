@@ -7,14 +7,18 @@
 //  weight (MF:10858), the metric ratio of the limiter argument -- is computed ONCE per step by the coefficient pass
 //  (adt_lean_coef_kernel, amortised over the N batched properties) and handed to the step kernel as four 32-byte
 //  packs per cell, each fetched with one 256-bit load:
-//      U = { Qa_u, hc_u, dh_u, rho_u }   west U face of the cell   (AD:4368-4582, 5156-5250)
-//      V = { Qa_v, hc_v, dh_v, rho_v }   south V face              (AD:4739-4953, 5254-5365)
-//      W = { qa_b, hv_b, rdu_b, rdc_b }  bottom W face             (AD:2941-3144)
+//      U = { Qh, A, B, rho }             west U face of the cell   (AD:4368-4582, 5156-5250)
+//      V = { Qh, A, B, rho }             south V face              (AD:4739-4953, 5254-5365)
+//      W = { qa, hv, rdu, rdc }          bottom W face             (AD:2941-3144)
 //      C = { DT/V, Vold/V, Diff_V_Const (bottom face), mask }
-//  Qa = face flux where the face advects, else 0; hc = 0.5 (1 - Q DT/V_upwind), 0 on near-boundary faces with Upwind2;
-//  dh = Diff_H_Const_U/V (AD:1549-1597); rho = (du_u+du_d)/(du_u+du_uu) of the upwind side; rdu/rdc = 1/(du+du) of the
-//  upwind pair and of the face; the mask carries four extra bits with the flow direction of the west, east, south and
-//  bottom face.
+//  With Qa the face flux where the face advects (else 0), Cr = Q DT/V_upwind and hc = 0.5 (1 - Cr) (0 on near-boundary
+//  faces with Upwind2), the flux of property through a horizontal face, Qa (Pu + hc psi dP) - dh (P_hi - P_lo), is
+//  evaluated in the direction-free form  Qh (P_lo + P_hi) - A g + B sgn(g) lim  with g = P_hi - P_lo, Qh = Qa/2,
+//  A = |Qa|/2 + dh (upwinding + Diff_H_Const_U/V, AD:1549-1597), B = |Qa| hc and lim = psi |dP| the limited increment;
+//  rho = (du_u+du_d)/(du_u+du_uu) of the upwind side; rdu/rdc = 1/(du+du) of the upwind pair and of the face; the
+//  mask carries four extra bits with the flow direction of the west, east, south and bottom face.
+//  The four packs of 32 consecutive cells lie next to each other (4 x 1 KB), so one per-thread pointer with constant
+//  offsets addresses all of them.
 //
 //  The step kernel keeps the warp <-> (31-cell strip, column j, property) mapping, the register look-ahead and the
 //  in-register Thomas elimination (W in shared memory, G parked in the output array) of the round-1 kernel, and
@@ -22,7 +26,7 @@
 //    * walks the column with the vertical faces skewed by one level: level k evaluates the face BELOW cell k, which
 //      completes row k-1 of the tridiagonal system, so every value it needs (DT/V and P of k-2 .. k+1) is already in
 //      registers and the vertical look-ahead of the round-1 kernel (five more loads per level) disappears.
-//  Results are bit-identical to the round-1 kernel (tests/test_gpu_parity.py::test_lean_kernel_*).
+//  Results agree with the round-1 kernel to rounding (tools/lean_check.py, tests/test_gpu_parity.py).
 // =====================================================================================
 #pragma once
 #include <type_traits>
@@ -40,7 +44,12 @@ enum : unsigned {
 
 __device__ __forceinline__ Pack4 ld_pack(const Pack4 *p) {
     Pack4 r;
-    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.a), "=d"(r.b), "=d"(r.c), "=d"(r.d) : "l"(p));
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.a), "=d"(r.b), "=d"(r.c), "=d"(r.d) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ double ld_f64(const double *p) {
+    double r;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(r) : "l"(p) : "memory");
     return r;
 }
 __device__ __forceinline__ void st_pack(Pack4 *p, double a, double b, double c, double d) {
@@ -48,17 +57,23 @@ __device__ __forceinline__ void st_pack(Pack4 *p, double a, double b, double c, 
 }
 
 // -------------------------------------------------------------------------------------
-// Coefficient pass of the lean path.  One thread per allocated cell of the column chunk jc0 .. jc0+ncol-1; the packs
-// live in chunk-sized arrays: cell (i,j,k) at i + ld*(j-jc0) + skc*k.
+// Coefficient pass of the lean path.  One thread per allocated cell of the column chunk jc0 .. jc0+ncol-1.
+// Pack layout: rows (j - jc0) + ncol*k of ldp = 32*nt32 cells; inside a row, groups of 32 cells hold their four packs
+// back to back: pack p of cell i at Pack4 index ((row*nt32 + i/32)*4 + p)*32 + i%32.
 // -------------------------------------------------------------------------------------
 struct LeanCoefArgs {
     CoefArgs c;                       // raw inputs, extents, strides, Schmidt numbers (its outputs are not used)
-    Pack4 *pkU, *pkV, *pkW, *pkC;
-    int jc0, ncol, skc;
+    Pack4 *pk;
+    int jc0, ncol, nt32;
     int tvd;                          // 1: P2_TVD (hc / hv are needed), 0: first-order upwind
     int upwind2_h, upwind2_v;
     const double *rhoUp, *rhoUn, *rhoVp, *rhoVn;   // 2-D metric ratios (adt_grid2d_rho_kernel)
 };
+constexpr int PK_U = 0, PK_V = 32, PK_W = 64, PK_C = 96;     // Pack4 offsets of the four packs inside a 32-cell group
+
+__host__ __device__ __forceinline__ long pack_index(int i, int row, int nt32) {
+    return ((long)row * nt32 + (i >> 5)) * 128 + (i & 31);
+}
 
 // rho of the limiter argument for both flow directions of the west U face and the south V face of every column;
 // the clamped probes repeat the ones of adt_transport_kernel (rdx_pp, rdy_p of the last lane)
@@ -85,7 +100,7 @@ __device__ __forceinline__ void adt_lean_coef_cell(const LeanCoefArgs &A, const 
     const int sj = a.sj, sk = a.sk, sj2 = a.ld;
     const int q2 = i + sj2 * j;
     const int q = i + sj * j + sk * k;
-    const int qc = i + a.ld * (j - A.jc0) + A.skc * k;
+    const long qc = pack_index(i, (j - A.jc0) + A.ncol * k, A.nt32);
     const bool im1 = !EDGE || i >= 1, im2 = !EDGE || i >= 2, ip1 = !EDGE || i + 1 < a.ni, ip2 = !EDGE || i + 2 < a.ni;
     const bool jm1 = !EDGE || j >= 1, jm2 = !EDGE || j >= 2, jp1 = !EDGE || j + 1 < a.nj, jp2 = !EDGE || j + 2 < a.nj;
     const bool km1 = !EDGE || k >= 1, km2 = !EDGE || k >= 2, kp1 = !EDGE || k + 1 < a.nk, kp2 = !EDGE || k + 2 < a.nk;
@@ -158,7 +173,13 @@ __device__ __forceinline__ void adt_lean_coef_cell(const LeanCoefArgs &A, const 
     auto dt_over = [&](bool inwork, double v) { return (inwork && v != 0.) ? a.dt / v : 0.; };
     const bool inwork = iin && jin && kin;
     const double dtv = dt_over(inwork, V);
-    const double vr = (inwork && V != 0.) ? Vold / V : 1.;
+    // closed cells keep their concentration (AD:4003-4006): Vold/V only where the cell is open
+    const double vr = (open_c == 1 && inwork && V != 0.) ? Vold / V : 1.;
+    // the face advects iff both cells are open and it is a compute face (MF:10559, AD:4467, 4833, 3041); vertical
+    // advection also needs an open surface cell in the column (AD:2966)
+    const double Qa_u = (cfu && open_c == 1 && ojm1b) ? Qx : 0.;
+    const double Qa_v = (cfv && open_c == 1 && oim1b) ? Qy : 0.;
+    const double qa_b = (cfw && open_c == 1 && okm1b && open_top == 1) ? Qz : 0.;
     double hc_u = 0., hc_v = 0., hv_b = 0.;
     if (A.tvd) {
         // upwind cell: (j-1 | j), (i-1 | i), (k-1 | k) for positive | non-positive flux (MF:10724-10736)
@@ -194,27 +215,24 @@ __device__ __forceinline__ void adt_lean_coef_cell(const LeanCoefArgs &A, const 
     // rdz(k-1) for upward flow; rdz(k+1) for downward flow, clamped to plane K+1 like the round-1 look-ahead
     const double rdu_b = pos_b ? rcp_sum(km2, dwz_m, dwz_m2)
                                : ((k + 1 <= a.K + 1) ? rcp_sum(kp1, dwz_p, dwz) : rdc_b);
-    // the face advects iff both cells are open and it is a compute face (MF:10559, AD:4467, 4833, 3041); vertical
-    // advection also needs an open surface cell in the column (AD:2966)
-    const double Qa_u = (cfu && open_c == 1 && ojm1b) ? Qx : 0.;
-    const double Qa_v = (cfv && open_c == 1 && oim1b) ? Qy : 0.;
-    const double qa_b = (cfw && open_c == 1 && okm1b && open_top == 1) ? Qz : 0.;
 
-    st_pack(A.pkU + qc, Qa_u, hc_u, hu, pos_u ? rUp : rUn);
-    st_pack(A.pkV + qc, Qa_v, hc_v, hv, pos_v ? rVp : rVn);
-    st_pack(A.pkW + qc, qa_b, hv_b, rdu_b, rdc_b);
-    st_pack(A.pkC + qc, dtv, vr, vz, __hiloint2double(0, (int)m));
+    Pack4 *g = A.pk + qc;
+    st_pack(g + PK_U, 0.5 * Qa_u, fma(0.5, fabs(Qa_u), hu), fabs(Qa_u) * hc_u, pos_u ? rUp : rUn);
+    st_pack(g + PK_V, 0.5 * Qa_v, fma(0.5, fabs(Qa_v), hv), fabs(Qa_v) * hc_v, pos_v ? rVp : rVn);
+    st_pack(g + PK_W, qa_b, hv_b, rdu_b, rdc_b);
+    st_pack(g + PK_C, dtv, vr, vz, __hiloint2double(0, (int)m));
 }
 
-__global__ void __launch_bounds__(128) adt_lean_coef_kernel(const LeanCoefArgs A) {
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) adt_lean_coef_kernel(const LeanCoefArgs A) {
     const CoefArgs &a = A.c;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int k = blockIdx.y, j = A.jc0 + blockIdx.z;
-    if (i >= a.ld) return;
-    if (i >= a.ni) {                                  // leading-dimension padding
-        const int qc = i + a.ld * (j - A.jc0) + A.skc * k;
-        st_pack(A.pkU + qc, 0., 0., 0., 0.); st_pack(A.pkV + qc, 0., 0., 0., 0.);
-        st_pack(A.pkW + qc, 0., 0., 0., 0.); st_pack(A.pkC + qc, 0., 1., 0., 0.);
+    if (i >= A.nt32 * 32) return;
+    if (i >= a.ni) {                                  // row padding
+        Pack4 *g = A.pk + pack_index(i, (j - A.jc0) + A.ncol * k, A.nt32);
+        st_pack(g + PK_U, 0., 0., 0., 0.); st_pack(g + PK_V, 0., 0., 0., 0.);
+        st_pack(g + PK_W, 0., 0., 0., 0.); st_pack(g + PK_C, 0., 1., 0., 0.);
         return;
     }
     const bool interior = i >= 2 && i + 2 < a.ni && j >= 2 && j + 2 < a.nj && k >= 2 && k + 2 < a.nk;
@@ -228,41 +246,52 @@ __global__ void __launch_bounds__(128) adt_lean_coef_kernel(const LeanCoefArgs A
 struct LeanArgs {
     int I, J, K, ld, sj, sk;                    // property / raw arrays: element (i,j,k) at i + sj*j + sk*k
     int nprop, ntile_i, j_begin, j_count;
-    int jc0, skc;                               // pack arrays: element (i,j,k) at i + ld*(j-jc0) + skc*k
+    int jc0, ncol, nt32;                        // pack array (see LeanCoefArgs)
     double dt;
-    const Pack4 *pkU, *pkV, *pkW, *pkC;
+    const Pack4 *pk;
     const double *qx, *qy, *qz, *VolumeZ, *VolumeZOld;   // raw: surface row of VolumeVariation, open-boundary flux
     unsigned long long *zero_pivots;
     PropArgs p[NPMAX];
 };
 
-// advective - diffusive flux through a horizontal face, positive toward the higher index.  g = P_hi - P_lo across the
-// face, dm / dp the same difference one cell to the lower / higher side, Plo / Phi the two cells, f the face pack.
+// a < b ? a : b and a > b ? a : b as one compare + select (written in PTX so that no NaN-aware min/max sequence is formed)
+__device__ __forceinline__ double sel_lt(double a, double b) {
+    double r;
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.f64 p, %1, %2;\n\tselp.f64 %0, %1, %2, p;\n\t}" : "=d"(r) : "d"(a), "d"(b));
+    return r;
+}
+__device__ __forceinline__ double sel_gt(double a, double b) {
+    double r;
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, %2;\n\tselp.f64 %0, %1, %2, p;\n\t}" : "=d"(r) : "d"(a), "d"(b));
+    return r;
+}
+__device__ __forceinline__ double abs_bits(double x) { return __hiloint2double(__double2hiint(x) & 0x7fffffff, __double2loint(x)); }
+// x >= 0 ? x : 0 for the sign taken from another word (s < 0 -> 0), then the sign bit `sg` put on: integer pipe only
+__device__ __forceinline__ double zero_if_neg_then_sign(double x, int s_hi, int sg) {
+    const int keep = ~(s_hi >> 31);
+    return __hiloint2double((__double2hiint(x) & keep) | sg, __double2loint(x) & keep);
+}
+
+// advective - diffusive flux through a horizontal face, positive toward the higher index, in the direction-free form
+// Qh (Plo + Phi) - A g + B sgn(g) lim (see the header).  g = Phi - Plo, dm / dp the same difference one cell to the
+// lower / higher side, f = {Qh, A, B, rho}.
 template <int M>
 __device__ __forceinline__ double lean_face(const bool pos, const double dm, const double g, const double dp,
                                             const double Plo, const double Phi, const Pack4 &f) {
-    const double Pu = pos ? Plo : Phi;
-    double fadv;
+    double F = fma(-f.b, g, f.a * (Plo + Phi));
     if constexpr (M == MOHID_P2_TVD) {
-        // Division-free SuperBee (see hface_flux): psi(r) dP = sgn(dP) max(0, min(hi, 2 lo)) with lo / hi the smaller /
-        // larger of |dP| and aS = sgn(dP) (Pu - Puu) rho.  For flow toward the lower index dP = -g and Pu - Puu = -dp,
-        // so aS = sgn(g) dp rho either way.
+        // Division-free SuperBee (see hface_flux): psi(r) |dP| = max(0, min(hi, 2 lo)) with lo / hi the smaller / larger
+        // of |g| and aS = sgn(g) (upwind difference) rho -- the same expression for both flow directions
         const double x = (pos ? dm : dp) * f.d;
-        const int gh = __double2hiint(g);
-        const double aS = __hiloint2double(__double2hiint(x) ^ (gh & 0x80000000), __double2loint(x));
-        const double ad = fabs(g);
+        const int gs = __double2hiint(g) & 0x80000000;
+        const double aS = __hiloint2double(__double2hiint(x) ^ gs, __double2loint(x));
+        const double ad = abs_bits(g);
         const bool c1 = ad < aS;
         const double lo = c1 ? ad : aS, hi = c1 ? aS : ad;
-        const double l2 = lo + lo;
-        double mn = hi < l2 ? hi : l2;
-        mn = (__double2hiint(aS) < 0) ? 0. : mn;
-        const int sg = (gh ^ (pos ? 0 : 0x80000000)) & 0x80000000;
-        const double lim = __hiloint2double(__double2hiint(mn) | sg, __double2loint(mn));
-        fadv = f.a * fma(f.b, lim, Pu);
-    } else {
-        fadv = f.a * Pu;
+        const double mn = sel_lt(hi, lo + lo);
+        F = fma(f.c, zero_if_neg_then_sign(mn, __double2hiint(aS), gs), F);
     }
-    return fma(-f.c, g, fadv);
+    return F;
 }
 
 // Open-boundary row (AD:5369-5672): the row of cell q is amended and eliminated again; returns (W, G).
@@ -279,16 +308,18 @@ __device__ __forceinline__ double2 lean_obc_row(const LeanArgs &s, const PropArg
 }
 
 struct LeanLevel {
-    Pack4 U0, U1, V, C;
+    Pack4 U0, U1, V, C, W;
     double Pw2, Pw1, Pe1, Pe2, hP;
 };
 
-template <int M, int WARPS, int MINB = 1>
-__global__ void __launch_bounds__(WARPS * 32, MINB) adt_transport_lean_kernel(const __grid_constant__ LeanArgs s) {
+// PFD > 0: the loads that miss L2 (the east-most property row and the packs of this column and of column j+1, which no
+// earlier block has touched) are requested PFD levels ahead with prefetch.global.L2 -- one instruction per warp and
+// level for the property row, two more by the first property's warp for the packs all warps of the block share.
+template <int M, int WARPS, int PFD = 0>
+__global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_lean_kernel(const __grid_constant__ LeanArgs s) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int wstride = WARPS * 32;
-    double *__restrict__ Wsm = smem + warp * 32 + lane;                  // [K][WARPS][32]
     const long nunits = (long)s.nprop * s.ntile_i * s.j_count;
     const long unit = (long)blockIdx.x * WARPS + warp;
     if (unit >= nunits) return;
@@ -300,33 +331,41 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) adt_transport_lean_kernel(co
     const int ic = min(i, s.I + 1);
     const PropArgs &pa = s.p[n];
     const double *__restrict__ P = pa.pin;
-    double *__restrict__ O = pa.pout;
-    const int sj = s.sj, sk = s.sk, skc = s.skc;
-    const int cp = ic + sj * j;                           // column base (k = 0) in the property arrays
-    const int cc = ic + s.ld * (j - s.jc0);               // ... in the pack arrays
+    const int sj = s.sj, sk = s.sk;
+    const long cp = ic + (long)sj * j;                    // column base (k = 0) in the property arrays
     const int je2 = (j + 2 <= s.J + 1) ? 2 * sj : sj;
     const int jw2 = (j >= 2) ? 2 * sj : sj;
-    const Pack4 *__restrict__ pkU = s.pkU, *__restrict__ pkV = s.pkV, *__restrict__ pkW = s.pkW, *__restrict__ pkC = s.pkC;
+    const long pk_plane = (long)s.ncol * s.nt32 * 128;    // Pack4 elements per k-plane of packs
+    const long pk_col = (long)s.nt32 * 128;               // ... per column
 
-    const unsigned mtop = (unsigned)__double2loint(pkC[cc + skc * s.K].d);
+    const Pack4 *__restrict__ pk0 = s.pk + pack_index(ic, j - s.jc0, s.nt32);      // (i, j, k = 0)
+    // from a lane's pack pointer to the start of the 32-cell group that holds the strip's first cell
+    const int goff = -(ic & 31) - ((ic >> 5) - ((1 + tile * 31) >> 5)) * 128;
+    const unsigned mtop = (unsigned)__double2loint(pk0[pk_plane * s.K + PK_C].d);
     const bool colwet = (mtop & M_COLWET) != 0;
     const bool obc = (mtop & M_BND) != 0 && pa.bc != MOHID_BC_None;
     const double theta = pa.theta_difv, omt = 1. - pa.theta_difv;
-    const double qz_top = s.qz[cp + sk * (s.K + 1)];
+    const double qz_top = s.qz[cp + (long)sk * (s.K + 1)];
     const bool halo_lane = (lane < 2) || (lane == 31);
     const int halo_off = (lane == 31) ? ((ic <= s.I) ? 1 : 0) : -2;
 
-    auto fetch = [&](int qp, int qc, LeanLevel &L) {
-        L.C = ld_pack(pkC + qc);
-        L.U0 = ld_pack(pkU + qc);
-        L.U1 = ld_pack(pkU + qc + s.ld);
-        L.V = ld_pack(pkV + qc);
-        L.Pw2 = __ldg(P + (qp - jw2)); L.Pw1 = __ldg(P + (qp - sj)); L.Pe1 = __ldg(P + (qp + sj)); L.Pe2 = __ldg(P + (qp + je2));
-        L.hP = halo_lane ? __ldg(P + (qp + halo_off)) : 0.;
+    // packs: one per-thread pointer (constant offsets reach the four packs); properties: one cell index
+    const Pack4 *__restrict__ pk = pk0 + pk_plane;                                // packs of level 1
+    int qp = (int)cp + sk;                                                       // cell (i, j, 1)
+    double *__restrict__ wsm = smem + warp * 32 + lane;                          // [K][WARPS][32]
+
+    auto fetch = [&](LeanLevel &L) {             // packs and horizontal neighbours of the level pk / qp are at
+        L.C = ld_pack(pk + PK_C);
+        L.U0 = ld_pack(pk + PK_U);
+        L.U1 = ld_pack(pk + pk_col + PK_U);
+        L.V = ld_pack(pk + PK_V);
+        L.W = ld_pack(pk + PK_W);
+        L.Pw2 = ld_f64(P + (qp - jw2)); L.Pw1 = ld_f64(P + (qp - sj)); L.Pe1 = ld_f64(P + (qp + sj)); L.Pe2 = ld_f64(P + (qp + je2));
+        L.hP = halo_lane ? ld_f64(P + (qp + halo_off)) : 0.;
     };
+    auto advance = [&]() { pk += pk_plane; qp += sk; };
 
     // ---- rolling state ----
-    int qp = cp + sk, qc = cc + skc;                      // cell (i,j,1)
     double Pm2 = 0., Pm1 = P[cp], Pc = P[qp], Pp1 = P[qp + sk];
     double dtv_m = 0.;
     double RD = 0., RE = 1., RTI = 0.;                    // row k-1 as far as it is known
@@ -335,7 +374,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) adt_transport_lean_kernel(co
     double Wp = 0., Gp = 0.;                              // W, G of the last eliminated row
     unsigned zp = 0;
     LeanLevel lvA, lvB;
-    fetch(qp, qc, lvA);
+    fetch(lvA);
 
     // the face below cell k (between k-1 and k): completes row k-1, eliminates it, returns the face's share of row k
     auto vface = [&](const int k, const Pack4 &C, const Pack4 &W, const unsigned m, double &Dn, double &En, double &TIn) {
@@ -352,17 +391,19 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) adt_transport_lean_kernel(co
         const bool pos = (m & M_POS_B) != 0;
         double w1, w2;                                                 // weights of cell k-1 and of cell k
         if constexpr (M == MOHID_P2_TVD) {
-            const double Puu = pos ? Pm2 : Pp1, Pu = pos ? Pm1 : Pc;
-            const double dPd = pos ? dP : -dP;                         // Pd - Pu
+            // r = ((Pu - Puu) rd_u) / ((Pd - Pu) rd_c) with dC = (Pd - Pu) rd_c kept away from zero (MF:10795-10803).  For
+            // downward flow numerator and denominator are the negated differences; Pd - Pu is formed by its own
+            // subtraction so that equal neighbours give +0 in both directions, as in the reference.
+            const double num = pos ? Pm1 - Pm2 : Pc - Pp1;
+            const double dPd = pos ? dP : Pm1 - Pc;
             double dC = dPd * W.d;
-            dC = (fabs(dC) < MIN_VALUE) ? with_sign_of(MIN_VALUE, dC) : dC;    // MF:10795-10803
-            const double r = (Pu - Puu) * W.c * fast_rcp(dC);
+            dC = (abs_bits(dC) < MIN_VALUE) ? with_sign_of(MIN_VALUE, dC) : dC;
+            const double r = num * W.c * fast_rcp(dC);
             // SuperBee max(0, min(1, 2r), min(r, 2)) (MF:10826-10829) as a chain of exact selections
-            const double r2 = r + r;
-            double ps = r2 < 1. ? r2 : 1.;
-            ps = ps > r ? ps : r;
-            ps = ps < 2. ? ps : 2.;
-            ps = (__double2hiint(r) < 0) ? 0. : ps;
+            double ps = sel_lt(r + r, 1.);
+            ps = sel_gt(ps, r);
+            ps = sel_lt(ps, 2.);
+            ps = zero_if_neg_then_sign(ps, __double2hiint(r), 0);
             const double th = ps * W.b;                                // 0.5 psi (1 - Cr), 0 near the boundary
             const double wu = 1. - th;
             w1 = pos ? wu : th; w2 = pos ? th : wu;
@@ -386,23 +427,35 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) adt_transport_lean_kernel(co
             zp += ok ? 0u : 1u;
         }
         if (obc_m) {                                                   // open-boundary row (rare): amend, eliminate again
-            const double2 wg = lean_obc_row(s, pa, qp - sk, m_m, Pm1, dtv_m, RD, RE, RF, RTI, Wp0, Gp0);
+            const double2 wg = lean_obc_row(s, pa, (int)(cp + (long)sk * (k - 1)), m_m, Pm1, dtv_m, RD, RE, RF, RTI, Wp0, Gp0);
             Wp = wg.x; Gp = wg.y;
         }
-        Wsm[(k - 2) * wstride] = Wp;
-        if (writer && colwet) O[qp - sk] = Gp;                         // G parked in the output array
+        wsm[0] = Wp;
+        wsm += wstride;
+        if (writer && colwet) pa.pout[cp + (long)sk * (k - 1)] = Gp;   // G parked in the output array
     };
 
-    auto level = [&](auto first_tag, const int k, const LeanLevel &cur, LeanLevel &nxt) {
-        constexpr bool FIRST = decltype(first_tag)::value;
-        // ---- look-ahead: horizontal data of level k+1, P of level k+2; this level's W pack ----
-        fetch(qp + sk, qc + skc, nxt);
-        const double Pp2 = __ldg(P + ((k + 2 <= s.K + 1) ? qp + 2 * sk : qp + sk));
-        Pack4 W{};
-        if constexpr (!FIRST) W = ld_pack(pkW + qc);
+    // POS: 0 = level 1 (no face below), 1 = levels 2 .. K-1, 2 = level K (surface row of VolumeVariation)
+    auto level = [&](auto pos_tag, const int k, const LeanLevel &cur, LeanLevel &nxt) {
+        constexpr int POS = decltype(pos_tag)::value;
+        // ---- look-ahead: packs and horizontal neighbours of level k+1, P of level k+2 ----
+        advance();
+        fetch(nxt);
+        if constexpr (PFD > 0) {
+            const int kk = min(k + PFD, s.K + 1) - k - 1;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(P + (qp + kk * sk + je2)));
+            if (n == 0) {
+                // the strip's cells lie in two 32-cell groups of 4 KB each: lane l requests line l of both (column j)
+                // and, for column j+1, the lines of the two U packs (lanes 0-7 / 8-15)
+                const Pack4 *f = pk + (long)kk * pk_plane + goff + lane * 4;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(f));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(f + 128));
+                if (lane < 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(f + pk_col + (lane >> 3) * (128 - 32)));
+            }
+        }
+        const double Pp2 = ld_f64(P + (POS == 2 ? qp : qp + sk));     // plane K+2 does not exist: clamped like round 1
         const unsigned m = (unsigned)__double2loint(cur.C.d);
         const double dtv_c = cur.C.a;
-        const bool open_c = (m & M_OPEN) != 0;
 
         // ---- horizontal faces (explicit) ----
         const double d1 = cur.Pw1 - cur.Pw2, d2 = Pc - cur.Pw1, d3 = cur.Pe1 - Pc, d4 = cur.Pe2 - cur.Pe1;
@@ -421,57 +474,72 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) adt_transport_lean_kernel(co
 
         // ---- the face below: row k-1 is complete, eliminate it ----
         double Dn = 0., En = 0., TIn = 0.;
-        if constexpr (!FIRST) vface(k, cur.C, W, m, Dn, En, TIn);
+        if constexpr (POS != 0) vface(k, cur.C, cur.W, m, Dn, En, TIn);
 
-        // ---- row k: VolumeVariation (AD:3966-4021) + the shares known so far ----
-        const double ti0 = open_c ? Pc * cur.C.b : Pc;
-        const double e0 = (open_c && k == s.K) ? 1.0 + dtv_c * qz_top : 1.0;
-        RTI = fma(fsum, dtv_c, ti0 + TIn);
+        // ---- row k: VolumeVariation (AD:3966-4021; Vold/V is 1 in closed cells) + the shares known so far ----
+        double e0 = 1.0;
+        if constexpr (POS == 2) e0 = (m & M_OPEN) ? 1.0 + dtv_c * qz_top : 1.0;
+        RTI = fma(fsum, dtv_c, Pc * cur.C.b + TIn);
         RE = e0 + En;
         RD = Dn;
         land_m = (m & M_LAND) != 0;
-        obc_m = obc && open_c;
+        obc_m = obc && (m & M_OPEN) != 0;
         m_m = m;
         // ---- roll ----
         Pm2 = Pm1; Pm1 = Pc; Pc = Pp1; Pp1 = Pp2;
         dtv_m = dtv_c;
-        qp += sk; qc += skc;
     };
     {
-        const std::true_type first{};
-        const std::false_type rest{};
+        const std::integral_constant<int, 0> first{};
+        const std::integral_constant<int, 1> mid{};
+        const std::integral_constant<int, 2> last{};
+        // level 1 (or the only level of a K = 1 ... not reachable: the lean path needs K >= 2)
         level(first, 1, lvA, lvB);
+        int nmid = s.K - 2;                                 // levels 2 .. K-1
         int k = 2;
-        bool inA = false;                                  // which struct holds the data of level k
-        for (; k + 1 <= s.K; k += 2) {
-            level(rest, k, lvB, lvA);
-            level(rest, k + 1, lvA, lvB);
+        if (nmid & 1) { level(mid, k, lvB, lvA); lvB = lvA; ++k; --nmid; }
+        for (; nmid > 0; nmid -= 2, k += 2) {
+            level(mid, k, lvB, lvA);
+            level(mid, k + 1, lvA, lvB);
         }
-        if (k <= s.K) { level(rest, k, lvB, lvA); inA = true; }
+        level(last, s.K, lvB, lvA);
         // ---- virtual level K+1: the face above the surface cell completes row K ----
-        const LeanLevel &last = inA ? lvA : lvB;
-        const Pack4 W = ld_pack(pkW + qc);
         double Dn, En, TIn;
-        vface(s.K + 1, last.C, W, (unsigned)__double2loint(last.C.d), Dn, En, TIn);
+        vface(s.K + 1, lvA.C, lvA.W, (unsigned)__double2loint(lvA.C.d), Dn, En, TIn);
     }
 
     // ---------------- back substitution (MF:4100-4105) ----------------
     if (writer && colwet) {
-        int qo = cp + sk * (s.K + 1);
+        double *__restrict__ O = pa.pout;
+        long qo = cp + (long)sk * (s.K + 1);
+        const double *__restrict__ Wsm = smem + warp * 32 + lane;
         double x = 0.0;                                   // RES(KUB+1) = G(KUB+1) = 0 (halo row is the identity)
         O[qo] = x;
         int k = s.K;
-        for (; k >= 8; k -= 8) {
-            double g[8];
+        // G comes back from the output array (L2): eight levels per batch, the next batch in flight while this one is solved
+        double ga[8], gb[8];
+        auto load8 = [&](double (&g)[8], long q0) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) g[u] = O[qo - (u + 1) * sk];
+            for (int u = 0; u < 8; ++u) g[u] = O[q0 - (long)(u + 1) * sk];
+        };
+        auto solve8 = [&](const double (&g)[8]) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 qo -= sk;
                 x = Wsm[(k - 1 - u) * wstride] * x + g[u];
                 O[qo] = x;
             }
+            k -= 8;
+        };
+        if (k >= 8) load8(ga, qo);
+        while (k >= 16) {
+            load8(gb, qo - 8L * sk);
+            solve8(ga);
+            if (k >= 16) { load8(ga, qo - 8L * sk); solve8(gb); }
+            else { solve8(gb); goto tail; }
         }
+        if (k >= 8) solve8(ga);
+    tail:
         for (; k >= 1; --k) {
             qo -= sk;
             x = Wsm[(k - 1) * wstride] * x + O[qo];

@@ -1,6 +1,7 @@
 #!/bin/bash
 # round-2 experiment 1: lean kernels: correctness + C3 timing per warps-per-block, ncu of the 16-warp form
 cd "$GRAFT_REPO_ROOT" || exit 1
+export MOHID_ADT_NO_REBUILD=1
 mkdir -p gpurun_out
 python tools/lean_check.py > gpurun_out/lean_check.log 2>&1
 tail -5 gpurun_out/lean_check.log
