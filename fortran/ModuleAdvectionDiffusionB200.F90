@@ -39,7 +39,7 @@ module ModuleAdvectionDiffusionB200
         real(c_double) :: VolumeRelMax, DTProp, ImpExp_AdvV, ImpExp_DifV, ImpExp_AdvXX, ImpExp_AdvYY, ImpExp_DifH
         integer(c_int) :: NullDif, BoundaryCondition
         real(c_double) :: DecayTime
-        integer(c_int) :: NoAdvFlux, NoDifFlux, CellFluxes, reserved1
+        integer(c_int) :: NoAdvFlux, NoDifFlux, CellFluxes, Optimize
     end type T_AdtParams
 
     type, bind(c) :: T_AdtOptions

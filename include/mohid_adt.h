@@ -83,7 +83,9 @@ typedef struct mohid_adt_params {
     int    NoAdvFlux;              /* logical; needs NoFluxU/V/W (mohid_adt_set_noflux) */
     int    NoDifFlux;              /* logical */
     int    CellFluxes;             /* logical: also produce the six cell-face fluxes (AD:1457-1470, 3356-3954) */
-    int    reserved1;
+    int    Optimize;            /* the Optimize argument of the reference call (AD:1146, WP:14580-14598): 0 = inferred
+                                  from the batch (all coupled properties are in it), 1 = on, 2 = off; read from the
+                                  first property of the batch */
 } mohid_adt_params;
 
 /* Instance-level flags = StartAdvectionDiffusion arguments (AD:400-411) */

@@ -20,9 +20,7 @@
 #include <nccl.h>      // types only: the library is dlopen'ed by mohid_adt_comm_init, never linked
 
 #include "adt_kernels.cuh"
-#include "adt_ring_kernel.cuh"
 #include "adt_hsolve_kernel.cuh"
-#include "adt_hflux_kernel.cuh"
 #include "adt_lean_kernel.cuh"
 
 using namespace adt;
@@ -35,18 +33,20 @@ struct Handle {
     bool own_stream = false;
     cudaStream_t s_up = nullptr, s_down = nullptr;      // copy streams of the pipelined host path (advect_batch)
     void *stage[3] = {nullptr, nullptr, nullptr};       // one field in the caller's pitch per stream (short padded rows)
-    // halo overlap (mohid_adt_set_overlap): the edge columns of a slab are advanced first, ev_edges is recorded, and
-    // pack / unpack run on the caller's communication stream while the interior columns are still being advanced
-    cudaStream_t comm = nullptr, s_edge = nullptr;      // s_edge: the edge columns run beside the interior ones
-    cudaEvent_t ev_edges = nullptr, ev_halo = nullptr, ev_fork = nullptr;
-    int overlap_ghost = 0;
-    bool halo_pending = false, allow_edge_first = false;
+    // halo exchange: pack / unpack run on a communication stream after the step (ev_edges), the next step waits (ev_halo)
+    cudaStream_t comm = nullptr;
+    cudaEvent_t ev_edges = nullptr, ev_halo = nullptr;
+    bool halo_pending = false;
     std::vector<cudaEvent_t> pipe_ev;
     mohid_adt_options opt{};
     int I = 0, J = 0, K = 0, ni = 0, nj = 0, nk = 0, ld_h = 0, ld = 0;
     long n2 = 0, n3 = 0;
     int sj = 0, sk = 0;                                 // element strides of j and k in the 3-D device arrays
-    bool kmid = false;                                  // optional device layout (i, k, j) (MOHID_ADT_LAYOUT=1); measured: no gain
+    // In-place shift: every 3-D array has njp = nj + S columns per plane.  A property's logical column 0 sits at
+    // physical column shift[n] (0 or S); a step reads the field where it is and writes the new one at the other
+    // position, S columns aside, walking the columns in chunks of C (S = C + 3) toward the side the data leaves, so
+    // that no chunk overwrites old columns a later chunk still reads (stencil reach 2).  One buffer per property.
+    int njp = 0, S = 0, C = 0;
     int maxprop = 0;
     // 2-D
     double *DUX = nullptr, *DVY = nullptr, *DZX = nullptr, *DZY = nullptr, *rdx = nullptr, *rdy = nullptr;
@@ -62,27 +62,28 @@ struct Handle {
     std::vector<int> lim_min_on, lim_max_on;            // SetLimitsProperty per property (mohid_adt_set_limits)
     std::vector<double> lim_min, lim_max;
     std::vector<double *> mass_created, mass_destroyed;
-    std::vector<double *> tih;                          // net horizontal flux per cell (adt_hflux_kernel -> HSPLIT K2)
-    std::vector<double *> wline;                        // W of the line recurrence (horizontally implicit advection)
+    std::vector<double *> wline, hs_tmp;                // horizontally implicit advection: W of the line recurrence, intermediate field
+    std::vector<double *> old_copy;                     // field at time n (CellFluxes: the explicit shares use it)
     unsigned char *nfmask = nullptr;                    // NF_* bits, rebuilt by K1 every step
     int n_bnd_cols = 0;
     bool bnd_off_ring = false;                          // a boundary point away from the outer ring (Orlanski stops on it)
     // raw per-step inputs
     double *raw_d[11] = {nullptr};
     int *raw_i[6] = {nullptr};
-    // packed per-step coefficients (K1 outputs)
+    // packed per-step coefficients (K1 outputs; allocated when a batch first takes the round-1 kernels)
     double *dtv = nullptr, *vr = nullptr, *dhu = nullptr, *dhv = nullptr, *dvz = nullptr, *rdz = nullptr;
     uint32_t *mask = nullptr;
-    // properties: ping-pong pairs + reference fields
-    std::vector<double *> prop[2];
+    // properties (one buffer each, see `shift` above) + reference fields
+    std::vector<double *> prop;
+    std::vector<int> shift;
     std::vector<double *> ref;
-    std::vector<int> cur;
     std::vector<char> has_ref;
     unsigned long long *d_zero_piv = nullptr;
     bool have_grid = false, have_step = false;
     long long launches = 0, bytes = 0, zero_piv_last = 0;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;   // K2 timing
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;   // K2 timing: one pair per chunk launch
     size_t ev_used = 0;
+    int ev_steps = 0;                                   // steps (launch groups) the pairs belong to
     std::string err;
     int smem_optin = 0, num_sms = 0;
     int j_begin = 1, j_count = 0;                       // columns advanced by this handle (slab decomposition)
@@ -186,6 +187,10 @@ int dalloc(Handle *h, T **p, size_t n) {
     return 0;
 }
 
+// current / next position of property n inside its buffer
+inline double *cur_ptr(const Handle *h, int n) { return h->prop[n] + (size_t)h->shift[n] * h->ld; }
+inline double *nxt_ptr(const Handle *h, int n) { return h->prop[n] + (size_t)(h->S - h->shift[n]) * h->ld; }
+
 // caller -> device mirror copy of a 2-D array (nj rows of ni elements, element size es).  cudaMemcpyDefault:
 // the caller's arrays may live in host memory (the Fortran case) or, under UVA, in device memory.
 int h2d2(Handle *h, void *dst, const void *src, size_t es) {
@@ -193,8 +198,6 @@ int h2d2(Handle *h, void *dst, const void *src, size_t es) {
                             cudaMemcpyDefault, h->stream));
     return 0;
 }
-// 3-D arrays: the caller's layout is Fortran (i, j, k); the device mirror is (i, k, j) when kmid, so each k-plane
-// of the caller is one strided 2-D copy (row pitch sj on the device).
 // Staging buffer of the stream (one field in the caller's pitch), or nullptr when the rows are long enough for the
 // copy engine to move them pitched at link speed.  When ld_h > ld the caller's padding columns travel too; the
 // D2H direction then leaves them untouched on the host only in the direct path, so staging is limited to ld_h <= ld.
@@ -208,68 +211,57 @@ void *staging(Handle *h, cudaStream_t st, size_t es) {
     }
     return h->stage[w];
 }
-
-int h2d3(Handle *h, void *dst, const void *src, size_t es, cudaStream_t st = nullptr) {
+// 3-D arrays: caller (ld_h, nj, nk) <-> device (ld, njp, nk), one 3-D copy; `dev` already points at the logical
+// column 0 of the field.  Short caller rows cross the link contiguously and change pitch on the device.
+int copy3(Handle *h, void *dev, const void *host, size_t es, bool to_dev, cudaStream_t st) {
     if (!st) st = h->stream;
-    if (h->ld == h->ld_h && h->sj == h->ld && h->sk == h->ld * h->nj) {      // same layout on both sides: one copy
-        CU(h, cudaMemcpyAsync(dst, src, es * h->n3, cudaMemcpyDefault, st));
-        return 0;
+    const size_t w = es * (size_t)std::min(h->ld, h->ld_h);
+    cudaMemcpy3DParms p{};
+    p.extent = make_cudaExtent(w, (size_t)h->nj, (size_t)h->nk);
+    p.kind = cudaMemcpyDefault;
+    const cudaPitchedPtr D = make_cudaPitchedPtr(dev, es * (size_t)h->ld, es * (size_t)h->ld, (size_t)h->njp);
+    cudaPitchedPtr H = make_cudaPitchedPtr(const_cast<void *>(host), es * (size_t)h->ld_h, es * (size_t)h->ld_h, (size_t)h->nj);
+    void *stg = staging(h, st, es);
+    const size_t nbytes = es * (size_t)h->ld_h * h->nj * h->nk;
+    if (stg && to_dev) {
+        CU(h, cudaMemcpyAsync(stg, host, nbytes, cudaMemcpyDefault, st));
+        H.ptr = stg;
     }
-    if (h->sj == h->ld && h->sk == h->ld * h->nj) {      // rows of all planes are equally spaced on both sides: one 2-D copy
-        void *stg = staging(h, st, es);
-        if (stg) {      // short rows: cross the link contiguously, change the pitch on the device
-            CU(h, cudaMemcpyAsync(stg, src, es * (size_t)h->ld_h * h->nj * h->nk, cudaMemcpyDefault, st));
-            src = stg;
-        }
-        CU(h, cudaMemcpy2DAsync(dst, es * h->ld, src, es * h->ld_h, es * std::min(h->ld, h->ld_h), (size_t)h->nj * h->nk,
-                                cudaMemcpyDefault, st));
-        return 0;
-    }
-    for (int k = 0; k < h->nk; ++k)
-        CU(h, cudaMemcpy2DAsync((char *)dst + es * (size_t)h->sk * k, es * h->sj,
-                                (const char *)src + es * (size_t)h->ld_h * h->nj * k, es * h->ld_h,
-                                es * std::min(h->ld, h->ld_h), h->nj, cudaMemcpyDefault, st));
+    if (stg && !to_dev) H.ptr = stg;
+    p.srcPtr = to_dev ? H : D;
+    p.dstPtr = to_dev ? D : H;
+    CU(h, cudaMemcpy3DAsync(&p, st));
+    if (stg && !to_dev) CU(h, cudaMemcpyAsync(const_cast<void *>(host), stg, nbytes, cudaMemcpyDefault, st));
     return 0;
 }
+int h2d3(Handle *h, void *dst, const void *src, size_t es, cudaStream_t st = nullptr) { return copy3(h, dst, src, es, true, st); }
 int d2h3(Handle *h, void *dst, const void *src, size_t es, cudaStream_t st = nullptr) {
-    if (!st) st = h->stream;
-    if (h->ld == h->ld_h && h->sj == h->ld && h->sk == h->ld * h->nj) {
-        CU(h, cudaMemcpyAsync(dst, src, es * h->n3, cudaMemcpyDefault, st));
-        return 0;
-    }
-    if (h->sj == h->ld && h->sk == h->ld * h->nj) {
-        void *stg = staging(h, st, es);
-        if (stg) {
-            CU(h, cudaMemcpy2DAsync(stg, es * h->ld_h, src, es * h->ld, es * std::min(h->ld, h->ld_h), (size_t)h->nj * h->nk,
-                                    cudaMemcpyDeviceToDevice, st));
-            CU(h, cudaMemcpyAsync(dst, stg, es * (size_t)h->ld_h * h->nj * h->nk, cudaMemcpyDefault, st));
-            return 0;
-        }
-        CU(h, cudaMemcpy2DAsync(dst, es * h->ld_h, src, es * h->ld, es * std::min(h->ld, h->ld_h), (size_t)h->nj * h->nk,
-                                cudaMemcpyDefault, st));
-        return 0;
-    }
-    for (int k = 0; k < h->nk; ++k)
-        CU(h, cudaMemcpy2DAsync((char *)dst + es * (size_t)h->ld_h * h->nj * k, es * h->ld_h,
-                                (const char *)src + es * (size_t)h->sk * k, es * h->sj,
-                                es * std::min(h->ld, h->ld_h), h->nj, cudaMemcpyDefault, st));
-    return 0;
+    return copy3(h, const_cast<void *>(src), dst, es, false, st);
 }
 
 int ensure_props(Handle *h, int nprop, bool need_ref_any) {
     if (nprop > NPMAX) return fail(h, MOHID_ADT_ERR_ARG, "nprop %d exceeds the batch limit %d", nprop, NPMAX);
-    while ((int)h->prop[0].size() < nprop) {
-        double *a = nullptr, *b = nullptr;
+    while ((int)h->prop.size() < nprop) {
+        double *a = nullptr;
         if (int rc = dalloc(h, &a, h->n3)) return rc;
-        if (int rc = dalloc(h, &b, h->n3)) return rc;
-        h->prop[0].push_back(a);
-        h->prop[1].push_back(b);
+        CU(h, cudaMemsetAsync(a, 0, h->n3 * sizeof(double), h->stream));      // padding and shift margin read as zero
+        h->prop.push_back(a);
+        h->shift.push_back(h->S);
         h->ref.push_back(nullptr);
-        h->cur.push_back(0);
         h->has_ref.push_back(0);
     }
     (void)need_ref_any;
     return 0;
+}
+
+// packed coefficient arrays of the round-1 kernels (52 B per cell), allocated on first use
+int ensure_legacy(Handle *h) {
+    if (h->mask) return 0;
+    int rc = 0;
+    rc |= dalloc(h, &h->dtv, h->n3); rc |= dalloc(h, &h->vr, h->n3); rc |= dalloc(h, &h->dhu, h->n3);
+    rc |= dalloc(h, &h->dhv, h->n3); rc |= dalloc(h, &h->dvz, h->n3); rc |= dalloc(h, &h->rdz, h->n3);
+    rc |= dalloc(h, &h->mask, h->n3);
+    return rc;
 }
 
 void free_all(Handle *h) {
@@ -280,14 +272,15 @@ void free_all(Handle *h) {
     for (auto p : h->noflux) F(p);
     F(h->nfmask);
     for (auto p : h->wline) F(p);
-    for (auto p : h->tih) F(p);
+    for (auto p : h->hs_tmp) F(p);
+    for (auto p : h->old_copy) F(p);
     F(h->density); F(h->wcol);
     for (auto p : h->mass_created) F(p);
     for (auto p : h->mass_destroyed) F(p);
     for (auto p : h->raw_d) F(p);
     for (auto p : h->raw_i) F(p);
     F(h->dtv); F(h->vr); F(h->dhu); F(h->dhv); F(h->dvz); F(h->rdz); F(h->mask);
-    for (int b = 0; b < 2; ++b) for (auto p : h->prop[b]) F(p);
+    for (auto p : h->prop) F(p);
     for (auto p : h->ref) F(p);
     F(h->d_zero_piv);
     F(h->pk);
@@ -303,9 +296,7 @@ void free_all(Handle *h) {
     for (auto &e : h->ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (h->ev_edges) cudaEventDestroy(h->ev_edges);
     if (h->ev_halo) cudaEventDestroy(h->ev_halo);
-    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-    if (h->s_edge) cudaStreamDestroy(h->s_edge);
-    h->ev_edges = h->ev_halo = h->ev_fork = nullptr; h->s_edge = nullptr;
+    h->ev_edges = h->ev_halo = nullptr;
     for (auto &p : h->stage) { if (p) cudaFree(p); p = nullptr; }
     if (h->s_up) cudaStreamDestroy(h->s_up);
     if (h->s_down) cudaStreamDestroy(h->s_down);
@@ -440,6 +431,9 @@ int validate(Handle *h, int nprop, const mohid_adt_params *p, Batch &b) {
             if (h->j_begin != 1 || h->j_count != h->J)
                 return fail(h, MOHID_ADT_ERR_UNSUPPORTED, "Orlanski boundary is not available on a column slab");
         }
+        if (bc == MOHID_BC_CyclicBoundary && (h->j_begin != 1 || h->j_count != h->J))
+            return fail(h, MOHID_ADT_ERR_UNSUPPORTED,
+                        "CyclicBoundary wraps the global columns 1 and J (AD:2121-2224): not available on a column slab");
         if (bc != MOHID_BC_None && bc != MOHID_BC_MassConservation && bc != MOHID_BC_ImposedValue &&
             bc != MOHID_BC_NullGradient && bc != MOHID_BC_SubModel && bc != MOHID_BC_MassConservNullGrad &&
             bc != MOHID_BC_CyclicBoundary && bc != MOHID_BC_Orlanski)
@@ -458,6 +452,10 @@ int validate(Handle *h, int nprop, const mohid_adt_params *p, Batch &b) {
             q.TVDLimitationH != MOHID_SuperBee || q.TVDLimitationV != MOHID_SuperBee || q.NoAdvFlux || q.NoDifFlux)
             optimize = false;
     }
+    // Optimize is an argument of the reference call (AD:1146), computed by the caller over ALL coupled properties of the
+    // model (WP:14580-14598): a batch that holds only some of them passes it explicitly (1 = on, 2 = off, 0 = inferred)
+    if (f.Optimize == 1) optimize = !h->opt.Vertical1D;
+    else if (f.Optimize == 2) optimize = false;
     b.nprop = nprop; b.optimize = optimize; b.p = p;
     resolve_effective_flags(h, b);
     return 0;
@@ -494,7 +492,7 @@ bool lean_eligible(const Handle *h, const Batch &b) {
     if (getenv("MOHID_ADT_NOLEAN")) return false;
     // the packs cost 128 B per cell to write and to read: they pay once they are shared by a few properties
     if (b.nprop < 3 && !getenv("MOHID_ADT_LEAN_ALWAYS")) return false;
-    if (h->opt.Vertical1D || h->opt.XZFlow || h->K < 2 || h->have_noflux || h->kmid) return false;
+    if (h->opt.Vertical1D || h->opt.XZFlow || h->K < 2 || h->have_noflux) return false;
     const mohid_adt_params &f = b.p[0];
     const bool tvd_sb = f.AdvMethodH == MOHID_P2_TVD && f.AdvMethodV == MOHID_P2_TVD &&
                         f.TVDLimitationH == MOHID_SuperBee && f.TVDLimitationV == MOHID_SuperBee;
@@ -571,7 +569,7 @@ int launch_premix(Handle *h, const std::vector<int> &idx, int sign) {
     a.limit = h->sd_limit;
     for (int m = 0; m < a.nprop; ++m) {
         const int n = idx[m];
-        a.pa[m] = h->prop[h->cur[n]][n]; a.pb[m] = h->prop[h->cur[n] ^ 1][n];
+        a.pa[m] = cur_ptr(h, n);
         a.pref[m] = h->has_ref[n] ? h->ref[n] : nullptr;
         a.off[m] = (n < (int)h->offsets.size()) ? sign * h->offsets[n] : 0.;
         // Property%DischConc(:) is shifted with the field (WP:14725-14727, 14834-14836)
@@ -596,13 +594,13 @@ int launch_limits(Handle *h, const std::vector<int> &idx) {
     LimitArgs a{};
     a.I = h->I; a.J = h->J; a.K = h->K; a.ld = h->ld; a.sj = h->sj; a.sk = h->sk; a.docycle = h->opt.Docycle_method;
     a.Water = h->raw_i[2]; a.KFloorZ = h->KFloorZ; a.VolumeZ = h->raw_d[4];
-    if (h->mass_created.size() < h->prop[0].size()) { h->mass_created.resize(h->prop[0].size(), nullptr); h->mass_destroyed.resize(h->prop[0].size(), nullptr); }
+    if (h->mass_created.size() < h->prop.size()) { h->mass_created.resize(h->prop.size(), nullptr); h->mass_destroyed.resize(h->prop.size(), nullptr); }
     for (int m = 0; m < (int)idx.size(); ++m) {
         const int n = idx[m];
         const bool on = n < (int)h->lim_min_on.size() && (h->lim_min_on[n] || h->lim_max_on[n]);
         a.min_on[m] = on ? h->lim_min_on[n] : 0; a.max_on[m] = on ? h->lim_max_on[n] : 0;
         a.vmin[m] = on ? h->lim_min[n] : 0.; a.vmax[m] = on ? h->lim_max[n] : 0.;
-        a.pa[m] = h->prop[h->cur[n]][n]; a.pb[m] = h->prop[h->cur[n] ^ 1][n];
+        a.pa[m] = cur_ptr(h, n);
         if (on) {
             for (auto *v : {&h->mass_created, &h->mass_destroyed})
                 if (!(*v)[n]) {
@@ -619,12 +617,27 @@ int launch_limits(Handle *h, const std::vector<int> &idx) {
     return 0;
 }
 
-// hdir: 0 = the whole step; 1 / 2 = horizontally implicit along j / i: adt_hsolve_kernel (stage 1) and then the
-// vertical half of the step from the intermediate field (stage 2)
-int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool timed, int hdir = 0, bool stage2 = false) {
-    if (!stage2) if (int rc = launch_premix(h, idx, +1)) return rc;
+// device copy of the logical field (nk planes of ld*nj elements, plane pitch ld*njp) between two positions
+int copy_field(Handle *h, double *dst, const double *src) {
+    CU(h, cudaMemcpy2DAsync(dst, sizeof(double) * (size_t)h->sk, src, sizeof(double) * (size_t)h->sk,
+                            sizeof(double) * (size_t)h->ld * h->nj, (size_t)h->nk, cudaMemcpyDeviceToDevice, h->stream));
+    return 0;
+}
+
+// columns 0 .. nj-1 in chunks of C, in the order that is safe for the direction of the in-place shift
+struct Chunk { int a, b; };
+std::vector<Chunk> chunk_order(const Handle *h, bool increasing) {
+    std::vector<Chunk> v;
+    for (int a = 0; a < h->nj; a += h->C) v.push_back({a, std::min(a + h->C, h->nj) - 1});
+    if (!increasing) std::reverse(v.begin(), v.end());
+    return v;
+}
+
+// hdir: 0 = the whole step; 1 / 2 = horizontally implicit along j / i: adt_hsolve_kernel (stage 1, into a scratch
+// field) and then the vertical half of the step from the intermediate field (stage 2)
+int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool timed, int hdir = 0) {
+    if (int rc = launch_premix(h, idx, +1)) return rc;
     StepArgs s{};
-    s.stage2 = stage2 ? 1 : 0;
     s.I = h->I; s.J = h->J; s.K = h->K; s.ld = h->ld; s.nj = h->nj; s.sj = h->sj; s.sk = h->sk;
     s.nprop = (int)idx.size();
     s.ntile_i = (h->I + 30) / 31;
@@ -643,12 +656,24 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
     s.disch.ncell = h->d_ncell; s.disch.K = h->K; s.disch.ci = h->d_ci; s.disch.cj = h->d_cj;
     s.disch.kmin_eff = h->d_kmin_eff; s.disch.kmax_eff = h->d_kmax_eff; s.disch.cbypass = h->d_cbypass;
     s.disch.flow_k = h->d_flow_k;
+    // all properties of a launch move the same way: a property that sits at the other position is re-homed first
+    const int shift0 = h->shift[idx[0]];
+    for (int n : idx) {
+        if (h->shift[n] == shift0) continue;
+        // via a scratch field: the two positions overlap
+        if ((int)h->hs_tmp.size() < (int)h->prop.size()) h->hs_tmp.resize(h->prop.size(), nullptr);
+        if (!h->hs_tmp[n]) if (int rc = dalloc(h, &h->hs_tmp[n], h->n3)) return rc;
+        if (int rc = copy_field(h, h->hs_tmp[n], cur_ptr(h, n))) return rc;
+        h->shift[n] = shift0;
+        if (int rc = copy_field(h, cur_ptr(h, n), h->hs_tmp[n])) return rc;
+    }
+    bool any_flux = false;
     for (int m = 0; m < s.nprop; ++m) {
         const int n = idx[m];
         const mohid_adt_params &q = b.p[n];
         PropArgs &pa = s.p[m];
-        pa.pin = h->prop[h->cur[n]][n];
-        pa.pout = h->prop[h->cur[n] ^ 1][n];
+        pa.pin = cur_ptr(h, n);
+        pa.pout = nxt_ptr(h, n);
         pa.pref = h->has_ref[n] ? h->ref[n] : nullptr;
         pa.theta_difv = (b.optimize && q.ImpExp_DifV > 0.0) ? 1.0 : q.ImpExp_DifV;     // AD:2797 vs AD:2741-2760
         pa.tdec = 1.0 / (1.0 + q.DecayTime / q.DTProp);
@@ -658,15 +683,30 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
         const bool hd = h->d_ncell > 0 && n < (int)h->d_conc.size() && h->d_conc[n];
         pa.dconc = hd ? h->d_conc[n] : nullptr;
         pa.dconcmf = hd ? h->d_concmf[n] : nullptr;
+        any_flux = any_flux || q.CellFluxes;
     }
+    // CellFluxes: the explicit shares are evaluated from the field at time n, which the in-place step overwrites
+    if (any_flux) {
+        if ((int)h->old_copy.size() < (int)h->prop.size()) h->old_copy.resize(h->prop.size(), nullptr);
+        for (int n : idx) {
+            if (!b.p[n].CellFluxes) continue;
+            if (!h->old_copy[n]) if (int rc = dalloc(h, &h->old_copy[n], h->n3)) return rc;
+            if (int rc = copy_field(h, h->old_copy[n], cur_ptr(h, n))) return rc;
+        }
+    }
+    bool stage2 = false;
     if (hdir) {
-        // ---- stage 1: implicit horizontal direction (adt_hsolve_kernel.cuh), then the vertical half ----
+        // ---- stage 1: implicit horizontal direction (adt_hsolve_kernel.cuh) into a scratch copy of the field ----
         HSolveArgs hs{};
-        if ((int)h->wline.size() < (int)h->prop[0].size()) h->wline.resize(h->prop[0].size(), nullptr);
+        if ((int)h->wline.size() < (int)h->prop.size()) h->wline.resize(h->prop.size(), nullptr);
+        if ((int)h->hs_tmp.size() < (int)h->prop.size()) h->hs_tmp.resize(h->prop.size(), nullptr);
         for (int m = 0; m < s.nprop; ++m) {
             const int n = idx[m];
             if (!h->wline[n]) if (int rc = dalloc(h, &h->wline[n], h->n3)) return rc;
+            if (!h->hs_tmp[n]) if (int rc = dalloc(h, &h->hs_tmp[n], h->n3)) return rc;
+            if (int rc = copy_field(h, h->hs_tmp[n], cur_ptr(h, n))) return rc;
             hs.wline[m] = h->wline[n];
+            s.p[m].pout = h->hs_tmp[n];
         }
         const int nc = hdir == 1 ? h->I : h->J;
         const long nunits = (long)s.nprop * ((nc + 30) / 31) * h->K;
@@ -676,9 +716,11 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
         else adt_hsolve_kernel<1><<<(unsigned)blocks, 256, 0, h->stream>>>(s, hs);
         CU(h, cudaGetLastError());
         h->launches++;
-        for (int n : idx) h->cur[n] ^= 1;
-        return launch_step(h, b, idx, timed, 0, true);
+        // ---- stage 2: the vertical half, from the intermediate field into the new position ----
+        for (int m = 0; m < s.nprop; ++m) { s.p[m].pin = h->hs_tmp[idx[m]]; s.p[m].pout = nxt_ptr(h, idx[m]); }
+        stage2 = true;
     }
+    s.stage2 = stage2 ? 1 : 0;
     // ---- kernel variant and launch shape ----
     bool any_disch = false, all_impv = true;
     for (int m = 0; m < s.nprop; ++m) {
@@ -692,25 +734,17 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
     const bool tvd_sb = s.method_h == MOHID_P2_TVD && s.method_v == MOHID_P2_TVD && s.limiter_h == MOHID_SuperBee &&
                         s.limiter_v == MOHID_SuperBee;
     const bool upw = s.method_h == MOHID_UpwindOrder1 && s.method_v == MOHID_UpwindOrder1;
+    const bool lean = h->lean_now && !stage2;
     void (*kern)(const StepArgs) = nullptr;
     void (*lkern)(const LeanArgs) = nullptr;      // lean path: the step kernel takes the packs
     LeanArgs la{};
     int wpb;
     size_t smem;
     // Occupancy is bounded by registers (16K per SM sub-partition): 8 warps allow 255 registers per thread,
-    // 12 warps 168.  The two headline variants fit 168 registers once G of the column solve is parked in the
-    // output array instead of shared memory (W needs K*32 doubles per warp, W+G twice that).
+    // 12 warps 168.  W of the column solve lives in shared memory (K*32 doubles per warp), G is parked in the output
+    // array by the 12-warp forms and kept in shared memory by the generic ones.
     const size_t w_bytes = (size_t)h->K * 32 * sizeof(double);
-    // Ring variant (adt_ring_kernel.cuh): one block per strip, one consumer warp per property, inputs staged through
-    // cp.async / mbarrier rings.  Bit-identical to the plain kernel and measured at the same speed on C3 (40-42 ms
-    // against 37.7 ms), so it stays opt-in (MOHID_ADT_RING=1).
-    constexpr int RING_NCW = 10, RING_MIN_PROPS = 4;
-    const bool ring_ok = full && !any_disch && (tvd_sb || upw) && s.nprop >= RING_MIN_PROPS && s.nprop <= RING_NCW &&
-                         h->ld % 4 == 0 && ring_smem_bytes(s.nprop, h->K) <= (size_t)h->smem_optin &&
-                         getenv("MOHID_ADT_RING") && atoi(getenv("MOHID_ADT_RING")) != 0;
-    long grid_override = 0;
-    if (h->lean_now) {
-        // warps per block / L2 prefetch distance: MOHID_ADT_LEAN_WARPS (12 or 16), MOHID_ADT_LEAN_PFD (0, 2, 3, 4)
+    if (lean) {
         // measured on C3 (profiles/r02_*): 12 warps at 168 registers without spills beat 16 at 128 with; prefetch
         // distance 3: 29.4 ms against 33.8 ms without
         int want = getenv("MOHID_ADT_LEAN_WARPS") ? atoi(getenv("MOHID_ADT_LEAN_WARPS")) : 12;
@@ -724,23 +758,12 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
         wpb = want >= 16 ? 16 : want >= 12 ? 12 : 8;
         smem = wpb * w_bytes;
         la.I = s.I; la.J = s.J; la.K = s.K; la.ld = s.ld; la.sj = s.sj; la.sk = s.sk;
-        la.nprop = s.nprop; la.ntile_i = s.ntile_i; la.j_begin = s.j_begin; la.j_count = s.j_count;
-        la.jc0 = h->pk_jc0; la.ncol = h->pk_ncol; la.nt32 = h->pk_nt32; la.dt = s.dt;
+        la.nprop = s.nprop; la.ntile_i = s.ntile_i;
+        la.ncol = h->pk_ncol; la.nt32 = h->pk_nt32; la.dt = s.dt;
         la.pk = h->pk;
         la.qx = s.qx; la.qy = s.qy; la.qz = s.qz; la.VolumeZ = s.VolumeZ; la.VolumeZOld = s.VolumeZOld;
         la.zero_pivots = s.zero_pivots;
         for (int m = 0; m < s.nprop; ++m) la.p[m] = s.p[m];
-    } else if (ring_ok) {
-        const int npt = atoi(getenv("MOHID_ADT_RING")) >= 2 ? 2 : 1;          // properties per consumer warp
-        if (npt == 2)
-            kern = tvd_sb ? adt_transport_ring_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, RING_NCW / 2, 2>
-                          : adt_transport_ring_kernel<MOHID_UpwindOrder1, MOHID_SuperBee, MOHID_UpwindOrder1, MOHID_SuperBee, RING_NCW / 2, 2>;
-        else
-            kern = tvd_sb ? adt_transport_ring_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, RING_NCW>
-                          : adt_transport_ring_kernel<MOHID_UpwindOrder1, MOHID_SuperBee, MOHID_UpwindOrder1, MOHID_SuperBee, RING_NCW>;
-        wpb = (s.nprop + npt - 1) / npt + 1;
-        smem = ring_smem_bytes(s.nprop, h->K);
-        grid_override = std::min<long>((long)s.ntile_i * h->j_count, (long)h->num_sms);
     } else if (full && !any_disch && s.method_h == MOHID_P2_TVD && s.method_v == MOHID_P2_TVD && !tvd_sb &&
                s.limiter_h == s.limiter_v && 12 * w_bytes <= (size_t)h->smem_optin) {
         // P2_TVD with one of the other limiters (MinMod, VanLeer, Muscl, PDM) in both directions: same 12-warp form
@@ -755,42 +778,8 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
     } else if (full && !any_disch && (tvd_sb || upw) && 12 * w_bytes <= (size_t)h->smem_optin) {
         kern = tvd_sb ? adt_transport_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, false, true, 12, 1, true>
                       : adt_transport_kernel<MOHID_UpwindOrder1, MOHID_SuperBee, MOHID_UpwindOrder1, MOHID_SuperBee, false, true, 12, 1, true>;
-        if (tvd_sb && getenv("MOHID_ADT_PFD")) {          // experiment: selective L2 prefetch in the round-1 kernel
-            const int d = atoi(getenv("MOHID_ADT_PFD"));
-            if (d >= 4) kern = adt_transport_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, false, true, 12, 1, true, false, 4>;
-            else if (d >= 2) kern = adt_transport_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, false, true, 12, 1, true, false, 2>;
-        }
         wpb = 12;
         smem = wpb * w_bytes;
-        if (const char *e = getenv("MOHID_ADT_HSPLIT")) {
-            // opt-in split: the explicit horizontal fluxes in their own kernel (adt_hflux_kernel.cuh), the column part
-            // in the HSPLIT variant of K2 with 12 or 16 warps per block
-            const int vw = atoi(e) == 16 && 16 * w_bytes <= (size_t)h->smem_optin ? 16 : 12;
-            if ((int)h->tih.size() < (int)h->prop[0].size()) h->tih.resize(h->prop[0].size(), nullptr);
-            for (int m = 0; m < s.nprop; ++m) {
-                const int n = idx[m];
-                if (!h->tih[n]) if (int rc = dalloc(h, &h->tih[n], h->n3)) return rc;
-                s.p[m].tih = h->tih[n];
-            }
-            constexpr int TJ = 7;
-            const long hblocks = (long)s.nprop * s.ntile_i * ((h->j_count + TJ - 1) / TJ);
-            if (tvd_sb) adt_hflux_kernel<MOHID_P2_TVD, MOHID_SuperBee, TJ><<<(unsigned)hblocks, (TJ + 1) * 32, 0, h->stream>>>(s);
-            else adt_hflux_kernel<MOHID_UpwindOrder1, MOHID_SuperBee, TJ><<<(unsigned)hblocks, (TJ + 1) * 32, 0, h->stream>>>(s);
-            CU(h, cudaGetLastError());
-            h->launches++;
-            if (vw == 16)
-                kern = tvd_sb ? adt_transport_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, false, true, 16, 1, true, true>
-                              : adt_transport_kernel<MOHID_UpwindOrder1, MOHID_SuperBee, MOHID_UpwindOrder1, MOHID_SuperBee, false, true, 16, 1, true, true>;
-            else
-                kern = tvd_sb ? adt_transport_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, false, true, 12, 1, true, true>
-                              : adt_transport_kernel<MOHID_UpwindOrder1, MOHID_SuperBee, MOHID_UpwindOrder1, MOHID_SuperBee, false, true, 12, 1, true, true>;
-            wpb = vw;
-            smem = wpb * w_bytes;
-        }
-        if (getenv("MOHID_ADT_PF2") && tvd_sb && wpb * (w_bytes + 2 * 16 * 32 * sizeof(double)) <= (size_t)h->smem_optin) {
-            kern = adt_transport_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, false, true, 12, 2, true>;
-            smem = wpb * (w_bytes + 2 * 16 * 32 * sizeof(double));
-        }
     } else {
 #define ADT_PICK(D, F)                                                                                              \
     (tvd_sb ? adt_transport_kernel<MOHID_P2_TVD, MOHID_SuperBee, MOHID_P2_TVD, MOHID_SuperBee, D, F>                \
@@ -805,132 +794,82 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
     }
     if (wpb < 1)
         return fail(h, MOHID_ADT_ERR_UNSUPPORTED, "K = %d layers need more shared memory than one SM has", h->K);
-    const long nunits = (long)s.nprop * s.ntile_i * h->j_count;
-    const long blocks = grid_override ? grid_override : (nunits + wpb - 1) / wpb;
-    if (blocks > 2147483647L) return fail(h, MOHID_ADT_ERR_ARG, "grid too large");
+    if ((long)s.nprop * s.ntile_i * h->C / wpb + 1 > 2147483647L) return fail(h, MOHID_ADT_ERR_ARG, "grid too large");
     if (lkern) CU(h, cudaFuncSetAttribute(lkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (timed) {
-        if (h->ev_used == h->ev.size()) {
-            cudaEvent_t a, c;
-            CU(h, cudaEventCreate(&a));
-            CU(h, cudaEventCreate(&c));
-            h->ev.emplace_back(a, c);
-        }
-        e0 = h->ev[h->ev_used].first; e1 = h->ev[h->ev_used].second;
-        h->ev_used++;
-        CU(h, cudaEventRecord(e0, h->stream));
-    }
-    cudaStream_t lst = h->stream;                        // stream of the range launches below
-    // NullGradient post-pass of the boundary columns jmin..jmax (AD:1874-1882, 1926-1987)
-    auto nullgrad_pass = [&](int jmin, int jmax) -> int {
-        for (int m = 0; m < s.nprop; ++m) {
-            if (b.p[idx[m]].BoundaryCondition != MOHID_BC_NullGradient || h->n_bnd_cols == 0) continue;
-            BndArgs ba{};
-            ba.I = h->I; ba.J = h->J; ba.K = h->K; ba.ld = h->ld; ba.nj = h->nj; ba.ncols = h->n_bnd_cols;
-            ba.sj = s.sj; ba.sk = s.sk; ba.cols = h->bnd_cols; ba.kfloor = h->KFloorZ; ba.CFU = h->raw_i[3]; ba.CFV = h->raw_i[4]; ba.Bnd = h->Bnd;
-            ba.prop = s.p[m].pout; ba.pref = s.p[m].pref; ba.jmin = jmin; ba.jmax = jmax;
-            const long tot = (long)h->n_bnd_cols * h->K;
-            adt_nullgrad_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, lst>>>(ba);
-            CU(h, cudaGetLastError());
-            h->launches++;
-        }
-        return 0;
-    };
-    // Edge-first order for the halo overlap: the first / last `g` owned columns (the ones the neighbours need) are
-    // advanced and post-processed before the interior; eligible when nothing else touches the new field afterwards.
-    const int g = h->overlap_ghost;
-    bool edge_first = g > 0 && h->comm && h->allow_edge_first && !grid_override && !hdir && !stage2 && h->j_count >= 4 * g;
-    for (int m = 0; m < s.nprop && edge_first; ++m) {
-        const int n = idx[m];
-        const int bc = b.p[n].BoundaryCondition;
-        if (b.p[n].CellFluxes || (bc == MOHID_BC_CyclicBoundary && h->has_ref[n]) || bc == MOHID_BC_Orlanski ||
-            (n < (int)h->offsets.size() && h->offsets[n] != 0.) ||
-            (n < (int)h->lim_min_on.size() && (h->lim_min_on[n] || h->lim_max_on[n])))
-            edge_first = false;
-    }
-    auto launch_range = [&](int jb, int jc) -> int {
-        s.j_begin = jb; s.j_count = jc;
-        la.j_begin = jb; la.j_count = jc;
-        const long nu = (long)s.nprop * s.ntile_i * jc;
-        if (lkern) lkern<<<(unsigned)((nu + wpb - 1) / wpb), wpb * 32, smem, lst>>>(la);
-        else kern<<<(unsigned)((nu + wpb - 1) / wpb), wpb * 32, smem, lst>>>(s);
+
+    // ---- the step, chunk by chunk ----
+    const int ja = h->j_begin, jb = h->j_begin + h->j_count - 1;      // columns the step kernel advances
+    CarryArgs ca{};
+    ca.ld = h->ld; ca.nk = h->nk; ca.I = h->I; ca.K = h->K; ca.sj = h->sj; ca.sk = h->sk; ca.ja = ja; ca.jb = jb;
+    ca.Water = h->raw_i[2];
+    for (int m = 0; m < s.nprop; ++m) { ca.src[m] = s.p[m].pin; ca.dst[m] = s.p[m].pout; }
+    const bool packs_per_chunk = lean && h->pk_ncol < h->nj;
+    if (timed) h->ev_steps++;
+    for (const Chunk &c : chunk_order(h, shift0 == h->S)) {
+        ca.j0 = c.a;
+        adt_carry_kernel<<<dim3((unsigned)((h->ld + 127) / 128), (unsigned)(c.b - c.a + 1), (unsigned)s.nprop), 128, 0, h->stream>>>(ca);
         CU(h, cudaGetLastError());
         h->launches++;
-        return 0;
-    };
-    if (edge_first) {
-        // the two edge launches fill less than one wave of SMs: they run on a side stream next to the interior
-        const int jb = h->j_begin, je = h->j_begin + h->j_count - 1;
-        CU(h, cudaEventRecord(h->ev_fork, h->stream));
-        CU(h, cudaStreamWaitEvent(h->s_edge, h->ev_fork, 0));
-        lst = h->s_edge;
-        if (int rc = launch_range(jb, g)) return rc;
-        if (int rc = launch_range(je - g + 1, g)) return rc;
-        if (int rc = nullgrad_pass(jb, jb + g - 1)) return rc;
-        if (int rc = nullgrad_pass(je - g + 1, je)) return rc;
-        CU(h, cudaEventRecord(h->ev_edges, h->s_edge));
-        lst = h->stream;
-        if (int rc = launch_range(jb + g, h->j_count - 2 * g)) return rc;
-        if (int rc = nullgrad_pass(jb + g, je - g)) return rc;
-        CU(h, cudaStreamWaitEvent(h->stream, h->ev_edges, 0));
-        s.j_begin = h->j_begin; s.j_count = h->j_count;
-        h->launches--;                                   // (counted once below, as in the single-launch order)
-    } else {
-        if (lkern) lkern<<<(unsigned)blocks, wpb * 32, smem, h->stream>>>(la);
-        else kern<<<(unsigned)blocks, wpb * 32, smem, h->stream>>>(s);
+        const int ka = std::max(c.a, ja), kb = std::min(c.b, jb);
+        if (ka > kb) continue;
+        if (packs_per_chunk) if (int rc = launch_lean_coef(h, b.p[idx[0]], b.eff[idx[0]], ka, kb - ka + 2)) return rc;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (timed) {
+            if (h->ev_used == h->ev.size()) {
+                cudaEvent_t x, y;
+                CU(h, cudaEventCreate(&x));
+                CU(h, cudaEventCreate(&y));
+                h->ev.emplace_back(x, y);
+            }
+            e0 = h->ev[h->ev_used].first; e1 = h->ev[h->ev_used].second;
+            h->ev_used++;
+            CU(h, cudaEventRecord(e0, h->stream));
+        }
+        const long nu = (long)s.nprop * s.ntile_i * (kb - ka + 1);
+        const unsigned blocks = (unsigned)((nu + wpb - 1) / wpb);
+        if (lkern) {
+            la.j_begin = ka; la.j_count = kb - ka + 1; la.jc0 = h->pk_jc0;
+            lkern<<<blocks, wpb * 32, smem, h->stream>>>(la);
+        } else {
+            s.j_begin = ka; s.j_count = kb - ka + 1;
+            kern<<<blocks, wpb * 32, smem, h->stream>>>(s);
+        }
         CU(h, cudaGetLastError());
+        h->launches++;
+        if (timed) CU(h, cudaEventRecord(e1, h->stream));
     }
-    if (timed) CU(h, cudaEventRecord(e1, h->stream));
-#ifdef ADT_EXPERIMENT
-    if (getenv("MOHID_ADT_DEBUG")) {
-        unsigned long long c[4];
-        cudaStreamSynchronize(h->stream);
-        cudaMemcpy(c, h->d_zero_piv, sizeof(c), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[ring] producer wait-empty cycles/plane %.0f  consumer0 wait-full cycles/level %.0f (planes %llu)\n",
-                (double)c[1] / (double)std::max(1ull, c[3]), (double)c[2] / (double)std::max(1ull, c[3]), c[3]);
-        cudaMemset(h->d_zero_piv + 1, 0, 3 * sizeof(unsigned long long));
-    }
-#endif
-    h->launches++;
+    for (int n : idx) h->shift[n] = h->S - h->shift[n];               // the new field is the current one now
 
-    // post-solve boundary passes (AD:1874-1882)
-    if (!edge_first) if (int rc = nullgrad_pass(0, 2147483647)) return rc;
+    // ---- post-solve boundary passes on the new field (AD:1874-1882) ----
     for (int m = 0; m < s.nprop; ++m) {
         const int n = idx[m];
         const int bc = b.p[n].BoundaryCondition;
-        if (bc == MOHID_BC_Orlanski && h->has_ref[n] && h->n_bnd_cols > 0) {
-            BndArgs ba{};
-            ba.I = h->I; ba.J = h->J; ba.K = h->K; ba.ld = h->ld; ba.nj = h->nj; ba.ncols = h->n_bnd_cols;
-            ba.sj = s.sj; ba.sk = s.sk; ba.cols = h->bnd_cols;
-            const long tot = (long)h->n_bnd_cols * h->K;
-            adt_orlanski_halo_sync_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(ba, s.p[m].pout,
-                                                                                             const_cast<double *>(s.p[m].pin));
-            CU(h, cudaGetLastError());
+        if (!h->has_ref[n] || h->n_bnd_cols == 0) continue;
+        BndArgs ba{};
+        ba.I = h->I; ba.J = h->J; ba.K = h->K; ba.ld = h->ld; ba.nj = h->nj; ba.ncols = h->n_bnd_cols;
+        ba.sj = s.sj; ba.sk = s.sk; ba.cols = h->bnd_cols; ba.kfloor = h->KFloorZ;
+        ba.CFU = h->raw_i[3]; ba.CFV = h->raw_i[4]; ba.Bnd = h->Bnd;
+        ba.prop = cur_ptr(h, n); ba.pref = h->ref[n]; ba.jmin = 0; ba.jmax = 2147483647;
+        const long tot = (long)h->n_bnd_cols * h->K;
+        if (bc == MOHID_BC_NullGradient) {
+            adt_nullgrad_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(ba);
             h->launches++;
+        } else if (bc == MOHID_BC_CyclicBoundary) {
+            adt_cyclic_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(ba, 0);
+            const long t1 = (long)std::max(h->I - 2, 0) * h->K, t2 = (long)std::max(h->J - 2, 0) * h->K;
+            if (t1 > 0) adt_cyclic_kernel<<<(unsigned)((t1 + 255) / 256), 256, 0, h->stream>>>(ba, 1);
+            if (t2 > 0) adt_cyclic_kernel<<<(unsigned)((t2 + 255) / 256), 256, 0, h->stream>>>(ba, 2);
+            h->launches += 3;
         }
-        if ((bc == MOHID_BC_CyclicBoundary && h->has_ref[n]) && h->n_bnd_cols > 0) {
-            BndArgs ba{};
-            ba.I = h->I; ba.J = h->J; ba.K = h->K; ba.ld = h->ld; ba.nj = h->nj; ba.ncols = h->n_bnd_cols;
-            ba.sj = s.sj; ba.sk = s.sk; ba.cols = h->bnd_cols; ba.kfloor = h->KFloorZ; ba.CFU = h->raw_i[3]; ba.CFV = h->raw_i[4]; ba.Bnd = h->Bnd;
-            ba.prop = s.p[m].pout; ba.pref = s.p[m].pref; ba.jmin = 0; ba.jmax = 2147483647;
-            const long tot = (long)h->n_bnd_cols * h->K;
-            {
-                adt_cyclic_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(ba, 0);
-                const long t1 = (long)std::max(h->I - 2, 0) * h->K, t2 = (long)std::max(h->J - 2, 0) * h->K;
-                if (t1 > 0) adt_cyclic_kernel<<<(unsigned)((t1 + 255) / 256), 256, 0, h->stream>>>(ba, 1);
-                if (t2 > 0) adt_cyclic_kernel<<<(unsigned)((t2 + 255) / 256), 256, 0, h->stream>>>(ba, 2);
-                h->launches += 3;
-            }
-            CU(h, cudaGetLastError());
-        }
+        CU(h, cudaGetLastError());
     }
     // cell-face fluxes of the properties that asked for them (AD:1885-1916: after the boundary passes)
     for (int m = 0; m < s.nprop; ++m) {
         const int n = idx[m];
         const mohid_adt_params &q = b.p[n];
         if (!q.CellFluxes) continue;
+        if (int rc = ensure_legacy(h)) return rc;
         for (auto &v : h->flux) if ((int)v.size() <= n) v.resize(n + 1, nullptr);
         for (auto &v : h->flux) {
             if (!v[n]) if (int rc = dalloc(h, &v[n], h->n3)) return rc;
@@ -942,9 +881,9 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
         fa.upwind2_h = q.Upwind2H; fa.upwind2_v = q.Upwind2V; fa.vertical1d = h->opt.Vertical1D; fa.xzflow = h->opt.XZFlow;
         fa.vrelmax = q.VolumeRelMax; fa.w_advv = q.ImpExp_AdvV; fa.theta = q.ImpExp_DifV;
         fa.nfmask = s.nfmask; fa.nfsel = b.eff[n].nfsel;
-        fa.pold = s.p[m].pin; fa.pnew = s.p[m].pout;
-        fa.qx = s.qx; fa.qy = s.qy; fa.qz = s.qz; fa.dtv = s.dtv; fa.dhu = s.dhu; fa.dhv = s.dhv; fa.dvz = s.dvz;
-        fa.rdz = s.rdz; fa.rdx = s.rdx; fa.rdy = s.rdy; fa.DUX = s.DUX; fa.DVY = s.DVY; fa.DWZ = s.DWZ; fa.mask = s.mask;
+        fa.pold = h->old_copy[n]; fa.pnew = cur_ptr(h, n);
+        fa.qx = s.qx; fa.qy = s.qy; fa.qz = s.qz; fa.dtv = h->dtv; fa.dhu = h->dhu; fa.dhv = h->dhv; fa.dvz = h->dvz;
+        fa.rdz = h->rdz; fa.rdx = s.rdx; fa.rdy = s.rdy; fa.DUX = s.DUX; fa.DVY = s.DVY; fa.DWZ = s.DWZ; fa.mask = h->mask;
         fa.ax = h->flux[0][n]; fa.ay = h->flux[1][n]; fa.az = h->flux[2][n];
         fa.dx = h->flux[3][n]; fa.dy = h->flux[4][n]; fa.dz = h->flux[5][n];
         const dim3 grid((unsigned)((h->I + 127) / 128), (unsigned)h->J, (unsigned)h->K);
@@ -952,10 +891,8 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
         CU(h, cudaGetLastError());
         h->launches++;
     }
-    for (int n : idx) h->cur[n] ^= 1;
     if (int rc = launch_premix(h, idx, -1)) return rc;
     if (int rc = launch_limits(h, idx)) return rc;
-    if (h->comm && !edge_first) CU(h, cudaEventRecord(h->ev_edges, h->stream));     // nothing to overlap: halo after the step
     return 0;
 }
 
@@ -968,14 +905,20 @@ int step_once(Handle *h, const Batch &b, int chunk = 0, const ChunkHook &before 
     std::vector<char> done(b.nprop, 0);
     bool geom_done = false;
     if (h->halo_pending) { CU(h, cudaStreamWaitEvent(h->stream, h->ev_halo, 0)); h->halo_pending = false; }
-    {   // edge-first needs the whole batch in one launch group
-        bool one = chunk == 0;
-        for (int n = 1; n < b.nprop && one; ++n) one = b.eff[0].same_dif(b.eff[n]);
-        for (int n = 0; n < b.nprop && one; ++n) one = !(b.p[n].ImpExp_AdvXX == 1.0 || b.p[n].ImpExp_AdvYY == 1.0);
-        h->allow_edge_first = one && !(h->premix_fc || h->premix_sd);
-    }
     h->lean_now = lean_eligible(h, b);
-    if (h->lean_now) if (int rc = ensure_lean(h, h->nj)) return rc;
+    if (h->lean_now) {
+        // the packs of the whole grid when they fit beside everything else (one coefficient pass per step), else of
+        // one column chunk at a time (the pass then runs chunk by chunk, interleaved with the step kernel)
+        int ncol = h->pk_ncol;
+        if (ncol == 0) {
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            const size_t full_b = (size_t)((h->ni + 31) / 32) * 128 * sizeof(Pack4) * h->nj * h->nk;
+            const bool want_full = getenv("MOHID_ADT_PACK_CHUNKED") ? false : (full_b < free_b / 2);
+            ncol = want_full ? h->nj : std::min(h->nj, h->C + 1);
+        }
+        if (int rc = ensure_lean(h, ncol)) return rc;
+    } else if (int rc = ensure_legacy(h)) return rc;
     if (h->premix_sd) {                                   // Me%SmallDepths%ON (WP:12975-12980), consumed by K1
         PremixArgs a{};
         a.I = h->I; a.J = h->J; a.K = h->K; a.ld = h->ld; a.sj = h->sj; a.sk = h->sk;
@@ -995,9 +938,10 @@ int step_once(Handle *h, const Batch &b, int chunk = 0, const ChunkHook &before 
                 done[m] = 1;
             }
         }
-        if (h->lean_now) { if (int rc = launch_lean_coef(h, b.p[n], b.eff[n], 0, h->nj)) return rc; }
-        else if (int rc = launch_coef(h, b.p[n], b.eff[n], !geom_done, true)) return rc;
-        if (!geom_done && h->d_ncell > 0) {               // flag the receiving cells, per-layer flows (AD:4063-4077)
+        if (h->lean_now) {
+            if (h->pk_ncol >= h->nj) if (int rc = launch_lean_coef(h, b.p[n], b.eff[n], 0, h->nj)) return rc;
+        } else if (int rc = launch_coef(h, b.p[n], b.eff[n], !geom_done, true)) return rc;
+        if (!geom_done && h->d_ncell > 0 && !h->lean_now) {   // flag the receiving cells, per-layer flows (AD:4063-4077)
             DischArgs d{};
             d.ncell = h->d_ncell; d.K = h->K; d.ld = h->ld; d.sj = h->sj; d.sk = h->sk;
             d.ci = h->d_ci; d.cj = h->d_cj; d.ck = h->d_ck; d.ckmin = h->d_ckmin; d.ckmax = h->d_ckmax;
@@ -1009,7 +953,9 @@ int step_once(Handle *h, const Batch &b, int chunk = 0, const ChunkHook &before 
             h->launches++;
         }
         geom_done = true;
-        const size_t step = chunk > 0 ? (size_t)chunk : idx.size();
+        // with per-chunk packs every piece would repeat the coefficient pass: the group then goes in one piece
+        const bool one_piece = chunk <= 0 || (h->lean_now && h->pk_ncol < h->nj);
+        const size_t step = one_piece ? idx.size() : (size_t)chunk;
         for (size_t c0 = 0; c0 < idx.size(); c0 += step) {
             const std::vector<int> part(idx.begin() + c0, idx.begin() + std::min(idx.size(), c0 + step));
             if (before) if (int rc = before(part)) return rc;
@@ -1026,6 +972,7 @@ int step_once(Handle *h, const Batch &b, int chunk = 0, const ChunkHook &before 
             if (after) if (int rc = after(part)) return rc;
         }
     }
+    if (h->ev_edges) CU(h, cudaEventRecord(h->ev_edges, h->stream));      // the halo exchange follows the step
     return 0;
 }
 
@@ -1075,10 +1022,13 @@ int mohid_adt_create(int *handle, const mohid_adt_size3d *size, const mohid_adt_
     if (h->ld_h < h->ni) { delete h; return fail(nullptr, MOHID_ADT_ERR_ARG, "ld_i smaller than I+2"); }
     h->ld = ((h->ni + 15) / 16) * 16;                // 128-byte aligned rows on the device
     h->n2 = (long)h->ld * h->nj;
-    h->n3 = h->n2 * h->nk;
-    if (const char *e = getenv("MOHID_ADT_LAYOUT")) h->kmid = atoi(e) != 0;
-    if (h->kmid) { h->sk = h->ld; h->sj = h->ld * h->nk; }          // element (i,j,k) at i + ld*(k + nk*j)
-    else         { h->sj = h->ld; h->sk = h->ld * h->nj; }          // element (i,j,k) at i + ld*(j + nj*k)
+    // chunk width of the in-place step and the shift margin it needs (see Handle)
+    h->C = std::min(h->nj, std::max(32, std::min(256, h->nj / 16)));
+    if (const char *e = getenv("MOHID_ADT_CHUNK_COLS")) h->C = std::max(1, std::min(h->nj, atoi(e)));
+    h->S = h->C + 3;
+    h->njp = h->nj + h->S;
+    h->n3 = (long)h->ld * h->njp * h->nk;
+    h->sj = h->ld; h->sk = h->ld * h->njp;                          // element (i,j,k) at i + ld*(j + njp*k)
     if (h->n3 >= 2147483647L || h->nj > 65535 || h->nk > 65535) {
         delete h;
         return fail(nullptr, MOHID_ADT_ERR_ARG, "one field must hold fewer than 2^31 elements (32-bit cell indices)");
@@ -1097,9 +1047,6 @@ int mohid_adt_create(int *handle, const mohid_adt_size3d *size, const mohid_adt_
     rc |= dalloc(h, &h->KFloorZ, h->n2); rc |= dalloc(h, &h->Bnd, h->n2); rc |= dalloc(h, &h->SmallDepths, h->n2);
     for (auto &p : h->raw_d) rc |= dalloc(h, &p, h->n3);
     for (auto &p : h->raw_i) rc |= dalloc(h, &p, h->n3);
-    rc |= dalloc(h, &h->dtv, h->n3); rc |= dalloc(h, &h->vr, h->n3); rc |= dalloc(h, &h->dhu, h->n3);
-    rc |= dalloc(h, &h->dhv, h->n3); rc |= dalloc(h, &h->dvz, h->n3); rc |= dalloc(h, &h->rdz, h->n3);
-    rc |= dalloc(h, &h->mask, h->n3);
     rc |= dalloc(h, &h->d_zero_piv, 1);
     if (rc) { std::string m = h->err; free_all(h); delete h; return fail(nullptr, MOHID_ADT_ERR_CUDA, "%s", m.c_str()); }
     // padded columns must read as zeros
@@ -1130,7 +1077,6 @@ int mohid_adt_destroy(int *handle) {
     // work queued on the communication / edge / copy streams may still touch the buffers freed below
     if (h->comm) cudaStreamSynchronize(h->comm);
     if (h->s_comm_own) cudaStreamSynchronize(h->s_comm_own);
-    if (h->s_edge) cudaStreamSynchronize(h->s_edge);
     if (h->s_up) cudaStreamSynchronize(h->s_up);
     if (h->s_down) cudaStreamSynchronize(h->s_down);
     cudaStreamSynchronize(h->stream);
@@ -1220,7 +1166,7 @@ int mohid_adt_step_input_device_ptr(const int *handle, const int *which, void **
         *dptr = g[w - 20];
     } else return fail(h, MOHID_ADT_ERR_ARG, "unknown array id %d", w);
     if (ld) *ld = h->ld;
-    if (nj) *nj = h->nj;
+    if (nj) *nj = (w < 17) ? h->njp : h->nj;
     if (nk) *nk = h->nk;
     return 0;
 }
@@ -1307,12 +1253,7 @@ int mohid_adt_unset_discharges(const int *handle) {
 // caller -> device copy of one property (and its reference field) on stream `st`
 static int upload_one(Handle *h, int n, const double *prop, const double *r, cudaStream_t st) {
     if (!prop) return fail(h, MOHID_ADT_ERR_ARG, "prop[%d] is null", n);
-    double *a = h->prop[0][n], *b = h->prop[1][n];
-    if (h->ld != h->ld_h) CU(h, cudaMemsetAsync(a, 0, h->n3 * sizeof(double), st));   // ld padding reads as zero
-    if (int rc = h2d3(h, a, prop, 8, st)) return rc;
-    // both ping-pong buffers start identical: halos, dry columns and closed cells are never rewritten
-    CU(h, cudaMemcpyAsync(b, a, h->n3 * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    h->cur[n] = 0;
+    if (int rc = h2d3(h, cur_ptr(h, n), prop, 8, st)) return rc;
     h->has_ref[n] = r != nullptr;
     if (r) {
         if (!h->ref[n]) {
@@ -1341,11 +1282,11 @@ int mohid_adt_download_props(const int *handle, const int *nprop, double *const 
     Handle *h = get(handle);
     if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
     if (!nprop || !prop) return fail(h, MOHID_ADT_ERR_ARG, "null argument");
-    if (*nprop > (int)h->prop[0].size()) return fail(h, MOHID_ADT_ERR_STATE, "properties were never uploaded");
+    if (*nprop > (int)h->prop.size()) return fail(h, MOHID_ADT_ERR_STATE, "properties were never uploaded");
     CU(h, cudaSetDevice(h->dev));
     if (h->halo_pending) { CU(h, cudaStreamWaitEvent(h->stream, h->ev_halo, 0)); h->halo_pending = false; }
     for (int n = 0; n < *nprop; ++n)
-        if (int rc = d2h3(h, prop[n], h->prop[h->cur[n]][n], 8)) return rc;
+        if (int rc = d2h3(h, prop[n], cur_ptr(h, n), 8)) return rc;
     CU(h, cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -1355,7 +1296,7 @@ int mohid_adt_advect_device(const int *handle, const int *nprop, const mohid_adt
     if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
     if (!nprop || !params) return fail(h, MOHID_ADT_ERR_ARG, "null argument");
     if (!h->have_grid || !h->have_step) return fail(h, MOHID_ADT_ERR_STATE, "set_grid2d / set_step must precede advect");
-    if (*nprop > (int)h->prop[0].size()) return fail(h, MOHID_ADT_ERR_STATE, "properties were never uploaded");
+    if (*nprop > (int)h->prop.size()) return fail(h, MOHID_ADT_ERR_STATE, "properties were never uploaded");
     CU(h, cudaSetDevice(h->dev));
     Batch b;
     if (int rc = validate(h, *nprop, params, b)) return rc;
@@ -1386,7 +1327,7 @@ int mohid_adt_advect_batch(const int *handle, const int *nprop, double *const *p
             if (int rc = upload_one(h, n, prop[n], reference_prop ? reference_prop[n] : nullptr, h->stream)) return rc;
         if (int rc = step_once(h, b)) return rc;
         for (int n = 0; n < *nprop; ++n)
-            if (int rc = d2h3(h, prop[n], h->prop[h->cur[n]][n], 8)) return rc;
+            if (int rc = d2h3(h, prop[n], cur_ptr(h, n), 8)) return rc;
         CU(h, cudaStreamSynchronize(h->stream));
         return 0;
     }
@@ -1424,7 +1365,7 @@ int mohid_adt_advect_batch(const int *handle, const int *nprop, double *const *p
         CU(h, cudaEventRecord(e, h->stream));
         CU(h, cudaStreamWaitEvent(h->s_down, e, 0));
         for (int n : part)
-            if (int rc = d2h3(h, prop[n], h->prop[h->cur[n]][n], 8, h->s_down)) return rc;
+            if (int rc = d2h3(h, prop[n], cur_ptr(h, n), 8, h->s_down)) return rc;
         return 0;
     };
     const int rc = step_once(h, b, chunk, before, after);
@@ -1442,9 +1383,9 @@ int mohid_adt_prop_device_ptr(const int *handle, const int *n, void **dptr, int 
     if (!n || !dptr) return fail(h, MOHID_ADT_ERR_ARG, "null argument");
     CU(h, cudaSetDevice(h->dev));
     if (int rc = ensure_props(h, *n + 1, false)) return rc;
-    *dptr = h->prop[h->cur[*n]][*n];
+    *dptr = cur_ptr(h, *n);
     if (ld) *ld = h->ld;
-    if (nj) *nj = h->nj;
+    if (nj) *nj = h->njp;
     if (nk) *nk = h->nk;
     return 0;
 }
@@ -1454,9 +1395,7 @@ int mohid_adt_sync_prop_buffers(const int *handle, const int *nprop) {
     Handle *h = get(handle);
     if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
     CU(h, cudaSetDevice(h->dev));
-    for (int n = 0; n < *nprop && n < (int)h->prop[0].size(); ++n)
-        CU(h, cudaMemcpyAsync(h->prop[h->cur[n] ^ 1][n], h->prop[h->cur[n]][n], h->n3 * sizeof(double),
-                              cudaMemcpyDeviceToDevice, h->stream));
+    (void)nprop;          // one buffer per property since the in-place step: nothing to synchronise (kept for the ABI)
     return 0;
 }
 
@@ -1478,12 +1417,12 @@ static int pack_common(const int *handle, const int *nprop, const int *j0, const
     Handle *h = get(handle);
     if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
     if (!nprop || !j0 || !width || !buf) return fail(h, MOHID_ADT_ERR_ARG, "null argument");
-    if (*nprop > (int)h->prop[0].size() || *nprop > NPMAX) return fail(h, MOHID_ADT_ERR_STATE, "properties were never uploaded");
+    if (*nprop > (int)h->prop.size() || *nprop > NPMAX) return fail(h, MOHID_ADT_ERR_STATE, "properties were never uploaded");
     if (*j0 < 0 || *width < 1 || *j0 + *width > h->nj) return fail(h, MOHID_ADT_ERR_ARG, "column range out of bounds");
     CU(h, cudaSetDevice(h->dev));
     PackArgs a{};
     a.ld = h->ld; a.nj = h->nj; a.nk = h->nk; a.nprop = *nprop; a.j0 = *j0; a.width = *width; a.sj = h->sj; a.sk = h->sk;
-    for (int n = 0; n < *nprop; ++n) a.prop[n] = h->prop[h->cur[n]][n];
+    for (int n = 0; n < *nprop; ++n) a.prop[n] = cur_ptr(h, n);
     const long tot = (long)a.nk * a.width * a.ld * a.nprop;
     const int blocks = (int)std::min<long>((tot + 255) / 256, (long)h->num_sms * 16);
     cudaStream_t st = h->comm ? h->comm : h->stream;
@@ -1626,15 +1565,15 @@ int mohid_adt_set_overlap(const int *handle, const int *ghost, void *comm_stream
     CU(h, cudaStreamSynchronize(h->stream));
     if (h->comm) CU(h, cudaStreamSynchronize(h->comm));
     h->halo_pending = false;
-    h->overlap_ghost = *ghost;
+    // ghost > 0: pack / unpack run on `comm_stream`, ordered after the step by an event; the next step waits for the
+    // unpack.  (Round 1 also advanced the edge columns first so that the exchange overlapped the interior; the
+    // in-place step walks the columns in one direction, and the exchange was measured at < 3 % of a step.)
     h->comm = (*ghost > 0) ? (cudaStream_t)comm_stream : nullptr;
     if (h->comm && !h->ev_edges) {
         CU(h, cudaEventCreateWithFlags(&h->ev_edges, cudaEventDisableTiming));
         CU(h, cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming));
-        CU(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-        CU(h, cudaStreamCreateWithFlags(&h->s_edge, cudaStreamNonBlocking));
-        CU(h, cudaEventRecord(h->ev_edges, h->stream));
     }
+    if (h->comm) CU(h, cudaEventRecord(h->ev_edges, h->stream));
     return 0;
 }
 
@@ -1691,7 +1630,7 @@ int mohid_adt_exchange_halos(const int *handle, const int *nprop) {
     Handle *h = get(handle);
     if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
     if (!h->nccl) return fail(h, MOHID_ADT_ERR_STATE, "mohid_adt_comm_init must precede exchange_halos");
-    if (!nprop || *nprop < 1 || *nprop > (int)h->prop[0].size() || *nprop > NPMAX)
+    if (!nprop || *nprop < 1 || *nprop > (int)h->prop.size() || *nprop > NPMAX)
         return fail(h, MOHID_ADT_ERR_ARG, "bad property count");
     CU(h, cudaSetDevice(h->dev));
     const int g = h->halo_ghost;
@@ -1717,7 +1656,7 @@ int mohid_adt_exchange_halos(const int *handle, const int *nprop) {
                                    : mohid_adt_pack_columns(handle, nprop, &j0, &g, buf);
         PackArgs a{};
         a.ld = h->ld; a.nj = h->nj; a.nk = h->nk; a.nprop = *nprop; a.j0 = j0; a.width = g; a.sj = h->sj; a.sk = h->sk;
-        for (int m = 0; m < *nprop; ++m) a.prop[m] = h->prop[h->cur[m]][m];
+        for (int m = 0; m < *nprop; ++m) a.prop[m] = cur_ptr(h, m);
         const int blocks = (int)std::min<long>(((long)n + 255) / 256, (long)h->num_sms * 16);
         adt_pack_columns_kernel<<<blocks, 256, 0, cs>>>(a, buf, unpack);
         CU(h, cudaGetLastError());
@@ -1764,7 +1703,6 @@ int mohid_adt_synchronize(const int *handle) {
     CU(h, cudaSetDevice(h->dev));
     if (h->comm) CU(h, cudaStreamSynchronize(h->comm));
     if (h->s_comm_own) CU(h, cudaStreamSynchronize(h->s_comm_own));
-    if (h->s_edge) CU(h, cudaStreamSynchronize(h->s_edge));
     h->halo_pending = false;
     CU(h, cudaStreamSynchronize(h->stream));
     return 0;
@@ -1775,7 +1713,6 @@ int mohid_adt_solve_thomas_z(const int *handle, const double *D, const double *E
     Handle *h = get(handle);
     if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
     if (!D || !E || !F || !TI || !Res) return fail(h, MOHID_ADT_ERR_ARG, "null array");
-    if (h->kmid) return fail(h, MOHID_ADT_ERR_UNSUPPORTED, "not available with MOHID_ADT_LAYOUT=1");
     CU(h, cudaSetDevice(h->dev));
     double *d[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};      // D, E, F, TI, Res, W
     int *wat = nullptr;
@@ -1834,9 +1771,11 @@ int mohid_adt_kernel_time_ms(const int *handle, double *ms, int *launches) {
         CU(h, cudaEventElapsedTime(&t, h->ev[i].first, h->ev[i].second));
         tot += t;
     }
-    if (ms) *ms = h->ev_used ? tot / (double)h->ev_used : 0.;
-    if (launches) *launches = (int)h->ev_used;
+    // the chunk launches of a step add up to one kernel time
+    if (ms) *ms = h->ev_steps ? tot / (double)h->ev_steps : 0.;
+    if (launches) *launches = h->ev_steps;
     h->ev_used = 0;
+    h->ev_steps = 0;
     return 0;
 }
 

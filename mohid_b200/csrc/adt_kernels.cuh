@@ -925,8 +925,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) adt_transport_kernel(const __gr
 //   SmallDepthsMixing_Processes (WP:12939-13012): columns thinner than the limit are mixed from KFloorZ to the surface
 //     (Me%SmallDepths%ON itself is produced by adt_small_depths_kernel before the coefficient pass);
 //   AddOffSet (WP:14724-14746): water points of the property and of its reference field are shifted by OffSet.
-// One thread per (i, j, property), k serial in the reference's summation order; both ping-pong buffers are written so
-// that cells the transport kernel never rewrites stay identical in the two.
+// One thread per (i, j, property), k serial in the reference's summation order.
 // -------------------------------------------------------------------------------------
 struct PremixArgs {
     int I, J, K, ld, sj, sk, nprop;
@@ -934,7 +933,7 @@ struct PremixArgs {
     const double *VolumeZ, *Density, *WaterColumnZ;      // Density / WaterColumnZ: nullptr = step not requested
     double limit;
     int *SmallDepths;                                     // adt_small_depths_kernel only
-    double *pa[NPMAX], *pb[NPMAX], *pref[NPMAX];
+    double *pa[NPMAX], *pref[NPMAX];
     double off[NPMAX];
 };
 
@@ -949,7 +948,7 @@ __global__ void adt_small_depths_kernel(const PremixArgs a) {
 __global__ void __launch_bounds__(128) adt_premix_kernel(const PremixArgs a) {
     const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y, n = blockIdx.z;
     if (i > a.I) return;
-    double *__restrict__ A = a.pa[n], *__restrict__ B = a.pb[n];
+    double *__restrict__ A = a.pa[n];
     const int c = i + a.sj * j, sk = a.sk;
     if (a.Density) {
         int ki = 0;
@@ -965,7 +964,7 @@ __global__ void __launch_bounds__(128) adt_premix_kernel(const PremixArgs a) {
                 Vsum = Vsum + a.VolumeZ[q];
             }
             const double Cnew = Msum / Vsum;
-            for (int k = ki; k <= a.K; ++k) { A[c + sk * k] = Cnew; B[c + sk * k] = Cnew; }
+            for (int k = ki; k <= a.K; ++k) A[c + sk * k] = Cnew;
         }
     }
     if (a.WaterColumnZ && a.Open[c + sk * a.K] == 1 && a.WaterColumnZ[i + a.ld * j] < a.limit) {
@@ -977,7 +976,7 @@ __global__ void __launch_bounds__(128) adt_premix_kernel(const PremixArgs a) {
             VolSum = VolSum + a.VolumeZ[q];
         }
         const double Cnew = MassSum / VolSum;
-        for (int k = kb; k <= a.K; ++k) { A[c + sk * k] = Cnew; B[c + sk * k] = Cnew; }
+        for (int k = kb; k <= a.K; ++k) A[c + sk * k] = Cnew;
     }
     const double off = a.off[n];
     if (off != 0.) {
@@ -985,8 +984,7 @@ __global__ void __launch_bounds__(128) adt_premix_kernel(const PremixArgs a) {
         for (int k = 1; k <= a.K; ++k) {
             const int q = c + sk * k;
             if (a.Water[q] == 1) {
-                const double v = A[q] + off;
-                A[q] = v; B[q] = v;
+                A[q] = A[q] + off;
                 if (R) R[q] = R[q] + off;
             }
         }
@@ -999,13 +997,12 @@ __global__ void __launch_bounds__(128) adt_offset_kernel(const PremixArgs a) {
     if (i > a.I) return;
     const double off = a.off[n];
     if (off == 0.) return;
-    double *__restrict__ A = a.pa[n], *__restrict__ B = a.pb[n], *__restrict__ R = a.pref[n];
+    double *__restrict__ A = a.pa[n], *__restrict__ R = a.pref[n];
     const int c = i + a.sj * j;
     for (int k = 1; k <= a.K; ++k) {
         const int q = c + a.sk * k;
         if (a.Water[q] == 1) {
             A[q] = A[q] + off;
-            B[q] = B[q] + off;
             if (R) R[q] = R[q] + off;
         }
     }
@@ -1017,14 +1014,14 @@ struct LimitArgs {
     int I, J, K, ld, sj, sk, docycle;
     const int *Water, *KFloorZ;
     const double *VolumeZ;
-    double *pa[NPMAX], *pb[NPMAX], *created[NPMAX], *destroyed[NPMAX];
+    double *pa[NPMAX], *created[NPMAX], *destroyed[NPMAX];
     double vmin[NPMAX], vmax[NPMAX];
     int min_on[NPMAX], max_on[NPMAX];
 };
 __global__ void __launch_bounds__(128) adt_limits_kernel(const LimitArgs a) {
     const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y, n = blockIdx.z;
     if (i > a.I || !(a.min_on[n] || a.max_on[n])) return;
-    double *__restrict__ A = a.pa[n], *__restrict__ B = a.pb[n];
+    double *__restrict__ A = a.pa[n];
     const int c = i + a.sj * j;
     int k0 = 1;
     if (a.docycle == 1) {
@@ -1043,7 +1040,7 @@ __global__ void __launch_bounds__(128) adt_limits_kernel(const LimitArgs a) {
             a.destroyed[n][q] = a.destroyed[n][q] + (a.vmax[n] - v) * a.VolumeZ[q];
             v = a.vmax[n];
         }
-        A[q] = v; B[q] = v;
+        A[q] = v;
     }
 }
 
@@ -1068,22 +1065,28 @@ struct BndArgs {
     int jmin, jmax;           // only boundary columns with jmin <= j <= jmax are processed (edge-first launches)
 };
 
-// Orlanski: the exterior cells written into the new buffer are copied to the other one, so that halo cells, which
-// no later step may rewrite, stay identical in the two ping-pong buffers
-__global__ void adt_orlanski_halo_sync_kernel(const BndArgs b, const double *newbuf, double *oldbuf) {
-    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long)b.ncols * b.K) return;
-    const int c = (int)(t / b.K), k = (int)(t % b.K) + 1;
-    const int i = b.cols[2 * c], j = b.cols[2 * c + 1];
-    const bool iedge = (i == 1 || i == b.I);
-    if (!iedge && !(j == 1 || j == b.J)) return;
-    if (iedge && i == b.I && j == 1 && b.I > 1) return;           // the corner whose "exterior" cell is interior
-    const long d = iedge ? 1 : b.sj;
-    const long q = (long)i + (long)b.sj * j + (long)b.sk * k;
-    const long qe = (i == 1 || j == 1) ? q - d : q + d;
-    oldbuf[qe] = newbuf[qe];
+// -------------------------------------------------------------------------------------
+// Carry: the new field of a step lives S columns beside the old one in the same buffer (in-place shift, see
+// adt_api.cu).  Every cell the step kernel does not write -- halo rows, columns and planes, the leading-dimension
+// padding, dry columns, columns outside the active range -- is copied from the old to the new position.  One thread per
+// (i, column, property); launched per column chunk right before the chunk's step kernel.
+// -------------------------------------------------------------------------------------
+struct CarryArgs {
+    int ld, nk, I, K, sj, sk, j0, ja, jb;     // columns j0 .. j0+gridDim.y-1; the step kernel advances columns ja .. jb
+    const int *Water;
+    const double *src[NPMAX];
+    double *dst[NPMAX];
+};
+__global__ void __launch_bounds__(128) adt_carry_kernel(const CarryArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = a.j0 + blockIdx.y, n = blockIdx.z;
+    if (i >= a.ld) return;
+    const double *__restrict__ S = a.src[n];
+    double *__restrict__ D = a.dst[n];
+    const int c = i + a.sj * j;
+    const bool solved = j >= a.ja && j <= a.jb && i >= 1 && i <= a.I && a.Water[c + a.sk * a.K] == 1;   // MF:4086
+    if (solved) { D[c] = S[c]; return; }       // rows 1 .. K+1 are written by the step kernel
+    for (int k = 0; k < a.nk; ++k) D[c + a.sk * k] = S[c + a.sk * k];
 }
-
 
 __global__ void adt_nullgrad_kernel(const BndArgs b) {
     const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;

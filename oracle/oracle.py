@@ -30,7 +30,7 @@ class Params(C.Structure):
                 ("ImpExp_DifV", C.c_double), ("ImpExp_AdvXX", C.c_double), ("ImpExp_AdvYY", C.c_double),
                 ("ImpExp_DifH", C.c_double), ("NullDif", C.c_int), ("BoundaryCondition", C.c_int),
                 ("DecayTime", C.c_double), ("NoAdvFlux", C.c_int), ("NoDifFlux", C.c_int),
-                ("CellFluxes", C.c_int), ("reserved1", C.c_int)]
+                ("CellFluxes", C.c_int), ("Optimize", C.c_int)]
 
 
 class Options(C.Structure):
