@@ -128,6 +128,18 @@ int mohid_adt_set_step(const int *handle,
                        const int *ComputeFacesU3D, const int *ComputeFacesV3D,
                        const int *ComputeFacesW3D, const int *SmallDepths);
 
+/* The same inputs for a window of columns: the arrays hold the columns j0 .. j0+ncols-1 (0-based, 0 = the halo column)
+ * and are shaped (ld_i, ncols, K+2).  A host that produces or reads its fields slab by slab -- an MPI sub-domain
+ * (ModuleHorizontalGrid.F90:1587-1757), a generator that cannot hold a second copy of a 100 GB case -- fills the
+ * device mirrors piecewise; a NULL array is skipped.  After the last window: mohid_adt_mark_step_resident. */
+int mohid_adt_set_step_columns(const int *handle, const int *j0, const int *ncols,
+                               const double *Wflux_X, const double *Wflux_Y, const double *Wflux_Z,
+                               const double *VolumeZOld, const double *VolumeZ,
+                               const double *Visc_H, const double *Diff_V,
+                               const double *DWZ, const double *DZZ, const double *AreaU, const double *AreaV,
+                               const int *OpenPoints3D, const int *LandPoints3D, const int *WaterPoints3D,
+                               const int *ComputeFacesU3D, const int *ComputeFacesV3D, const int *ComputeFacesW3D);
+
 /* The optional NoFluxU / NoFluxV / NoFluxW dummies of AdvectionDiffusion (AD:1146, 1332-1334; int32 3-D):
  * faces whose advective (NoAdvFlux) or diffusive (NoDifFlux) coefficients are zeroed for the properties that
  * set those flags.  All three NULL = not present. */
@@ -148,11 +160,12 @@ int mohid_adt_get_small_depths(const int *handle, int *SmallDepthsOn);
  * reference field and its DischConc are shifted by OffSet[n] before the step and shifted back after it. */
 int mohid_adt_set_offsets(const int *handle, const int *nprop, const double *OffSet);
 
-/* Halo overlap for a column slab: with ghost > 0 and a communication stream, advect_device advances
- * the first / last `ghost` owned columns first, pack_columns / unpack_columns run on the communication stream as
- * soon as those are final (while the interior is still being advanced), and the next step -- or
- * mohid_adt_join_halo / download_props / synchronize -- waits for the exchange.  The caller issues its NCCL
- * send/recv between pack and unpack on the same communication stream.  ghost = 0 switches it off. */
+/* Communication stream of a column slab: with ghost > 0, pack_columns / unpack_columns run on
+ * `comm_stream`, ordered after the step by an event, and the next step -- or mohid_adt_join_halo / download_props /
+ * synchronize -- waits for the unpack.  The caller issues its NCCL send/recv between pack and unpack on the same
+ * stream (mohid_adt_exchange_halos does all of it inside the library).  ghost = 0 switches it off.  Round 1 also
+ * advanced the edge columns first to overlap the exchange with the interior; the in-place step of round 2 walks the
+ * columns in one direction, and the exchange is < 3 % of a step over NVLink. */
 int mohid_adt_set_overlap(const int *handle, const int *ghost, void *comm_stream);
 int mohid_adt_join_halo(const int *handle);
 
@@ -206,8 +219,19 @@ int mohid_adt_download_props(const int *handle, const int *nprop, double *const 
  * set_step inputs; no host<->device traffic.  Includes the per-step coefficient pass. */
 int mohid_adt_advect_device(const int *handle, const int *nprop, const mohid_adt_params *params,
                             const int *nsteps);
-/* Raw device pointer of property n (current buffer) and its leading dimension / plane
- * stride in elements: element (i,j,k) is at ptr[i + ld*(j + nj*k)]. */
+/* The same for a window of columns j0 .. j0+ncols-1 (arrays shaped (ld_i, ncols, K+2)), see set_step_columns. */
+int mohid_adt_upload_props_columns(const int *handle, const int *nprop, const double *const *prop,
+                                   const double *const *reference_prop, const int *j0, const int *ncols);
+int mohid_adt_download_props_columns(const int *handle, const int *nprop, double *const *prop, const int *j0,
+                                     const int *ncols);
+/* mass[n*(J+2) + j] = sum over i, k of PROP_n * VolumeZ on the water points of column j (0-based j, halo columns
+ * included), summed in an order that does not depend on the decomposition: the per-column terms a box-budget or a
+ * conservation check needs (ModuleWaterProperties.F90:14956-15032 sums the same products on the host), and the
+ * witness bench.py prints to show that 1, 2, 4 and 8 GPUs computed the same field.  `mass` is a host array. */
+int mohid_adt_column_mass(const int *handle, const int *nprop, double *mass);
+/* Raw device pointer of property n and its leading dimension / plane stride in elements: element (i,j,k) is at
+ * ptr[i + ld*(j + nj*k)] with nj the ALLOCATED column count returned here (>= J+2: the in-place step keeps a margin of
+ * columns).  The pointer is valid until the next advect call, which moves the field inside its buffer. */
 int mohid_adt_prop_device_ptr(const int *handle, const int *n, void **dptr, int *ld, int *nj, int *nk);
 
 /* Every array pointer accepted above may be a host pointer (the Fortran caller) or, under CUDA
@@ -215,13 +239,13 @@ int mohid_adt_prop_device_ptr(const int *handle, const int *n, void **dptr, int 
  * copies use cudaMemcpyDefault. */
 /* Wait for all work queued on the handle's stream. */
 int mohid_adt_synchronize(const int *handle);
-/* After writing a property in place through mohid_adt_prop_device_ptr: make the twin ping-pong
- * buffer identical (halos, dry columns and closed cells are never rewritten by the kernels). */
+/* No-op since round 2 (one buffer per property); kept so that round-1 hosts still link. */
 int mohid_adt_sync_prop_buffers(const int *handle, const int *nprop);
 /* Device pointer of the ReferenceProp mirror of property n (allocated on first use). */
 int mohid_adt_set_reference_device(const int *handle, const int *n, void **dptr);
 /* Device pointer of a staged input: which = 0..10 the fp64 arrays of set_step in argument order,
- * 11..16 its int32 masks, 17 SmallDepths, 20..25 the set_grid2d arrays. */
+ * 11..16 its int32 masks, 17 SmallDepths, 20..25 the set_grid2d arrays.  nj returns the allocated column count of
+ * the 3-D arrays (see mohid_adt_prop_device_ptr), J+2 for the 2-D ones. */
 int mohid_adt_step_input_device_ptr(const int *handle, const int *which, void **dptr, int *ld, int *nj, int *nk);
 /* Declare the staged inputs valid after filling them through the pointers above. */
 int mohid_adt_mark_step_resident(const int *handle, const int *small_depths_present);

@@ -221,6 +221,40 @@ class TransportStep:
         """Edge-first stepping + pack/unpack on `comm_stream`; ghost = 0 switches it off."""
         self._check(self.lib.mohid_adt_set_overlap(C.byref(self.h), C.byref(C.c_int(ghost)), C.c_void_p(comm_stream)))
 
+    # ---- column windows (slab-wise hosts, generators of cases too large to hold twice) ----
+    def set_step_columns(self, j0: int, arrays: Dict[str, object]):
+        """Columns j0 .. j0+ncols-1 of the per-step inputs; arrays shaped (K+2, ncols, ld); missing names are skipped."""
+        ncols = next(iter(arrays.values())).shape[1]
+        n = (self.K + 2) * ncols * self.ld
+        args = [_ptr(arrays.get(k), "f8", n, k) for k in STEP_F64] + [_ptr(arrays.get(k), "i4", n, k) for k in STEP_I32]
+        self._check(self.lib.mohid_adt_set_step_columns(C.byref(self.h), C.byref(C.c_int(j0)), C.byref(C.c_int(ncols)), *args))
+
+    def mark_step_resident(self, small_depths_present: bool = False):
+        self._check(self.lib.mohid_adt_mark_step_resident(C.byref(self.h), C.byref(C.c_int(int(small_depths_present)))))
+
+    def upload_columns(self, j0: int, props: Sequence, refs: Optional[Sequence] = None):
+        nprop, ncols = len(props), props[0].shape[1]
+        n = (self.K + 2) * ncols * self.ld
+        pp = (C.c_void_p * nprop)(*[_ptr(a, "f8", n, "prop") for a in props])
+        rp = (C.c_void_p * nprop)(*[_ptr(a, "f8", n, "ref") for a in refs]) if refs else None
+        self._check(self.lib.mohid_adt_upload_props_columns(C.byref(self.h), C.byref(C.c_int(nprop)), pp, rp,
+                                                            C.byref(C.c_int(j0)), C.byref(C.c_int(ncols))))
+        self.nprop = max(self.nprop, nprop)
+
+    def download_columns(self, j0: int, props: Sequence):
+        nprop, ncols = len(props), props[0].shape[1]
+        n = (self.K + 2) * ncols * self.ld
+        pp = (C.c_void_p * nprop)(*[_ptr(a, "f8", n, "prop") for a in props])
+        self._check(self.lib.mohid_adt_download_props_columns(C.byref(self.h), C.byref(C.c_int(nprop)), pp,
+                                                              C.byref(C.c_int(j0)), C.byref(C.c_int(ncols))))
+
+    def column_mass(self, nprop: int) -> np.ndarray:
+        """(nprop, J+2) array: sum over i, k of PROP * VolumeZ on the water points of every column, in a summation order
+        that does not depend on the decomposition."""
+        out = np.zeros((nprop, self.J + 2))
+        self._check(self.lib.mohid_adt_column_mass(C.byref(self.h), C.byref(C.c_int(nprop)), out.ctypes.data_as(C.c_void_p)))
+        return out
+
     # ---- NCCL halo exchange inside the library (mohid_adt_comm_*) -------------------
     def comm_unique_id(self) -> bytes:
         """128-byte NCCL id (rank 0 obtains it; the host hands it to the other ranks)."""

@@ -22,6 +22,7 @@
 #include "adt_kernels.cuh"
 #include "adt_hsolve_kernel.cuh"
 #include "adt_lean_kernel.cuh"
+#include "adt_fused_kernel.cuh"
 
 using namespace adt;
 
@@ -99,7 +100,7 @@ struct Handle {
     Pack4 *pk = nullptr;                               // layout: adt_lean_kernel.cuh (LeanCoefArgs)
     int pk_ncol = 0, pk_jc0 = 0, pk_nt32 = 0;
     double *rho2d[4] = {nullptr, nullptr, nullptr, nullptr};
-    bool rho_valid = false, lean_now = false;
+    bool rho_valid = false, lean_now = false, fused_now = false;
     // NCCL halo exchange behind the C-ABI (mohid_adt_comm_init): communicator, neighbour buffers, own comm stream
     ncclComm_t nccl = nullptr;
     int nranks = 1, rank = 0, halo_ghost = 0;
@@ -211,18 +212,20 @@ void *staging(Handle *h, cudaStream_t st, size_t es) {
     }
     return h->stage[w];
 }
-// 3-D arrays: caller (ld_h, nj, nk) <-> device (ld, njp, nk), one 3-D copy; `dev` already points at the logical
-// column 0 of the field.  Short caller rows cross the link contiguously and change pitch on the device.
-int copy3(Handle *h, void *dev, const void *host, size_t es, bool to_dev, cudaStream_t st) {
+// 3-D arrays: caller (ld_h, ncols, nk) <-> device (ld, njp, nk), one 3-D copy; `dev` points at the logical column 0
+// of the field, the caller's array holds the columns j0 .. j0+ncols-1 (the whole field: j0 = 0, ncols = nj).  Short
+// caller rows cross the link contiguously and change pitch on the device.
+int copy3(Handle *h, void *dev, const void *host, size_t es, bool to_dev, cudaStream_t st, int j0 = 0, int ncols = -1) {
     if (!st) st = h->stream;
+    if (ncols < 0) ncols = h->nj;
     const size_t w = es * (size_t)std::min(h->ld, h->ld_h);
     cudaMemcpy3DParms p{};
-    p.extent = make_cudaExtent(w, (size_t)h->nj, (size_t)h->nk);
+    p.extent = make_cudaExtent(w, (size_t)ncols, (size_t)h->nk);
     p.kind = cudaMemcpyDefault;
-    const cudaPitchedPtr D = make_cudaPitchedPtr(dev, es * (size_t)h->ld, es * (size_t)h->ld, (size_t)h->njp);
-    cudaPitchedPtr H = make_cudaPitchedPtr(const_cast<void *>(host), es * (size_t)h->ld_h, es * (size_t)h->ld_h, (size_t)h->nj);
-    void *stg = staging(h, st, es);
-    const size_t nbytes = es * (size_t)h->ld_h * h->nj * h->nk;
+    const cudaPitchedPtr D = make_cudaPitchedPtr((char *)dev + es * (size_t)h->ld * j0, es * (size_t)h->ld, es * (size_t)h->ld, (size_t)h->njp);
+    cudaPitchedPtr H = make_cudaPitchedPtr(const_cast<void *>(host), es * (size_t)h->ld_h, es * (size_t)h->ld_h, (size_t)ncols);
+    void *stg = (ncols == h->nj) ? staging(h, st, es) : nullptr;
+    const size_t nbytes = es * (size_t)h->ld_h * ncols * h->nk;
     if (stg && to_dev) {
         CU(h, cudaMemcpyAsync(stg, host, nbytes, cudaMemcpyDefault, st));
         H.ptr = stg;
@@ -508,7 +511,27 @@ bool lean_eligible(const Handle *h, const Batch &b) {
     return (size_t)h->K * 32 * sizeof(double) * 8 <= (size_t)h->smem_optin;
 }
 
-int ensure_lean(Handle *h, int ncol) {
+// The fused kernel (adt_fused_kernel.cuh) serves the same configurations as the lean pair -- for any number of
+// properties, since nothing is written for later re-use -- as long as W of FUSED_MAXP columns and the ring fit.
+constexpr int FUSED_MAXP = 12;              // property warps per block (+ FR_NCW coefficient warps = 16 warps at 128 registers)
+size_t fused_smem(int K, int nc) { return sizeof(double) * fused_smem_doubles(K, nc); }
+// most property warps one block can take: bounded by the shared memory W of the column solve and the staging need
+int fused_max_props(const Handle *h) {
+    int nc = FUSED_MAXP;
+    if (const char *e = getenv("MOHID_ADT_FUSED_MAXP")) nc = std::max(1, std::min(FUSED_MAXP, atoi(e)));
+    while (nc > 0 && fused_smem(h->K, nc) > (size_t)h->smem_optin) --nc;
+    return nc;
+}
+bool fused_eligible(const Handle *h, const Batch &b) {
+    if (getenv("MOHID_ADT_NOFUSED")) return false;
+    const char *save = getenv("MOHID_ADT_LEAN_ALWAYS");
+    if (!save) setenv("MOHID_ADT_LEAN_ALWAYS", "1", 1);       // same conditions, without the "pays from 3 properties" rule
+    const bool ok = lean_eligible(h, b);
+    if (!save) unsetenv("MOHID_ADT_LEAN_ALWAYS");
+    return ok && fused_max_props(h) >= 1;
+}
+
+int ensure_rho(Handle *h) {
     for (auto &p : h->rho2d) if (!p) { if (int rc = dalloc(h, &p, h->n2)) return rc; h->rho_valid = false; }
     if (!h->rho_valid) {
         adt_grid2d_rho_kernel<<<std::max(1, (int)std::min<long>((h->n2 + 255) / 256, 4096)), 256, 0, h->stream>>>(
@@ -517,6 +540,11 @@ int ensure_lean(Handle *h, int ncol) {
         h->launches++;
         h->rho_valid = true;
     }
+    return 0;
+}
+
+int ensure_lean(Handle *h, int ncol) {
+    if (int rc = ensure_rho(h)) return rc;
     if (h->pk_ncol < ncol) {
         CU(h, cudaStreamSynchronize(h->stream));
         if (h->pk) { cudaFree(h->pk); h->pk = nullptr; }
@@ -527,9 +555,8 @@ int ensure_lean(Handle *h, int ncol) {
     return 0;
 }
 
-// packs of the columns jc0 .. jc0+ncol-1 for the diffusion flags `e`
-int launch_lean_coef(Handle *h, const mohid_adt_params &q, const PropEff &e, int jc0, int ncol) {
-    LeanCoefArgs A{};
+// raw inputs, metrics and Schmidt numbers of the coefficient work (lean pass and fused kernel) for the diffusion flags `e`
+void fill_lean_coef_args(const Handle *h, const mohid_adt_params &q, const PropEff &e, LeanCoefArgs &A) {
     CoefArgs &a = A.c;
     a.ni = h->ni; a.nj = h->nj; a.nk = h->nk; a.ld = h->ld; a.I = h->I; a.J = h->J; a.K = h->K;
     a.sj = h->sj; a.sk = h->sk;
@@ -541,9 +568,15 @@ int launch_lean_coef(Handle *h, const mohid_adt_params &q, const PropEff &e, int
     a.Open = h->raw_i[0]; a.Land = h->raw_i[1]; a.Water = h->raw_i[2]; a.CFU = h->raw_i[3]; a.CFV = h->raw_i[4];
     a.CFW = h->raw_i[5]; a.SmallDepths = h->have_small ? h->SmallDepths : nullptr;
     a.DUX = h->DUX; a.DVY = h->DVY; a.DZX = h->DZX; a.DZY = h->DZY; a.Bnd = h->Bnd;
-    A.pk = h->pk; A.jc0 = jc0; A.ncol = h->pk_ncol; A.nt32 = h->pk_nt32;
     A.tvd = q.AdvMethodH == MOHID_P2_TVD; A.upwind2_h = q.Upwind2H; A.upwind2_v = q.Upwind2V;
     A.rhoUp = h->rho2d[0]; A.rhoUn = h->rho2d[1]; A.rhoVp = h->rho2d[2]; A.rhoVn = h->rho2d[3];
+}
+
+// packs of the columns jc0 .. jc0+ncol-1 for the diffusion flags `e`
+int launch_lean_coef(Handle *h, const mohid_adt_params &q, const PropEff &e, int jc0, int ncol) {
+    LeanCoefArgs A{};
+    fill_lean_coef_args(h, q, e, A);
+    A.pk = h->pk; A.jc0 = jc0; A.ncol = h->pk_ncol; A.nt32 = h->pk_nt32;
     const dim3 grid((unsigned)((h->pk_nt32 * 32 + 127) / 128), (unsigned)h->nk, (unsigned)ncol);
     const int minb = getenv("MOHID_ADT_COEF_MINB") ? atoi(getenv("MOHID_ADT_COEF_MINB")) : 4;
     if (minb >= 8) adt_lean_coef_kernel<8><<<grid, 128, 0, h->stream>>>(A);
@@ -734,10 +767,13 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
     const bool tvd_sb = s.method_h == MOHID_P2_TVD && s.method_v == MOHID_P2_TVD && s.limiter_h == MOHID_SuperBee &&
                         s.limiter_v == MOHID_SuperBee;
     const bool upw = s.method_h == MOHID_UpwindOrder1 && s.method_v == MOHID_UpwindOrder1;
-    const bool lean = h->lean_now && !stage2;
+    const bool fused = h->fused_now && !stage2;
+    const bool lean = (h->lean_now || fused) && !stage2;
     void (*kern)(const StepArgs) = nullptr;
     void (*lkern)(const LeanArgs) = nullptr;      // lean path: the step kernel takes the packs
+    void (*fkern)(const FusedArgs) = nullptr;     // fused path: the step kernel builds the packs itself
     LeanArgs la{};
+    FusedArgs fa{};
     int wpb;
     size_t smem;
     // Occupancy is bounded by registers (16K per SM sub-partition): 8 warps allow 255 registers per thread,
@@ -757,6 +793,37 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
 #undef ADT_LEAN_W
         wpb = want >= 16 ? 16 : want >= 12 ? 12 : 8;
         smem = wpb * w_bytes;
+        if (fused) {
+            lkern = nullptr;
+            fkern = tvd_sb ? adt_transport_fused_kernel<MOHID_P2_TVD, FUSED_MAXP + FR_NCW> : adt_transport_fused_kernel<MOHID_UpwindOrder1, FUSED_MAXP + FR_NCW>;
+            if (s.nprop > fused_max_props(h)) return fail(h, MOHID_ADT_ERR_UNKNOWN, "internal: fused launch with %d properties", s.nprop);
+            wpb = s.nprop + FR_NCW;
+            smem = fused_smem(h->K, s.nprop);
+            fill_lean_coef_args(h, f, b.eff[idx[0]], fa.co);
+            fa.tiles_per_group = getenv("MOHID_ADT_FUSED_TPG") ? std::max(1, atoi(getenv("MOHID_ADT_FUSED_TPG"))) : 4;
+            fa.tiles_per_group = std::min(fa.tiles_per_group, s.ntile_i);
+            fa.ngroups = (s.ntile_i + fa.tiles_per_group - 1) / fa.tiles_per_group;
+            // roles: warp w runs on SM sub-partition w % 4; a coefficient warp issues about half the instructions of a
+            // property warp, so they go, one after the other, to the sub-partition that is loaded most by warp COUNT
+            {
+                const int T = wpb;
+                int load[4] = {0, 0, 0, 0}, cnt[4] = {0, 0, 0, 0};
+                for (int w = 0; w < T; ++w) { cnt[w % 4]++; fa.role[w] = 0; }
+                bool prod[16] = {false};
+                for (int c = 0; c < FR_NCW; ++c) {
+                    int best = -1;
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        if (load[q4] >= cnt[q4]) continue;                      // no warp left on this sub-partition
+                        if (best < 0 || cnt[q4] * 2 - load[q4] > cnt[best] * 2 - load[best]) best = q4;
+                    }
+                    for (int w = T - 1; w >= 0; --w) if (w % 4 == best && !prod[w]) { prod[w] = true; break; }
+                    load[best] += 1;          // 2 per property warp, 1 per coefficient warp: remaining weight = 2 cnt - load
+                }
+                if (getenv("MOHID_ADT_FUSED_PLAINROLES")) { for (int w = 0; w < T; ++w) prod[w] = w >= s.nprop; }
+                int np = 0, nc = 0;
+                for (int w = 0; w < T; ++w) fa.role[w] = prod[w] ? (signed char)(-1 - np++) : (signed char)(nc++);
+            }
+        }
         la.I = s.I; la.J = s.J; la.K = s.K; la.ld = s.ld; la.sj = s.sj; la.sk = s.sk;
         la.nprop = s.nprop; la.ntile_i = s.ntile_i;
         la.ncol = h->pk_ncol; la.nt32 = h->pk_nt32; la.dt = s.dt;
@@ -795,7 +862,8 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
     if (wpb < 1)
         return fail(h, MOHID_ADT_ERR_UNSUPPORTED, "K = %d layers need more shared memory than one SM has", h->K);
     if ((long)s.nprop * s.ntile_i * h->C / wpb + 1 > 2147483647L) return fail(h, MOHID_ADT_ERR_ARG, "grid too large");
-    if (lkern) CU(h, cudaFuncSetAttribute(lkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (fkern) CU(h, cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else if (lkern) CU(h, cudaFuncSetAttribute(lkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     // ---- the step, chunk by chunk ----
@@ -804,7 +872,7 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
     ca.ld = h->ld; ca.nk = h->nk; ca.I = h->I; ca.K = h->K; ca.sj = h->sj; ca.sk = h->sk; ca.ja = ja; ca.jb = jb;
     ca.Water = h->raw_i[2];
     for (int m = 0; m < s.nprop; ++m) { ca.src[m] = s.p[m].pin; ca.dst[m] = s.p[m].pout; }
-    const bool packs_per_chunk = lean && h->pk_ncol < h->nj;
+    const bool packs_per_chunk = lean && !fused && h->pk_ncol < h->nj;
     if (timed) h->ev_steps++;
     for (const Chunk &c : chunk_order(h, shift0 == h->S)) {
         ca.j0 = c.a;
@@ -828,7 +896,11 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
         }
         const long nu = (long)s.nprop * s.ntile_i * (kb - ka + 1);
         const unsigned blocks = (unsigned)((nu + wpb - 1) / wpb);
-        if (lkern) {
+        if (fkern) {
+            la.j_begin = ka; la.j_count = kb - ka + 1;
+            fa.st = la;
+            fkern<<<(unsigned)((long)fa.ngroups * fa.tiles_per_group * la.j_count), wpb * 32, smem, h->stream>>>(fa);
+        } else if (lkern) {
             la.j_begin = ka; la.j_count = kb - ka + 1; la.jc0 = h->pk_jc0;
             lkern<<<blocks, wpb * 32, smem, h->stream>>>(la);
         } else {
@@ -905,8 +977,11 @@ int step_once(Handle *h, const Batch &b, int chunk = 0, const ChunkHook &before 
     std::vector<char> done(b.nprop, 0);
     bool geom_done = false;
     if (h->halo_pending) { CU(h, cudaStreamWaitEvent(h->stream, h->ev_halo, 0)); h->halo_pending = false; }
-    h->lean_now = lean_eligible(h, b);
-    if (h->lean_now) {
+    h->fused_now = fused_eligible(h, b);
+    h->lean_now = !h->fused_now && lean_eligible(h, b);
+    if (h->fused_now) {
+        if (int rc = ensure_rho(h)) return rc;
+    } else if (h->lean_now) {
         // the packs of the whole grid when they fit beside everything else (one coefficient pass per step), else of
         // one column chunk at a time (the pass then runs chunk by chunk, interleaved with the step kernel)
         int ncol = h->pk_ncol;
@@ -938,10 +1013,12 @@ int step_once(Handle *h, const Batch &b, int chunk = 0, const ChunkHook &before 
                 done[m] = 1;
             }
         }
-        if (h->lean_now) {
+        if (h->fused_now) {
+            // no coefficient pass: the fused kernel builds the packs on the fly
+        } else if (h->lean_now) {
             if (h->pk_ncol >= h->nj) if (int rc = launch_lean_coef(h, b.p[n], b.eff[n], 0, h->nj)) return rc;
         } else if (int rc = launch_coef(h, b.p[n], b.eff[n], !geom_done, true)) return rc;
-        if (!geom_done && h->d_ncell > 0 && !h->lean_now) {   // flag the receiving cells, per-layer flows (AD:4063-4077)
+        if (!geom_done && h->d_ncell > 0 && !h->lean_now && !h->fused_now) {   // flag the receiving cells, per-layer flows (AD:4063-4077)
             DischArgs d{};
             d.ncell = h->d_ncell; d.K = h->K; d.ld = h->ld; d.sj = h->sj; d.sk = h->sk;
             d.ci = h->d_ci; d.cj = h->d_cj; d.ck = h->d_ck; d.ckmin = h->d_ckmin; d.ckmax = h->d_ckmax;
@@ -955,7 +1032,13 @@ int step_once(Handle *h, const Batch &b, int chunk = 0, const ChunkHook &before 
         geom_done = true;
         // with per-chunk packs every piece would repeat the coefficient pass: the group then goes in one piece
         const bool one_piece = chunk <= 0 || (h->lean_now && h->pk_ncol < h->nj);
-        const size_t step = one_piece ? idx.size() : (size_t)chunk;
+        size_t step = one_piece ? idx.size() : (size_t)chunk;
+        if (h->fused_now) {                             // at most `maxp` property warps per block, pieces of equal size
+            const size_t maxp = (size_t)fused_max_props(h);
+            const size_t pieces = (idx.size() + maxp - 1) / maxp;
+            const size_t even = (idx.size() + pieces - 1) / pieces;
+            step = one_piece ? even : std::min(step, even);
+        }
         for (size_t c0 = 0; c0 < idx.size(); c0 += step) {
             const std::vector<int> part(idx.begin() + c0, idx.begin() + std::min(idx.size(), c0 + step));
             if (before) if (int rc = before(part)) return rc;
@@ -1150,6 +1233,70 @@ int mohid_adt_set_step(const int *handle, const double *Wflux_X, const double *W
     if (SmallDepths) if (int rc = h2d2(h, h->SmallDepths, SmallDepths, 4)) return rc;
     CU(h, cudaStreamSynchronize(h->stream));     // the host arrays are only borrowed for the call (AD:2229-2349)
     h->have_step = true;
+    return 0;
+}
+
+static int check_cols(Handle *h, const int *j0, const int *ncols) {
+    if (!j0 || !ncols || *j0 < 0 || *ncols < 1 || *j0 + *ncols > h->nj)
+        return fail(h, MOHID_ADT_ERR_ARG, "column window must lie inside 0..J+1");
+    return 0;
+}
+
+int mohid_adt_set_step_columns(const int *handle, const int *j0, const int *ncols, const double *Wflux_X,
+                               const double *Wflux_Y, const double *Wflux_Z, const double *VolumeZOld,
+                               const double *VolumeZ, const double *Visc_H, const double *Diff_V, const double *DWZ,
+                               const double *DZZ, const double *AreaU, const double *AreaV, const int *OpenPoints3D,
+                               const int *LandPoints3D, const int *WaterPoints3D, const int *ComputeFacesU3D,
+                               const int *ComputeFacesV3D, const int *ComputeFacesW3D) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    if (int rc = check_cols(h, j0, ncols)) return rc;
+    CU(h, cudaSetDevice(h->dev));
+    const double *d[11] = {Wflux_X, Wflux_Y, Wflux_Z, VolumeZOld, VolumeZ, Visc_H, Diff_V, DWZ, DZZ, AreaU, AreaV};
+    const int *m[6] = {OpenPoints3D, LandPoints3D, WaterPoints3D, ComputeFacesU3D, ComputeFacesV3D, ComputeFacesW3D};
+    for (int a = 0; a < 11; ++a) if (d[a]) if (int rc = copy3(h, h->raw_d[a], d[a], 8, true, nullptr, *j0, *ncols)) return rc;
+    for (int a = 0; a < 6; ++a) if (m[a]) if (int rc = copy3(h, h->raw_i[a], m[a], 4, true, nullptr, *j0, *ncols)) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int mohid_adt_upload_props_columns(const int *handle, const int *nprop, const double *const *prop,
+                                   const double *const *reference_prop, const int *j0, const int *ncols) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    if (!nprop || !prop) return fail(h, MOHID_ADT_ERR_ARG, "null argument");
+    if (int rc = check_cols(h, j0, ncols)) return rc;
+    CU(h, cudaSetDevice(h->dev));
+    if (int rc = ensure_props(h, *nprop, reference_prop != nullptr)) return rc;
+    for (int n = 0; n < *nprop; ++n) {
+        if (!prop[n]) return fail(h, MOHID_ADT_ERR_ARG, "prop[%d] is null", n);
+        if (int rc = copy3(h, cur_ptr(h, n), prop[n], 8, true, nullptr, *j0, *ncols)) return rc;
+        const double *r = reference_prop ? reference_prop[n] : nullptr;
+        if (r) {
+            if (!h->ref[n]) {
+                if (int rc = dalloc(h, &h->ref[n], h->n3)) return rc;
+                CU(h, cudaMemsetAsync(h->ref[n], 0, h->n3 * sizeof(double), h->stream));
+            }
+            if (int rc = copy3(h, h->ref[n], r, 8, true, nullptr, *j0, *ncols)) return rc;
+            h->has_ref[n] = 1;
+        }
+    }
+    CU(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int mohid_adt_download_props_columns(const int *handle, const int *nprop, double *const *prop, const int *j0,
+                                     const int *ncols) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    if (!nprop || !prop) return fail(h, MOHID_ADT_ERR_ARG, "null argument");
+    if (*nprop > (int)h->prop.size()) return fail(h, MOHID_ADT_ERR_STATE, "properties were never uploaded");
+    if (int rc = check_cols(h, j0, ncols)) return rc;
+    CU(h, cudaSetDevice(h->dev));
+    if (h->halo_pending) { CU(h, cudaStreamWaitEvent(h->stream, h->ev_halo, 0)); h->halo_pending = false; }
+    for (int n = 0; n < *nprop; ++n)
+        if (int rc = copy3(h, cur_ptr(h, n), prop[n], 8, false, nullptr, *j0, *ncols)) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
     return 0;
 }
 
@@ -1743,6 +1890,31 @@ int mohid_adt_solve_thomas_z(const int *handle, const double *D, const double *E
     const cudaError_t e = cudaStreamSynchronize(h->stream);
     cleanup();
     if (rc) return rc;
+    CU(h, e);
+    return 0;
+}
+
+int mohid_adt_column_mass(const int *handle, const int *nprop, double *mass) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    if (!nprop || !mass || *nprop < 1 || *nprop > (int)h->prop.size() || *nprop > NPMAX)
+        return fail(h, MOHID_ADT_ERR_ARG, "bad property count");
+    if (!h->have_step) return fail(h, MOHID_ADT_ERR_STATE, "set_step must precede column_mass");
+    CU(h, cudaSetDevice(h->dev));
+    if (h->halo_pending) { CU(h, cudaStreamWaitEvent(h->stream, h->ev_halo, 0)); h->halo_pending = false; }
+    double *out = nullptr;
+    const size_t cnt = (size_t)*nprop * h->nj;
+    CU(h, cudaMalloc((void **)&out, cnt * sizeof(double)));
+    MassArgs a{};
+    a.I = h->I; a.K = h->K; a.sj = h->sj; a.sk = h->sk; a.nj = h->nj;
+    a.Water = h->raw_i[2]; a.VolumeZ = h->raw_d[4]; a.out = out;
+    for (int n = 0; n < *nprop; ++n) a.prop[n] = cur_ptr(h, n);
+    adt_column_mass_kernel<<<dim3((unsigned)h->nj, (unsigned)*nprop), 256, 0, h->stream>>>(a);
+    h->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(mass, out, cnt * sizeof(double), cudaMemcpyDefault, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(out);
     CU(h, e);
     return 0;
 }

@@ -1274,6 +1274,37 @@ __global__ void __launch_bounds__(128) adt_thomas_z_kernel(int I, int J, int K, 
 }
 
 // -------------------------------------------------------------------------------------
+// Mass of every property in every column j: sum over i and k of P * VolumeZ on water points, in a fixed summation
+// order (thread-serial over its cells, then a shared-memory tree), so the value of a column does not depend on how the
+// domain is split over GPUs.  One block per (j, property).
+// -------------------------------------------------------------------------------------
+struct MassArgs {
+    int I, K, sj, sk, nj;
+    const int *Water;
+    const double *VolumeZ;
+    const double *prop[NPMAX];
+    double *out;               // [nprop][nj]
+};
+__global__ void __launch_bounds__(256) adt_column_mass_kernel(const MassArgs a) {
+    __shared__ double red[256];
+    const int j = blockIdx.x, n = blockIdx.y;
+    const double *__restrict__ P = a.prop[n];
+    double acc = 0.;
+    for (int i = 1 + (int)threadIdx.x; i <= a.I; i += 256)
+        for (int k = 1; k <= a.K; ++k) {
+            const int q = i + a.sj * j + a.sk * k;
+            if (a.Water[q] == 1) acc += P[q] * a.VolumeZ[q];
+        }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) a.out[(size_t)n * a.nj + j] = red[0];
+}
+
+// -------------------------------------------------------------------------------------
 // K4: gather / scatter `width` j-columns of nprop properties to / from a contiguous buffer
 // laid out [n][k][w][i] (i fastest).  Coalesced on both sides.
 // -------------------------------------------------------------------------------------

@@ -301,3 +301,32 @@ def default_params(method_h: int = 4, limiter_h: int = 4, method_v: int = 4, lim
                 ImpExp_AdvV=impexp_advv, ImpExp_DifV=theta_difv, ImpExp_AdvXX=0.0, ImpExp_AdvYY=0.0,
                 ImpExp_DifH=0.0, NullDif=0, BoundaryCondition=bc, DecayTime=decay_time,
                 NoAdvFlux=0, NoDifFlux=0, CellFluxes=0)
+
+
+def case_pieces(I: int, J: int, K: int, nprop: int, *, j_lo: int = 1, j_hi: Optional[int] = None, piece: int = 256,
+                device: str = "cpu", make_refs: bool = False, **kw):
+    """The columns ``j_lo-1 .. j_hi+1`` of a case (work columns ``j_lo..j_hi`` plus one halo column each side, as
+    ``make_case(j_range=(j_lo, j_hi))`` returns them) in pieces of at most ``piece`` columns, so that a case that fills
+    most of a GPU never exists twice.  Yields ``(j0, case)``: ``case`` holds the local columns ``j0 .. j0+ncols-1``
+    (0-based inside the ``j_lo-1 .. j_hi+1`` window) in tensors of shape ``(K+2, ncols, ld)`` / ``(ncols, ld)``; every
+    column is generated with two neighbour columns around it, which makes it identical to the same column of the
+    undivided case.
+    """
+    j_hi = J if j_hi is None else j_hi
+    first, last = j_lo - 1, j_hi + 1                      # global columns wanted (0 and J+1 are the domain halo)
+    g = first
+    while g <= last:
+        e = min(g + piece - 1, last)
+        lo, hi = max(1, g - 2), min(J, e + 2)             # work columns generated (margin 2)
+        c = make_case(I, J, K, nprop, device=device, make_refs=make_refs, j_range=(lo, hi), **kw)
+        a, b = g - (lo - 1), e - (lo - 1)                 # local columns of g .. e inside that piece
+        cut3 = lambda t: t[:, a:b + 1, :].contiguous()
+        cut2 = lambda t: t[a:b + 1, :].contiguous()
+        out = Case(I=I, J=e - g + 1, K=K, ld=c.ld, dt=c.dt, J_global=J, j_offset=g)
+        out.grid2d = {k: cut2(v) for k, v in c.grid2d.items()}
+        out.step = {k: cut3(v) for k, v in c.step.items()}
+        out.props = [cut3(p) for p in c.props]
+        out.refs = [cut3(r) for r in c.refs]
+        del c
+        yield g - first, out
+        g = e + 1
