@@ -33,7 +33,8 @@ WORKLOADS = {
     "c3": (2048, 2048, 40, 10, 4, 4),       # 10 properties, TVD SuperBee  (headline, 1 GPU)
     "c3pdm": (2048, 2048, 40, 10, 4, 5),    # ULTIMATE-QUICKEST style limiter
     "c1": (305, 232, 75, 2, 4, 4),          # Coastal3D-like dimensions
-    "c4": (4096, 4096, 40, 10, 4, 4),       # needs >= 2 GPUs
+    "c4": (4096, 4096, 40, 10, 4, 4),       # the configuration the metric target is quoted on (headline, default)
+    "c5": (8192, 8192, 50, 32, 4, 4),       # 32 WaterQuality properties; 172 GB per GPU at 8 GPUs (the smallest count that fits)
     "small": (256, 256, 20, 4, 4, 4),
     "c3q": (1024, 1024, 40, 10, 4, 4),      # quarter of C3 (size-sensitivity checks)
     "c3s": (512, 512, 40, 10, 4, 4),
@@ -195,7 +196,7 @@ def run_ours(args):
     import torch.distributed as dist
     from mohid_b200 import capi
     from mohid_b200.advection_diffusion import TransportStep
-    from mohid_b200.synthetic import make_case, STEP_ORDER
+    from mohid_b200.synthetic import case_pieces, STEP_ORDER
     from mohid_b200.partition import SlabDecomposition, HaloExchanger
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -212,27 +213,67 @@ def run_ours(args):
     I, J, K, nprop, method, limiter = WORKLOADS[args.workload]
     dec = SlabDecomposition(J, world, ghost=2)
     sl = dec.slab(rank)
-    # every rank generates its slab (+ghost columns) of the same global case
-    case = make_case(I, J, K, nprop=nprop, device=str(dev), make_refs=False, j_range=(sl.j_lo_ext, sl.j_hi_ext))
-    prm = params_for(nprop, method, limiter, case.dt)
-
-    ts = TransportStep(I, case.J, K, device=local)
+    Jl = sl.j_hi_ext - sl.j_lo_ext + 1
+    ts = TransportStep(I, Jl, K, device=local)
     stream = torch.cuda.current_stream()
     ts.set_stream(stream.cuda_stream)
-    ts.set_grid2d(**case.grid2d)
-    ts.set_step(case.step)
-    ts.upload(case.props)
-    halo = HaloExchanger(ts, dec, rank, nprop, dev, overlap=not os.environ.get("MOHID_ADT_NO_OVERLAP")) if world > 1 else None
 
-    # pinned host copies for the end-to-end leg (what a Fortran host would own)
+    # pinned host copies for the end-to-end leg (what a Fortran host would own), when the host has the memory for them
     e2e_steps = max(1, min(args.steps, 3))
+    shape3 = (K + 2, Jl + 2, I + 2)
+    f8, i4 = 8 * shape3[0] * shape3[1] * shape3[2], 4 * shape3[0] * shape3[1] * shape3[2]
+    host_need = (11 + nprop) * f8 + 6 * i4
     host = None
+    e2e_skip = None
     if args.e2e:
-        host = {"step": {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v) for k, v in case.step.items()},
-                "props": [torch.empty(p.shape, dtype=p.dtype, pin_memory=True).copy_(p) for p in case.props]}
-    cells_local = I * sl.n_owned * K
-    del case
+        try:
+            avail = int([l for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0].split()[1]) * 1024
+        except Exception:
+            avail = 0
+        try:                                    # a container may be capped below the machine's memory
+            lim = open("/sys/fs/cgroup/memory.max").read().strip()
+            if lim != "max":
+                avail = min(avail, int(lim) - int(open("/sys/fs/cgroup/memory.current").read()))
+        except Exception:
+            pass
+        if avail // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))) > 1.25 * host_need + (8 << 30):
+            # page-locked with cudaHostRegister: torch's pinned allocator rounds every tensor up to a power of two
+            # (a 5.6 GB field would take 8 GB)
+            def pinned(dtype):
+                t = torch.empty(shape3, dtype=dtype)
+                rc = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), t.numel() * t.element_size(), 0)
+                if int(rc) != 0:
+                    raise RuntimeError(f"cudaHostRegister failed: {rc}")
+                return t
+            host = {"step": {k: pinned(torch.float64 if n < 11 else torch.int32) for n, k in enumerate(STEP_ORDER)},
+                    "props": [pinned(torch.float64) for _ in range(nprop)]}
+        else:
+            e2e_skip = "host memory: %.0f GB needed per rank, %.0f GB available on the box" % (host_need / 1e9, avail / 1e9)
+
+    # every rank generates its slab (+ghost columns) of the same global case, in pieces of 128 columns written straight
+    # into the library's device mirrors (a case that fills most of the GPU never exists twice)
+    g2 = {}
+    dt = None
+    for j0, pc in case_pieces(I, J, K, nprop, j_lo=sl.j_lo_ext, j_hi=sl.j_hi_ext, piece=128, device=str(dev)):
+        dt = pc.dt
+        ts.set_step_columns(j0, pc.step)
+        ts.upload_columns(j0, pc.props)
+        for k, v in pc.grid2d.items():
+            g2.setdefault(k, []).append(v)
+        if host is not None:
+            n = pc.props[0].shape[1]
+            for k, v in pc.step.items():
+                host["step"][k][:, j0:j0 + n, :].copy_(v)
+            for hp, v in zip(host["props"], pc.props):
+                hp[:, j0:j0 + n, :].copy_(v)
+        del pc
+    ts.set_grid2d(**{k: torch.cat(v, 0).contiguous() for k, v in g2.items()})
+    ts.mark_step_resident()
+    del g2
     torch.cuda.empty_cache()
+    prm = params_for(nprop, method, limiter, dt)
+    halo = HaloExchanger(ts, dec, rank, nprop, dev, overlap=not os.environ.get("MOHID_ADT_NO_OVERLAP")) if world > 1 else None
+    cells_local = I * sl.n_owned * K
 
     def one_step():
         ts.advect_device(prm, 1)
@@ -277,6 +318,19 @@ def run_ours(args):
         k2_ms = float(k.item())
     ms_step = ms_total / args.steps
     units_global = I * J * K * nprop
+    # witness of the computed fields: sum over the global columns, in global order, of the per-column masses
+    # (sum_i,k P * VolumeZ on water points; every column value is independent of the decomposition, and so is the order
+    # in which they are added up here) after warm-up + timed steps -- the same number at 1, 2, 4 and 8 GPUs
+    import numpy as np
+    cm = ts.column_mass(nprop)                                      # (nprop, Jl + 2)
+    glob = np.zeros((nprop, J + 2))
+    jb = sl.j_begin
+    glob[:, sl.j_lo:sl.j_hi + 1] = cm[:, jb:jb + sl.n_owned]
+    if world > 1:
+        t = torch.from_numpy(glob).to(dev)
+        dist.all_reduce(t)                                         # every column is owned by one rank: x + 0 is exact
+        glob = t.cpu().numpy()
+    checksum = [float(np.sum(glob[n])) for n in range(nprop)]
     value = units_global / (ms_step * 1e-3) / 1e9
 
     # ---- end-to-end leg: host buffers through the C-ABI, H2D + D2H inside the timed region ----
@@ -332,9 +386,17 @@ def run_ours(args):
                              "traffic": (measured_traffic(args.workload) if world == 1 else None), "peak_source": peak_src,
                              "bytes_per_unit": b_alg(nprop), "kernel_ms": k2_ms, "kernel_launches_timed": k2_n,
                              "step_achieved": step_achieved, "step_frac": step_achieved / peak},
-                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "checksum": {"what": "sum over all columns of sum_i,k P*VolumeZ (water points) per property after %d steps"
+                                     % (max(args.warmup, 3) + args.steps),
+                             "total": float(sum(checksum)), "per_property": checksum}}
+        if e2e is None and e2e_skip:
+            line["e2e_skipped"] = e2e_skip
         print(json.dumps(line))
     ts.close()
+    if host is not None:
+        for t in list(host["step"].values()) + host["props"]:
+            torch.cuda.cudart().cudaHostUnregister(t.data_ptr())
     if world > 1:
         dist.destroy_process_group()
 
@@ -345,7 +407,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-e2e", dest="e2e", action="store_false")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     args = ap.parse_args()

@@ -524,11 +524,9 @@ int fused_max_props(const Handle *h) {
 }
 bool fused_eligible(const Handle *h, const Batch &b) {
     if (getenv("MOHID_ADT_NOFUSED")) return false;
-    const char *save = getenv("MOHID_ADT_LEAN_ALWAYS");
-    if (!save) setenv("MOHID_ADT_LEAN_ALWAYS", "1", 1);       // same conditions, without the "pays from 3 properties" rule
-    const bool ok = lean_eligible(h, b);
-    if (!save) unsetenv("MOHID_ADT_LEAN_ALWAYS");
-    return ok && fused_max_props(h) >= 1;
+    // measured on C2 (1 property): four coefficient warps per property warp cost more than the separate coefficient
+    // pass of the round-1 kernels (0.50 against 0.33 ms per step); from 3 properties on the fused form wins
+    return lean_eligible(h, b) && fused_max_props(h) >= 1;
 }
 
 int ensure_rho(Handle *h) {
@@ -1107,6 +1105,8 @@ int mohid_adt_create(int *handle, const mohid_adt_size3d *size, const mohid_adt_
     h->n2 = (long)h->ld * h->nj;
     // chunk width of the in-place step and the shift margin it needs (see Handle)
     h->C = std::min(h->nj, std::max(32, std::min(256, h->nj / 16)));
+    // small fields: one chunk (the margin then doubles the field, which costs nothing at this size, and a step is one launch)
+    if ((size_t)h->ld * h->nj * h->nk * sizeof(double) <= ((size_t)256 << 20)) h->C = h->nj;
     if (const char *e = getenv("MOHID_ADT_CHUNK_COLS")) h->C = std::max(1, std::min(h->nj, atoi(e)));
     h->S = h->C + 3;
     h->njp = h->nj + h->S;
@@ -1515,6 +1515,8 @@ int mohid_adt_advect_batch(const int *handle, const int *nprop, double *const *p
             if (int rc = d2h3(h, prop[n], cur_ptr(h, n), 8, h->s_down)) return rc;
         return 0;
     };
+    // which properties come with a reference field decides the kernel variant: known before the first upload
+    for (int n = 0; n < *nprop; ++n) h->has_ref[n] = reference_prop && reference_prop[n];
     const int rc = step_once(h, b, chunk, before, after);
     // the caller's arrays are only borrowed for the call: drain all three streams, also when a launch failed midway
     const cudaError_t e1 = cudaStreamSynchronize(h->s_up), e2 = cudaStreamSynchronize(h->s_down),

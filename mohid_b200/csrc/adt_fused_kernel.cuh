@@ -15,7 +15,7 @@
 //  array is ever written to HBM, the step reads the 112 B per cell of raw inputs once (plus neighbour-column re-reads
 //  that hit L2) and 16 B per cell and property.  Same expressions, in the same order, as adt_lean_coef_kernel and
 //  adt_transport_lean_kernel: results equal that path to the last bit wherever the compiler contracts the same way
-//  (tools/lean_check.py reports the difference), and the oracle within the tolerances of tests/test_gpu_parity.py.
+//  (tools/fused_check.py reports the difference), and the CPU restatement within the tolerances of tests/test_gpu_parity.py.
 //
 //  Global loads: every per-level load of every warp is a cp.async (LDGSTS) into a private staging area, FR_NS - 1
 //  levels ahead, awaited with cp.async.wait_group and read back with LDS.  Measured reason (tools/sassctl.py on the
