@@ -207,6 +207,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL announces its version on stdout when a communicator is created outside torch (mohid_adt_comm_init):
+        # keep stdout for the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     capi.load(build_if_missing=True)
 

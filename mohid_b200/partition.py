@@ -91,6 +91,24 @@ def _p2p_exchange(dist, send_left, recv_left, send_right, recv_right, rank: int,
             req.wait()
 
 
+class _stdout_to_stderr:
+    """NCCL prints its version banner on stdout when a communicator is created outside torch; a launcher that parses
+    stdout (bench.py prints one JSON line) should not see it."""
+
+    def __enter__(self):
+        import os
+        import sys
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        import os
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 class HaloExchanger:
     """Device-resident halo exchange of all properties of a :class:`TransportStep`.
 
@@ -112,9 +130,12 @@ class HaloExchanger:
         on_gpu = dist.get_backend() == "nccl"
         idt = torch.zeros(128, dtype=torch.uint8, device=device if on_gpu else "cpu")
         if rank == 0:
-            idt.copy_(torch.frombuffer(bytearray(ts.comm_unique_id()), dtype=torch.uint8))
+            with _stdout_to_stderr():
+                uid = ts.comm_unique_id()
+            idt.copy_(torch.frombuffer(bytearray(uid), dtype=torch.uint8))
         dist.broadcast(idt, 0)
-        ts.comm_init(dec.world, rank, bytes(idt.cpu().numpy().tobytes()), dec.ghost, overlap)
+        with _stdout_to_stderr():
+            ts.comm_init(dec.world, rank, bytes(idt.cpu().numpy().tobytes()), dec.ghost, overlap)
 
     def exchange(self):
         self.ts.exchange_halos(self.nprop)
