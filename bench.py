@@ -49,10 +49,11 @@ def b_alg(nprop: int) -> float:
 
 
 def measured_traffic(workload: str):
-    """DRAM bytes per K2 launch from the committed ncu capture of this workload (profiles/), or None."""
+    """DRAM bytes (read + write) of the transport kernel over one step, from the committed ncu capture of this workload
+    (profiles/r02_traffic.json: bytes per launch x launches per step), or None."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            return float(json.load(f)[workload]["dram_bytes_per_launch"])
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            return float(json.load(f)[workload]["dram_bytes_per_step"])
     except Exception:
         return None
 
@@ -131,10 +132,10 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def params_for(nprop, method, limiter, dt):
+def params_for(nprop, method, limiter, dt, bc=0):
     from mohid_b200.synthetic import default_params
     mv = method if method not in (2, 3) else 1          # implicit vertical forbids QUICK/QUICKEST (AD:1234)
-    return [default_params(method, limiter, mv, limiter, dt=dt) for _ in range(nprop)]
+    return [default_params(method, limiter, mv, limiter, dt=dt, bc=bc) for _ in range(nprop)]
 
 
 # -----------------------------------------------------------------------------------------
@@ -228,7 +229,7 @@ def run_ours(args):
     host_need = (11 + nprop) * f8 + 6 * i4
     host = None
     e2e_skip = None
-    if args.e2e:
+    if args.e2e and args.bc == 0:
         try:
             avail = int([l for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0].split()[1]) * 1024
         except Exception:
@@ -257,10 +258,11 @@ def run_ours(args):
     # into the library's device mirrors (a case that fills most of the GPU never exists twice)
     g2 = {}
     dt = None
-    for j0, pc in case_pieces(I, J, K, nprop, j_lo=sl.j_lo_ext, j_hi=sl.j_hi_ext, piece=128, device=str(dev)):
+    for j0, pc in case_pieces(I, J, K, nprop, j_lo=sl.j_lo_ext, j_hi=sl.j_hi_ext, piece=128, device=str(dev),
+                              make_refs=args.bc != 0):
         dt = pc.dt
         ts.set_step_columns(j0, pc.step)
-        ts.upload_columns(j0, pc.props)
+        ts.upload_columns(j0, pc.props, pc.refs if args.bc else None)
         for k, v in pc.grid2d.items():
             g2.setdefault(k, []).append(v)
         if host is not None:
@@ -274,7 +276,8 @@ def run_ours(args):
     ts.mark_step_resident()
     del g2
     torch.cuda.empty_cache()
-    prm = params_for(nprop, method, limiter, dt)
+    prm = params_for(nprop, method, limiter, dt, args.bc)
+    fused = nprop >= 3 and method in (1, 4) and not os.environ.get("MOHID_ADT_NOFUSED")      # lean_eligible() of adt_api.cu
     halo = HaloExchanger(ts, dec, rank, nprop, dev, overlap=not os.environ.get("MOHID_ADT_NO_OVERLAP")) if world > 1 else None
     cells_local = I * sl.n_owned * K
 
@@ -383,8 +386,12 @@ def run_ours(args):
                            "adv_method_h_v": method, "tvd_limiter": limiter, "vertical": "implicit",
                            "partition": f"{world} j-slab(s), ghost 2, NCCL halo" if world > 1 else "single GPU",
                            "l2": "inputs >> L2 (each field %.2f GB)" % (8.0 * (I + 2) * (J + 2) * (K + 2) / 1e9),
-                           "step_includes": "K1 coefficient pass + K2 fused kernel + boundary passes"},
-                "roofline": {"bound": "hbm", "kernel": "adt_transport_kernel", "achieved": achieved, "peak": peak,
+                           "boundary_condition": args.bc,
+                           "step_includes": ("fused transport kernel (per-step coefficients, faces, column solve) + carry copies"
+                                             if fused else "coefficient pass + transport kernel + carry copies") +
+                                            (" + open-boundary passes" if args.bc else " (no open-boundary condition)")},
+                "roofline": {"bound": "hbm", "kernel": "adt_transport_fused_kernel" if fused else "adt_transport_kernel",
+                             "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak,
                              "traffic": (measured_traffic(args.workload) if world == 1 else None), "peak_source": peak_src,
                              "bytes_per_unit": b_alg(nprop), "kernel_ms": k2_ms, "kernel_launches_timed": k2_n,
@@ -411,6 +418,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--bc", type=int, default=0, help="BoundaryCondition of every property (0 = none, 4 = NullGradient, ...); "
+                    "a reference field per property is then resident too")
     ap.add_argument("--no-e2e", dest="e2e", action="store_false")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     args = ap.parse_args()

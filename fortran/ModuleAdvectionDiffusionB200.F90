@@ -26,6 +26,19 @@ module ModuleAdvectionDiffusionB200
 
     public :: T_AdtParams, T_AdtOptions, T_AdtSize3D
     public :: B200_Start, B200_Kill, B200_SetGrid2D, B200_SetStep, B200_SetNoFlux, B200_AdvectBatch, B200_LastError
+    public :: B200_SetDischarges, B200_UnSetDischarges, B200_GetAdvFlux, B200_GetDifFlux
+    public :: B200_UploadProps, B200_AdvectDevice, B200_DownloadProps
+    public :: B200_CommInit, B200_ExchangeHalos, B200_CommKill
+    ! every entry point of include/mohid_adt.h is bound below (tests/test_fortran_shim.py checks the interface block
+    ! against the header: symbol, argument count, by-value / by-reference, base type); the B200_* wrappers cover what
+    ! ModuleAdvectionDiffusion and ModuleWaterProperties call, the rest is reached through the interfaces directly
+    public :: mohid_adt_set_step_columns, mohid_adt_set_premix, mohid_adt_get_small_depths, mohid_adt_set_offsets
+    public :: mohid_adt_set_limits, mohid_adt_get_limit_mass, mohid_adt_set_overlap, mohid_adt_join_halo
+    public :: mohid_adt_upload_props_columns, mohid_adt_download_props_columns, mohid_adt_column_mass
+    public :: mohid_adt_prop_device_ptr, mohid_adt_synchronize, mohid_adt_sync_prop_buffers, mohid_adt_set_reference_device
+    public :: mohid_adt_step_input_device_ptr, mohid_adt_mark_step_resident, mohid_adt_set_active_columns
+    public :: mohid_adt_pack_columns, mohid_adt_unpack_columns, mohid_adt_set_stream, mohid_adt_solve_thomas_z
+    public :: mohid_adt_get_counters, mohid_adt_kernel_time_ms, mohid_adt_version
 
     ! mohid_adt_size3d == T_Size3D (ModuleGlobalData.F90:2041-2052)
     type, bind(c) :: T_AdtSize3D
@@ -68,13 +81,12 @@ module ModuleAdvectionDiffusionB200
         integer(c_int) function mohid_adt_set_step(handle, Wflux_X, Wflux_Y, Wflux_Z, VolumeZOld, VolumeZ,      &
                 Visc_H, Diff_V, DWZ, DZZ, AreaU, AreaV, OpenPoints3D, LandPoints3D, WaterPoints3D,               &
                 ComputeFacesU3D, ComputeFacesV3D, ComputeFacesW3D, SmallDepths) bind(c, name="mohid_adt_set_step")
-            import :: c_int, c_double, c_ptr
-            integer(c_int)               :: handle
-            real(c_double), dimension(*) :: Wflux_X, Wflux_Y, Wflux_Z, VolumeZOld, VolumeZ, Visc_H, Diff_V
-            real(c_double), dimension(*) :: DWZ, DZZ, AreaU, AreaV
-            integer(c_int), dimension(*) :: OpenPoints3D, LandPoints3D, WaterPoints3D
-            integer(c_int), dimension(*) :: ComputeFacesU3D, ComputeFacesV3D, ComputeFacesW3D
-            type(c_ptr), value           :: SmallDepths          ! c_null_ptr when not present (AD:1297-1302)
+            import :: c_int, c_ptr
+            integer(c_int)     :: handle
+            ! c_loc(array(0,0,0)); after the first complete call c_null_ptr = unchanged since the last step
+            type(c_ptr), value :: Wflux_X, Wflux_Y, Wflux_Z, VolumeZOld, VolumeZ, Visc_H, Diff_V, DWZ, DZZ, AreaU, AreaV
+            type(c_ptr), value :: OpenPoints3D, LandPoints3D, WaterPoints3D, ComputeFacesU3D, ComputeFacesV3D, ComputeFacesW3D
+            type(c_ptr), value :: SmallDepths                    ! c_null_ptr when not present (AD:1297-1302)
         end function
         integer(c_int) function mohid_adt_set_noflux(handle, NoFluxU, NoFluxV, NoFluxW) bind(c, name="mohid_adt_set_noflux")
             import :: c_int, c_ptr
@@ -118,6 +130,179 @@ module ModuleAdvectionDiffusionB200
             import :: c_int, c_char
             integer(c_int)                       :: handle, buflen
             character(kind=c_char), dimension(*) :: buf
+        end function
+        integer(c_int) function mohid_adt_set_step_columns(handle, j0, ncols, Wflux_X, Wflux_Y, Wflux_Z, VolumeZOld,   &
+                VolumeZ, Visc_H, Diff_V, DWZ, DZZ, AreaU, AreaV, OpenPoints3D, LandPoints3D, WaterPoints3D,             &
+                ComputeFacesU3D, ComputeFacesV3D, ComputeFacesW3D) bind(c, name="mohid_adt_set_step_columns")
+            import :: c_int, c_ptr
+            integer(c_int)     :: handle, j0, ncols
+            ! windows of the arrays, (ld_i, ncols, K+2) each; c_null_ptr = skipped
+            type(c_ptr), value :: Wflux_X, Wflux_Y, Wflux_Z, VolumeZOld, VolumeZ, Visc_H, Diff_V, DWZ, DZZ, AreaU, AreaV
+            type(c_ptr), value :: OpenPoints3D, LandPoints3D, WaterPoints3D, ComputeFacesU3D, ComputeFacesV3D, ComputeFacesW3D
+        end function
+        integer(c_int) function mohid_adt_get_small_depths(handle, SmallDepthsOn) bind(c, name="mohid_adt_get_small_depths")
+            import :: c_int
+            integer(c_int)               :: handle
+            integer(c_int), dimension(*) :: SmallDepthsOn
+        end function
+        integer(c_int) function mohid_adt_set_overlap(handle, ghost, comm_stream) bind(c, name="mohid_adt_set_overlap")
+            import :: c_int, c_ptr
+            integer(c_int)     :: handle, ghost
+            type(c_ptr), value :: comm_stream                       ! cudaStream_t
+        end function
+        integer(c_int) function mohid_adt_join_halo(handle) bind(c, name="mohid_adt_join_halo")
+            import :: c_int
+            integer(c_int) :: handle
+        end function
+        ! SetDischarges (AD:978-1034): same argument names; DischConcMF may be c_null_ptr
+        integer(c_int) function mohid_adt_set_discharges(handle, prop_index, DischNumber, n_cells, DischFlow, DischConc,  &
+                DischI, DischJ, DischK, DischKmin, DischKmax, DischVert, IgnoreDisch, DischnCells, ByPass, DischConcMF)  &
+                bind(c, name="mohid_adt_set_discharges")
+            import :: c_int, c_double, c_ptr
+            integer(c_int)               :: handle, prop_index, DischNumber, n_cells
+            real(c_double), dimension(*) :: DischFlow, DischConc
+            integer(c_int), dimension(*) :: DischI, DischJ, DischK, DischKmin, DischKmax, DischVert
+            integer(c_int), dimension(*) :: IgnoreDisch, DischnCells, ByPass          ! logicals as 0/1
+            type(c_ptr), value           :: DischConcMF
+        end function
+        integer(c_int) function mohid_adt_unset_discharges(handle) bind(c, name="mohid_adt_unset_discharges")
+            import :: c_int
+            integer(c_int) :: handle
+        end function
+        ! GetAdvFlux / GetDifFlux (AD:697-851) of a property advanced with CellFluxes = 1
+        integer(c_int) function mohid_adt_get_cell_fluxes(handle, prop_index, AdvFluxX, AdvFluxY, AdvFluxZ, DifFluxX,    &
+                DifFluxY, DifFluxZ) bind(c, name="mohid_adt_get_cell_fluxes")
+            import :: c_int, c_double
+            integer(c_int)               :: handle, prop_index
+            real(c_double), dimension(*) :: AdvFluxX, AdvFluxY, AdvFluxZ, DifFluxX, DifFluxY, DifFluxZ
+        end function
+        ! device-resident properties: upload once, advance nsteps without host traffic, download when needed
+        integer(c_int) function mohid_adt_upload_props(handle, nprop, prop, reference_prop) bind(c, name="mohid_adt_upload_props")
+            import :: c_int, c_ptr
+            integer(c_int)            :: handle, nprop
+            type(c_ptr), dimension(*) :: prop
+            type(c_ptr), value        :: reference_prop          ! c_loc of an array of c_ptr, or c_null_ptr
+        end function
+        integer(c_int) function mohid_adt_download_props(handle, nprop, prop) bind(c, name="mohid_adt_download_props")
+            import :: c_int, c_ptr
+            integer(c_int)            :: handle, nprop
+            type(c_ptr), dimension(*) :: prop
+        end function
+        integer(c_int) function mohid_adt_advect_device(handle, nprop, params, nsteps) bind(c, name="mohid_adt_advect_device")
+            import :: c_int, T_AdtParams
+            integer(c_int)                  :: handle, nprop, nsteps
+            type(T_AdtParams), dimension(*) :: params
+        end function
+        integer(c_int) function mohid_adt_upload_props_columns(handle, nprop, prop, reference_prop, j0, ncols) &
+                bind(c, name="mohid_adt_upload_props_columns")
+            import :: c_int, c_ptr
+            integer(c_int)            :: handle, nprop, j0, ncols
+            type(c_ptr), dimension(*) :: prop
+            type(c_ptr), value        :: reference_prop
+        end function
+        integer(c_int) function mohid_adt_download_props_columns(handle, nprop, prop, j0, ncols) &
+                bind(c, name="mohid_adt_download_props_columns")
+            import :: c_int, c_ptr
+            integer(c_int)            :: handle, nprop, j0, ncols
+            type(c_ptr), dimension(*) :: prop
+        end function
+        integer(c_int) function mohid_adt_column_mass(handle, nprop, mass) bind(c, name="mohid_adt_column_mass")
+            import :: c_int, c_double
+            integer(c_int)               :: handle, nprop
+            real(c_double), dimension(*) :: mass                    ! (0:J+1, nprop)
+        end function
+        integer(c_int) function mohid_adt_prop_device_ptr(handle, n, dptr, ld, nj, nk) bind(c, name="mohid_adt_prop_device_ptr")
+            import :: c_int, c_ptr
+            integer(c_int) :: handle, n, ld, nj, nk
+            type(c_ptr)    :: dptr                                  ! out: device address
+        end function
+        integer(c_int) function mohid_adt_synchronize(handle) bind(c, name="mohid_adt_synchronize")
+            import :: c_int
+            integer(c_int) :: handle
+        end function
+        integer(c_int) function mohid_adt_sync_prop_buffers(handle, nprop) bind(c, name="mohid_adt_sync_prop_buffers")
+            import :: c_int
+            integer(c_int) :: handle, nprop
+        end function
+        integer(c_int) function mohid_adt_set_reference_device(handle, n, dptr) bind(c, name="mohid_adt_set_reference_device")
+            import :: c_int, c_ptr
+            integer(c_int) :: handle, n
+            type(c_ptr)    :: dptr
+        end function
+        integer(c_int) function mohid_adt_step_input_device_ptr(handle, which, dptr, ld, nj, nk) &
+                bind(c, name="mohid_adt_step_input_device_ptr")
+            import :: c_int, c_ptr
+            integer(c_int) :: handle, which, ld, nj, nk
+            type(c_ptr)    :: dptr
+        end function
+        integer(c_int) function mohid_adt_mark_step_resident(handle, small_depths_present) &
+                bind(c, name="mohid_adt_mark_step_resident")
+            import :: c_int
+            integer(c_int) :: handle, small_depths_present
+        end function
+        ! one MPI sub-domain = one column slab: the owned columns, the halo staging and the NCCL exchange that
+        ! replaces ReceiveSendProperitiesMPI (ModuleHorizontalGrid.F90:8479-8658)
+        integer(c_int) function mohid_adt_set_active_columns(handle, j_begin, j_count) bind(c, name="mohid_adt_set_active_columns")
+            import :: c_int
+            integer(c_int) :: handle, j_begin, j_count
+        end function
+        integer(c_int) function mohid_adt_pack_columns(handle, nprop, j0, width, device_buffer) bind(c, name="mohid_adt_pack_columns")
+            import :: c_int, c_ptr
+            integer(c_int)     :: handle, nprop, j0, width
+            type(c_ptr), value :: device_buffer
+        end function
+        integer(c_int) function mohid_adt_unpack_columns(handle, nprop, j0, width, device_buffer) &
+                bind(c, name="mohid_adt_unpack_columns")
+            import :: c_int, c_ptr
+            integer(c_int)     :: handle, nprop, j0, width
+            type(c_ptr), value :: device_buffer
+        end function
+        integer(c_int) function mohid_adt_set_stream(handle, cuda_stream) bind(c, name="mohid_adt_set_stream")
+            import :: c_int, c_ptr
+            integer(c_int)     :: handle
+            type(c_ptr), value :: cuda_stream
+        end function
+        integer(c_int) function mohid_adt_comm_get_unique_id(unique_id, nbytes) bind(c, name="mohid_adt_comm_get_unique_id")
+            import :: c_int, c_char
+            character(kind=c_char), dimension(*) :: unique_id       ! 128 bytes: rank 0 obtains it, MPI_Bcast hands it on
+            integer(c_int)                       :: nbytes
+        end function
+        integer(c_int) function mohid_adt_comm_init(handle, nranks, rank, unique_id, ghost, overlap) &
+                bind(c, name="mohid_adt_comm_init")
+            import :: c_int, c_char
+            integer(c_int)                       :: handle, nranks, rank, ghost, overlap
+            character(kind=c_char), dimension(*) :: unique_id
+        end function
+        integer(c_int) function mohid_adt_exchange_halos(handle, nprop) bind(c, name="mohid_adt_exchange_halos")
+            import :: c_int
+            integer(c_int) :: handle, nprop
+        end function
+        integer(c_int) function mohid_adt_comm_destroy(handle) bind(c, name="mohid_adt_comm_destroy")
+            import :: c_int
+            integer(c_int) :: handle
+        end function
+        ! THOMASZ_NewType2 on caller-supplied coefficient fields (ModuleCuda.F90:103-111 SolveThomas_C analogue)
+        integer(c_int) function mohid_adt_solve_thomas_z(handle, D, E, F, TI, WaterPoints3D, Res) &
+                bind(c, name="mohid_adt_solve_thomas_z")
+            import :: c_int, c_double
+            integer(c_int)               :: handle
+            real(c_double), dimension(*) :: D, E, F, TI, Res
+            integer(c_int), dimension(*) :: WaterPoints3D
+        end function
+        integer(c_int) function mohid_adt_get_counters(handle, counters, n) bind(c, name="mohid_adt_get_counters")
+            import :: c_int, c_long_long
+            integer(c_int)                     :: handle, n
+            integer(c_long_long), dimension(*) :: counters
+        end function
+        integer(c_int) function mohid_adt_kernel_time_ms(handle, ms, launches) bind(c, name="mohid_adt_kernel_time_ms")
+            import :: c_int, c_double
+            integer(c_int) :: handle, launches
+            real(c_double) :: ms
+        end function
+        integer(c_int) function mohid_adt_version(buf, buflen) bind(c, name="mohid_adt_version")
+            import :: c_int, c_char
+            character(kind=c_char), dimension(*) :: buf
+            integer(c_int)                       :: buflen
         end function
     end interface
 
@@ -171,10 +356,28 @@ contains
         type(c_ptr) :: sd
         sd = c_null_ptr
         if (associated(SmallDepthsInt)) sd = c_loc(SmallDepthsInt(lbound(SmallDepthsInt,1), lbound(SmallDepthsInt,2)))
-        STAT = mohid_adt_set_step(Handle, Wflux_X, Wflux_Y, Wflux_Z, VolumeZOld, VolumeZ, Visc_H, Diff_V, DWZ, DZZ, &
-                                  AreaU, AreaV, OpenPoints3D, LandPoints3D, WaterPoints3D, ComputeFacesU3D,          &
-                                  ComputeFacesV3D, ComputeFacesW3D, sd)
+        ! a pointer that is not associated travels as NULL = "unchanged since the last step" (the land / water maps never
+        ! change, the other masks only with wetting and drying): 4 of the 112 bytes per cell stay off the bus
+        STAT = mohid_adt_set_step(Handle, L3R(Wflux_X), L3R(Wflux_Y), L3R(Wflux_Z), L3R(VolumeZOld), L3R(VolumeZ),   &
+                                  L3R(Visc_H), L3R(Diff_V), L3R(DWZ), L3R(DZZ), L3R(AreaU), L3R(AreaV),              &
+                                  L3I(OpenPoints3D), L3I(LandPoints3D), L3I(WaterPoints3D), L3I(ComputeFacesU3D),    &
+                                  L3I(ComputeFacesV3D), L3I(ComputeFacesW3D), sd)
     end subroutine B200_SetStep
+
+    ! address of the first element (ILB,JLB,KLB) of a 3-D array, c_null_ptr when the pointer is not associated
+    function L3R(A) result(p)
+        real(c_double), dimension(:,:,:), pointer :: A
+        type(c_ptr) :: p
+        p = c_null_ptr
+        if (associated(A)) p = c_loc(A(lbound(A,1), lbound(A,2), lbound(A,3)))
+    end function L3R
+
+    function L3I(A) result(p)
+        integer(c_int), dimension(:,:,:), pointer :: A
+        type(c_ptr) :: p
+        p = c_null_ptr
+        if (associated(A)) p = c_loc(A(lbound(A,1), lbound(A,2), lbound(A,3)))
+    end function L3I
 
     ! The optional NoFluxU/V/W dummies (AD:1143-1146); not associated = not present.
     subroutine B200_SetNoFlux(Handle, NoFluxU, NoFluxV, NoFluxW, STAT)
@@ -216,5 +419,115 @@ contains
             Message(i:i) = buf(i)
         enddo
     end subroutine B200_LastError
+
+    !--------------------------------------------------------------------------
+    ! SetDischarges (AD:978-1034) for the property at position PropIndex (0-based) of the next batch; the logical
+    ! arrays of the reference (IgnoreDisch, ByPass) arrive as integer 0/1.
+    subroutine B200_SetDischarges(Handle, PropIndex, DischFlow, DischConc, DischI, DischJ, DischK, DischKmin, DischKmax, &
+                                  DischVert, IgnoreDisch, DischnCells, ByPass, DischNumber, nCells, STAT)
+        integer(c_int)                        :: Handle
+        integer, intent(IN)                   :: PropIndex, DischNumber, nCells
+        real(c_double), dimension(:), pointer :: DischFlow, DischConc
+        integer(c_int), dimension(:), pointer :: DischI, DischJ, DischK, DischKmin, DischKmax, DischVert
+        integer(c_int), dimension(:), pointer :: IgnoreDisch, DischnCells, ByPass
+        integer, intent(OUT)                  :: STAT
+        integer(c_int) :: ip, nd, nc
+        ip = PropIndex; nd = DischNumber; nc = nCells
+        STAT = mohid_adt_set_discharges(Handle, ip, nd, nc, DischFlow, DischConc, DischI, DischJ, DischK, DischKmin,     &
+                                        DischKmax, DischVert, IgnoreDisch, DischnCells, ByPass, c_null_ptr)
+    end subroutine B200_SetDischarges
+
+    ! UnSetDischarges (AD:1040-1095)
+    subroutine B200_UnSetDischarges(Handle, STAT)
+        integer(c_int)       :: Handle
+        integer, intent(OUT) :: STAT
+        STAT = mohid_adt_unset_discharges(Handle)
+    end subroutine B200_UnSetDischarges
+
+    ! GetAdvFlux / GetDifFlux (AD:697-851): the reference hands out pointers to its module arrays; here the caller's
+    ! arrays (0:I+1, 0:J+1, 0:K+1) are filled.  Both are served by one library call.
+    subroutine B200_GetAdvFlux(Handle, PropIndex, AdvFluxX, AdvFluxY, AdvFluxZ, DifFluxX, DifFluxY, DifFluxZ, STAT)
+        integer(c_int)                            :: Handle
+        integer, intent(IN)                       :: PropIndex
+        real(c_double), dimension(:,:,:), pointer :: AdvFluxX, AdvFluxY, AdvFluxZ, DifFluxX, DifFluxY, DifFluxZ
+        integer, intent(OUT)                      :: STAT
+        integer(c_int) :: ip
+        ip = PropIndex
+        STAT = mohid_adt_get_cell_fluxes(Handle, ip, AdvFluxX, AdvFluxY, AdvFluxZ, DifFluxX, DifFluxY, DifFluxZ)
+    end subroutine B200_GetAdvFlux
+
+    subroutine B200_GetDifFlux(Handle, PropIndex, AdvFluxX, AdvFluxY, AdvFluxZ, DifFluxX, DifFluxY, DifFluxZ, STAT)
+        integer(c_int)                            :: Handle
+        integer, intent(IN)                       :: PropIndex
+        real(c_double), dimension(:,:,:), pointer :: AdvFluxX, AdvFluxY, AdvFluxZ, DifFluxX, DifFluxY, DifFluxZ
+        integer, intent(OUT)                      :: STAT
+        call B200_GetAdvFlux(Handle, PropIndex, AdvFluxX, AdvFluxY, AdvFluxZ, DifFluxX, DifFluxY, DifFluxZ, STAT)
+    end subroutine B200_GetDifFlux
+
+    !--------------------------------------------------------------------------
+    ! Resident-property mode: the concentrations stay on the device between time steps (no 16 B per cell and property
+    ! over PCIe every step); the host downloads them when an output, a sink/source module or an assimilation step needs
+    ! them.  B200_SetStep may pass non-associated masks after the first step (land / water maps never change).
+    subroutine B200_UploadProps(Handle, nProp, PropPtr, RefPtr, STAT)
+        integer(c_int)                    :: Handle
+        integer, intent(IN)               :: nProp
+        type(c_ptr), dimension(:), target :: PropPtr, RefPtr
+        integer, intent(OUT)              :: STAT
+        integer(c_int) :: n
+        n = nProp
+        STAT = mohid_adt_upload_props(Handle, n, PropPtr, c_loc(RefPtr(1)))
+    end subroutine B200_UploadProps
+
+    subroutine B200_AdvectDevice(Handle, nProp, Params, nSteps, STAT)
+        integer(c_int)                  :: Handle
+        integer, intent(IN)             :: nProp, nSteps
+        type(T_AdtParams), dimension(:) :: Params
+        integer, intent(OUT)            :: STAT
+        integer(c_int) :: n, ns
+        n = nProp; ns = nSteps
+        STAT = mohid_adt_advect_device(Handle, n, Params, ns)
+    end subroutine B200_AdvectDevice
+
+    subroutine B200_DownloadProps(Handle, nProp, PropPtr, STAT)
+        integer(c_int)            :: Handle
+        integer, intent(IN)       :: nProp
+        type(c_ptr), dimension(:) :: PropPtr
+        integer, intent(OUT)      :: STAT
+        integer(c_int) :: n
+        n = nProp
+        STAT = mohid_adt_download_props(Handle, n, PropPtr)
+    end subroutine B200_DownloadProps
+
+    !--------------------------------------------------------------------------
+    ! Domain decomposition (ModuleHorizontalGrid.F90:1587-1757): every MPI rank drives one GPU and one column slab.
+    ! Rank 0 obtains the NCCL id, MPI_Bcast carries its 128 bytes to the other ranks (UniqueId), and the exchange that
+    ! ReceiveSendProperitiesMPI (HG:8479-8658, called at WP:15034-15045) performs on host arrays becomes one call on
+    ! the device-resident fields.  JBegin / JCount: the owned local columns (the halo of width Ghost lies outside them).
+    subroutine B200_CommInit(Handle, nRanks, Rank, UniqueId, JBegin, JCount, Ghost, STAT)
+        integer(c_int)                                        :: Handle
+        integer, intent(IN)                                   :: nRanks, Rank, JBegin, JCount, Ghost
+        character(kind=c_char), dimension(128), intent(INOUT) :: UniqueId
+        integer, intent(OUT)                                  :: STAT
+        integer(c_int) :: nr, r, jb, jc, g, ov
+        nr = nRanks; r = Rank; jb = JBegin; jc = JCount; g = Ghost; ov = 1
+        STAT = mohid_adt_set_active_columns(Handle, jb, jc)
+        if (STAT /= 0) return
+        STAT = mohid_adt_comm_init(Handle, nr, r, UniqueId, g, ov)
+    end subroutine B200_CommInit
+
+    subroutine B200_ExchangeHalos(Handle, nProp, STAT)
+        integer(c_int)       :: Handle
+        integer, intent(IN)  :: nProp
+        integer, intent(OUT) :: STAT
+        integer(c_int) :: n
+        n = nProp
+        STAT = mohid_adt_exchange_halos(Handle, n)
+    end subroutine B200_ExchangeHalos
+
+    subroutine B200_CommKill(Handle, STAT)
+        integer(c_int)       :: Handle
+        integer, intent(OUT) :: STAT
+        STAT = mohid_adt_comm_destroy(Handle)
+    end subroutine B200_CommKill
 
 end module ModuleAdvectionDiffusionB200
