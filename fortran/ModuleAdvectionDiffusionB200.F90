@@ -38,7 +38,7 @@ module ModuleAdvectionDiffusionB200
     public :: mohid_adt_prop_device_ptr, mohid_adt_synchronize, mohid_adt_sync_prop_buffers, mohid_adt_set_reference_device
     public :: mohid_adt_step_input_device_ptr, mohid_adt_mark_step_resident, mohid_adt_set_active_columns
     public :: mohid_adt_pack_columns, mohid_adt_unpack_columns, mohid_adt_set_stream, mohid_adt_solve_thomas_z
-    public :: mohid_adt_get_counters, mohid_adt_kernel_time_ms, mohid_adt_version
+    public :: mohid_adt_get_counters, mohid_adt_kernel_time_ms, mohid_adt_version, mohid_adt_set_boxes, mohid_adt_box_fluxes
 
     ! mohid_adt_size3d == T_Size3D (ModuleGlobalData.F90:2041-2052)
     type, bind(c) :: T_AdtSize3D
@@ -175,6 +175,17 @@ module ModuleAdvectionDiffusionB200
             import :: c_int, c_double
             integer(c_int)               :: handle, prop_index
             real(c_double), dimension(*) :: AdvFluxX, AdvFluxY, AdvFluxZ, DifFluxX, DifFluxY, DifFluxZ
+        end function
+        ! BoxDifFluxes3D on the device (ModuleBoxDif.F90:2659-2776 as called at WP:14992-15001)
+        integer(c_int) function mohid_adt_set_boxes(handle, Boxes3D, NumberOfBoxes3D) bind(c, name="mohid_adt_set_boxes")
+            import :: c_int
+            integer(c_int)               :: handle, NumberOfBoxes3D
+            integer(c_int), dimension(*) :: Boxes3D
+        end function
+        integer(c_int) function mohid_adt_box_fluxes(handle, prop_index, Fluxes3D) bind(c, name="mohid_adt_box_fluxes")
+            import :: c_int, c_double
+            integer(c_int)               :: handle, prop_index
+            real(c_double), dimension(*) :: Fluxes3D              ! (0:NumberOfBoxes3D, 0:NumberOfBoxes3D)
         end function
         ! device-resident properties: upload once, advance nsteps without host traffic, download when needed
         integer(c_int) function mohid_adt_upload_props(handle, nprop, prop, reference_prop) bind(c, name="mohid_adt_upload_props")

@@ -210,6 +210,15 @@ int mohid_adt_advect_batch(const int *handle, const int *nprop,
 int mohid_adt_get_cell_fluxes(const int *handle, const int *prop_index, double *AdvFluxX, double *AdvFluxY,
                               double *AdvFluxZ, double *DifFluxX, double *DifFluxY, double *DifFluxZ);
 
+/* Box budgets on the device instead of six full-field copies to the host: BoxDifFluxes3D (ModuleBoxDif.F90:2659-2776)
+ * as ModuleWaterProperties feeds it (WP:14956-15032: MassFluxes = AdvFlux + DifFlux, mask = OpenPoints3D).
+ * set_boxes: Boxes3D is Me%Boxes3D (int32 3-D, box number per cell, values <= -55 = no box), NumberOfBoxes3D its count;
+ * box_fluxes: Fluxes3D is the (0:NumberOfBoxes3D, 0:NumberOfBoxes3D) matrix Me%Fluxes3D, element (OUT, IN) the mass flux
+ * of property `prop_index` from box OUT into box IN through the faces that separate them (antisymmetric), for a property
+ * advanced with CellFluxes = 1.  Summation order differs from the reference's serial loop: equal to rounding. */
+int mohid_adt_set_boxes(const int *handle, const int *Boxes3D, const int *NumberOfBoxes3D);
+int mohid_adt_box_fluxes(const int *handle, const int *prop_index, double *Fluxes3D);
+
 /* ---- device-resident variants (benchmarks, device-side callers) ------------------- */
 /* Copy properties host->device / device->host without stepping. */
 int mohid_adt_upload_props(const int *handle, const int *nprop, const double *const *prop,

@@ -203,6 +203,21 @@ class TransportStep:
                                                        *[C.c_void_p(out[k].ctypes.data) for k in names]))
         return out
 
+    # ---- box budgets (ModuleBoxDif) ---------------------------------------------------
+    def set_boxes(self, Boxes3D, NumberOfBoxes3D: int):
+        """Me%Boxes3D of ModuleBoxDif (int32, (K+2, J+2, ld)); values <= -55 = no box."""
+        self._nboxes = int(NumberOfBoxes3D)
+        self._check(self.lib.mohid_adt_set_boxes(C.byref(self.h), _ptr(Boxes3D, "i4", self.n3, "Boxes3D"),
+                                                 C.byref(C.c_int(self._nboxes))))
+
+    def box_fluxes(self, prop_index: int) -> np.ndarray:
+        """BoxDifFluxes3D (BoxDif:2659-2776) of AdvFlux + DifFlux of a property advanced with CellFluxes = 1:
+        out[IN, OUT] (C order of the Fortran (OUT, IN) matrix), shape (nb+1, nb+1)."""
+        nb1 = self._nboxes + 1
+        out = np.zeros((nb1, nb1))
+        self._check(self.lib.mohid_adt_box_fluxes(C.byref(self.h), C.byref(C.c_int(prop_index)), out.ctypes.data_as(C.c_void_p)))
+        return out
+
     # ---- halo staging for the j-slab decomposition ----------------------------------
     def pack_columns(self, nprop: int, j0: int, width: int, device_buffer):
         self._check(self.lib.mohid_adt_pack_columns(C.byref(self.h), C.byref(C.c_int(nprop)), C.byref(C.c_int(j0)),

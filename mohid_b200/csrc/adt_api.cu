@@ -55,6 +55,8 @@ struct Handle {
     bool have_small = false;
     int *bnd_cols = nullptr;
     int *noflux[3] = {nullptr, nullptr, nullptr};       // NoFluxU/V/W mirrors (allocated by set_noflux)
+    int *boxes = nullptr; int nboxes = -1;              // Boxes3D of ModuleBoxDif (mohid_adt_set_boxes)
+    double *box_flux = nullptr;
     bool have_noflux = false;
     double *density = nullptr, *wcol = nullptr;         // caller-side pre-steps (mohid_adt_set_premix)
     bool premix_fc = false, premix_sd = false;
@@ -273,7 +275,7 @@ void free_all(Handle *h) {
     F(h->DUX); F(h->DVY); F(h->DZX); F(h->DZY); F(h->rdx); F(h->rdy); F(h->KFloorZ); F(h->Bnd); F(h->SmallDepths);
     F(h->bnd_cols);
     for (auto p : h->noflux) F(p);
-    F(h->nfmask);
+    F(h->nfmask); F(h->boxes); F(h->box_flux);
     for (auto p : h->wline) F(p);
     for (auto p : h->hs_tmp) F(p);
     for (auto p : h->old_copy) F(p);
@@ -1691,6 +1693,52 @@ int mohid_adt_get_cell_fluxes(const int *handle, const int *prop_index, double *
     double *out[6] = {AdvFluxX, AdvFluxY, AdvFluxZ, DifFluxX, DifFluxY, DifFluxZ};
     for (int w = 0; w < 6; ++w)
         if (out[w]) if (int rc = d2h3(h, out[w], h->flux[w][n], 8)) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int mohid_adt_set_boxes(const int *handle, const int *Boxes3D, const int *NumberOfBoxes3D) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    if (!Boxes3D || !NumberOfBoxes3D || *NumberOfBoxes3D < 0 || *NumberOfBoxes3D > 4095)
+        return fail(h, MOHID_ADT_ERR_ARG, "Boxes3D and 0 <= NumberOfBoxes3D <= 4095 are required");
+    CU(h, cudaSetDevice(h->dev));
+    if (!h->boxes) {
+        if (int rc = dalloc(h, &h->boxes, h->n3)) return rc;
+        CU(h, cudaMemsetAsync(h->boxes, 0xff, h->n3 * sizeof(int), h->stream));      // -1 outside the caller's rows
+    }
+    if (int rc = h2d3(h, h->boxes, Boxes3D, 4)) return rc;
+    if (h->box_flux) { CU(h, cudaStreamSynchronize(h->stream)); cudaFree(h->box_flux); h->box_flux = nullptr; }
+    h->nboxes = *NumberOfBoxes3D;
+    if (int rc = dalloc(h, &h->box_flux, (size_t)(h->nboxes + 1) * (h->nboxes + 1))) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int mohid_adt_box_fluxes(const int *handle, const int *prop_index, double *Fluxes3D) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    if (!prop_index || !Fluxes3D) return fail(h, MOHID_ADT_ERR_ARG, "null argument");
+    if (!h->boxes) return fail(h, MOHID_ADT_ERR_STATE, "mohid_adt_set_boxes must precede box_fluxes");
+    const int n = *prop_index;
+    if (n < 0 || n >= (int)h->flux[0].size() || !h->flux[0][n])
+        return fail(h, MOHID_ADT_ERR_STATE, "BoxDif - no fluxes were computed for property %d (CellFluxes was not set)", n);
+    CU(h, cudaSetDevice(h->dev));
+    const size_t cnt = (size_t)(h->nboxes + 1) * (h->nboxes + 1);
+    CU(h, cudaMemsetAsync(h->box_flux, 0, cnt * sizeof(double), h->stream));           // Me%Fluxes3D(:,:) = 0.
+    BoxArgs a{};
+    a.I = h->I; a.J = h->J; a.K = h->K; a.ld = h->ld; a.sj = h->sj; a.sk = h->sk; a.nb1 = h->nboxes + 1;
+    a.with_z = h->K > 1;
+    a.Boxes = h->boxes; a.Water = h->raw_i[2]; a.Open = h->raw_i[0];
+    a.ax = h->flux[0][n]; a.ay = h->flux[1][n]; a.az = h->flux[2][n];
+    a.dx = h->flux[3][n]; a.dy = h->flux[4][n]; a.dz = h->flux[5][n];
+    a.fluxes = h->box_flux;
+    // only the owned columns of a slab: every face is then counted by exactly one rank (the host adds the matrices)
+    const dim3 grid((unsigned)((h->I + 127) / 128), (unsigned)h->J, (unsigned)h->K);
+    adt_box_flux_kernel<<<grid, 128, 0, h->stream>>>(a);
+    CU(h, cudaGetLastError());
+    h->launches++;
+    CU(h, cudaMemcpyAsync(Fluxes3D, h->box_flux, cnt * sizeof(double), cudaMemcpyDefault, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     return 0;
 }

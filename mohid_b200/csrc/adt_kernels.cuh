@@ -1305,6 +1305,37 @@ __global__ void __launch_bounds__(256) adt_column_mass_kernel(const MassArgs a) 
 }
 
 // -------------------------------------------------------------------------------------
+// Box budgets (BoxDifFluxes3D, MOHIDBase2/ModuleBoxDif.F90:2659-2776, fed by WP:14956-15032 with
+// MassFluxes = AdvFlux + DifFlux and OpenPoints3D as the mask): the flux through every cell face that separates two
+// boxes is added to Fluxes(OUT, IN) and subtracted from Fluxes(IN, OUT).  Boundary faces are the ones
+// FindAdjacentBoxesBoundaries3D marks (BoxDif:1697-1735): the cell has a box (> -55) and is a water point, the
+// neighbour across the face has another box (> -55).  The matrix is (0:nb, 0:nb) in Fortran order.
+// -------------------------------------------------------------------------------------
+struct BoxArgs {
+    int I, J, K, ld, sj, sk, nb1;           // nb1 = NumberOfBoxes3D + 1
+    int with_z;                             // KUB > KLB (WP:14981)
+    const int *Boxes, *Water, *Open;
+    const double *ax, *ay, *az, *dx, *dy, *dz;
+    double *fluxes;                         // [nb1 * nb1]
+};
+__global__ void __launch_bounds__(128) adt_box_flux_kernel(const BoxArgs a) {
+    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y, k = 1 + blockIdx.z;
+    if (i > a.I) return;
+    const int q = i + a.sj * j + a.sk * k;
+    const int b = a.Boxes[q];
+    if (b <= -55 || a.Water[q] != 1 || a.Open[q] != 1) return;
+    auto add = [&](int out, int in, double f) {
+        if (out < 0 || in < 0 || out >= a.nb1 || in >= a.nb1) return;
+        atomicAdd(a.fluxes + out + (size_t)a.nb1 * in, f);
+        atomicAdd(a.fluxes + in + (size_t)a.nb1 * out, -f);
+    };
+    const int bx = a.Boxes[q + a.sj], by = a.Boxes[q + 1], bz = a.Boxes[q + a.sk];
+    if (bx != b && bx > -55) add(b, bx, a.ax[q + a.sj] + a.dx[q + a.sj]);
+    if (by != b && by > -55) add(b, by, a.ay[q + 1] + a.dy[q + 1]);
+    if (bz != b && bz > -55 && a.with_z) add(b, bz, a.az[q + a.sk] + a.dz[q + a.sk]);
+}
+
+// -------------------------------------------------------------------------------------
 // K4: gather / scatter `width` j-columns of nprop properties to / from a contiguous buffer
 // laid out [n][k][w][i] (i fastest).  Coalesced on both sides.
 // -------------------------------------------------------------------------------------
