@@ -141,7 +141,7 @@ def params_for(nprop, method, limiter, dt, bc=0):
 # -----------------------------------------------------------------------------------------
 # CPU arm: the oracle (C++ restatement of the reference path, OpenMP) on a bounded sample
 # -----------------------------------------------------------------------------------------
-def cpu_reference_run(workload: str, steps: int, warmup: int, budget_s: float = 20.0):
+def cpu_reference_run(workload: str, steps: int, warmup: int, budget_s: float = 20.0, sample=None):
     import numpy as np
     from mohid_b200.synthetic import make_case
     from oracle import oracle as _oracle
@@ -149,7 +149,7 @@ def cpu_reference_run(workload: str, steps: int, warmup: int, budget_s: float = 
     _oracle.use_fast_build(True)                       # g++ -O3 -mavx2 -fopenmp -ffp-contract=off
     I, J, K, nprop, method, limiter = WORKLOADS[workload]
     # bounded sample: same K, N, numerics; horizontal extent cut so one step is ~1 s of CPU work
-    si, sj = min(I, 384), min(J, 384)
+    si, sj = (min(I, 384), min(J, 384)) if not sample else (min(I, sample[0]), min(J, sample[1]))
     case = make_case(si, sj, K, nprop=nprop)
     g, s, props, refs = case_to_numpy(case)
     # all the host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which is not the machine's limit)
@@ -175,7 +175,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference_run(args.workload, args.steps, args.warmup, budget_s=60.0)
+    sample = tuple(int(x) for x in args.ref_sample.lower().split("x")) if args.ref_sample else None
+    r = cpu_reference_run(args.workload, args.steps, args.warmup, budget_s=60.0 if not sample else 600.0, sample=sample)
     I, J, K, nprop, method, limiter = WORKLOADS[args.workload]
     line = {"impl": "reference", "metric": "Gcell-property updates/s per transport step", "value": r["value"],
             "unit": r["unit"], "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -254,11 +255,14 @@ def run_ours(args):
         else:
             e2e_skip = "host memory: %.0f GB needed per rank, %.0f GB available on the box" % (host_need / 1e9, avail / 1e9)
 
-    # every rank generates its slab (+ghost columns) of the same global case, in pieces of 128 columns written straight
+    # every rank generates its slab (+ghost columns) of the same global case, in pieces of at most 128 columns written straight
     # into the library's device mirrors (a case that fills most of the GPU never exists twice)
     g2 = {}
     dt = None
-    for j0, pc in case_pieces(I, J, K, nprop, j_lo=sl.j_lo_ext, j_hi=sl.j_hi_ext, piece=128, device=str(dev),
+    # piece width: the generator's transient fields (~60 + one per property) stay below ~6 GB beside a handle that may
+    # hold 170 GB
+    piece = max(8, min(128, int(6e9 / ((nprop + 60) * (I + 2) * (K + 2) * 8.0))))
+    for j0, pc in case_pieces(I, J, K, nprop, j_lo=sl.j_lo_ext, j_hi=sl.j_hi_ext, piece=piece, device=str(dev),
                               make_refs=args.bc != 0):
         dt = pc.dt
         ts.set_step_columns(j0, pc.step)
@@ -452,6 +456,8 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--bc", type=int, default=0, help="BoundaryCondition of every property (0 = none, 4 = NullGradient, ...); "
                     "a reference field per property is then resident too")
+    ap.add_argument("--ref-sample", default="", help="--impl reference: horizontal extent IxJ of the CPU sample (default 384x384; "
+                    "the full grid of C3 needs ~150 GB of host memory with the oracle's work arrays)")
     ap.add_argument("--no-e2e", dest="e2e", action="store_false")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     args = ap.parse_args()

@@ -309,7 +309,7 @@ int mohid_adt_solve_thomas_z(const int *handle, const double *D, const double *E
 int mohid_adt_last_error(const int *handle, char *buf, const int *buflen);
 /* counters[0] = kernels launched since create, [1] = zero-pivot rows seen by the column
  * solver in the last batch (MF:4092-4098 leaves W,G stale; the GPU path counts them),
- * [2] = mask-consistency violations found by set_step, [3] = bytes of device memory held. */
+ * [2] = reserved (0), [3] = bytes of device memory held. */
 int mohid_adt_get_counters(const int *handle, long long *counters, const int *n);
 /* Average device time in ms of the main transport kernel over the launches since the
  * last call (CUDA events on the handle's stream) and the number of launches averaged. */

@@ -39,13 +39,29 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every CUDA source of the package into mohid_b200/libmohid_adt.so."""
     if not force and not needs_build():
         return LIB
+    # one builder at a time: the ranks of a torchrun launch all come through here
+    import fcntl
+    lock = open(LIB + ".lock", "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+        if not force and not needs_build():            # another rank built it while this one waited
+            return LIB
+        return _compile(verbose)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _compile(verbose: bool) -> str:
     ccbin = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-ccbin", ccbin, "-o", LIB, *SOURCES]
+    tmp = LIB + f".tmp{os.getpid()}"
+    cmd = [nvcc_path(), *NVCC_FLAGS, "-ccbin", ccbin, "-o", tmp, *SOURCES]
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    os.replace(tmp, LIB)                                # readers never see a half-written library
     if verbose:
         print(r.stderr)
     return LIB

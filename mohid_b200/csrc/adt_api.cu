@@ -1352,11 +1352,25 @@ int mohid_adt_set_discharges(const int *handle, const int *prop_index, const int
             if (n >= nc) return fail(h, MOHID_ADT_ERR_ARG, "DischnCells lists more cells than n_cells");
             if (DischI[n] < 1 || DischI[n] > h->I || DischJ[n] < 1 || DischJ[n] > h->J)
                 return fail(h, MOHID_ADT_ERR_ARG, "discharge cell %d lies outside the work range", n);
+            // the layers the cell feeds (adt_discharge_prep_kernel): FillValueInt = "from the bottom / to the surface"
+            const bool uniform = DischVert[dis] == MOHID_DischUniform;
+            auto k_ok = [&](int k) { return k >= 1 && k <= h->K; };
+            if (uniform ? ((DischKmin[n] != MOHID_FILL_INT && !k_ok(DischKmin[n])) ||
+                           (DischKmax[n] != MOHID_FILL_INT && !k_ok(DischKmax[n])))
+                        : !k_ok(DischK[n]))
+                return fail(h, MOHID_ADT_ERR_ARG, "discharge cell %d: layer outside 1..%d", n, h->K);
             vert.push_back(DischVert[dis]);
             byp.push_back(ByPass[dis] ? 1 : 0);
         }
     }
     const int ncell = n;
+    // the cell list is shared by all properties (Me%Discharge, WP:14761-14773): a list of another length invalidates the
+    // concentrations other properties still hold
+    if (h->d_ncell > 0 && ncell != h->d_ncell)
+        for (size_t m = 0; m < h->d_conc.size(); ++m)
+            if ((int)m != pi && h->d_conc[m])
+                return fail(h, MOHID_ADT_ERR_STATE, "SetDischarges: %d cells, but property %d holds concentrations for %d "
+                            "(call UnSetDischarges first)", ncell, (int)m, h->d_ncell);
     auto up_i = [&](int *&d, const int *src) -> int {
         if (d) { cudaFree(d); d = nullptr; }
         if (ncell == 0) return 0;
