@@ -219,7 +219,7 @@ def run_ours(args):
     dec = SlabDecomposition(J, world, ghost=2)
     sl = dec.slab(rank)
     Jl = sl.j_hi_ext - sl.j_lo_ext + 1
-    ts = TransportStep(I, Jl, K, device=local)
+    ts = TransportStep(I, Jl, K, device=local, max_properties=nprop)
     stream = torch.cuda.current_stream()
     ts.set_stream(stream.cuda_stream)
 

@@ -1106,9 +1106,22 @@ int mohid_adt_create(int *handle, const mohid_adt_size3d *size, const mohid_adt_
     h->ld = ((h->ni + 15) / 16) * 16;                // 128-byte aligned rows on the device
     h->n2 = (long)h->ld * h->nj;
     // chunk width of the in-place step and the shift margin it needs (see Handle)
-    h->C = std::min(h->nj, std::max(32, std::min(256, h->nj / 16)));
-    // small fields: one chunk (the margin then doubles the field, which costs nothing at this size, and a step is one launch)
-    if ((size_t)h->ld * h->nj * h->nk * sizeof(double) <= ((size_t)256 << 20)) h->C = h->nj;
+    // The margin of S = C + 3 columns is what the single buffer per property costs; the wider the chunk, the fewer launches
+    // and tail waves per step (C3: 40.8 ms with 17 chunks, 40.1 with 5).  The widest of nj, nj/2, .. nj/16 is taken whose
+    // footprint -- 112 B of raw mirrors + 8 B per property per cell, for max_properties (at least 16) properties --
+    // stays below 55 % of the free device memory; nj/16 (32 .. 256 columns) is the floor.
+    {
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const double per_cell = 112.0 + 8.0 * std::max(h->opt.max_properties, 16);
+        const int floor_c = std::min(h->nj, std::max(32, std::min(256, h->nj / 16)));
+        h->C = floor_c;
+        for (int div = 1; div <= 8; div *= 2) {
+            const int c = std::max(floor_c, (h->nj + div - 1) / div);
+            const double cells = (double)h->ld * (h->nj + c + 3) * h->nk;
+            if (cells < 2.0e9 && cells * per_cell < 0.55 * (double)free_b) { h->C = c; break; }
+        }
+    }
     if (const char *e = getenv("MOHID_ADT_CHUNK_COLS")) h->C = std::max(1, std::min(h->nj, atoi(e)));
     h->S = h->C + 3;
     h->njp = h->nj + h->S;
