@@ -68,12 +68,12 @@ def test_product_does_not_import_the_oracle():
                 assert "oracle" not in txt.lower() or f == "synthetic.py" and "oracle" not in txt, (dirpath, f)
 
 
-def _build_c_driver(tmp_path):
+def _build_c_driver(tmp_path, name="c_driver"):
     import subprocess
-    exe = str(tmp_path / "c_driver")
+    exe = str(tmp_path / name)
     libdir = os.path.join(ROOT, "mohid_b200")
-    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
-           os.path.join(ROOT, "examples", "c_driver.c"), "-L", libdir, "-lmohid_adt", f"-Wl,-rpath,{libdir}", "-lm", "-o", exe]
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pthread", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", name + ".c"), "-L", libdir, "-lmohid_adt", f"-Wl,-rpath,{libdir}", "-lm", "-o", exe]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     return exe
@@ -85,9 +85,11 @@ def test_header_is_plain_c_and_a_c_host_links(lib, tmp_path):
     import subprocess
     import torch
     exe = _build_c_driver(tmp_path)
+    exe2 = _build_c_driver(tmp_path, "c_driver_2rank")            # two ranks, NCCL halo exchange through the C-ABI
     if not torch.cuda.is_available():
-        r = subprocess.run([exe], capture_output=True, text=True)
-        assert r.returncode == 1 and "no CPU fallback" in r.stderr
+        for e in (exe, exe2):
+            r = subprocess.run([e], capture_output=True, text=True)
+            assert r.returncode == 1 and "no CPU fallback" in r.stderr
 
 
 @pytest.mark.gpu
@@ -95,3 +97,13 @@ def test_c_host_runs_a_step(lib, tmp_path):
     import subprocess
     r = subprocess.run([_build_c_driver(tmp_path)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_c_host_two_ranks_equal_one(lib, tmp_path):
+    """examples/c_driver_2rank.c: two slabs with the library's NCCL exchange == the undivided run, from plain C
+    (prints `skipped` on a one-GPU box)."""
+    import subprocess
+    r = subprocess.run([_build_c_driver(tmp_path, "c_driver_2rank")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    print(r.stdout.strip())
