@@ -13,7 +13,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmohid_adt.so")
 SOURCES = [os.path.join(CSRC, "adt_api.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, "adt_fused_kernel.cuh"), os.path.join(CSRC, "adt_lean_kernel.cuh"), os.path.join(CSRC, "adt_kernels.cuh"), os.path.join(CSRC, "adt_ring_kernel.cuh"), os.path.join(CSRC, "adt_hsolve_kernel.cuh"), os.path.join(CSRC, "adt_hflux_kernel.cuh"), os.path.join(ROOT, "include", "mohid_adt.h")]
+DEPS = SOURCES + [os.path.join(CSRC, "adt_fused_kernel.cuh"), os.path.join(CSRC, "adt_lean_kernel.cuh"), os.path.join(CSRC, "adt_kernels.cuh"), os.path.join(CSRC, "adt_hsolve_kernel.cuh"), os.path.join(ROOT, "include", "mohid_adt.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--compiler-options", "-fPIC", "-shared"]
