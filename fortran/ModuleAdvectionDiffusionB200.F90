@@ -39,6 +39,7 @@ module ModuleAdvectionDiffusionB200
     public :: mohid_adt_step_input_device_ptr, mohid_adt_mark_step_resident, mohid_adt_set_active_columns
     public :: mohid_adt_pack_columns, mohid_adt_unpack_columns, mohid_adt_set_stream, mohid_adt_solve_thomas_z
     public :: mohid_adt_get_counters, mohid_adt_kernel_time_ms, mohid_adt_version, mohid_adt_set_boxes, mohid_adt_box_fluxes
+    public :: mohid_adt_free_vertical_movement
 
     ! mohid_adt_size3d == T_Size3D (ModuleGlobalData.F90:2041-2052)
     type, bind(c) :: T_AdtSize3D
@@ -186,6 +187,16 @@ module ModuleAdvectionDiffusionB200
             import :: c_int, c_double
             integer(c_int)               :: handle, prop_index
             real(c_double), dimension(*) :: Fluxes3D              ! (0:NumberOfBoxes3D, 0:NumberOfBoxes3D)
+        end function
+        ! FreeVerticalMovementIteration (ModuleFreeVerticalMovement.F90:1531-1650) on a device-resident property
+        integer(c_int) function mohid_adt_free_vertical_movement(handle, prop_index, Velocity, GridCellArea,             &
+                DepositionProbability, Deposition, NonCohesive, DepositionIntertidalZones, ImpExp_AdvV, DTProp,          &
+                FreeConvFlux) bind(c, name="mohid_adt_free_vertical_movement")
+            import :: c_int, c_double, c_ptr
+            integer(c_int)               :: handle, prop_index, Deposition, NonCohesive, DepositionIntertidalZones
+            real(c_double), dimension(*) :: Velocity, GridCellArea
+            type(c_ptr), value           :: DepositionProbability, FreeConvFlux     ! c_null_ptr when not needed
+            real(c_double)               :: ImpExp_AdvV, DTProp
         end function
         ! device-resident properties: upload once, advance nsteps without host traffic, download when needed
         integer(c_int) function mohid_adt_upload_props(handle, nprop, prop, reference_prop) bind(c, name="mohid_adt_upload_props")

@@ -219,6 +219,19 @@ int mohid_adt_get_cell_fluxes(const int *handle, const int *prop_index, double *
 int mohid_adt_set_boxes(const int *handle, const int *Boxes3D, const int *NumberOfBoxes3D);
 int mohid_adt_box_fluxes(const int *handle, const int *prop_index, double *Fluxes3D);
 
+/* FreeVerticalMovementIteration (MOHIDWater/ModuleFreeVerticalMovement.F90:1531-1650, reached through
+ * Modify_FreeVerticalMovement :1455-1527, which ModuleWaterProperties calls per settling property): the vertical movement
+ * of the device-resident property `prop_index` with its own velocity field -- BottomBoundary, VerticalFreeConvection (first
+ * order upwind), land fill, THOMASZ_NewType2 for the implicit scheme -- using VolumeZ, the masks and KFloorZ of set_step /
+ * set_grid2d.  Velocity is PropertyX%Velocity as Vertical_Velocity left it (fp64 3-D, value at the bottom face of cell k),
+ * GridCellArea and DepositionProbability fp64 2-D (the latter may be NULL unless Deposition and not NonCohesive);
+ * ImpExp_AdvV in THIS module's convention: 0 = implicit, 1 = explicit.  FreeConvFlux (fp64 3-D, host, may be NULL) receives
+ * PropertyX%FreeConvFlux.  The caller's velocity array is not modified (the reference zeroes / scales its bottom value). */
+int mohid_adt_free_vertical_movement(const int *handle, const int *prop_index, const double *Velocity,
+                                     const double *GridCellArea, const double *DepositionProbability, const int *Deposition,
+                                     const int *NonCohesive, const int *DepositionIntertidalZones, const double *ImpExp_AdvV,
+                                     const double *DTProp, double *FreeConvFlux);
+
 /* ---- device-resident variants (benchmarks, device-side callers) ------------------- */
 /* Copy properties host->device / device->host without stepping. */
 int mohid_adt_upload_props(const int *handle, const int *nprop, const double *const *prop,

@@ -218,6 +218,21 @@ class TransportStep:
         self._check(self.lib.mohid_adt_box_fluxes(C.byref(self.h), C.byref(C.c_int(prop_index)), out.ctypes.data_as(C.c_void_p)))
         return out
 
+    # ---- settling (ModuleFreeVerticalMovement) ----------------------------------------
+    def free_vertical_movement(self, prop_index: int, Velocity, GridCellArea, *, DepositionProbability=None,
+                               Deposition: bool = False, NonCohesive: bool = False, DepositionIntertidalZones: bool = False,
+                               ImpExp_AdvV: float = 0.0, DTProp: float = 30.0, want_flux: bool = False):
+        """FreeVerticalMovementIteration (FVM:1531-1650) on the device-resident property ``prop_index``; returns
+        FreeConvFlux when ``want_flux``."""
+        flux = np.zeros((self.K + 2, self.J + 2, self.ld)) if want_flux else None
+        ci = lambda v: C.byref(C.c_int(int(v)))
+        self._check(self.lib.mohid_adt_free_vertical_movement(
+            C.byref(self.h), ci(prop_index), _ptr(Velocity, "f8", self.n3, "Velocity"),
+            _ptr(GridCellArea, "f8", self.n2, "GridCellArea"), _ptr(DepositionProbability, "f8", self.n2, "DepositionProbability"),
+            ci(Deposition), ci(NonCohesive), ci(DepositionIntertidalZones), C.byref(C.c_double(ImpExp_AdvV)),
+            C.byref(C.c_double(DTProp)), flux.ctypes.data_as(C.c_void_p) if want_flux else None))
+        return flux
+
     # ---- halo staging for the j-slab decomposition ----------------------------------
     def pack_columns(self, nprop: int, j0: int, width: int, device_buffer):
         self._check(self.lib.mohid_adt_pack_columns(C.byref(self.h), C.byref(C.c_int(nprop)), C.byref(C.c_int(j0)),

@@ -1971,6 +1971,71 @@ int mohid_adt_solve_thomas_z(const int *handle, const double *D, const double *E
     return 0;
 }
 
+int mohid_adt_free_vertical_movement(const int *handle, const int *prop_index, const double *Velocity,
+                                     const double *GridCellArea, const double *DepositionProbability, const int *Deposition,
+                                     const int *NonCohesive, const int *DepositionIntertidalZones, const double *ImpExp_AdvV,
+                                     const double *DTProp, double *FreeConvFlux) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    if (!prop_index || !Velocity || !GridCellArea || !Deposition || !NonCohesive || !DepositionIntertidalZones ||
+        !ImpExp_AdvV || !DTProp)
+        return fail(h, MOHID_ADT_ERR_ARG, "null argument");
+    const int n = *prop_index;
+    if (n < 0 || n >= (int)h->prop.size()) return fail(h, MOHID_ADT_ERR_STATE, "property %d was never uploaded", n);
+    if (!h->have_step || !h->have_grid) return fail(h, MOHID_ADT_ERR_STATE, "set_grid2d and set_step must precede the call");
+    if (!(*ImpExp_AdvV == 0.0 || *ImpExp_AdvV == 1.0))
+        return fail(h, MOHID_ADT_ERR_ARG, "VerticalFreeConvection - ModuleFreeVerticalMovement - ERR04");
+    if (*Deposition && !*NonCohesive && !DepositionProbability)
+        return fail(h, MOHID_ADT_ERR_ARG, "DepositionProbability is required for a cohesive property that deposits");
+    if (!(*DTProp > 0.0)) return fail(h, MOHID_ADT_ERR_ARG, "DTProp must be positive");
+    CU(h, cudaSetDevice(h->dev));
+    if (h->halo_pending) { CU(h, cudaStreamWaitEvent(h->stream, h->ev_halo, 0)); h->halo_pending = false; }
+    // scratch: D, E, F, TI, W, velocity, flux (3-D), area, probability (2-D)
+    double *d3[7] = {nullptr}, *d2[2] = {nullptr, nullptr};
+    auto cleanup = [&]() { for (auto p : d3) if (p) cudaFree(p); for (auto p : d2) if (p) cudaFree(p); };
+    int rc = 0;
+    for (int a = 0; a < 7 && !rc; ++a)
+        if ((a < 6 || FreeConvFlux) && cudaMalloc((void **)&d3[a], (size_t)(h->n3 + 64) * sizeof(double)) != cudaSuccess)
+            rc = fail(h, MOHID_ADT_ERR_CUDA, "out of device memory (free_vertical_movement)");
+    for (int a = 0; a < 2 && !rc; ++a)
+        if ((a == 0 || DepositionProbability) && cudaMalloc((void **)&d2[a], (size_t)(h->n2 + 64) * sizeof(double)) != cudaSuccess)
+            rc = fail(h, MOHID_ADT_ERR_CUDA, "out of device memory (free_vertical_movement)");
+    if (!rc) rc = h2d3(h, d3[5], Velocity, 8);
+    if (!rc) rc = h2d2(h, d2[0], GridCellArea, 8);
+    if (!rc && DepositionProbability) rc = h2d2(h, d2[1], DepositionProbability, 8);
+    if (!rc) {
+        FvmArgs a{};
+        a.I = h->I; a.J = h->J; a.K = h->K; a.sj = h->sj; a.sk = h->sk; a.ld = h->ld;
+        a.Mask = *DepositionIntertidalZones ? h->raw_i[2] : h->raw_i[0];
+        a.Land = h->raw_i[1]; a.KFloorZ = h->KFloorZ; a.VolumeZ = h->raw_d[4];
+        a.Velocity = d3[5]; a.Area = d2[0]; a.DepProb = d2[1];
+        a.deposition = *Deposition; a.non_cohesive = *NonCohesive; a.dt = *DTProp; a.impexp = *ImpExp_AdvV;
+        a.C = cur_ptr(h, n);
+        a.D = d3[0]; a.E = d3[1]; a.F = d3[2]; a.TI = d3[3]; a.flux = FreeConvFlux ? d3[6] : nullptr;
+        adt_fvm_coef_kernel<<<dim3((unsigned)((h->ld + 127) / 128), (unsigned)h->nj, (unsigned)h->nk), 128, 0, h->stream>>>(a);
+        h->launches++;
+        if (*ImpExp_AdvV != 1.0) {
+            cudaMemsetAsync(h->d_zero_piv, 0, sizeof(unsigned long long), h->stream);
+            adt_thomas_z_kernel<<<dim3((unsigned)((h->I + 127) / 128), (unsigned)h->J), 128, 0, h->stream>>>(
+                h->I, h->J, h->K, h->sj, h->sk, d3[0], d3[1], d3[2], d3[3], h->raw_i[2], cur_ptr(h, n), d3[4], h->d_zero_piv);
+            h->launches++;
+        } else if (copy_field(h, cur_ptr(h, n), d3[3])) {
+            rc = MOHID_ADT_ERR_CUDA;
+        }
+        if (!rc && FreeConvFlux) {
+            adt_fvm_flux_kernel<<<dim3((unsigned)((h->I + 127) / 128), (unsigned)h->J, (unsigned)h->K), 128, 0, h->stream>>>(a);
+            h->launches++;
+        }
+        if (!rc && cudaGetLastError() != cudaSuccess) rc = fail(h, MOHID_ADT_ERR_CUDA, "free_vertical_movement launch failed");
+    }
+    if (!rc && FreeConvFlux) rc = d2h3(h, FreeConvFlux, d3[6], 8);
+    const cudaError_t e = cudaStreamSynchronize(h->stream);
+    cleanup();
+    if (rc) return rc;
+    CU(h, e);
+    return 0;
+}
+
 int mohid_adt_column_mass(const int *handle, const int *nprop, double *mass) {
     Handle *h = get(handle);
     if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");

@@ -1336,6 +1336,64 @@ __global__ void __launch_bounds__(128) adt_box_flux_kernel(const BoxArgs a) {
 }
 
 // -------------------------------------------------------------------------------------
+// FreeVerticalMovementIteration (MOHIDWater/ModuleFreeVerticalMovement.F90:1531-1650): settling / rising of a property
+// with its own vertical velocity, first-order upwind, implicit (ImpExp_AdvV = 0 in THIS module's convention) or explicit
+// (= 1).  Pass 1 builds D, E, F, TI (SetMatrixValue fills :1555-1558, BottomBoundary :2141-2227, VerticalFreeConvection
+// :1651-1775, land fill :1583-1592) and the explicit share of FreeConvFlux (:1779-1805); the column solve is
+// adt_thomas_z_kernel (THOMASZ_NewType2, :1610-1622); pass 2 adds the implicit share of the flux from the new field.
+// -------------------------------------------------------------------------------------
+struct FvmArgs {
+    int I, J, K, sj, sk, ld;
+    const int *Mask, *Land, *KFloorZ;       // WaterPointsorOpenPoints (:1549-1553), LandPoints3D, KFloor_Z
+    const double *VolumeZ, *Velocity, *Area, *DepProb;   // DepProb may be null
+    int deposition, non_cohesive;
+    double dt, impexp;                      // DTProp, ImpExp_AdvV (0 implicit, 1 explicit)
+    const double *C;                        // concentration (old in pass 1, new in pass 2)
+    double *D, *E, *F, *TI, *flux;          // flux may be null
+};
+__device__ __forceinline__ double fvm_velocity(const FvmArgs &a, int c2, int q, int k) {
+    // BottomBoundary: the velocity at the bottom face of the column is zero, or scaled by the deposition probability
+    double v = a.Velocity[q];
+    if (k == a.KFloorZ[c2]) {
+        if (!a.deposition) v = 0.;
+        else if (!a.non_cohesive) v = v * a.DepProb[c2];
+    }
+    return v;
+}
+__global__ void __launch_bounds__(128) adt_fvm_coef_kernel(const FvmArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;
+    if (i >= a.ld) return;
+    const int c2 = i + a.ld * j, q = i + a.sj * j + a.sk * k;
+    double D = 0., E = 1., F = 0., TI = a.C[q], fl = 0.;
+    const bool inwork = i >= 1 && i <= a.I && j >= 1 && j <= a.J && k >= 1 && k <= a.K;
+    if (inwork && a.Mask[i + a.sj * j + a.sk * a.K] == 1) {
+        const double dtv = a.dt / a.VolumeZ[q];
+        const double w1 = fvm_velocity(a, c2, q, k) * a.Area[c2];
+        const double w2 = k < a.K ? fvm_velocity(a, c2, q + a.sk, k + 1) * a.Area[c2] : 0.;
+        const double aw1 = fabs(w1), aw2 = fabs(w2);
+        const double d_flux = -(w1 + aw1) / 2.0, e_flux = -(w1 - aw1) / 2.0;
+        const double coef_d = d_flux * dtv, coef_e = ((w2 + aw2) / 2.0 + e_flux) * dtv, coef_f = ((w2 - aw2) / 2.0) * dtv;
+        if (a.impexp == 0.0) { D = D + coef_d; E = E + coef_e; F = F + coef_f; }
+        if (a.impexp == 1.0) TI = TI - (coef_d * a.C[q - a.sk] + coef_e * a.C[q] + coef_f * a.C[q + a.sk]);
+        if (a.Mask[q] == 1) fl = -a.impexp * (d_flux * a.C[q - a.sk] + e_flux * a.C[q]);
+    }
+    if (inwork) TI = TI * (1. - (double)a.Land[q]) + (double)a.Land[q] * NULL_REAL;
+    a.D[q] = D; a.E[q] = E; a.F[q] = F; a.TI[q] = TI;
+    if (a.flux) a.flux[q] = fl;
+}
+// implicit share of FreeConvFlux from the new field (CalcVerticalFreeConvFlux with Weigth = 1 - ImpExp_AdvV)
+__global__ void __launch_bounds__(128) adt_fvm_flux_kernel(const FvmArgs a) {
+    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y, k = 1 + blockIdx.z;
+    if (i > a.I) return;
+    const int c2 = i + a.ld * j, q = i + a.sj * j + a.sk * k;
+    if (a.Mask[q] != 1 || a.Mask[i + a.sj * j + a.sk * a.K] != 1) return;
+    const double w1 = fvm_velocity(a, c2, q, k) * a.Area[c2];
+    const double aw1 = fabs(w1);
+    const double d_flux = -(w1 + aw1) / 2.0, e_flux = -(w1 - aw1) / 2.0;
+    a.flux[q] = a.flux[q] - (1.0 - a.impexp) * (d_flux * a.C[q - a.sk] + e_flux * a.C[q]);
+}
+
+// -------------------------------------------------------------------------------------
 // K4: gather / scatter `width` j-columns of nprop properties to / from a contiguous buffer
 // laid out [n][k][w][i] (i fastest).  Coalesced on both sides.
 // -------------------------------------------------------------------------------------
