@@ -40,6 +40,8 @@ module ModuleAdvectionDiffusionB200
     public :: mohid_adt_pack_columns, mohid_adt_unpack_columns, mohid_adt_set_stream, mohid_adt_solve_thomas_z
     public :: mohid_adt_get_counters, mohid_adt_kernel_time_ms, mohid_adt_version, mohid_adt_set_boxes, mohid_adt_box_fluxes
     public :: mohid_adt_free_vertical_movement
+    public :: mohid_adt_hydro_integration_reinit, mohid_adt_hydro_integration_step, mohid_adt_hydro_integration_end
+    public :: mohid_adt_download_step_input
 
     ! mohid_adt_size3d == T_Size3D (ModuleGlobalData.F90:2041-2052)
     type, bind(c) :: T_AdtSize3D
@@ -197,6 +199,34 @@ module ModuleAdvectionDiffusionB200
             real(c_double), dimension(*) :: Velocity, GridCellArea
             type(c_ptr), value           :: DepositionProbability, FreeConvFlux     ! c_null_ptr when not needed
             real(c_double)               :: ImpExp_AdvV, DTProp
+        end function
+        ! ModuleHydroIntegration on the device mirrors (ModuleHydroIntegration.F90:767-994, used at WP:14615-14647)
+        integer(c_int) function mohid_adt_hydro_integration_reinit(handle, VolumeZOld) &
+                bind(c, name="mohid_adt_hydro_integration_reinit")
+            import :: c_int, c_double
+            integer(c_int)               :: handle
+            real(c_double), dimension(*) :: VolumeZOld
+        end function
+        integer(c_int) function mohid_adt_hydro_integration_step(handle, WaterFluxX, WaterFluxY, Discharges, ComputeFacesU,  &
+                ComputeFacesV) bind(c, name="mohid_adt_hydro_integration_step")
+            import :: c_int, c_double, c_ptr
+            integer(c_int)               :: handle
+            real(c_double), dimension(*) :: WaterFluxX, WaterFluxY
+            type(c_ptr), value           :: Discharges                              ! c_null_ptr: no discharges
+            integer(c_int), dimension(*) :: ComputeFacesU, ComputeFacesV
+        end function
+        integer(c_int) function mohid_adt_hydro_integration_end(handle, VolumeZ, WaterPoints3D, DT) &
+                bind(c, name="mohid_adt_hydro_integration_end")
+            import :: c_int, c_double
+            integer(c_int)               :: handle
+            real(c_double), dimension(*) :: VolumeZ
+            integer(c_int), dimension(*) :: WaterPoints3D
+            real(c_double)               :: DT
+        end function
+        integer(c_int) function mohid_adt_download_step_input(handle, which, array) bind(c, name="mohid_adt_download_step_input")
+            import :: c_int, c_ptr
+            integer(c_int)     :: handle, which
+            type(c_ptr), value :: array                     ! c_loc of a real(8) (which <= 10) or integer (11..16) 3-D array
         end function
         ! device-resident properties: upload once, advance nsteps without host traffic, download when needed
         integer(c_int) function mohid_adt_upload_props(handle, nprop, prop, reference_prop) bind(c, name="mohid_adt_upload_props")

@@ -232,6 +232,24 @@ int mohid_adt_free_vertical_movement(const int *handle, const int *prop_index, c
                                      const int *NonCohesive, const int *DepositionIntertidalZones, const double *ImpExp_AdvV,
                                      const double *DTProp, double *FreeConvFlux);
 
+/* ModuleHydroIntegration (MOHIDBase1/ModuleHydroIntegration.F90) on the device: a property whose DTInterval spans n
+ * hydrodynamic steps is transported with the time-mean of the horizontal water fluxes, the union of the compute faces,
+ * the vertical flux that closes continuity over the interval and the volume at its start (GetHydroIntegrationWaterFluxes /
+ * ComputeFaces / VolumeZOld at WP:14615-14647).  The integration arrays are the handle's own step mirrors:
+ *   reinit  = ReInitalizeIntegration (:767-796) at the first hydrodynamic step of the interval (VolumeZOld = initial volume);
+ *   step    = OneIntegrationStep (:843-906) once per hydrodynamic step (Discharges fp64 3-D or NULL);
+ *   end     = EndIntegrationStep (:910-994) at the last one (VolumeZ, WaterPoints3D of that instant, DT = the interval):
+ *             afterwards Wflux_X/Y/Z, VolumeZOld, VolumeZ, OpenPoints3D, WaterPoints3D and ComputeFacesU/V/W3D of the
+ *             handle are those of the interval; mohid_adt_set_step then passes NULL for them and the other arrays as usual
+ *             (or mohid_adt_mark_step_resident when they are already in place). */
+int mohid_adt_hydro_integration_reinit(const int *handle, const double *VolumeZOld);
+int mohid_adt_hydro_integration_step(const int *handle, const double *WaterFluxX, const double *WaterFluxY,
+                                     const double *Discharges, const int *ComputeFacesU, const int *ComputeFacesV);
+int mohid_adt_hydro_integration_end(const int *handle, const double *VolumeZ, const int *WaterPoints3D, const double *DT);
+/* Copy of a step mirror back into a caller array of the interface shape: which = 0..10 the fp64 arrays of set_step in
+ * argument order (fp64 array), 11..16 its int32 masks (int32 array) -- e.g. the integrated fluxes for an output. */
+int mohid_adt_download_step_input(const int *handle, const int *which, void *array);
+
 /* ---- device-resident variants (benchmarks, device-side callers) ------------------- */
 /* Copy properties host->device / device->host without stepping. */
 int mohid_adt_upload_props(const int *handle, const int *nprop, const double *const *prop,

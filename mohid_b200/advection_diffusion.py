@@ -218,6 +218,28 @@ class TransportStep:
         self._check(self.lib.mohid_adt_box_fluxes(C.byref(self.h), C.byref(C.c_int(prop_index)), out.ctypes.data_as(C.c_void_p)))
         return out
 
+    # ---- time integration of the hydrodynamic fluxes (ModuleHydroIntegration) ----------
+    def hydro_integration_reinit(self, VolumeZOld):
+        self._check(self.lib.mohid_adt_hydro_integration_reinit(C.byref(self.h), _ptr(VolumeZOld, "f8", self.n3, "VolumeZOld")))
+
+    def hydro_integration_step(self, WaterFluxX, WaterFluxY, ComputeFacesU, ComputeFacesV, Discharges=None):
+        self._check(self.lib.mohid_adt_hydro_integration_step(
+            C.byref(self.h), _ptr(WaterFluxX, "f8", self.n3, "WaterFluxX"), _ptr(WaterFluxY, "f8", self.n3, "WaterFluxY"),
+            _ptr(Discharges, "f8", self.n3, "Discharges"), _ptr(ComputeFacesU, "i4", self.n3, "ComputeFacesU"),
+            _ptr(ComputeFacesV, "i4", self.n3, "ComputeFacesV")))
+
+    def hydro_integration_end(self, VolumeZ, WaterPoints3D, DT: float):
+        self._check(self.lib.mohid_adt_hydro_integration_end(C.byref(self.h), _ptr(VolumeZ, "f8", self.n3, "VolumeZ"),
+                                                             _ptr(WaterPoints3D, "i4", self.n3, "WaterPoints3D"),
+                                                             C.byref(C.c_double(DT))))
+
+    def step_input(self, which: int) -> np.ndarray:
+        """Host copy of a device mirror of set_step (0..10 the fp64 arrays in argument order, 11..16 the masks)."""
+        out = np.zeros((self.K + 2, self.J + 2, self.ld), np.float64 if which < 11 else np.int32)
+        self._check(self.lib.mohid_adt_download_step_input(C.byref(self.h), C.byref(C.c_int(which)),
+                                                           out.ctypes.data_as(C.c_void_p)))
+        return out
+
     # ---- settling (ModuleFreeVerticalMovement) ----------------------------------------
     def free_vertical_movement(self, prop_index: int, Velocity, GridCellArea, *, DepositionProbability=None,
                                Deposition: bool = False, NonCohesive: bool = False, DepositionIntertidalZones: bool = False,

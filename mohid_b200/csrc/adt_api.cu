@@ -57,6 +57,9 @@ struct Handle {
     int *noflux[3] = {nullptr, nullptr, nullptr};       // NoFluxU/V/W mirrors (allocated by set_noflux)
     int *boxes = nullptr; int nboxes = -1;              // Boxes3D of ModuleBoxDif (mohid_adt_set_boxes)
     double *box_flux = nullptr;
+    int hint_n = -1;                                    // ModuleHydroIntegration: steps integrated since the re-initialisation (-1 = idle)
+    double *hint_disch = nullptr, *hint_in[3] = {nullptr, nullptr, nullptr};   // integrated discharges; staging of one step
+    int *hint_cf[2] = {nullptr, nullptr};
     bool have_noflux = false;
     double *density = nullptr, *wcol = nullptr;         // caller-side pre-steps (mohid_adt_set_premix)
     bool premix_fc = false, premix_sd = false;
@@ -275,7 +278,9 @@ void free_all(Handle *h) {
     F(h->DUX); F(h->DVY); F(h->DZX); F(h->DZY); F(h->rdx); F(h->rdy); F(h->KFloorZ); F(h->Bnd); F(h->SmallDepths);
     F(h->bnd_cols);
     for (auto p : h->noflux) F(p);
-    F(h->nfmask); F(h->boxes); F(h->box_flux);
+    F(h->nfmask); F(h->boxes); F(h->box_flux); F(h->hint_disch);
+    for (auto p : h->hint_in) F(p);
+    for (auto p : h->hint_cf) F(p);
     for (auto p : h->wline) F(p);
     for (auto p : h->hs_tmp) F(p);
     for (auto p : h->old_copy) F(p);
@@ -2033,6 +2038,92 @@ int mohid_adt_free_vertical_movement(const int *handle, const int *prop_index, c
     cleanup();
     if (rc) return rc;
     CU(h, e);
+    return 0;
+}
+
+// ---- ModuleHydroIntegration on the device mirrors ----
+static void hint_args(Handle *h, HintArgs &a) {
+    a.I = h->I; a.J = h->J; a.K = h->K; a.ni = h->ni; a.nj = h->nj; a.ld = h->ld; a.sj = h->sj; a.sk = h->sk;
+    a.WX = h->raw_d[0]; a.WY = h->raw_d[1]; a.WZ = h->raw_d[2]; a.D = h->hint_disch;
+    a.CFU = h->raw_i[3]; a.CFV = h->raw_i[4]; a.CFW = h->raw_i[5]; a.Open = h->raw_i[0];
+    a.Water = h->raw_i[2]; a.Bnd = h->Bnd; a.V = h->raw_d[4]; a.V0 = h->raw_d[3];
+}
+
+int mohid_adt_hydro_integration_reinit(const int *handle, const double *VolumeZOld) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    if (!VolumeZOld) return fail(h, MOHID_ADT_ERR_ARG, "null array");
+    CU(h, cudaSetDevice(h->dev));
+    // ReInitalizeIntegration (HI:767-796): n = 0, InitialVolume = VolumeZOld, fluxes / discharges / mapping = 0
+    if (int rc = h2d3(h, h->raw_d[3], VolumeZOld, 8)) return rc;
+    for (int a : {0, 1, 2}) CU(h, cudaMemsetAsync(h->raw_d[a], 0, h->n3 * sizeof(double), h->stream));
+    for (int a : {0, 3, 4, 5}) CU(h, cudaMemsetAsync(h->raw_i[a], 0, h->n3 * sizeof(int), h->stream));
+    if (h->hint_disch) CU(h, cudaMemsetAsync(h->hint_disch, 0, h->n3 * sizeof(double), h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->hint_n = 0;
+    return 0;
+}
+
+int mohid_adt_hydro_integration_step(const int *handle, const double *WaterFluxX, const double *WaterFluxY,
+                                     const double *Discharges, const int *ComputeFacesU, const int *ComputeFacesV) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    if (!WaterFluxX || !WaterFluxY || !ComputeFacesU || !ComputeFacesV) return fail(h, MOHID_ADT_ERR_ARG, "null array");
+    if (h->hint_n < 0) return fail(h, MOHID_ADT_ERR_STATE, "hydro_integration_reinit must precede hydro_integration_step");
+    CU(h, cudaSetDevice(h->dev));
+    for (auto &p : h->hint_in) if (!p) if (int rc = dalloc(h, &p, h->n3)) return rc;
+    for (auto &p : h->hint_cf) if (!p) if (int rc = dalloc(h, &p, h->n3)) return rc;
+    if (Discharges && !h->hint_disch) {
+        if (h->hint_n > 0) return fail(h, MOHID_ADT_ERR_STATE, "Discharges must be passed from the first step of an integration on");
+        if (int rc = dalloc(h, &h->hint_disch, h->n3)) return rc;
+        CU(h, cudaMemsetAsync(h->hint_disch, 0, h->n3 * sizeof(double), h->stream));
+    }
+    int rc = h2d3(h, h->hint_in[0], WaterFluxX, 8);
+    if (!rc) rc = h2d3(h, h->hint_in[1], WaterFluxY, 8);
+    if (!rc && Discharges) rc = h2d3(h, h->hint_in[2], Discharges, 8);
+    if (!rc) rc = h2d3(h, h->hint_cf[0], ComputeFacesU, 4);
+    if (!rc) rc = h2d3(h, h->hint_cf[1], ComputeFacesV, 4);
+    if (rc) return rc;
+    HintArgs a{};
+    hint_args(h, a);
+    a.n = ++h->hint_n;
+    a.fx = h->hint_in[0]; a.fy = h->hint_in[1]; a.disch = Discharges ? h->hint_in[2] : nullptr;
+    a.cfu = h->hint_cf[0]; a.cfv = h->hint_cf[1];
+    adt_hint_step_kernel<<<dim3((unsigned)((h->ni + 127) / 128), (unsigned)h->nj, (unsigned)h->nk), 128, 0, h->stream>>>(a);
+    CU(h, cudaGetLastError());
+    h->launches++;
+    CU(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int mohid_adt_hydro_integration_end(const int *handle, const double *VolumeZ, const int *WaterPoints3D, const double *DT) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    if (!VolumeZ || !WaterPoints3D || !DT || !(*DT > 0.)) return fail(h, MOHID_ADT_ERR_ARG, "VolumeZ, WaterPoints3D and DT > 0 are required");
+    if (h->hint_n < 1) return fail(h, MOHID_ADT_ERR_STATE, "no hydrodynamic step was integrated");
+    if (!h->have_grid) return fail(h, MOHID_ADT_ERR_STATE, "set_grid2d must precede hydro_integration_end (BoundaryPoints2D)");
+    CU(h, cudaSetDevice(h->dev));
+    if (int rc = h2d3(h, h->raw_d[4], VolumeZ, 8)) return rc;
+    if (int rc = h2d3(h, h->raw_i[2], WaterPoints3D, 4)) return rc;
+    HintArgs a{};
+    hint_args(h, a);
+    a.dt = *DT;
+    adt_hint_end_kernel<<<dim3((unsigned)((h->I + 127) / 128), (unsigned)h->J), 128, 0, h->stream>>>(a);
+    CU(h, cudaGetLastError());
+    h->launches++;
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->hint_n = -1;
+    return 0;
+}
+
+int mohid_adt_download_step_input(const int *handle, const int *which, void *array) {
+    Handle *h = get(handle);
+    if (!h) return fail(nullptr, MOHID_ADT_ERR_HANDLE, "bad handle");
+    if (!which || !array || *which < 0 || *which > 16) return fail(h, MOHID_ADT_ERR_ARG, "which must be 0..16 and the array present");
+    CU(h, cudaSetDevice(h->dev));
+    const int w = *which;
+    if (int rc = w < 11 ? d2h3(h, array, h->raw_d[w], 8) : d2h3(h, array, h->raw_i[w - 11], 4)) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
     return 0;
 }
 

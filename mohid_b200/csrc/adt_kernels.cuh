@@ -1394,6 +1394,59 @@ __global__ void __launch_bounds__(128) adt_fvm_flux_kernel(const FvmArgs a) {
 }
 
 // -------------------------------------------------------------------------------------
+// ModuleHydroIntegration (MOHIDBase1/ModuleHydroIntegration.F90): the fluxes, mapping and initial volume a property
+// with DTInterval = n hydrodynamic steps is transported with (GetHydroIntegration* at WP:14615-14647).  The integration
+// arrays ARE the handle's step mirrors: OneIntegrationStep (:843-906) keeps the running mean of the horizontal fluxes
+// and the union of the compute faces, EndIntegrationStep (:910-994) closes continuity for Wflux_Z and derives
+// ComputeFacesW3D / OpenPoints3D.
+// -------------------------------------------------------------------------------------
+struct HintArgs {
+    int I, J, K, ni, nj, ld, sj, sk, n;             // n = CurrentIntegration%n after the increment
+    const double *fx, *fy, *disch;                  // this hydrodynamic step (device copies; disch may be null)
+    const int *cfu, *cfv;
+    double *WX, *WY, *WZ, *D;                       // integrated fluxes, discharges
+    int *CFU, *CFV, *CFW, *Open;
+    const int *Water, *Bnd;
+    const double *V, *V0;                           // VolumeZ, InitialVolume
+    double dt;
+};
+__global__ void __launch_bounds__(128) adt_hint_step_kernel(const HintArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;
+    if (i >= a.ni) return;
+    const int q = i + a.sj * j + a.sk * k;
+    if (k < 1 || k > a.K || i < 1 || j < 1) return;
+    const double n = (double)a.n;
+    if (i <= a.I + 1 && j <= a.J + 1) {             // faces: ILB..IUB+1, JLB..JUB+1
+        a.WX[q] = (a.WX[q] * (n - 1.) + a.fx[q]) / n;
+        a.WY[q] = (a.WY[q] * (n - 1.) + a.fy[q]) / n;
+        if (a.cfu[q] > 0) a.CFU[q] = 1;
+        if (a.cfv[q] > 0) a.CFV[q] = 1;
+    }
+    if (i <= a.I && j <= a.J && a.D) a.D[q] = (a.D[q] * (n - 1.) + (a.disch ? a.disch[q] : 0.)) / n;
+}
+__global__ void __launch_bounds__(128) adt_hint_end_kernel(const HintArgs a) {
+    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y;
+    if (i > a.I) return;
+    const int c = i + a.sj * j, c2 = i + a.ld * j, sk = a.sk, sj = a.sj;
+    const double keep = 1.0 - (double)a.Bnd[c2];
+    double wz = a.WZ[c + sk];                                     // Wflux_Z(KLB) = 0 since the re-initialisation
+    for (int k = 1; k <= a.K; ++k) {
+        const int q = c + sk * k;
+        const double dVdt = (a.V[q] - a.V0[q]) / a.dt;
+        wz = (wz + a.WX[q] - a.WX[q + sj] + a.WY[q] - a.WY[q + 1] - dVdt + (a.D ? a.D[q] : 0.)) * keep;
+        a.WZ[q + sk] = wz;
+    }
+    const int qt = c + sk * a.K;
+    if (a.CFU[qt] + a.CFU[qt + sj] + a.CFV[qt] + a.CFV[qt + 1] > 0)
+        for (int k = 2; k <= a.K; ++k)
+            if (a.Water[c + sk * (k - 1)] == 1) a.CFW[c + sk * k] = 1;
+    for (int k = 1; k <= a.K; ++k) {
+        const int q = c + sk * k;
+        if (a.CFU[q] + a.CFU[q + sj] + a.CFV[q] + a.CFV[q + 1] + a.CFW[q] + a.CFW[q + sk] > 0) a.Open[q] = 1;
+    }
+}
+
+// -------------------------------------------------------------------------------------
 // K4: gather / scatter `width` j-columns of nprop properties to / from a contiguous buffer
 // laid out [n][k][w][i] (i fastest).  Coalesced on both sides.
 // -------------------------------------------------------------------------------------
