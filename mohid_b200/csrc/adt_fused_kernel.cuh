@@ -380,6 +380,9 @@ __global__ void __launch_bounds__(MAXW * 32, 1) adt_transport_fused_kernel(const
     if (tile >= s.ntile_i) return;                       // whole block: the last group may be short
     const int i = 1 + tile * 31 + lane;
     const int ic = min(i, s.I + 1);
+    // a strip without a single wet column (land, dry tidal flat) has nothing to solve: adt_carry_kernel has already moved its
+    // cells to the new position.  Every warp of the block sees the same 31 columns, so they all leave, before any hand-over
+    if (!__any_sync(0xffffffffu, lane < 31 && i <= s.I && fa.co.c.Water[ic + s.sj * j + s.sk * s.K] == 1)) return;
 
     // staging areas: property warps first (FC_NV values each), then the four coefficient warps
     double *__restrict__ stage0 = smem + FR_D * FR_SLOT + 2 * FR_D;
