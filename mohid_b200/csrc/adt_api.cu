@@ -1102,7 +1102,7 @@ int mohid_adt_create(int *handle, const mohid_adt_size3d *size, const mohid_adt_
     if (dev < 0) cudaGetDevice(&dev);
     if (dev >= ndev) { delete h; return fail(nullptr, MOHID_ADT_ERR_ARG, "device %d does not exist", dev); }
     h->dev = dev;
-    CU(nullptr, cudaSetDevice(dev));
+    if (cudaSetDevice(dev) != cudaSuccess) { delete h; return fail(nullptr, MOHID_ADT_ERR_CUDA, "cudaSetDevice(%d) failed", dev); }
     h->I = worksize->IUB; h->J = worksize->JUB; h->K = worksize->KUB;
     h->ni = h->I + 2; h->nj = h->J + 2; h->nk = h->K + 2;
     h->j_begin = 1; h->j_count = h->J;
@@ -1158,7 +1158,11 @@ int mohid_adt_create(int *handle, const mohid_adt_size3d *size, const mohid_adt_
     for (auto p : {h->DUX, h->DVY, h->DZX, h->DZY}) cudaMemsetAsync(p, 0, h->n2 * sizeof(double), h->stream);
     for (auto p : {h->KFloorZ, h->Bnd, h->SmallDepths}) cudaMemsetAsync(p, 0, h->n2 * sizeof(int), h->stream);
     cudaMemsetAsync(h->d_zero_piv, 0, sizeof(unsigned long long), h->stream);
-    CU(h, cudaStreamSynchronize(h->stream));
+    if (const cudaError_t e2 = cudaStreamSynchronize(h->stream)) {
+        free_all(h);
+        delete h;
+        return fail(nullptr, MOHID_ADT_ERR_CUDA, "clearing the device mirrors failed: %s", cudaGetErrorString(e2));
+    }
     std::lock_guard<std::mutex> lk(g_mu);
     h->id = g_next++;
     g_h[h->id] = h;
