@@ -54,11 +54,20 @@ __device__ __forceinline__ unsigned fsmem_u32(const void *p) { return (unsigned)
 __device__ __forceinline__ void fbar_init(uint64_t *bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fsmem_u32(bar)), "r"(count));
 }
-// one arrival for the whole warp, after its lanes' shared-memory accesses are ordered by __syncwarp
+// every lane arrives for itself (the barriers count threads): each thread's own shared-memory accesses are then ordered
+// before its own release, with no reliance on warp-level ordering, and compute-sanitizer's racecheck can follow it
+#ifndef FUSED_ELECTED_ARRIVE
+constexpr unsigned FBAR_PER_WARP = 32;
+__device__ __forceinline__ void fbar_arrive_warp(uint64_t *bar, int) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fsmem_u32(bar)) : "memory");
+}
+#else
+constexpr unsigned FBAR_PER_WARP = 1;
 __device__ __forceinline__ void fbar_arrive_warp(uint64_t *bar, int lane) {
     __syncwarp();
     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fsmem_u32(bar)) : "memory");
 }
+#endif
 __device__ __forceinline__ void fbar_wait(uint64_t *bar, unsigned parity) {
     asm volatile(
         "{\n"
@@ -360,14 +369,15 @@ __host__ __device__ constexpr size_t fused_smem_doubles(int K, int nc) {
 
 template <int M, int MAXW>
 __global__ void __launch_bounds__(MAXW * 32, 1) adt_transport_fused_kernel(const __grid_constant__ FusedArgs fa) {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(128) double fused_smem_base[];     // 128-bit shared accesses: the base must be 16-byte aligned
+    double *const smem = fused_smem_base;
     const LeanArgs &s = fa.st;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nthreads = blockDim.x, NC = (nthreads >> 5) - FR_NCW;
     double *__restrict__ ring = smem;
     uint64_t *__restrict__ bars = reinterpret_cast<uint64_t *>(smem + FR_D * FR_SLOT);   // full[FR_D], empty[FR_D]
     if (threadIdx.x == 0) {
-        for (int t = 0; t < FR_D; ++t) { fbar_init(bars + t, FR_NCW); fbar_init(bars + FR_D + t, (unsigned)NC); }
+        for (int t = 0; t < FR_D; ++t) { fbar_init(bars + t, FR_NCW * FBAR_PER_WARP); fbar_init(bars + FR_D + t, (unsigned)NC * FBAR_PER_WARP); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
