@@ -417,9 +417,11 @@ int validate(Handle *h, int nprop, const mohid_adt_params *p, Batch &b) {
             if (h->K == 1)
                 return fail(h, MOHID_ADT_ERR_UNSUPPORTED,
                             "horizontally implicit advection of a 2-D domain (AD:1758-1841) is not available on the GPU path");
-            if (h->j_begin != 1 || h->j_count != h->J)
+            // lines along j (ImpExp_AdvXX) cross the slabs of a decomposed domain (THOMAS_DDecompHorizGrid, HG:8245-8478);
+            // lines along i (ImpExp_AdvYY) lie inside one slab and are solved locally
+            if (q.ImpExp_AdvXX == 1.0 && (h->j_begin != 1 || h->j_count != h->J))
                 return fail(h, MOHID_ADT_ERR_UNSUPPORTED,
-                            "horizontally implicit advection couples whole rows: not available on a column slab (AD:4200-4244)");
+                            "implicit advection along j couples the columns of all slabs: not available on a column slab (AD:4200-4244)");
             if (q.CellFluxes)
                 return fail(h, MOHID_ADT_ERR_UNSUPPORTED, "CellFluxes with horizontally implicit advection are not available");
         }
@@ -876,7 +878,8 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
     CarryArgs ca{};
     ca.ld = h->ld; ca.nk = h->nk; ca.I = h->I; ca.K = h->K; ca.sj = h->sj; ca.sk = h->sk; ca.ja = ja; ca.jb = jb;
     ca.Water = h->raw_i[2];
-    for (int m = 0; m < s.nprop; ++m) { ca.src[m] = s.p[m].pin; ca.dst[m] = s.p[m].pout; }
+    // cells the step does not advance keep the field at time n (in a two-stage step pin is the intermediate field)
+    for (int m = 0; m < s.nprop; ++m) { ca.src[m] = cur_ptr(h, idx[m]); ca.dst[m] = s.p[m].pout; }
     const bool packs_per_chunk = lean && !fused && h->pk_ncol < h->nj;
     if (timed) h->ev_steps++;
     for (const Chunk &c : chunk_order(h, shift0 == h->S)) {

@@ -62,3 +62,22 @@ def test_chunks_on_a_column_slab(monkeypatch):
     for a, b, p0 in zip(whole, parts, props):
         assert np.array_equal(a, b)
         assert np.array_equal(b[:, :9, :], p0[:, :9, :]) and np.array_equal(b[:, 41:, :], p0[:, 41:, :])
+
+
+def test_implicit_advection_along_i_on_a_column_slab():
+    """ImpExp_AdvYY = 1: the line solve (THOMAS_3D, di = 1) runs along i, inside the slab; the owned columns of a slab equal
+    those of the undivided run after one step.  Along j (ImpExp_AdvXX = 1) the lines cross the slabs: refused."""
+    from mohid_b200.advection_diffusion import TransportStep
+    from mohid_b200.capi import AdtError
+    case = make_case(45, 58, 7, nprop=2, stepped_bottom=True)
+    _, g, s, props, refs = oracle_for(case)
+    prm = [dict(default_params(1, 4, 1, 4, bc=4), ImpExp_AdvYY=1.0) for _ in range(2)]
+    whole, _ = _run(case, g, s, props, refs, prm, 1)
+    part, _ = _run(case, g, s, props, refs, prm, 1, active=(9, 32))
+    for a, b, p0 in zip(whole, part, props):
+        assert np.array_equal(a[:, 9:41, :], b[:, 9:41, :])
+        assert np.array_equal(b[:, :9, :], p0[:, :9, :]) and np.array_equal(b[:, 41:, :], p0[:, 41:, :])
+        assert not np.array_equal(b[:, 9:41, :], p0[:, 9:41, :])
+    prm_x = [dict(default_params(1, 4, 1, 4, bc=4), ImpExp_AdvXX=1.0) for _ in range(2)]
+    with pytest.raises(AdtError, match="column slab"):
+        _run(case, g, s, props, refs, prm_x, 1, active=(9, 32))
