@@ -276,7 +276,9 @@ int mohid_adt_prop_device_ptr(const int *handle, const int *n, void **dptr, int 
 
 /* Every array pointer accepted above may be a host pointer (the Fortran caller) or, under CUDA
  * unified virtual addressing, a device pointer (device-side producers, the benchmark generator):
- * copies use cudaMemcpyDefault. */
+ * copies use cudaMemcpyDefault.
+ * A device array must be complete when the call is made: the library copies on its own stream (or on the one given to
+ * mohid_adt_set_stream, which orders it after that stream's earlier work). */
 /* Wait for all work queued on the handle's stream. */
 int mohid_adt_synchronize(const int *handle);
 /* No-op since round 2 (one buffer per property); kept so that round-1 hosts still link. */

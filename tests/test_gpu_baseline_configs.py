@@ -90,6 +90,7 @@ def test_c3_window_20_steps(oracle_lib):
     from mohid_b200.advection_diffusion import TransportStep
     I, J, K, N, steps = 2048, 2048, 40, 10, 20
     case = make_case(I, J, K, nprop=N, device="cuda", make_refs=False)
+    torch.cuda.synchronize()
     ts = TransportStep(I, J, K)
     ts.set_grid2d(**case.grid2d)
     ts.set_step(case.step)
@@ -163,3 +164,65 @@ def test_limiter_argument_clamp_on_plateaus(oracle_lib, nprop):
     worst = _check(gpu, cpu, s, 1e-13)
     print(f"clamp plateaus, {nprop} properties: max relative difference {worst:.3e}")
     ts.close()
+
+
+def test_c4_window_across_a_chunk_boundary(oracle_lib):
+    """C4 (4096 x 4096 x 40, 10 properties: bench.py's default workload) on ONE GPU, generated in column pieces straight into
+    the device mirrors and advanced with the in-place step in 17 chunks of 256 columns; a window that straddles the chunk
+    boundary at column 1024 (and an island corner) is read back with the column-window download and compared with the
+    oracle run on that window."""
+    free, _ = torch.cuda.mem_get_info()
+    if free / 2**30 < 165:
+        pytest.skip("needs ~150 GB of device memory")
+    from mohid_b200.advection_diffusion import TransportStep
+    from mohid_b200.synthetic import case_pieces
+    I, J, K, N, steps = 4096, 4096, 40, 10, 5
+    ts = TransportStep(I, J, K, max_properties=N)
+    g2, dt = {}, None
+    for j0, pc in case_pieces(I, J, K, N, piece=64, device="cuda"):
+        dt = pc.dt
+        torch.cuda.synchronize()          # the library copies on its own stream: the generator's kernels must have finished
+        ts.set_step_columns(j0, pc.step)
+        ts.upload_columns(j0, pc.props)
+        for k, v in pc.grid2d.items():
+            g2.setdefault(k, []).append(v)
+        del pc
+    ts.set_grid2d(**{k: torch.cat(v, 0).contiguous() for k, v in g2.items()})
+    ts.mark_step_resident()
+    del g2
+    prm = [default_params(4, 4, 4, 4, dt=dt) for _ in range(N)]
+    ts.advect_device(prm, nsteps=steps)
+    m = 3 * steps
+    wi, wj = 70 + 2 * m, 60 + 2 * m
+    i0, j0 = int(0.20 * I) - 30 - m, 1024 - 30 - m                   # window columns j0 .. j0+wj-1 around column 1024
+    # the window's own inputs: the same generator, restricted to its columns (identical to the undivided case)
+    pcs = list(case_pieces(I, J, K, N, j_lo=j0, j_hi=j0 + wj - 1, piece=wj + 2, device="cpu"))
+    assert len(pcs) == 1
+    wc = pcs[0][1]
+    si = slice(i0 - 1, i0 + wi + 1)
+    g = {k: np.ascontiguousarray(v[:, si].numpy()) for k, v in wc.grid2d.items()}
+    s = {k: np.ascontiguousarray(v[:, :, si].numpy()) for k, v in wc.step.items()}
+    s["OpenPoints3D"][:, 0, :] = 0; s["OpenPoints3D"][:, -1, :] = 0
+    s["OpenPoints3D"][:, :, 0] = 0; s["OpenPoints3D"][:, :, -1] = 0
+    cpu = [np.ascontiguousarray(p[:, :, si].numpy()) for p in wc.props]
+    out_full = [np.zeros((K + 2, wj + 2, I + 2)) for _ in range(N)]
+    ts.download_columns(j0 - 1, out_full)                             # local column index = global column (single GPU)
+    out = [np.ascontiguousarray(p[:, :, si]) for p in out_full]
+    ts.close()
+    o = oracle_lib.OracleAdvectionDiffusion(wi, wj, K)
+    o.set_grid2d(g)
+    o.set_step(s)
+    for _ in range(steps):
+        o.advect_batch(cpu, prm)
+    inner = (slice(1, K + 1), slice(1 + m, wj + 1 - m), slice(1 + m, wi + 1 - m))
+    wmask = s["WaterPoints3D"][inner] == 1
+    assert wmask.sum() > 1000 and (~wmask).sum() > 1000
+    worst = 0.0
+    for a, b in zip(out, cpu):
+        ga, cb = a[inner], b[inner]
+        assert np.array_equal(ga == NULL_REAL, cb == NULL_REAL)
+        assert np.array_equal(ga[~wmask], cb[~wmask])
+        d = np.abs(ga[wmask] - cb[wmask]) / np.maximum(np.abs(cb[wmask]), 1.0)
+        worst = max(worst, float(d.max()))
+    assert worst < 1e-11, worst
+    print(f"C4 window across the chunk boundary after {steps} steps: max relative difference {worst:.3e}")

@@ -31,6 +31,7 @@ def test_mass_conservation_closed_basin_large():
     from mohid_b200.advection_diffusion import TransportStep
     I2, J2, K2, N2 = 1024, 1024, 40, 4
     case = make_case(I2, J2, K2, nprop=N2, device="cuda", make_refs=False, closed=True, volume_change=0.0)
+    torch.cuda.synchronize()              # the library copies on its own stream
     ts = TransportStep(I2, J2, K2)
     ts.set_grid2d(**case.grid2d)
     ts.set_step(case.step)
@@ -55,6 +56,7 @@ def big():
         pytest.skip("needs ~110 GB of device memory")
     from mohid_b200.advection_diffusion import TransportStep
     case = make_case(I, J, K, nprop=N, device="cuda", make_refs=False)
+    torch.cuda.synchronize()              # the library copies on its own stream
     ts = TransportStep(I, J, K)
     ts.set_grid2d(**case.grid2d)
     ts.set_step(case.step)
