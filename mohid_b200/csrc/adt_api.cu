@@ -414,9 +414,6 @@ int validate(Handle *h, int nprop, const mohid_adt_params *p, Batch &b) {
         if (q.ImpExp_AdvV != 0.0 && q.ImpExp_AdvV != 1.0)
             return fail(h, MOHID_ADT_ERR_ARG, "sub. VerticalAdvection - ModuleAdvectionDiffusion - ERR01");
         if ((q.ImpExp_AdvXX == 1.0 || q.ImpExp_AdvYY == 1.0) && !h->opt.Vertical1D) {
-            if (h->K == 1)
-                return fail(h, MOHID_ADT_ERR_UNSUPPORTED,
-                            "horizontally implicit advection of a 2-D domain (AD:1758-1841) is not available on the GPU path");
             // lines along j (ImpExp_AdvXX) cross the slabs of a decomposed domain (THOMAS_DDecompHorizGrid, HG:8245-8478);
             // lines along i (ImpExp_AdvYY) lie inside one slab and are solved locally
             if (q.ImpExp_AdvXX == 1.0 && (h->j_begin != 1 || h->j_count != h->J))
@@ -748,6 +745,7 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
             hs.wline[m] = h->wline[n];
             s.p[m].pout = h->hs_tmp[n];
         }
+        s.twod = h->K == 1 ? 1 : 0;
         const int nc = hdir == 1 ? h->I : h->J;
         const long nunits = (long)s.nprop * ((nc + 30) / 31) * h->K;
         const long blocks = (nunits + 7) / 8;
@@ -761,6 +759,9 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
         stage2 = true;
     }
     s.stage2 = stage2 ? 1 : 0;
+    // 2-D domain, horizontally implicit (AD:1758-1841): the line solve was the whole step; the chunk walk below only moves
+    // its result into the new position
+    const bool line_only = stage2 && h->K == 1;
     // ---- kernel variant and launch shape ----
     bool any_disch = false, all_impv = true;
     for (int m = 0; m < s.nprop; ++m) {
@@ -880,6 +881,7 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
     ca.Water = h->raw_i[2];
     // cells the step does not advance keep the field at time n (in a two-stage step pin is the intermediate field)
     for (int m = 0; m < s.nprop; ++m) { ca.src[m] = cur_ptr(h, idx[m]); ca.dst[m] = s.p[m].pout; }
+    if (line_only) { ca.twod = 1; for (int m = 0; m < s.nprop; ++m) ca.line[m] = h->hs_tmp[idx[m]]; }
     const bool packs_per_chunk = lean && !fused && h->pk_ncol < h->nj;
     if (timed) h->ev_steps++;
     for (const Chunk &c : chunk_order(h, shift0 == h->S)) {
@@ -888,7 +890,7 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
         CU(h, cudaGetLastError());
         h->launches++;
         const int ka = std::max(c.a, ja), kb = std::min(c.b, jb);
-        if (ka > kb) continue;
+        if (ka > kb || line_only) continue;
         if (packs_per_chunk) if (int rc = launch_lean_coef(h, b.p[idx[0]], b.eff[idx[0]], ka, kb - ka + 2)) return rc;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (timed) {

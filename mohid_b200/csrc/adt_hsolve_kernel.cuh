@@ -13,6 +13,8 @@
 //   option, off by default, WP:9565, and the reference serves it by gathering whole rows on the master).
 //   G of the recurrence is parked in the output array, W in a per-property scratch array.
 //
+// StepArgs::twod (K = 1): the line solve is the whole step, see below.
+//
 // A zero pivot stops the reference ('Instability in THOMAS3D', MF:3799); here it is counted in zero_pivots.
 #pragma once
 
@@ -121,9 +123,19 @@ __global__ void __launch_bounds__(256) adt_hsolve_kernel(const __grid_constant__
                   (m & O_LP2) != 0, t_w, dtv_c, t_e, t_e2, rdL[p2], rdL[p2 + sl2], rdL[p2 + lp2_2], duL[p2], duL[p2 + sl2],
                   dfl_e, efl_e);
         (void)Pw2; (void)O_LM2;
-        const double D = -dfl_w * dtv_c;
-        const double E = (e0 - efl_w * dtv_c) + dfl_e * dtv_c;
-        const double F = efl_e * dtv_c;
+        double D = -dfl_w * dtv_c;
+        double E = (e0 - efl_w * dtv_c) + dfl_e * dtv_c;
+        double F = efl_e * dtv_c;
+        if (s.twod) {
+            // 2-D domain (K = 1, AD:1758-1841): there is no second stage; the open-boundary rows (AD:1745-1747) and the land
+            // fill (AD:1753) enter the line system itself
+            if ((m & M_BND) && open_c && pa.bc != MOHID_BC_None) {
+                Row row{D, E, F, ti};
+                open_boundary_row<false>(s, pa, q, m, Pc, s.qz[q], s.qz[q + sk], dtv_c, row);
+                D = row.D; E = row.E; F = row.F; ti = row.TI;
+            }
+            if (m & M_LAND) ti = NULL_REAL;
+        }
         // ---------------- recurrence along the line (MF:3790-3801) ----------------
         const double aux = E + D * Wprev;
         if (aux != 0.) {

@@ -319,7 +319,7 @@ struct StepArgs {
     int j_begin, j_count;                       // columns j_begin .. j_begin+j_count-1 are advanced
     int method_h, limiter_h, method_v, limiter_v, upwind2_h, upwind2_v;
     int vertical1d, xzflow;
-    int stage2, pad1;                           // see adt_transport_kernel
+    int stage2, twod;                           // see adt_transport_kernel; twod: adt_hsolve_kernel on a 2-D domain (K = 1)
     double vrelmax, dt;
     const double *qx, *qy, *qz, *dtv, *vr, *dhu, *dhv, *dvz, *rdz;
     const uint32_t *mask;
@@ -1076,6 +1076,8 @@ struct CarryArgs {
     const int *Water;
     const double *src[NPMAX];
     double *dst[NPMAX];
+    const double *line[NPMAX];                // 2-D horizontally implicit step: the line solve's result, which IS the new field
+    int twod;
 };
 __global__ void __launch_bounds__(128) adt_carry_kernel(const CarryArgs a) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x, j = a.j0 + blockIdx.y, n = blockIdx.z;
@@ -1084,6 +1086,12 @@ __global__ void __launch_bounds__(128) adt_carry_kernel(const CarryArgs a) {
     double *__restrict__ D = a.dst[n];
     const int c = i + a.sj * j;
     const bool solved = j >= a.ja && j <= a.jb && i >= 1 && i <= a.I && a.Water[c + a.sk * a.K] == 1;   // MF:4086
+    if (a.twod) {
+        // every cell of a line was solved (land cells included, THOMAS_3D has no water mask, MF:3751-3875)
+        const bool on_line = j >= a.ja && j <= a.jb && i >= 1 && i <= a.I;
+        for (int k = 0; k < a.nk; ++k) D[c + a.sk * k] = (on_line && k >= 1 && k <= a.K ? a.line[n] : S)[c + a.sk * k];
+        return;
+    }
     if (solved) { D[c] = S[c]; return; }       // rows 1 .. K+1 are written by the step kernel
     for (int k = 0; k < a.nk; ++k) D[c + a.sk * k] = S[c + a.sk * k];
 }

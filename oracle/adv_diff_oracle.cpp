@@ -24,8 +24,8 @@
 //     WP  = MOHIDWater/ModuleWaterProperties.F90
 //
 //  Not restated (returns ORACLE_ERR_UNSUPPORTED): AdvectionNudging (AD:1989-2068; it reads
-//  uninitialised indices in the reference) and the 2-D (K = 1) / decomposed forms of the
-//  horizontally implicit solve (AD:1758-1841, HG:8245-8478).  Horizontally implicit advection
+//  uninitialised indices in the reference) and the decomposed form of the horizontally implicit
+//  solve (THOMAS_DDecompHorizGrid, HG:8245-8478); its 2-D (K = 1) form (AD:1758-1841) is.  Horizontally implicit advection
 //  in 3-D (AD:4167-4258, THOMAS_3D MF:3667-3875) and the Orlanski boundary (MF:4129-4500) are.
 // =====================================================================================
 #include <algorithm>
@@ -1591,10 +1591,13 @@ int AdvectionDiffusionIteration(Oracle &o) {
     SetMatrixValue(o, o.TI, null_real, o.LandPoints3D);       // AD:1753
 
     if (o.W.KUB == 1 && (o.P.ImpExp_AdvXX == ImplicitScheme || o.P.ImpExp_AdvYY == ImplicitScheme)) {
-        o.err = "THOMAS_3D (2-D horizontally implicit, AD:1758-1841) is not restated in the oracle";
-        return ORACLE_ERR_UNSUPPORTED;
+        // 2-D domain, horizontally implicit (AD:1758-1841, the branch without domain decomposition): the one system --
+        // explicit terms, the implicit direction's D / E / F, open-boundary rows, land fill -- is solved along the lines
+        if (o.P.ImpExp_AdvXX == ImplicitScheme) { if ((rc = THOMAS_3D(o, 0, 1))) return rc; }
+        else if ((rc = THOMAS_3D(o, 1, 0))) return rc;
+    } else {
+        THOMASZ_NewType2(o);
     }
-    THOMASZ_NewType2(o);
 
     if (o.P.BoundaryCondition == MOHID_BC_NullGradient) ImposeNullGradient(o);
     else if (o.P.BoundaryCondition == MOHID_BC_CyclicBoundary) Prop_CyclicBoundary(o);

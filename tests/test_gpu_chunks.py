@@ -81,3 +81,31 @@ def test_implicit_advection_along_i_on_a_column_slab():
     prm_x = [dict(default_params(1, 4, 1, 4, bc=4), ImpExp_AdvXX=1.0) for _ in range(2)]
     with pytest.raises(AdtError, match="column slab"):
         _run(case, g, s, props, refs, prm_x, 1, active=(9, 32))
+
+
+@pytest.mark.parametrize("chunk", [0, 5])
+def test_2d_domain_line_solve_in_chunks_and_on_a_slab(oracle_lib, monkeypatch, chunk):
+    """K = 1, horizontally implicit (AD:1758-1841): the line solve's result is moved into the shifted position chunk by
+    chunk; along i it also runs on a column slab."""
+    case = make_case(45, 58, 1, nprop=2)
+    o, g, s, props, refs = oracle_for(case)
+    prm = [dict(default_params(4, 4, 4, 4, bc=4), ImpExp_AdvYY=1.0), dict(default_params(4, 4, 4, 4, bc=1), ImpExp_AdvXX=1.0)]
+    if chunk:
+        monkeypatch.setenv("MOHID_ADT_CHUNK_COLS", str(chunk))
+    else:
+        monkeypatch.delenv("MOHID_ADT_CHUNK_COLS", raising=False)
+    gpu, zp = _run(case, g, s, props, refs, prm, 3)
+    assert zp == 0
+    cpu = [p.copy() for p in props]
+    for _ in range(3):
+        o.advect_batch(cpu, prm, refs)
+    w = water_mask(s)
+    for a, b in zip(gpu, cpu):
+        assert np.array_equal(a[~w], b[~w])
+        assert rel_err(a, b, w) <= 5e-12
+    prm_y = [prm[0], prm[0]]
+    whole, _ = _run(case, g, s, props, refs, prm_y, 1)
+    part, _ = _run(case, g, s, props, refs, prm_y, 1, active=(9, 32))
+    for a, b, p0 in zip(whole, part, props):
+        assert np.array_equal(a[:, 9:41, :], b[:, 9:41, :])
+        assert np.array_equal(b[:, :9, :], p0[:, :9, :]) and np.array_equal(b[:, 41:, :], p0[:, 41:, :])

@@ -459,14 +459,24 @@ def test_horizontally_implicit_advection(oracle_lib, method, bc):
     ts.close()
 
 
-def test_horizontally_implicit_limits():
-    from mohid_b200.capi import AdtError
-    case = make_case(20, 20, 1, nprop=1)
+@pytest.mark.parametrize("method", [(1, 4), (4, 4)])
+@pytest.mark.parametrize("bc", [0, 4, 1, 5])
+def test_horizontally_implicit_2d_domain(oracle_lib, method, bc):
+    """K = 1 (AD:1758-1841): no vertical system; explicit terms, the implicit direction, open-boundary rows and land fill
+    are one tridiagonal system per line (THOMAS_3D).  XX-implicit, YY-implicit and explicit properties in one batch."""
+    mh, lim = method
+    case = make_case(45, 38, 1, nprop=3)
     o, g, s, props, refs = oracle_for(case)
+    base = default_params(mh, lim, mh, lim, bc=bc, decay_time=600.0)
+    prm = [dict(base, ImpExp_AdvXX=1.0), dict(base, ImpExp_AdvYY=1.0), dict(base)]
     ts = gpu_for(case, g, s)
-    with pytest.raises(AdtError) as e:
-        ts.advect_batch([props[0].copy()], [dict(default_params(1, 4, 1, 4), ImpExp_AdvXX=1.0)])
-    assert e.value.code == 21
+    gpu, cpu = [p.copy() for p in props], [p.copy() for p in props]
+    for step in range(3):
+        ts.advect_batch(gpu, prm, refs)
+        o.advect_batch(cpu, prm, refs)
+        prm[0], prm[1] = dict(prm[1]), dict(prm[0])
+    compare(gpu, cpu, s, 3 * TOL_STEP)
+    assert ts.counters()["zero_pivots"] == 0
     ts.close()
 
 

@@ -210,6 +210,26 @@ def test_horizontally_implicit_conserves_mass(oracle_lib, mh, direction):
     assert np.array_equal(a[0] == NULL_REAL, props[0] == NULL_REAL)
 
 
+@pytest.mark.parametrize("direction", ["xx", "yy"])
+def test_horizontally_implicit_2d_domain_conserves_mass(oracle_lib, direction):
+    """K = 1 (AD:1758-1841): the line solve is the whole step.  Closed basin: mass conserved to round-off, land stays
+    land, the result stays close to the explicit one."""
+    case = make_case(40, 36, 1, nprop=1, closed=True, volume_change=False)
+    o, g, s, props, refs = oracle_for(case)
+    w = water_mask(s)
+    V = s["VolumeZ"]
+    imp = dict(default_params(4, 4, 4, 4), **({"ImpExp_AdvXX": 1.0} if direction == "xx" else {"ImpExp_AdvYY": 1.0}))
+    exp = default_params(4, 4, 4, 4)
+    a, b = [props[0].copy()], [props[0].copy()]
+    m0 = (a[0] * V)[w].sum()
+    for _ in range(3):
+        o.advect_batch(a, [imp])
+        o.advect_batch(b, [exp])
+    assert abs((a[0] * V)[w].sum() - m0) <= 1e-12 * abs(m0)
+    assert np.abs(a[0] - b[0])[w].max() < 0.5 and not np.array_equal(a[0], b[0])
+    assert np.array_equal(a[0] == NULL_REAL, props[0] == NULL_REAL)
+
+
 def test_caller_premix_conserves_mass_and_flags_shallow_columns(oracle_lib):
     """FreeConvection / SmallDepthsMixing_Processes (WP:13017-13074, 12939-13012) replace part of a column by its
     volume-weighted mean: the column mass is unchanged, mixed cells are uniform, the ON flag marks thin open columns."""
