@@ -419,8 +419,6 @@ int validate(Handle *h, int nprop, const mohid_adt_params *p, Batch &b) {
             if (q.ImpExp_AdvXX == 1.0 && (h->j_begin != 1 || h->j_count != h->J))
                 return fail(h, MOHID_ADT_ERR_UNSUPPORTED,
                             "implicit advection along j couples the columns of all slabs: not available on a column slab (AD:4200-4244)");
-            if (q.CellFluxes)
-                return fail(h, MOHID_ADT_ERR_UNSUPPORTED, "CellFluxes with horizontally implicit advection are not available");
         }
         for (int m : {q.AdvMethodH, q.AdvMethodV})
             if (m < MOHID_UpwindOrder1 || m > MOHID_LeapFrog)
@@ -437,8 +435,6 @@ int validate(Handle *h, int nprop, const mohid_adt_params *p, Batch &b) {
         if (bc == MOHID_BC_Orlanski) {
             if (h->bnd_off_ring)
                 return fail(h, MOHID_ADT_ERR_ARG, "Orlanski Advection 2 (a boundary point is not on the outer ring, AD:5518)");
-            if (h->j_begin != 1 || h->j_count != h->J)
-                return fail(h, MOHID_ADT_ERR_UNSUPPORTED, "Orlanski boundary is not available on a column slab");
         }
         if (bc == MOHID_BC_CyclicBoundary && (h->j_begin != 1 || h->j_count != h->J))
             return fail(h, MOHID_ADT_ERR_UNSUPPORTED,
@@ -964,6 +960,9 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
         fa.vrelmax = q.VolumeRelMax; fa.w_advv = q.ImpExp_AdvV; fa.theta = q.ImpExp_DifV;
         fa.nfmask = s.nfmask; fa.nfsel = b.eff[n].nfsel;
         fa.pold = h->old_copy[n]; fa.pnew = cur_ptr(h, n);
+        // split step (K > 1): the vertical half restarted from the line solve's result, still in its scratch field
+        fa.pmid = (hdir && h->K > 1) ? h->hs_tmp[n] : fa.pold;
+        fa.impl_x = hdir == 1; fa.impl_y = hdir == 2;
         fa.qx = s.qx; fa.qy = s.qy; fa.qz = s.qz; fa.dtv = h->dtv; fa.dhu = h->dhu; fa.dhv = h->dhv; fa.dvz = h->dvz;
         fa.rdz = h->rdz; fa.rdx = s.rdx; fa.rdy = s.rdy; fa.DUX = s.DUX; fa.DVY = s.DVY; fa.DWZ = s.DWZ; fa.mask = h->mask;
         fa.ax = h->flux[0][n]; fa.ay = h->flux[1][n]; fa.az = h->flux[2][n];

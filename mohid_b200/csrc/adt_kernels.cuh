@@ -1158,7 +1158,9 @@ struct FluxArgs {
     int method_h, limiter_h, method_v, limiter_v, upwind2_h, upwind2_v, vertical1d, xzflow;
     const unsigned char *nfmask; unsigned nfsel;   // as in StepArgs / PropArgs
     double vrelmax, w_advv, theta;                 // ImpExp_AdvV (0 or 1), ImpExp_DifV as passed by the caller
-    const double *pold, *pnew;
+    const double *pold, *pnew;                     // field at time n / n+1
+    const double *pmid;                            // the field the vertical half started from (= pold unless the step was split)
+    int impl_x, impl_y;                            // ImpExp_AdvXX / ImpExp_AdvYY == ImplicitScheme: that direction's flux takes the new field
     const double *qx, *qy, *qz, *dtv, *dhu, *dhv, *dvz, *rdz, *rdx, *rdy, *DUX, *DVY, *DWZ;
     const uint32_t *mask;
     double *ax, *ay, *az, *dx, *dy, *dz;
@@ -1196,7 +1198,8 @@ __global__ void __launch_bounds__(128) adt_cell_flux_kernel(const FluxArgs a) {
             double adv = 0.;
             if (all_set(m, M_O_JM1 | M_OPEN) && !(nf & NF_WEST)) {
                 const double t[4] = {a.dtv[q - jw2], a.dtv[q - sj], a.dtv[q], a.dtv[q + sj]};
-                adv = adv_face_flux(a.method_h, a.limiter_h, a.upwind2_h != 0, a.vrelmax, a.qx[q], Pw, Pw,
+                const double Pn[4] = {N[q - jw2], N[q - sj], N[q], N[q + sj]};
+                adv = adv_face_flux(a.method_h, a.limiter_h, a.upwind2_h != 0, a.vrelmax, a.qx[q], Pw, a.impl_x ? Pn : Pw,
                                     (m & M_O_JM2) != 0, (m & M_O_JP1) != 0, t, a.rdx[q2 - sj2], a.rdx[q2],
                                     a.rdx[q2 + sj2], a.DUX[q2 - sj2], a.DUX[q2]);
             }
@@ -1209,7 +1212,8 @@ __global__ void __launch_bounds__(128) adt_cell_flux_kernel(const FluxArgs a) {
             double adv = 0.;
             if (all_set(m, M_O_IM1 | M_OPEN)) {
                 const double t[4] = {a.dtv[q - (i >= 2 ? 2 : 1)], a.dtv[q - 1], a.dtv[q], a.dtv[q + 1]};
-                adv = adv_face_flux(a.method_h, a.limiter_h, a.upwind2_h != 0, a.vrelmax, a.qy[q], Pw, Pw,
+                const double Pn[4] = {N[q - (i >= 2 ? 2 : 1)], N[q - 1], N[q], N[q + 1]};
+                adv = adv_face_flux(a.method_h, a.limiter_h, a.upwind2_h != 0, a.vrelmax, a.qy[q], Pw, a.impl_y ? Pn : Pw,
                                     (m & M_O_IM2) != 0, (m & M_O_IP1) != 0, t, a.rdy[q2 - 1], a.rdy[q2], a.rdy[q2 + 1],
                                     a.DVY[q2 - 1], a.DVY[q2]);
             }
@@ -1221,7 +1225,8 @@ __global__ void __launch_bounds__(128) adt_cell_flux_kernel(const FluxArgs a) {
     if (a.K > 1 && (m & M_CFWT)) {
         const int qt = q + sk;
         const int q2k = (k + 2 <= a.K + 1) ? q + 2 * sk : qt;
-        const double Pw[4] = {P[q - sk], P[q], P[qt], P[q2k]};
+        const double *__restrict__ Mf = a.pmid;
+        const double Pw[4] = {Mf[q - sk], Mf[q], Mf[qt], Mf[q2k]};
         const double Pn[4] = {N[q - sk], N[q], N[qt], N[q2k]};
         double dif = 0.;
         if (a.theta < 1.) dif = dif - (1. - a.theta) * a.dvz[qt] * (Pw[2] - Pw[1]);      // VerticalDiffusion share (AD:2768)

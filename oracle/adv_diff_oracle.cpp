@@ -1605,6 +1605,10 @@ int AdvectionDiffusionIteration(Oracle &o) {
     if (o.st_CellFluxes) {
         if (o.P.ImpExp_AdvV > 0.0 && o.W.KUB > 1) CalcVerticalAdvFlux(o, o.P.ImpExp_AdvV);
         if (o.P.ImpExp_DifV > 0.0 && o.W.KUB > 1) CalcVerticalDifFlux(o, o.P.ImpExp_DifV);
+        // an implicit horizontal direction: its coefficients (built from the field at time n) times the FINAL field
+        // (AD:1895-1899 / 1908-1912) -- after a split step not the flux the line solve applied, which used the intermediate field
+        if (o.P.ImpExp_AdvXX == ImplicitScheme) CalcHorizontalAdvFluxXX(o, o.P.ImpExp_AdvXX);
+        if (o.P.ImpExp_AdvYY == ImplicitScheme) CalcHorizontalAdvFluxYY(o, o.P.ImpExp_AdvYY);
     }
     return 0;
 }

@@ -480,6 +480,31 @@ def test_horizontally_implicit_2d_domain(oracle_lib, method, bc):
     ts.close()
 
 
+@pytest.mark.parametrize("K", [7, 1])
+@pytest.mark.parametrize("direction", ["XX", "YY"])
+@pytest.mark.parametrize("method", [1, 4])
+def test_cell_fluxes_with_horizontally_implicit_advection(oracle_lib, K, direction, method):
+    """AD:1895-1899 / 1908-1912: the implicit direction's cell flux is its coefficients (field at time n) times the final
+    field; after a split step the vertical shares start from the line solve's result."""
+    case = make_case(44, 38, K, nprop=2, stepped_bottom=K > 1)
+    o, g, s, props, refs = oracle_for(case)
+    ts = gpu_for(case, g, s)
+    prm = [dict(default_params(method, 4, method, 4, impexp_advv=1.0, theta_difv=0.6, bc=4), CellFluxes=1,
+                **{"ImpExp_Adv" + direction: 1.0}) for _ in range(2)]
+    gpu, cpu = [p.copy() for p in props], [p.copy() for p in props]
+    for _ in range(2):
+        ts.advect_batch(gpu, prm, refs)
+        o.advect_batch(cpu, prm, refs)
+    compare(gpu, cpu, s, 2 * TOL_STEP)
+    fg, fc = ts.get_cell_fluxes(1), o.get_cell_fluxes()
+    for name in fc:
+        scale = max(np.abs(fc[name]).max(), 1e-30)
+        assert np.abs(fg[name] - fc[name]).max() / scale < 1e-12, name
+        assert np.array_equal(fg[name] == 0, fc[name] == 0), name
+    assert np.abs(fc["AdvFlux" + direction[0]]).max() > 0
+    ts.close()
+
+
 @pytest.mark.parametrize("use", ["free_convection", "small_depths", "offsets", "all"])
 def test_caller_side_pre_steps(oracle_lib, use):
     """FreeConvection, SmallDepthsMixing_Processes and AddOffSet of WP:14716-14759 / 14833-14858, done by the library

@@ -157,6 +157,30 @@ def test_cell_fluxes_close_the_cell_budget(oracle_lib, optimize):
     assert np.abs(lhs - net)[w].max() / np.abs(tot["X"]).max() < 1e-12
 
 
+@pytest.mark.parametrize("direction", ["XX", "YY"])
+def test_cell_fluxes_close_the_budget_of_a_2d_implicit_step(oracle_lib, direction):
+    """K = 1, horizontally implicit: one system, so the implicit direction's flux with the final field (AD:1895-1899) closes
+    the cell budget exactly like the explicit ones."""
+    case = make_case(30, 26, 1, nprop=1, closed=True)
+    o, g, s, props, refs = oracle_for(case)
+    p = props[0]
+    p0 = p.copy()
+    prm = dict(default_params(4, 4, 4, 4), CellFluxes=1, **{"ImpExp_Adv" + direction: 1.0})
+    o.now += 30.0
+    o.advection_diffusion(p, prm, optimize=False, first_property=True)
+    fl = o.get_cell_fluxes()
+    J, I = case.J, case.I
+    tot = {d: fl["AdvFlux" + d] + fl["DifFlux" + d] for d in "XY"}
+    c = (slice(1, 2), slice(1, J + 1), slice(1, I + 1))
+    net = tot["X"][c] - tot["X"][1:2, 2:J + 2, 1:I + 1] + tot["Y"][c] - tot["Y"][1:2, 1:J + 1, 2:I + 2]
+    V = s["VolumeZ"]
+    # the only layer is the surface layer: its row carries the water flux through the top face implicitly (AD:3990-4005)
+    lhs = (V * (p - p0 * s["VolumeZOld"] / V) / 30.0 + s["Wflux_Z"][2:3] * p)[c]
+    w = s["OpenPoints3D"][c] == 1
+    assert not np.array_equal(p, p0)
+    assert np.abs(lhs - net)[w].max() / np.abs(tot["X"]).max() < 1e-12
+
+
 def test_noflux_cells_block_fluxes_and_carry_over(oracle_lib):
     """NoAdvFlux / NoDifFlux (AD:4434-4443, 4804-4813, 3004-3013, 2497-2501): with every face listed and closed
     boundaries a flagged property only feels the volume change; NoFluxV alone changes nothing for the flagged
