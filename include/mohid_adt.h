@@ -320,7 +320,11 @@ int mohid_adt_set_stream(const int *handle, void *cuda_stream);
  *   exchange_halos     : after a step: first / last `ghost` owned columns of properties 0..nprop-1 -> neighbours'
  *                        ghost columns (pack -> ncclSend/ncclRecv -> unpack on the handle's communication stream;
  *                        the next step, a download or mohid_adt_synchronize waits for it);
- *   comm_destroy       : collective. */
+ *   comm_destroy       : collective.
+ * With a communicator the steps themselves become collective when a property is advected implicitly along j
+ * (ImpExp_AdvXX = 1): the lines cross the slabs and their tridiagonal recurrence passes from rank to rank inside
+ * mohid_adt_advect_batch / mohid_adt_advect_device (the reference gathers such rows on one process,
+ * THOMAS_DDecompHorizGrid, ModuleHorizontalGrid.F90:8245-8478); every rank must then make the same calls. */
 int mohid_adt_comm_get_unique_id(void *unique_id, const int *nbytes);
 int mohid_adt_comm_init(const int *handle, const int *nranks, const int *rank, const void *unique_id, const int *ghost,
                         const int *overlap);

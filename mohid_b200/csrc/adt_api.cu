@@ -109,6 +109,8 @@ struct Handle {
     // NCCL halo exchange behind the C-ABI (mohid_adt_comm_init): communicator, neighbour buffers, own comm stream
     ncclComm_t nccl = nullptr;
     int nranks = 1, rank = 0, halo_ghost = 0;
+    double *line_buf[4] = {nullptr, nullptr, nullptr, nullptr};   // split line solve: edge in / out, x in / out
+    size_t line_cap = 0;
     cudaStream_t s_comm_own = nullptr;
     double *halo_buf[4] = {nullptr, nullptr, nullptr, nullptr};     // send left, recv left, send right, recv right
     size_t halo_cap = 0;
@@ -296,6 +298,7 @@ void free_all(Handle *h) {
     F(h->pk);
     for (auto p : h->rho2d) F(p);
     for (auto p : h->halo_buf) F(p);
+    for (auto p : h->line_buf) F(p);
     if (h->nccl && g_nccl.CommDestroy) { g_nccl.CommDestroy(h->nccl); h->nccl = nullptr; }
     if (h->s_comm_own) { cudaStreamDestroy(h->s_comm_own); h->s_comm_own = nullptr; }
     F(h->d_ci); F(h->d_cj); F(h->d_ck); F(h->d_ckmin); F(h->d_ckmax); F(h->d_cvert); F(h->d_cbypass);
@@ -416,9 +419,9 @@ int validate(Handle *h, int nprop, const mohid_adt_params *p, Batch &b) {
         if ((q.ImpExp_AdvXX == 1.0 || q.ImpExp_AdvYY == 1.0) && !h->opt.Vertical1D) {
             // lines along j (ImpExp_AdvXX) cross the slabs of a decomposed domain (THOMAS_DDecompHorizGrid, HG:8245-8478);
             // lines along i (ImpExp_AdvYY) lie inside one slab and are solved locally
-            if (q.ImpExp_AdvXX == 1.0 && (h->j_begin != 1 || h->j_count != h->J))
-                return fail(h, MOHID_ADT_ERR_UNSUPPORTED,
-                            "implicit advection along j couples the columns of all slabs: not available on a column slab (AD:4200-4244)");
+            if (q.ImpExp_AdvXX == 1.0 && (h->j_begin != 1 || h->j_count != h->J) && !h->nccl)
+                return fail(h, MOHID_ADT_ERR_STATE,
+                            "implicit advection along j couples the columns of all slabs (AD:4200-4244): call mohid_adt_comm_init first");
         }
         for (int m : {q.AdvMethodH, q.AdvMethodV})
             if (m < MOHID_UpwindOrder1 || m > MOHID_LeapFrog)
@@ -746,10 +749,42 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
         const long nunits = (long)s.nprop * ((nc + 30) / 31) * h->K;
         const long blocks = (nunits + 7) / 8;
         if (blocks > 2147483647L) return fail(h, MOHID_ADT_ERR_ARG, "grid too large");
-        if (hdir == 1) adt_hsolve_kernel<0><<<(unsigned)blocks, 256, 0, h->stream>>>(s, hs);
-        else adt_hsolve_kernel<1><<<(unsigned)blocks, 256, 0, h->stream>>>(s, hs);
-        CU(h, cudaGetLastError());
-        h->launches++;
+        const bool split = hdir == 1 && (h->j_begin != 1 || h->j_count != h->J);
+        if (split) {
+            // lines along j on a column slab: the recurrence passes from rank to rank (THOMAS_DDecompHorizGrid gathers the rows
+            // on one process instead, HG:8245-8478): forward left to right, back substitution right to left, (W, G) and x of
+            // one cell per (i, level, property) on the wire
+            if (!h->nccl) return fail(h, MOHID_ADT_ERR_STATE, "implicit advection along j on a column slab needs mohid_adt_comm_init");
+            const size_t ne = (size_t)s.nprop * h->K * h->I;
+            if (h->line_cap < ne) {
+                CU(h, cudaStreamSynchronize(h->stream));
+                for (auto &p : h->line_buf) { if (p) cudaFree(p); p = nullptr; }
+                for (auto &p : h->line_buf) if (int rc = dalloc(h, &p, 2 * ne)) return rc;
+                h->line_cap = ne;
+            }
+            const bool has_l = h->rank > 0, has_r = h->rank < h->nranks - 1;
+            auto nccl_ok = [&](ncclResult_t r) { return r == ncclSuccess ? 0 : fail(h, MOHID_ADT_ERR_CUDA, "NCCL line solve: %s", g_nccl.GetErrorString(r)); };
+            hs.split = 1; hs.l0 = h->j_begin; hs.l1 = h->j_begin + h->j_count - 1;
+            hs.edge_in = has_l ? h->line_buf[0] : nullptr; hs.edge_out = h->line_buf[1];
+            if (has_l) if (int rc = nccl_ok(g_nccl.Recv(h->line_buf[0], 2 * ne, ncclDouble, h->rank - 1, h->nccl, h->stream))) return rc;
+            adt_hsolve_kernel<0><<<(unsigned)blocks, 256, 0, h->stream>>>(s, hs);
+            CU(h, cudaGetLastError());
+            if (has_r) if (int rc = nccl_ok(g_nccl.Send(h->line_buf[1], 2 * ne, ncclDouble, h->rank + 1, h->nccl, h->stream))) return rc;
+            HBackArgs ba{};
+            ba.I = h->I; ba.K = h->K; ba.sj = h->sj; ba.sk = h->sk; ba.nprop = s.nprop; ba.l0 = hs.l0; ba.l1 = hs.l1; ba.last = has_r ? 0 : 1;
+            ba.x_in = h->line_buf[2]; ba.x_out = h->line_buf[3];
+            for (int m = 0; m < s.nprop; ++m) { ba.out[m] = h->hs_tmp[idx[m]]; ba.wline[m] = h->wline[idx[m]]; ba.pin[m] = cur_ptr(h, idx[m]); }
+            if (has_r) if (int rc = nccl_ok(g_nccl.Recv(h->line_buf[2], ne, ncclDouble, h->rank + 1, h->nccl, h->stream))) return rc;
+            adt_hsolve_back_kernel<<<dim3((unsigned)((h->I + 127) / 128), (unsigned)h->K, (unsigned)s.nprop), 128, 0, h->stream>>>(ba);
+            CU(h, cudaGetLastError());
+            if (has_l) if (int rc = nccl_ok(g_nccl.Send(h->line_buf[3], ne, ncclDouble, h->rank - 1, h->nccl, h->stream))) return rc;
+            h->launches += 2;
+        } else {
+            if (hdir == 1) adt_hsolve_kernel<0><<<(unsigned)blocks, 256, 0, h->stream>>>(s, hs);
+            else adt_hsolve_kernel<1><<<(unsigned)blocks, 256, 0, h->stream>>>(s, hs);
+            CU(h, cudaGetLastError());
+            h->launches++;
+        }
         // ---- stage 2: the vertical half, from the intermediate field into the new position ----
         for (int m = 0; m < s.nprop; ++m) { s.p[m].pin = h->hs_tmp[idx[m]]; s.p[m].pout = nxt_ptr(h, idx[m]); }
         stage2 = true;

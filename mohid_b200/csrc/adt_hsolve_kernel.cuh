@@ -22,6 +22,14 @@ namespace adt {
 
 struct HSolveArgs {
     double *wline[NPMAX];            // W of the line recurrence, one scratch field per property of the launch
+    // Lines along j on a column slab (the reference gathers such rows on one process, THOMAS_DDecompHorizGrid HG:8245-8478):
+    // the recurrence runs over the owned cells l0 .. l1 only, takes (W, G) of cell l0 - 1 from the rank on the left and
+    // hands (W, G) of cell l1 to the rank on the right; adt_hsolve_back_kernel then substitutes back from the right.
+    // State per (property, level, cross cell): edge[((n * K + k - 1) * NC + c - 1) * 2 + {0, 1}].
+    int split;                       // 0: the whole line in one launch (forward and back substitution)
+    int l0, l1;
+    const double *edge_in;           // nullptr on the first rank
+    double *edge_out;
 };
 
 template <int DIR>
@@ -81,7 +89,19 @@ __global__ void __launch_bounds__(256) adt_hsolve_kernel(const __grid_constant__
     double Wprev = 0., Gprev = 0.;
     double dfl_w = 0., efl_w = 0.;
     unsigned zp = 0;
-    {   // west face of the first cell of the line (a = 1)
+    const int L0 = hs.split ? hs.l0 : 1, L1 = hs.split ? hs.l1 : NL;
+    const long eidx = (((long)n * s.K + (k - 1)) * NC + (min(c, NC) - 1)) * 2;
+    if (hs.split && hs.edge_in) { Wprev = hs.edge_in[eidx]; Gprev = hs.edge_in[eidx + 1]; }
+    if (L0 > 1) {   // the face between cells L0 - 1 and L0, as cell L0 - 1 (a ghost cell) sees its far face in the loop below
+        const int l = L0 - 1;
+        const int q = q0 + sl * l, p2 = c2 + sl2 * l;
+        const int lp2 = (l + 2 <= NL + 1) ? 2 * sl : sl, lp2_2 = (l + 2 <= NL + 1) ? 2 * sl2 : sl2;
+        const unsigned m = s.mask[q];
+        const unsigned nf = nfsel ? (s.nfmask[q] & nfsel) : 0u;
+        line_face(all_set(m, CF_LN | O_LP1 | M_OPEN) && !(nf & NF_LE), qL[q + sl], P[q - sl], P[q], P[q + sl], P[q + lp2],
+                  (m & O_LM1) != 0, (m & O_LP2) != 0, s.dtv[q - sl], s.dtv[q], s.dtv[q + sl], s.dtv[q + lp2], rdL[p2],
+                  rdL[p2 + sl2], rdL[p2 + lp2_2], duL[p2], duL[p2 + sl2], dfl_w, efl_w);
+    } else {   // west face of the first cell of the line (a = 1)
         const int q = q0 + sl, p2 = c2 + sl2;
         const unsigned m = s.mask[q];
         const unsigned nf = nfsel ? (s.nfmask[q] & nfsel) : 0u;
@@ -89,7 +109,7 @@ __global__ void __launch_bounds__(256) adt_hsolve_kernel(const __grid_constant__
                   (m & O_LP1) != 0, 0., s.dtv[q - sl], s.dtv[q], s.dtv[q + sl], rdL[p2 - sl2], rdL[p2], rdL[p2 + sl2],
                   duL[p2 - sl2], duL[p2], dfl_w, efl_w);
     }
-    for (int l = 1; l <= NL; ++l) {
+    for (int l = L0; l <= L1; ++l) {
         const int q = q0 + sl * l, p2 = c2 + sl2 * l;
         const int lm2 = (l >= 2) ? 2 * sl : sl, lp2 = (l + 2 <= NL + 1) ? 2 * sl : sl;
         const int lp2_2 = (l + 2 <= NL + 1) ? 2 * sl2 : sl2;
@@ -147,6 +167,13 @@ __global__ void __launch_bounds__(256) adt_hsolve_kernel(const __grid_constant__
         if (writer) { Wl[q] = Wprev; O[q] = Gprev; }
         dfl_w = dfl_e; efl_w = efl_e;
     }
+    if (hs.split) {
+        if (writer) {
+            hs.edge_out[eidx] = Wprev; hs.edge_out[eidx + 1] = Gprev;
+            if (zp) atomicAdd(s.zero_pivots, (unsigned long long)zp);
+        }
+        return;
+    }
     if (writer) {
         // halo cell NL+1: identity row with TI = 0 (MF:3803); the reference writes it into PROP
         int q = q0 + sl * (NL + 1);
@@ -160,6 +187,34 @@ __global__ void __launch_bounds__(256) adt_hsolve_kernel(const __grid_constant__
         }
         if (zp) atomicAdd(s.zero_pivots, (unsigned long long)zp);
     }
+}
+
+// Back substitution of a split line solve (lines along j): x of cell l1 + 1 comes from the rank on the right (last rank: the
+// halo cell NL + 1, 0), x of cell l0 goes to the rank on the left.  One thread per (i, level, property), lanes along i.
+struct HBackArgs {
+    int I, K, sj, sk, nprop, l0, l1, last;
+    const double *x_in;              // [n][k][i] x of cell l1 + 1; unused on the last rank
+    double *x_out;                   // [n][k][i] x of cell l0
+    double *out[NPMAX];              // G in, x out
+    const double *wline[NPMAX];
+    double *pin[NPMAX];              // last rank: the halo cell of the old field takes the 0 as well (see adt_hsolve_kernel)
+};
+__global__ void __launch_bounds__(128) adt_hsolve_back_kernel(const HBackArgs a) {
+    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, k = 1 + blockIdx.y, n = blockIdx.z;
+    if (i > a.I) return;
+    const long e = ((long)n * a.K + (k - 1)) * a.I + (i - 1);
+    double *__restrict__ O = a.out[n];
+    const double *__restrict__ Wl = a.wline[n];
+    long q = i + (long)a.sk * k + (long)a.sj * (a.l1 + 1);
+    double x = 0.;
+    if (a.last) { O[q] = x; a.pin[n][q] = x; }
+    else x = a.x_in[e];
+    for (int l = a.l1; l >= a.l0; --l) {
+        q -= a.sj;
+        x = Wl[q] * x + O[q];
+        O[q] = x;
+    }
+    a.x_out[e] = x;
 }
 
 }  // namespace adt

@@ -20,7 +20,15 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out_dir):
+def _params(kind):
+    base = default_params(4, 4, 4, 4, bc=4)
+    if kind == "implicit":
+        # lines along j cross the slabs (the recurrence passes from rank to rank), lines along i lie inside them
+        return [dict(base, ImpExp_AdvXX=1.0), dict(base, ImpExp_AdvYY=1.0), dict(base)]
+    return [dict(base) for _ in range(NPROP)]
+
+
+def _worker(rank, world, port, out_dir, kind):
     import torch.distributed as dist
     from mohid_b200.advection_diffusion import TransportStep
     from mohid_b200.partition import SlabDecomposition, HaloExchanger
@@ -37,7 +45,7 @@ def _worker(rank, world, port, out_dir):
     ts.set_step(case.step)
     ts.upload(case.props, case.refs)
     halo = HaloExchanger(ts, dec, rank, NPROP, dev)
-    prm = [default_params(4, 4, 4, 4, bc=4) for _ in range(NPROP)]
+    prm = _params(kind)
     for _ in range(STEPS):
         ts.advect_device(prm, 1)
         halo.exchange()
@@ -50,21 +58,21 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("kind", ["explicit", "implicit"])
 @pytest.mark.parametrize("world", [2, 4])
-def test_slabs_with_nccl_halos_equal_single_gpu(tmp_path, world):
+def test_slabs_with_nccl_halos_equal_single_gpu(tmp_path, world, kind):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
     from mohid_b200.advection_diffusion import TransportStep
     from mohid_b200.partition import SlabDecomposition
-    mp.start_processes(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True, start_method="spawn")
+    mp.start_processes(_worker, args=(world, _free_port(), str(tmp_path), kind), nprocs=world, join=True, start_method="spawn")
     case = make_case(I, J, K, nprop=NPROP, device="cuda:0")
     ts = TransportStep(I, J, K, device=0)
     ts.set_grid2d(**case.grid2d)
     ts.set_step(case.step)
     ts.upload(case.props, case.refs)
-    prm = [default_params(4, 4, 4, 4, bc=4) for _ in range(NPROP)]
-    ts.advect_device(prm, STEPS)
+    ts.advect_device(_params(kind), STEPS)
     out = [torch.empty_like(p) for p in case.props]
     ts.download(out)
     torch.cuda.synchronize()
