@@ -324,7 +324,9 @@ int mohid_adt_set_stream(const int *handle, void *cuda_stream);
  * With a communicator the steps themselves become collective when a property is advected implicitly along j
  * (ImpExp_AdvXX = 1): the lines cross the slabs and their tridiagonal recurrence passes from rank to rank inside
  * mohid_adt_advect_batch / mohid_adt_advect_device (the reference gathers such rows on one process,
- * THOMAS_DDecompHorizGrid, ModuleHorizontalGrid.F90:8245-8478); every rank must then make the same calls. */
+ * THOMAS_DDecompHorizGrid, ModuleHorizontalGrid.F90:8245-8478); likewise with BoundaryCondition = CyclicBoundary, whose
+ * j wrap (ModuleAdvectionDiffusion.F90:2167-2190) joins the first and the last rank.  Every rank must then make the same
+ * calls. */
 int mohid_adt_comm_get_unique_id(void *unique_id, const int *nbytes);
 int mohid_adt_comm_init(const int *handle, const int *nranks, const int *rank, const void *unique_id, const int *ghost,
                         const int *overlap);

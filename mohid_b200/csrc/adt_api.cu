@@ -110,6 +110,8 @@ struct Handle {
     ncclComm_t nccl = nullptr;
     int nranks = 1, rank = 0, halo_ghost = 0;
     double *line_buf[4] = {nullptr, nullptr, nullptr, nullptr};   // split line solve: edge in / out, x in / out
+    double *cyc_buf[2] = {nullptr, nullptr};                      // cyclic boundary across the slabs: send / receive
+    size_t cyc_cap = 0;
     size_t line_cap = 0;
     cudaStream_t s_comm_own = nullptr;
     double *halo_buf[4] = {nullptr, nullptr, nullptr, nullptr};     // send left, recv left, send right, recv right
@@ -299,6 +301,7 @@ void free_all(Handle *h) {
     for (auto p : h->rho2d) F(p);
     for (auto p : h->halo_buf) F(p);
     for (auto p : h->line_buf) F(p);
+    for (auto p : h->cyc_buf) F(p);
     if (h->nccl && g_nccl.CommDestroy) { g_nccl.CommDestroy(h->nccl); h->nccl = nullptr; }
     if (h->s_comm_own) { cudaStreamDestroy(h->s_comm_own); h->s_comm_own = nullptr; }
     F(h->d_ci); F(h->d_cj); F(h->d_ck); F(h->d_ckmin); F(h->d_ckmax); F(h->d_cvert); F(h->d_cbypass);
@@ -439,9 +442,9 @@ int validate(Handle *h, int nprop, const mohid_adt_params *p, Batch &b) {
             if (h->bnd_off_ring)
                 return fail(h, MOHID_ADT_ERR_ARG, "Orlanski Advection 2 (a boundary point is not on the outer ring, AD:5518)");
         }
-        if (bc == MOHID_BC_CyclicBoundary && (h->j_begin != 1 || h->j_count != h->J))
-            return fail(h, MOHID_ADT_ERR_UNSUPPORTED,
-                        "CyclicBoundary wraps the global columns 1 and J (AD:2121-2224): not available on a column slab");
+        if (bc == MOHID_BC_CyclicBoundary && (h->j_begin != 1 || h->j_count != h->J) && !h->nccl)
+            return fail(h, MOHID_ADT_ERR_STATE,
+                        "CyclicBoundary wraps the global columns 1 and J (AD:2121-2224): on a column slab call mohid_adt_comm_init first");
         if (bc != MOHID_BC_None && bc != MOHID_BC_MassConservation && bc != MOHID_BC_ImposedValue &&
             bc != MOHID_BC_NullGradient && bc != MOHID_BC_SubModel && bc != MOHID_BC_MassConservNullGrad &&
             bc != MOHID_BC_CyclicBoundary && bc != MOHID_BC_Orlanski)
@@ -971,7 +974,31 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
         } else if (bc == MOHID_BC_CyclicBoundary) {
             adt_cyclic_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(ba, 0);
             const long t1 = (long)std::max(h->I - 2, 0) * h->K, t2 = (long)std::max(h->J - 2, 0) * h->K;
-            if (t1 > 0) adt_cyclic_kernel<<<(unsigned)((t1 + 255) / 256), 256, 0, h->stream>>>(ba, 1);
+            const bool slab = h->j_begin != 1 || h->j_count != h->J;
+            if (!slab) {
+                if (t1 > 0) adt_cyclic_kernel<<<(unsigned)((t1 + 255) / 256), 256, 0, h->stream>>>(ba, 1);
+            } else if (h->nranks > 1 && (h->rank == 0 || h->rank == h->nranks - 1)) {
+                // the j wrap joins the first and the last rank: each sends the column next to its boundary column
+                const size_t ne = (size_t)h->K * h->I + 2 * (size_t)h->I;
+                if (h->cyc_cap < ne) {
+                    CU(h, cudaStreamSynchronize(h->stream));
+                    for (auto &p : h->cyc_buf) { if (p) cudaFree(p); p = nullptr; }
+                    for (auto &p : h->cyc_buf) if (int rc = dalloc(h, &p, ne)) return rc;
+                    h->cyc_cap = ne;
+                }
+                const bool first = h->rank == 0;
+                const int j_bnd = first ? 1 : h->J, j_val = first ? 2 : h->J - 1, peer = first ? h->nranks - 1 : 0;
+                const long tp = (long)h->K * h->I + h->I;
+                adt_cyclic_edge_pack_kernel<<<(unsigned)((tp + 255) / 256), 256, 0, h->stream>>>(ba, j_val, j_bnd, h->cyc_buf[0]);
+                ncclResult_t r = g_nccl.GroupStart();
+                if (r == ncclSuccess) r = g_nccl.Send(h->cyc_buf[0], ne, ncclDouble, peer, h->nccl, h->stream);
+                if (r == ncclSuccess) r = g_nccl.Recv(h->cyc_buf[1], ne, ncclDouble, peer, h->nccl, h->stream);
+                const ncclResult_t r2 = g_nccl.GroupEnd();
+                if (r != ncclSuccess || r2 != ncclSuccess)
+                    return fail(h, MOHID_ADT_ERR_CUDA, "NCCL cyclic boundary: %s", g_nccl.GetErrorString(r != ncclSuccess ? r : r2));
+                if (t1 > 0) adt_cyclic_edge_apply_kernel<<<(unsigned)((t1 + 255) / 256), 256, 0, h->stream>>>(ba, j_bnd, h->cyc_buf[1]);
+                h->launches += 1;
+            }
             if (t2 > 0) adt_cyclic_kernel<<<(unsigned)((t2 + 255) / 256), 256, 0, h->stream>>>(ba, 2);
             h->launches += 3;
         }

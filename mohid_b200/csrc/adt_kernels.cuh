@@ -1146,6 +1146,31 @@ __global__ void adt_cyclic_kernel(const BndArgs b, int phase) {
     }
 }
 
+// Prop_CyclicBoundary across column slabs: the j wrap joins global column 1 (first rank) and J (last rank).  Each of the two
+// packs what the other needs -- PROP of its column next to the boundary column, BoundaryPoints2D of its boundary column and
+// KFloorZ of the packed column -- and applies the other's buffer to its own boundary column.
+//   buf: [K][I] values (k = 1 .. K, i = 1 .. I), then [I] BoundaryPoints2D, then [I] KFloorZ (as doubles)
+__global__ void adt_cyclic_edge_pack_kernel(const BndArgs b, int j_val, int j_bnd, double *buf) {
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long nv = (long)b.K * b.I;
+    if (t < nv) {
+        const int i = (int)(t % b.I) + 1, k = (int)(t / b.I) + 1;
+        buf[t] = b.prop[(long)i + (long)b.sj * j_val + (long)b.sk * k];
+    } else if (t < nv + b.I) {
+        const int i = (int)(t - nv) + 1;
+        buf[t] = (double)b.Bnd[(long)i + (long)b.ld * j_bnd];
+        buf[t + b.I] = (double)b.kfloor[(long)i + (long)b.ld * j_val];
+    }
+}
+__global__ void adt_cyclic_edge_apply_kernel(const BndArgs b, int j_bnd, const double *buf) {
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long)(b.I - 2) * b.K) return;
+    const int i = (int)(t % (b.I - 2)) + 2, k = (int)(t / (b.I - 2)) + 1;
+    const long nv = (long)b.K * b.I;
+    if (b.Bnd[(long)i + (long)b.ld * j_bnd] == 1 && buf[nv + i - 1] == 1.0 && k >= (int)buf[nv + b.I + i - 1])
+        b.prop[(long)i + (long)b.sj * j_bnd + (long)b.sk * k] = buf[(long)(k - 1) * b.I + (i - 1)];
+}
+
 // -------------------------------------------------------------------------------------
 // K5: cell-face mass fluxes for the box budgets (CalcHorizontal/Vertical Adv/Dif Flux, AD:3356-3954;
 // GetAdvFlux / GetDifFlux, AD:697-851).  Only launched for properties whose call carries CellFluxes (box

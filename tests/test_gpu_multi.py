@@ -25,6 +25,9 @@ def _params(kind):
     if kind == "implicit":
         # lines along j cross the slabs (the recurrence passes from rank to rank), lines along i lie inside them
         return [dict(base, ImpExp_AdvXX=1.0), dict(base, ImpExp_AdvYY=1.0), dict(base)]
+    if kind == "cyclic":
+        # Prop_CyclicBoundary joins global column 1 (first rank) and J (last rank)
+        return [default_params(4, 4, 4, 4, bc=8) for _ in range(NPROP)]
     return [dict(base) for _ in range(NPROP)]
 
 
@@ -58,7 +61,7 @@ def _worker(rank, world, port, out_dir, kind):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kind", ["explicit", "implicit"])
+@pytest.mark.parametrize("kind", ["explicit", "implicit", "cyclic"])
 @pytest.mark.parametrize("world", [2, 4])
 def test_slabs_with_nccl_halos_equal_single_gpu(tmp_path, world, kind):
     if torch.cuda.device_count() < world:
