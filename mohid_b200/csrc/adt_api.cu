@@ -975,8 +975,9 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
             adt_cyclic_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(ba, 0);
             const long t1 = (long)std::max(h->I - 2, 0) * h->K, t2 = (long)std::max(h->J - 2, 0) * h->K;
             const bool slab = h->j_begin != 1 || h->j_count != h->J;
+            h->launches += 1;
             if (!slab) {
-                if (t1 > 0) adt_cyclic_kernel<<<(unsigned)((t1 + 255) / 256), 256, 0, h->stream>>>(ba, 1);
+                if (t1 > 0) { adt_cyclic_kernel<<<(unsigned)((t1 + 255) / 256), 256, 0, h->stream>>>(ba, 1); h->launches++; }
             } else if (h->nranks > 1 && (h->rank == 0 || h->rank == h->nranks - 1)) {
                 // the j wrap joins the first and the last rank: each sends the column next to its boundary column
                 const size_t ne = (size_t)h->K * h->I + 2 * (size_t)h->I;
@@ -996,11 +997,10 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
                 const ncclResult_t r2 = g_nccl.GroupEnd();
                 if (r != ncclSuccess || r2 != ncclSuccess)
                     return fail(h, MOHID_ADT_ERR_CUDA, "NCCL cyclic boundary: %s", g_nccl.GetErrorString(r != ncclSuccess ? r : r2));
-                if (t1 > 0) adt_cyclic_edge_apply_kernel<<<(unsigned)((t1 + 255) / 256), 256, 0, h->stream>>>(ba, j_bnd, h->cyc_buf[1]);
+                if (t1 > 0) { adt_cyclic_edge_apply_kernel<<<(unsigned)((t1 + 255) / 256), 256, 0, h->stream>>>(ba, j_bnd, h->cyc_buf[1]); h->launches++; }
                 h->launches += 1;
             }
-            if (t2 > 0) adt_cyclic_kernel<<<(unsigned)((t2 + 255) / 256), 256, 0, h->stream>>>(ba, 2);
-            h->launches += 3;
+            if (t2 > 0) { adt_cyclic_kernel<<<(unsigned)((t2 + 255) / 256), 256, 0, h->stream>>>(ba, 2); h->launches++; }
         }
         CU(h, cudaGetLastError());
     }

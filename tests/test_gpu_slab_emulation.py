@@ -69,3 +69,18 @@ def test_slab_ranks_on_one_gpu_equal_the_undivided_run(world, bc, method, extra)
             assert np.array_equal(part[:, :, -1, :], glob[:, :, -1, :])
         ts.close()
     assert not np.array_equal(glob, np.stack([p.cpu().numpy() for p in whole_case.props]))
+
+
+@pytest.mark.parametrize("prm", [dict(default_params(4, 4, 4, 4, bc=8)), dict(default_params(4, 4, 4, 4, bc=4), ImpExp_AdvXX=1.0)])
+def test_options_that_couple_the_slabs_need_the_communicator(prm):
+    """Cyclic j wrap and lines along j cross the slabs: without mohid_adt_comm_init the step is refused, not silently local."""
+    from mohid_b200.capi import AdtError
+    from mohid_b200.partition import SlabDecomposition
+    sl = SlabDecomposition(J, 2, ghost=G).slab(0)
+    case = make_case(I, J, K, nprop=1, device="cuda", j_range=(sl.j_lo_ext, sl.j_hi_ext))
+    ts = _handle(case)
+    ts.set_active_columns(sl.j_begin, sl.n_owned)
+    with pytest.raises(AdtError, match="mohid_adt_comm_init") as e:
+        ts.advect_device([prm], 1)
+    assert e.value.code == 31           # MOHID_ADT_ERR_STATE
+    ts.close()
