@@ -668,6 +668,11 @@ struct Chunk { int a, b; };
 std::vector<Chunk> chunk_order(const Handle *h, bool increasing) {
     std::vector<Chunk> v;
     for (int a = 0; a < h->nj; a += h->C) v.push_back({a, std::min(a + h->C, h->nj) - 1});
+    // A halo column stays with the work column beside it: the Orlanski boundary writes the exterior cell of a boundary
+    // point (orlanski_exterior), which the carry of a later chunk would put back.  C + 1 columns are still inside the
+    // margin of the shift (S = C + 3 against a stencil reach of 2), and the halo column itself is never advanced.
+    if (v.size() >= 2 && v.back().a == v.back().b) { v[v.size() - 2].b = v.back().b; v.pop_back(); }
+    if (v.size() >= 2 && v.front().a == v.front().b) { v[1].a = v.front().a; v.erase(v.begin()); }
     if (!increasing) std::reverse(v.begin(), v.end());
     return v;
 }
@@ -911,7 +916,7 @@ int launch_step(Handle *h, const Batch &b, const std::vector<int> &idx, bool tim
     // ---- the step, chunk by chunk ----
     const int ja = h->j_begin, jb = h->j_begin + h->j_count - 1;      // columns the step kernel advances
     CarryArgs ca{};
-    ca.ld = h->ld; ca.nk = h->nk; ca.I = h->I; ca.K = h->K; ca.sj = h->sj; ca.sk = h->sk; ca.ja = ja; ca.jb = jb;
+    ca.ld = h->ld; ca.nk = h->nk; ca.I = h->I; ca.J = h->J; ca.K = h->K; ca.sj = h->sj; ca.sk = h->sk; ca.ja = ja; ca.jb = jb;
     ca.Water = h->raw_i[2];
     // cells the step does not advance keep the field at time n (in a two-stage step pin is the intermediate field)
     for (int m = 0; m < s.nprop; ++m) { ca.src[m] = cur_ptr(h, idx[m]); ca.dst[m] = s.p[m].pout; }

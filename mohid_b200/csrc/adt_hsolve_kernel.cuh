@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(256) adt_hsolve_kernel(const __grid_constant__
     constexpr unsigned O_CP1 = DIR == 0 ? M_O_IP1 : M_O_JP1;
     constexpr unsigned NF_LW = DIR == 0 ? NF_WEST : 0u, NF_LE = DIR == 0 ? NF_EAST : 0u;   // NoFlux bits act on U faces only
     const bool cross_on = !(DIR == 0 && s.xzflow);        // XZFlow: no YY terms (AD:4163)
+    const bool line_on = !(DIR == 1 && s.xzflow);         // ... also when YY is the implicit direction: identity rows along i
     const unsigned nfsel = pa.nfsel;
 
     // implicit face between line cells a-1 and a (cells a-2 .. a+1 = P1 .. P4): D_flux, E_flux (MF:10583-10586)
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(256) adt_hsolve_kernel(const __grid_constant__
         oriented_weights<0, 0>(s.method_h, s.limiter_h, s.upwind2_h != 0, s.vrelmax, Q, Puu, Pu, Pd, pos ? !o1 : !o4,
                                sel(pos, t1, t4), sel(pos, t2, t3), sel(pos, t3, t2), sel(pos, rd12, rd34), rd23,
                                sel(pos, du2, du3), sel(pos, du3, du2), wuu, wu, wd);
-        const double qa = on ? Q : 0.;
+        const double qa = (on && line_on) ? Q : 0.;
         dfl = qa * sel(pos, wu, wd);
         efl = qa * sel(pos, wd, wu);
     };
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(256) adt_hsolve_kernel(const __grid_constant__
         if ((m & M_DISCH) && pa.dconc)
             apply_discharges(s.disch, pa.dconc, pa.dconcmf, DIR == 0 ? cc : l, DIR == 0 ? l : cc, k, open_c, Pc, vr, dtv_c, ti, e0);
         // ---------------- explicit terms: diffusion along the line, full flux across it ----------------
-        double fsum = -dhL[q] * (Pc - Pw1) + dhL[q + sl] * (Pe1 - Pc);
+        double fsum = line_on ? -dhL[q] * (Pc - Pw1) + dhL[q + sl] * (Pe1 - Pc) : 0.;
         if (cross_on) {
             const double fs = hface_flux<0, 0>(s, all_set(m, CF_C | O_CM1 | M_OPEN), qC[q], dhC[q], P[q - cm2], P[q - sc], Pc,
                                                P[q + cp1], (m & O_CM2) != 0, (m & O_CP1) != 0, s.dtv[q - cm2], s.dtv[q - sc],
@@ -151,7 +152,8 @@ __global__ void __launch_bounds__(256) adt_hsolve_kernel(const __grid_constant__
             // fill (AD:1753) enter the line system itself
             if ((m & M_BND) && open_c && pa.bc != MOHID_BC_None) {
                 Row row{D, E, F, ti};
-                open_boundary_row<false>(s, pa, q, m, Pc, s.qz[q], s.qz[q + sk], dtv_c, row);
+                open_boundary_row<true>(s, pa, q, m, Pc, s.qz[q], s.qz[q + sk], dtv_c, row, DIR == 0 ? cc : l, DIR == 0 ? l : cc,
+                                        writer);
                 D = row.D; E = row.E; F = row.F; ti = row.TI;
             }
             if (m & M_LAND) ti = NULL_REAL;

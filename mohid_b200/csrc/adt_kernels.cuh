@@ -1072,7 +1072,7 @@ struct BndArgs {
 // (i, column, property); launched per column chunk right before the chunk's step kernel.
 // -------------------------------------------------------------------------------------
 struct CarryArgs {
-    int ld, nk, I, K, sj, sk, j0, ja, jb;     // columns j0 .. j0+gridDim.y-1; the step kernel advances columns ja .. jb
+    int ld, nk, I, J, K, sj, sk, j0, ja, jb;  // columns j0 .. j0+gridDim.y-1; the step kernel advances columns ja .. jb
     const int *Water;
     const double *src[NPMAX];
     double *dst[NPMAX];
@@ -1087,8 +1087,9 @@ __global__ void __launch_bounds__(128) adt_carry_kernel(const CarryArgs a) {
     const int c = i + a.sj * j;
     const bool solved = j >= a.ja && j <= a.jb && i >= 1 && i <= a.I && a.Water[c + a.sk * a.K] == 1;   // MF:4086
     if (a.twod) {
-        // every cell of a line was solved (land cells included, THOMAS_3D has no water mask, MF:3751-3875)
-        const bool on_line = j >= a.ja && j <= a.jb && i >= 1 && i <= a.I;
+        // every cell of a line was solved (land cells included, THOMAS_3D has no water mask, MF:3751-3875); the halo cells
+        // around the solved columns carry what the Orlanski boundary wrote beside its boundary points
+        const bool on_line = (j >= a.ja && j <= a.jb) || (j == 0 && a.ja == 1) || (j == a.J + 1 && a.jb == a.J);
         for (int k = 0; k < a.nk; ++k) D[c + a.sk * k] = (on_line && k >= 1 && k <= a.K ? a.line[n] : S)[c + a.sk * k];
         return;
     }
