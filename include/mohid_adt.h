@@ -299,7 +299,9 @@ int mohid_adt_mark_step_resident(const int *handle, const int *small_depths_pres
  * (the reference instead recomputes overlapping HALOPOINTS columns, HG:1048-1105). */
 int mohid_adt_set_active_columns(const int *handle, const int *j_begin, const int *j_count);
 /* Pack `width` j-columns starting at j0 of all nprop device-resident properties into a
- * contiguous DEVICE buffer (nprop * nk * width * ld doubles) / scatter them back. */
+ * contiguous DEVICE buffer / scatter them back.  The buffer holds nprop * nk * width * ld doubles, laid out
+ * [property][k][column][i], with ld the DEVICE leading dimension that mohid_adt_prop_device_ptr returns (rows are
+ * padded to 128 bytes on the device: ld >= ld_i of mohid_adt_create) and nk = K + 2. */
 int mohid_adt_pack_columns(const int *handle, const int *nprop, const int *j0, const int *width,
                            void *device_buffer);
 int mohid_adt_unpack_columns(const int *handle, const int *nprop, const int *j0, const int *width,

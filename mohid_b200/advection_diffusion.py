@@ -256,11 +256,29 @@ class TransportStep:
         return flux
 
     # ---- halo staging for the j-slab decomposition ----------------------------------
+    def device_layout(self, n: int = 0):
+        """(ld, nj, nk) of the device arrays: element (i, j, k) of property n at ptr[i + ld * (j + nj * k)].  ld is the
+        DEVICE leading dimension (rows padded to 128 bytes), not the ld of the caller's arrays."""
+        ptr, ld, nj, nk = C.c_void_p(), C.c_int(), C.c_int(), C.c_int()
+        self._check(self.lib.mohid_adt_prop_device_ptr(C.byref(self.h), C.byref(C.c_int(n)), C.byref(ptr), C.byref(ld),
+                                                       C.byref(nj), C.byref(nk)))
+        return ld.value, nj.value, nk.value
+
+    def pack_elems(self, nprop: int, width: int) -> int:
+        """Doubles a pack_columns / unpack_columns buffer of `width` columns must hold."""
+        ld, _, nk = self.device_layout()
+        return nprop * nk * width * ld
+
     def pack_columns(self, nprop: int, j0: int, width: int, device_buffer):
+        if device_buffer.numel() < self.pack_elems(nprop, width):
+            raise ValueError(f"pack buffer holds {device_buffer.numel()} doubles, {self.pack_elems(nprop, width)} needed "
+                             "(nprop * (K + 2) * width * device ld)")
         self._check(self.lib.mohid_adt_pack_columns(C.byref(self.h), C.byref(C.c_int(nprop)), C.byref(C.c_int(j0)),
                                                     C.byref(C.c_int(width)), C.c_void_p(device_buffer.data_ptr())))
 
     def unpack_columns(self, nprop: int, j0: int, width: int, device_buffer):
+        if device_buffer.numel() < self.pack_elems(nprop, width):
+            raise ValueError(f"pack buffer holds {device_buffer.numel()} doubles, {self.pack_elems(nprop, width)} needed")
         self._check(self.lib.mohid_adt_unpack_columns(C.byref(self.h), C.byref(C.c_int(nprop)), C.byref(C.c_int(j0)),
                                                       C.byref(C.c_int(width)), C.c_void_p(device_buffer.data_ptr())))
 
