@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(256) adt_hsolve_kernel(const __grid_constant__
         // ---------------- explicit terms: diffusion along the line, full flux across it ----------------
         double fsum = line_on ? -dhL[q] * (Pc - Pw1) + dhL[q + sl] * (Pe1 - Pc) : 0.;
         if (cross_on) {
-            const double fs = hface_flux<0, 0>(s, all_set(m, CF_C | O_CM1 | M_OPEN), qC[q], dhC[q], P[q - cm2], P[q - sc], Pc,
+            // the explicit face across the line; when that is a U face (lines along i) the NoFlux bits act on it as in K2
+            const double fs = hface_flux<0, 0>(s, all_set(m, CF_C | O_CM1 | M_OPEN) && !(DIR == 1 && (nf & NF_WEST)), qC[q], dhC[q], P[q - cm2], P[q - sc], Pc,
                                                P[q + cp1], (m & O_CM2) != 0, (m & O_CP1) != 0, s.dtv[q - cm2], s.dtv[q - sc],
                                                dtv_c, s.dtv[q + cp1], rdC[p2 - sc2], rdC[p2], rdC[p2 + cp1_2], duC[p2 - sc2],
                                                duC[p2]);

@@ -106,3 +106,37 @@ def test_random_configuration_resident_chunked_with_fluxes(oracle_lib, monkeypat
             assert np.abs(fg[name] - fc[name]).max() / scale < 1e-11, name
     assert ts.counters()["zero_pivots"] == 0
     ts.close()
+
+
+@pytest.mark.parametrize("seed", range(192, 256))
+def test_random_configuration_with_noflux_cell_lists(oracle_lib, monkeypatch, seed):
+    """The same draw with random NoFluxU / V / W cell lists and NoAdvFlux / NoDifFlux flags on some properties (their
+    zeroing carries over to later properties of the step, AD:5768-5785), chunked or not."""
+    (I, J, K, nprop), case_kw, opt, prm = draw(seed)
+    r = np.random.default_rng(9000 + seed)
+    chunk = int(r.choice([0, 6]))
+    if chunk:
+        monkeypatch.setenv("MOHID_ADT_CHUNK_COLS", str(chunk))
+    else:
+        monkeypatch.delenv("MOHID_ADT_CHUNK_COLS", raising=False)
+    for p in prm:
+        p["NoAdvFlux"], p["NoDifFlux"] = int(r.integers(3) == 0), int(r.integers(3) == 0)
+    case = make_case(I, J, K, nprop=nprop, **case_kw)
+    o, g, s, props, refs = oracle_for(case, **opt)
+    nf = [np.ascontiguousarray((r.random(s["OpenPoints3D"].shape) < 0.15).astype(np.int32)) for _ in range(3)]
+    ts = gpu_for(case, g, s, **opt)
+    ts.set_noflux(*nf)
+    o.set_noflux(*nf)
+    gpu, cpu = [p.copy() for p in props], [p.copy() for p in props]
+    for _ in range(3):
+        ts.advect_batch(gpu, prm, refs)
+        o.advect_batch(cpu, prm, refs)
+    w = water_mask(s)
+    for n, p in enumerate(prm):
+        if p["BoundaryCondition"] == 6:
+            ext = ~w & (cpu[n] != props[n])
+            assert np.allclose(gpu[n][ext], cpu[n][ext], rtol=1e-12, atol=0)
+            gpu[n][ext] = cpu[n][ext]
+    compare(gpu, cpu, s, 3 * TOL_STEP)
+    assert ts.counters()["zero_pivots"] == 0
+    ts.close()
