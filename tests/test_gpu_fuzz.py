@@ -140,3 +140,38 @@ def test_random_configuration_with_noflux_cell_lists(oracle_lib, monkeypatch, se
     compare(gpu, cpu, s, 3 * TOL_STEP)
     assert ts.counters()["zero_pivots"] == 0
     ts.close()
+
+
+@pytest.mark.parametrize("seed", range(256, 304))
+def test_random_configuration_with_discharges(oracle_lib, monkeypatch, seed):
+    """One property with point discharges (bottom source, uniform over the column, withdrawal; AD:4025-4128) under the
+    drawn options -- the discharge terms enter the explicit rows, the line solve of an implicit direction and the column
+    solve alike."""
+    from test_gpu_parity import _discharge_set
+    (I, J, K, nprop), case_kw, opt, prm = draw(seed)
+    K = max(K, 2)
+    case_kw = dict(case_kw, stepped_bottom=False)
+    prm = prm[:1]
+    r = np.random.default_rng(11000 + seed)
+    chunk = int(r.choice([0, 7]))
+    if chunk:
+        monkeypatch.setenv("MOHID_ADT_CHUNK_COLS", str(chunk))
+    else:
+        monkeypatch.delenv("MOHID_ADT_CHUNK_COLS", raising=False)
+    case = make_case(I, J, K, nprop=1, **case_kw)
+    o, g, s, props, refs = oracle_for(case, **opt)
+    dset = _discharge_set(case, s, [float(r.uniform(0, 40)), float(r.uniform(0, 10)), 0.0], [1.0, float(r.integers(2)), 0.5])
+    ts = gpu_for(case, g, s, **opt)
+    ts.set_discharges(0, dset)
+    o.set_discharges(dset)
+    gpu, cpu = [props[0].copy()], [props[0].copy()]
+    for _ in range(3):
+        ts.advect_batch(gpu, prm, refs)
+        o.advect_batch(cpu, prm, refs)
+    w = water_mask(s)
+    if prm[0]["BoundaryCondition"] == 6:
+        ext = ~w & (cpu[0] != props[0])
+        assert np.allclose(gpu[0][ext], cpu[0][ext], rtol=1e-12, atol=0)
+        gpu[0][ext] = cpu[0][ext]
+    compare(gpu, cpu, s, 3 * TOL_STEP)
+    ts.close()
