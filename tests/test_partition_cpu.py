@@ -86,3 +86,43 @@ def test_decomposed_oracle_equals_global_run(oracle_lib, tmp_path, world):
         lo, hi = dec.bounds[r]
         part = np.load(tmp_path / f"r{r}.npy")
         assert np.array_equal(part, glob[:, :, lo:hi + 1, :]), f"rank {r} differs from the global run"
+
+
+def test_line_recurrence_passed_from_slab_to_slab_equals_the_whole_line():
+    """The scheme of the split line solve (adt_hsolve_kernel with HSolveArgs::split + adt_hsolve_back_kernel): the forward
+    recurrence of THOMAS_3D (MF:3790-3801) over each slab's owned cells starting from (W, G) of the neighbour's last cell,
+    then the back substitution from the right starting from x of the neighbour's first cell, is the same sequence of
+    operations as the undivided recurrence -- bit for bit, whatever the split."""
+    rng = np.random.default_rng(11)
+    n = 57
+    D, F = rng.uniform(-0.4, 0.0, n + 2), rng.uniform(-0.4, 0.0, n + 2)
+    E = 1.0 - D - F + rng.uniform(0, 0.2, n + 2)
+    TI = rng.uniform(0, 30, n + 2)
+
+    def forward(lo, hi, w, g, W, G):
+        for l in range(lo, hi + 1):
+            aux = E[l] + D[l] * w
+            w, g = -F[l] / aux, (TI[l] - D[l] * g) / aux
+            W[l], G[l] = w, g
+        return w, g
+
+    def backward(lo, hi, x, X, W, G):
+        for l in range(hi, lo - 1, -1):
+            x = W[l] * x + G[l]
+            X[l] = x
+        return x
+
+    W, G, X = np.zeros(n + 2), np.zeros(n + 2), np.zeros(n + 2)
+    forward(1, n, 0.0, 0.0, W, G)
+    backward(1, n, 0.0, X, W, G)
+    for world in (2, 3, 5):
+        dec = SlabDecomposition(n, world)
+        W2, G2, X2 = np.zeros(n + 2), np.zeros(n + 2), np.zeros(n + 2)
+        edge = (0.0, 0.0)
+        for r in range(world):                       # left to right: what ncclSend / ncclRecv carry
+            edge = forward(*dec.bounds[r], *edge, W2, G2)
+        x = 0.0
+        for r in reversed(range(world)):             # right to left
+            x = backward(*dec.bounds[r], x, X2, W2, G2)
+        assert np.array_equal(X, X2) and np.array_equal(W, W2) and np.array_equal(G, G2)
+    assert np.allclose(D[1:n + 1] * np.r_[0.0, X[1:n]] + E[1:n + 1] * X[1:n + 1] + F[1:n + 1] * np.r_[X[2:n + 1], 0.0], TI[1:n + 1])
