@@ -1602,21 +1602,21 @@ int mohid_adt_advect_batch(const int *handle, const int *nprop, double *const *p
         return 0;
     };
     // everything queued earlier on the compute stream (set_step precompute, ...) precedes the uploads
-    cudaEvent_t e0;
+    cudaEvent_t e0 = nullptr;
     if (int rc = next_event(&e0)) return rc;
     CU(h, cudaEventRecord(e0, h->stream));
     CU(h, cudaStreamWaitEvent(h->s_up, e0, 0));
     auto before = [&](const std::vector<int> &part) -> int {
         for (int n : part)
             if (int rc = upload_one(h, n, prop[n], reference_prop ? reference_prop[n] : nullptr, h->s_up)) return rc;
-        cudaEvent_t e;
+        cudaEvent_t e = nullptr;
         if (int rc = next_event(&e)) return rc;
         CU(h, cudaEventRecord(e, h->s_up));
         CU(h, cudaStreamWaitEvent(h->stream, e, 0));
         return 0;
     };
     auto after = [&](const std::vector<int> &part) -> int {
-        cudaEvent_t e;
+        cudaEvent_t e = nullptr;
         if (int rc = next_event(&e)) return rc;
         CU(h, cudaEventRecord(e, h->stream));
         CU(h, cudaStreamWaitEvent(h->s_down, e, 0));
