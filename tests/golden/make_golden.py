@@ -31,6 +31,11 @@ CASES = {
     "central_massconsnullgrad": (14, 11, 4, 1, [default_params(5, 4, 5, 4, bc=7)], 3),
     "implicit_xx": (14, 11, 4, 1, [dict(default_params(4, 4, 4, 4), ImpExp_AdvXX=1.0)], 2),
     "implicit_yy": (14, 11, 4, 1, [dict(default_params(1, 4, 1, 4), ImpExp_AdvYY=1.0)], 2),
+    "implicit_xx_2d_domain": (14, 11, 1, 2, [dict(default_params(4, 4, 4, 4, bc=4), ImpExp_AdvXX=1.0),
+                                               dict(default_params(4, 4, 4, 4, bc=1), ImpExp_AdvYY=1.0)], 2),
+    "cyclic_boundary": (14, 11, 4, 1, [default_params(4, 4, 4, 4, bc=8)], 3),
+    "leapfrog_explicit_v": (14, 11, 4, 1, [default_params(6, 4, 6, 4, impexp_advv=0.0, theta_difv=0.3, bc=2)], 3),
+    "tvd_pdm": (14, 11, 4, 2, [default_params(4, 5, 4, 5, bc=7), default_params(4, 5, 4, 5, decay_time=600.0, bc=5)], 3),
 }
 
 
@@ -43,7 +48,7 @@ def digest(arrays):
 
 def run_case(name):
     I, J, K, N, prm, steps = CASES[name]
-    case = make_case(I, J, K, nprop=N, stepped_bottom=True, seed=20260101)
+    case = make_case(I, J, K, nprop=N, stepped_bottom=K > 1, seed=20260101)
     o, g, s, props, refs = oracle_for(case)
     out = [p.copy() for p in props]
     for _ in range(steps):
