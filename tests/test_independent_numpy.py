@@ -1,6 +1,6 @@
-"""An independent, equation-level restatement of the default transport step in plain numpy (first-order upwind and
-P2_TVD with the SuperBee limiter, explicit horizontal terms, theta-weighted vertical diffusion, implicit vertical advection, dense column solve with
-numpy.linalg.solve) checked against the C++ oracle.
+"""An independent, equation-level restatement of the transport step in plain numpy (first-order upwind and P2_TVD with
+the five limiters, explicit horizontal terms, theta-weighted vertical diffusion, implicit or explicit vertical advection,
+the NullGradient open boundary, dense column solve with numpy.linalg.solve) checked against the C++ oracle.
 
 It shares no code and no structure with oracle/adv_diff_oracle.cpp: it is written from the discrete equations of
 SURVEY.md A.3 / A.5 (cell-wise assembly of one matrix per column instead of the reference's pass-by-pass scatter into
@@ -13,7 +13,7 @@ from mohid_b200.synthetic import make_case, default_params
 from helpers import oracle_for, water_mask, NULL_REAL
 
 
-def superbee_theta(q, Puu, Pu, Pd, du_uu, du_u, du_d, dt_over_vu, second_upwind_open):
+def superbee_theta(q, Puu, Pu, Pd, du_uu, du_u, du_d, dt_over_vu, second_upwind_open, limiter=4):
     """Weight of the downwind value in the face value, theta = psi(r) (1 - Cr) / 2 (MF:10785-10858): r compares the
     upwind gradient with the face gradient (distance-weighted), Cr = Q DT / V_upwind keeps the sign of Q (quirk A.4),
     faces whose second upwind cell is not an open point fall back to first order (Upwind2)."""
@@ -23,12 +23,25 @@ def superbee_theta(q, Puu, Pu, Pd, du_uu, du_u, du_d, dt_over_vu, second_upwind_
     if abs(dc) < 1e-16:
         dc = 1e-16 if dc >= 0 else -1e-16
     r = ((Pu - Puu) / (du_u + du_uu)) / dc
-    psi = max(0.0, min(2.0 * r, 1.0), min(r, 2.0))
     cr = q * dt_over_vu
+    if limiter == 1:                                   # MinMod (Roe 1986)
+        psi = max(0.0, min(1.0, r))
+    elif limiter == 2:                                 # van Leer (1974)
+        psi = 0.0 if r < 0 else 2.0 * r / (1.0 + r)
+    elif limiter == 3:                                 # MUSCL / monotonized central (van Leer 1977)
+        psi = max(0.0, min(2.0, 2.0 * r, 0.5 * (1.0 + r)))
+    elif limiter == 4:                                 # SuperBee (Roe 1986)
+        psi = max(0.0, min(2.0 * r, 1.0), min(r, 2.0))
+    else:                                              # PDM: third-order flux bounded by the universal limiter (MF:10842-10853)
+        a, b = 0.5 + (1.0 - 2.0 * abs(cr)) / 6.0, 0.5 - (1.0 - 2.0 * abs(cr)) / 6.0
+        if abs(cr) < 1e-16:
+            cr = 1e-16
+        psi = max(0.0, min(a + b * r, 2.0 / (1.0 - cr), 2.0 * r / cr))
     return 0.5 * psi * (1.0 - cr)
 
 
-def numpy_step(g, s, P, dt, theta, schmidt_h=1.0, coef_v=1.0, bg_v=1.0e-8, tvd=False):
+def numpy_step(g, s, P, dt, theta, schmidt_h=1.0, coef_v=1.0, bg_v=1.0e-8, tvd=False, limiter=4, advv_implicit=True,
+               null_gradient=False):
     """One step of one property; arrays are (K+2, J+2, ld) / (J+2, ld), index order [k, j, i]."""
     K, J, I = P.shape[0] - 2, P.shape[1] - 2, g["_I"]         # the i extent may be padded: the work size comes along
     Open, Water, Land = s["OpenPoints3D"], s["WaterPoints3D"], s["LandPoints3D"]
@@ -64,7 +77,7 @@ def numpy_step(g, s, P, dt, theta, schmidt_h=1.0, coef_v=1.0, bg_v=1.0e-8, tvd=F
                     uu, u, d = c[0], c[1], c[2]
                 else:
                     uu, u, d = c[3], c[2], c[1]
-                th = superbee_theta(q, P[k][uu], P[k][u], P[k][d], du[uu], du[u], du[d], dt / V[k][u], Open[k][uu] == 1)
+                th = superbee_theta(q, P[k][uu], P[k][u], P[k][d], du[uu], du[u], du[d], dt / V[k][u], Open[k][uu] == 1, limiter)
                 adv = q * ((1.0 - th) * P[k][u] + th * P[k][d])
         difflux = -dif * area / dz * (P[k, j, i] - P[k, jm, im])
         return adv, difflux
@@ -114,15 +127,70 @@ def numpy_step(g, s, P, dt, theta, schmidt_h=1.0, coef_v=1.0, bg_v=1.0e-8, tvd=F
                             uu = min(max(up + (up - dn), 0), K + 1)
                             dwz = s["DWZ"]
                             th = superbee_theta(q, P[uu, j, i], P[up, j, i], P[dn, j, i], dwz[uu, j, i], dwz[up, j, i],
-                                                dwz[dn, j, i], dt / V[up, j, i], Open[uu, j, i] == 1)
-                        A[r, up - 1] -= sign * q * dtv * (1.0 - th)
-                        A[r, dn - 1] -= sign * q * dtv * th
+                                                dwz[dn, j, i], dt / V[up, j, i], Open[uu, j, i] == 1, limiter)
+                        if advv_implicit:
+                            A[r, up - 1] -= sign * q * dtv * (1.0 - th)
+                            A[r, dn - 1] -= sign * q * dtv * th
+                        else:                                      # the same face value from the field at time n
+                            b[r] += sign * q * dtv * ((1.0 - th) * P[up, j, i] + th * P[dn, j, i])
+                if null_gradient and g["BoundaryPoints2D"][j, i] == 1 and is_open:
+                    A[r, :] = 0.0; A[r, r] = 1.0; b[r] = P[k, j, i]        # kept through the solve, replaced below
                 if Land[k, j, i] == 1:
                     A[r, :] = 0.0; A[r, r] = 1.0; b[r] = NULL_REAL
             A[n - 1, n - 1] = 1.0
             x = np.linalg.solve(A, b)
             out[1:K + 2, j, i] = x
+    if null_gradient:
+        # boundary cells take the mean of the new values across their compute faces (AD:1926-1987); a compute face never
+        # joins two boundary points, so the order does not matter
+        new = out.copy()
+        for j in range(1, J + 1):
+            for i in range(1, I + 1):
+                if g["BoundaryPoints2D"][j, i] != 1:
+                    continue
+                for k in range(abs(int(g["KFloorZ"][j, i])), K + 1):
+                    nb = [(CFU[k, j, i], out[k, j - 1, i]), (CFU[k, j + 1, i], out[k, j + 1, i]),
+                          (CFV[k, j, i], out[k, j, i - 1]), (CFV[k, j, i + 1], out[k, j, i + 1])]
+                    wsum = sum(1 for c, _ in nb if c == 1)
+                    if wsum > 0:
+                        new[k, j, i] = sum(v for c, v in nb if c == 1) / wsum
+        out = new
     return out
+
+
+@pytest.mark.parametrize("limiter", [1, 2, 3, 5])
+@pytest.mark.parametrize("advv", [1.0, 0.0])
+def test_oracle_matches_equation_level_numpy_limiters_and_explicit_vertical_advection(oracle_lib, limiter, advv):
+    """The other four limiters (MF:10823-10853) and the explicit form of the vertical advection (AD:3148-3207)."""
+    case = make_case(13, 11, 5, nprop=1, stepped_bottom=True)
+    o, g, s, props, refs = oracle_for(case)
+    g = dict(g); g["_I"] = case.I
+    prm = [default_params(4, limiter, 4, limiter, theta_difv=0.6, impexp_advv=advv)]
+    a = [props[0].copy()]
+    o.advect_batch(a, prm)
+    want = numpy_step(g, s, props[0], case.dt, 0.6, tvd=True, limiter=limiter, advv_implicit=advv == 1.0)
+    w = water_mask(s)
+    scale = np.abs(props[0][w]).max()
+    assert np.abs(a[0] - want)[w].max() <= 1e-11 * scale
+    assert np.array_equal(a[0][~w], want[~w])
+
+
+@pytest.mark.parametrize("tvd", [False, True])
+def test_oracle_matches_equation_level_numpy_null_gradient_boundary(oracle_lib, tvd):
+    """BoundaryCondition = NullGradient (AD:5369-5400 rows, AD:1926-1987 post pass)."""
+    case = make_case(13, 11, 5, nprop=1, stepped_bottom=True)
+    o, g, s, props, refs = oracle_for(case)
+    g = dict(g); g["_I"] = case.I
+    m = 4 if tvd else 1
+    prm = [default_params(m, 4, m, 4, bc=4)]
+    a = [props[0].copy()]
+    o.advect_batch(a, prm, refs)
+    want = numpy_step(g, s, props[0], case.dt, 1.0, tvd=tvd, null_gradient=True)
+    w = water_mask(s)
+    scale = np.abs(props[0][w]).max()
+    assert (g["BoundaryPoints2D"] == 1).sum() > 0 and not np.array_equal(want, numpy_step(g, s, props[0], case.dt, 1.0, tvd=tvd))
+    assert np.abs(a[0] - want)[w].max() <= 1e-11 * scale
+    assert np.array_equal(a[0][~w], want[~w])
 
 
 @pytest.mark.parametrize("theta", [1.0, 0.4])
