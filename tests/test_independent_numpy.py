@@ -1,6 +1,7 @@
 """An independent, equation-level restatement of the transport step in plain numpy (first-order upwind and P2_TVD with
 the five limiters, explicit horizontal terms, theta-weighted vertical diffusion, implicit or explicit vertical advection,
-the NullGradient open boundary, dense column solve with numpy.linalg.solve) checked against the C++ oracle.
+the NullGradient, MassConservation and ImposedValue open boundaries, dense column solve with numpy.linalg.solve)
+checked against the C++ oracle.
 
 It shares no code and no structure with oracle/adv_diff_oracle.cpp: it is written from the discrete equations of
 SURVEY.md A.3 / A.5 (cell-wise assembly of one matrix per column instead of the reference's pass-by-pass scatter into
@@ -41,7 +42,7 @@ def superbee_theta(q, Puu, Pu, Pd, du_uu, du_u, du_d, dt_over_vu, second_upwind_
 
 
 def numpy_step(g, s, P, dt, theta, schmidt_h=1.0, coef_v=1.0, bg_v=1.0e-8, tvd=False, limiter=4, advv_implicit=True,
-               null_gradient=False):
+               null_gradient=False, bc=0, ref=None, decay_time=0.0):
     """One step of one property; arrays are (K+2, J+2, ld) / (J+2, ld), index order [k, j, i]."""
     K, J, I = P.shape[0] - 2, P.shape[1] - 2, g["_I"]         # the i extent may be padded: the work size comes along
     Open, Water, Land = s["OpenPoints3D"], s["WaterPoints3D"], s["LandPoints3D"]
@@ -135,6 +136,27 @@ def numpy_step(g, s, P, dt, theta, schmidt_h=1.0, coef_v=1.0, bg_v=1.0e-8, tvd=F
                             b[r] += sign * q * dtv * ((1.0 - th) * P[up, j, i] + th * P[dn, j, i])
                 if null_gradient and g["BoundaryPoints2D"][j, i] == 1 and is_open:
                     A[r, :] = 0.0; A[r, r] = 1.0; b[r] = P[k, j, i]        # kept through the solve, replaced below
+                if bc in (1, 2) and g["BoundaryPoints2D"][j, i] == 1 and is_open:
+                    Bnd = g["BoundaryPoints2D"]
+                    tdec = 1.0 / (1.0 + decay_time / dt)                   # relaxation towards the reference field (AD:5418-5419)
+                    if bc == 2:
+                        # ImposedValue (AD:5440-5500): the cell takes the mean of its interior neighbours at time n, relaxed
+                        nb = [(j, i + 1), (j, i - 1), (j + 1, i), (j - 1, i)]
+                        inner = [P[k, jj, ii] for jj, ii in nb if Open[k, jj, ii] == 1 and Bnd[jj, ii] != 1]
+                        ext = ref[k, j, i] if not inner else (sum(inner) / len(inner)) * (1.0 - tdec) + ref[k, j, i] * tdec
+                        A[r, :] = 0.0; A[r, r] = 1.0; b[r] = ext
+                    else:
+                        # MassConservation (AD:5572-5672): the water the compute faces and the volume change do not account
+                        # for crosses the open boundary: leaving, it takes the cell's (new) value along; entering, it
+                        # brings the exterior value
+                        qb = (Qx[k, j, i] * (CFU[k, j, i] == 1) - Qx[k, j + 1, i] * (CFU[k, j + 1, i] == 1)
+                              + Qy[k, j, i] * (CFV[k, j, i] == 1) - Qy[k, j, i + 1] * (CFV[k, j, i + 1] == 1)
+                              + Qz[k, j, i] * (CFW[k, j, i] == 1) - Qz[k + 1, j, i] * (CFW[k + 1, j, i] == 1)
+                              - (V[k, j, i] - Vold[k, j, i]) / dt)
+                        if qb < 0:
+                            b[r] -= qb * dtv * (P[k, j, i] * (1.0 - tdec) + ref[k, j, i] * tdec)
+                        else:
+                            A[r, r] += qb * dtv
                 if Land[k, j, i] == 1:
                     A[r, :] = 0.0; A[r, r] = 1.0; b[r] = NULL_REAL
             A[n - 1, n - 1] = 1.0
@@ -189,6 +211,24 @@ def test_oracle_matches_equation_level_numpy_null_gradient_boundary(oracle_lib, 
     w = water_mask(s)
     scale = np.abs(props[0][w]).max()
     assert (g["BoundaryPoints2D"] == 1).sum() > 0 and not np.array_equal(want, numpy_step(g, s, props[0], case.dt, 1.0, tvd=tvd))
+    assert np.abs(a[0] - want)[w].max() <= 1e-11 * scale
+    assert np.array_equal(a[0][~w], want[~w])
+
+
+@pytest.mark.parametrize("decay", [0.0, 900.0])
+@pytest.mark.parametrize("bc", [1, 2])
+def test_oracle_matches_equation_level_numpy_flux_and_value_boundaries(oracle_lib, bc, decay):
+    """BoundaryCondition = MassConservation (1) and ImposedValue (2), with and without relaxation (DecayTime)."""
+    case = make_case(13, 11, 5, nprop=1, stepped_bottom=True)
+    o, g, s, props, refs = oracle_for(case)
+    g = dict(g); g["_I"] = case.I
+    prm = [default_params(4, 4, 4, 4, bc=bc, decay_time=decay)]
+    a = [props[0].copy()]
+    o.advect_batch(a, prm, refs)
+    want = numpy_step(g, s, props[0], case.dt, 1.0, tvd=True, bc=bc, ref=refs[0], decay_time=decay)
+    w = water_mask(s)
+    scale = np.abs(props[0][w]).max()
+    assert not np.array_equal(want, numpy_step(g, s, props[0], case.dt, 1.0, tvd=True))
     assert np.abs(a[0] - want)[w].max() <= 1e-11 * scale
     assert np.array_equal(a[0][~w], want[~w])
 
