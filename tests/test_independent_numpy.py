@@ -251,17 +251,22 @@ def test_oracle_matches_equation_level_numpy(oracle_lib, theta, tvd):
     assert np.array_equal(a[0][~w], want[~w])
 
 
-def numpy_step_2d_implicit_xx(g, s, P, dt, tvd):
-    """K = 1, ImpExp_AdvXX = 1 (AD:1758-1841): per row i one dense system over the cells j = 1 .. J.  Advection along j is
-    implicit (face value from the new field, weights from the old one), everything else explicit; the only layer is
-    the surface layer, whose row carries the water flux through its top face."""
+def numpy_step_2d_implicit(g, s, P, dt, tvd, direction="xx"):
+    """K = 1, ImpExp_AdvXX = 1 or ImpExp_AdvYY = 1 (AD:1758-1841): one dense system per line of the implicit direction.
+    Advection along the line is implicit (face value from the new field, weights from the old one), everything else
+    explicit; the only layer is the surface layer, whose row carries the water flux through its top face."""
     J, I = P.shape[1] - 2, g["_I"]
     k = 1
     Open, Land = s["OpenPoints3D"], s["LandPoints3D"]
-    CFU, CFV = s["ComputeFacesU3D"], s["ComputeFacesV3D"]
-    V, Vold = s["VolumeZ"], s["VolumeZOld"]
-    Qx, Qy, Qz = s["Wflux_X"], s["Wflux_Y"], s["Wflux_Z"]
-    DUX, DVY, DZX, DZY = g["DUX"], g["DVY"], g["DZX"], g["DZY"]
+    V, Vold, Qz = s["VolumeZ"], s["VolumeZOld"], s["Wflux_Z"]
+    xx = direction == "xx"
+    NL, NC = (J, I) if xx else (I, J)                           # cells along / across the lines
+    at = (lambda a, c: (a, c)) if xx else (lambda a, c: (c, a))  # (along, across) -> (j, i)
+    # along the line / across it: compute faces, face flows, metrics, face areas
+    CFL, QL, DUL, DZL, AL = ((s["ComputeFacesU3D"], s["Wflux_X"], g["DUX"], g["DZX"], s["AreaU"]) if xx else
+                             (s["ComputeFacesV3D"], s["Wflux_Y"], g["DVY"], g["DZY"], s["AreaV"]))
+    CFC, QC, DUC, DZC, AC = ((s["ComputeFacesV3D"], s["Wflux_Y"], g["DVY"], g["DZY"], s["AreaV"]) if xx else
+                             (s["ComputeFacesU3D"], s["Wflux_X"], g["DUX"], g["DZX"], s["AreaU"]))
     out = P.copy()
 
     def face_weights(q, cells, du):
@@ -270,56 +275,60 @@ def numpy_step_2d_implicit_xx(g, s, P, dt, tvd):
         th = superbee_theta(q, P[k][uu], P[k][u], P[k][d], du[uu], du[u], du[d], dt / V[k][u], Open[k][uu] == 1) if tvd else 0.0
         return ((u, 1.0 - th), (d, th))
 
-    def dif_coef(j, i, dj, di):
-        jm, im = j - dj, i - di
-        du, dz, area = (DUX, DZX, s["AreaU"]) if dj else (DVY, DZY, s["AreaV"])
-        nu = (s["Visc_H"][k, j, i] * du[jm, im] + s["Visc_H"][k, jm, im] * du[j, i]) / (du[j, i] + du[jm, im])
-        return nu * area[k, j, i] / dz[jm, im]
+    def dif_coef(hi, lo, du, dz, area):
+        nu = (s["Visc_H"][k][hi] * du[lo] + s["Visc_H"][k][lo] * du[hi]) / (du[hi] + du[lo])
+        return nu * area[k][hi] / dz[lo]
 
-    for i in range(1, I + 1):
-        A = np.eye(J + 2)
-        b = np.array([P[k, j, i] for j in range(J + 2)])
-        b[J + 1] = 0.0                                          # the halo cell behind the line: identity row, 0 (MF:3803)
-        for j in range(1, J + 1):
-            if Land[k, j, i] == 1:
-                b[j] = NULL_REAL
+    for c in range(1, NC + 1):
+        A = np.eye(NL + 2)
+        b = np.array([P[k][at(a, c)] for a in range(NL + 2)])
+        b[NL + 1] = 0.0                                         # the halo cell behind the line: identity row, 0 (MF:3803)
+        for a in range(1, NL + 1):
+            me = at(a, c)
+            if Land[k][me] == 1:
+                b[a] = NULL_REAL
                 continue
-            if Open[k, j, i] != 1:
+            if Open[k][me] != 1:
                 continue
-            dtv = dt / V[k, j, i]
-            b[j] = P[k, j, i] * Vold[k, j, i] / V[k, j, i]
-            A[j, j] += dtv * Qz[k + 1, j, i]
-            for jf, sign in ((j, +1.0), (j + 1, -1.0)):          # U faces: west (inflow positive) and east
-                if jf > J or CFU[k, jf, i] != 1:
+            dtv = dt / V[k][me]
+            b[a] = P[k][me] * Vold[k][me] / V[k][me]
+            A[a, a] += dtv * Qz[(k + 1,) + me]
+            for af, sign in ((a, +1.0), (a + 1, -1.0)):          # faces along the line: low (inflow positive) and high
+                hi, lo = at(af, c), at(af - 1, c)
+                if af > NL or CFL[k][hi] != 1:
                     continue
-                b[j] += sign * dtv * (-dif_coef(jf, i, 1, 0) * (P[k, jf, i] - P[k, jf - 1, i]))
-                if Open[k, jf - 1, i] == 1 and Open[k, jf, i] == 1:
-                    cells = [(max(jf - 2, 0), i), (jf - 1, i), (jf, i), (jf + 1, i)]
-                    for (jj, _), wgt in face_weights(Qx[k, jf, i], cells, DUX):
-                        A[j, jj] -= sign * dtv * Qx[k, jf, i] * wgt
-            for jf_i, sign in ((i, +1.0), (i + 1, -1.0)):        # V faces: explicit
-                if jf_i > I or CFV[k, j, jf_i] != 1:
+                b[a] += sign * dtv * (-dif_coef(hi, lo, DUL, DZL, AL) * (P[k][hi] - P[k][lo]))
+                if Open[k][lo] == 1 and Open[k][hi] == 1:
+                    cells = [at(max(af - 2, 0), c), lo, hi, at(af + 1, c)]
+                    pos = {cells[1]: af - 1, cells[2]: af}
+                    for cell, wgt in face_weights(QL[k][hi], cells, DUL):
+                        A[a, pos[cell]] -= sign * dtv * QL[k][hi] * wgt
+            for cf, sign in ((c, +1.0), (c + 1, -1.0)):          # faces across the line: explicit
+                hi, lo = at(a, cf), at(a, cf - 1)
+                if cf > NC or CFC[k][hi] != 1:
                     continue
-                b[j] += sign * dtv * (-dif_coef(j, jf_i, 0, 1) * (P[k, j, jf_i] - P[k, j, jf_i - 1]))
-                if Open[k, j, jf_i - 1] == 1 and Open[k, j, jf_i] == 1:
-                    cells = [(j, max(jf_i - 2, 0)), (j, jf_i - 1), (j, jf_i), (j, jf_i + 1)]
-                    q = Qy[k, j, jf_i]
-                    b[j] += sign * dtv * q * sum(wgt * P[k][c] for c, wgt in face_weights(q, cells, DVY))
+                b[a] += sign * dtv * (-dif_coef(hi, lo, DUC, DZC, AC) * (P[k][hi] - P[k][lo]))
+                if Open[k][lo] == 1 and Open[k][hi] == 1:
+                    cells = [at(a, max(cf - 2, 0)), lo, hi, at(a, cf + 1)]
+                    q = QC[k][hi]
+                    b[a] += sign * dtv * q * sum(wgt * P[k][cell] for cell, wgt in face_weights(q, cells, DUC))
         x = np.linalg.solve(A[1:, 1:], b[1:])
-        out[k, 1:J + 2, i] = x
+        for a in range(1, NL + 2):
+            out[(k,) + at(a, c)] = x[a - 1]
     return out
 
 
+@pytest.mark.parametrize("direction", ["xx", "yy"])
 @pytest.mark.parametrize("tvd", [False, True])
-def test_oracle_2d_implicit_line_solve_matches_equation_level_numpy(oracle_lib, tvd):
+def test_oracle_2d_implicit_line_solve_matches_equation_level_numpy(oracle_lib, tvd, direction):
     case = make_case(12, 14, 1, nprop=1)
     o, g, s, props, refs = oracle_for(case)
     g = dict(g); g["_I"] = case.I
     m = 4 if tvd else 1
-    prm = [dict(default_params(m, 4, m, 4), ImpExp_AdvXX=1.0)]
+    prm = [dict(default_params(m, 4, m, 4), **{"ImpExp_Adv" + direction.upper(): 1.0})]
     a = [props[0].copy()]
     o.advect_batch(a, prm)
-    want = numpy_step_2d_implicit_xx(g, s, props[0], case.dt, tvd)
+    want = numpy_step_2d_implicit(g, s, props[0], case.dt, tvd, direction)
     w = water_mask(s)
     scale = np.abs(props[0][w]).max()
     assert np.abs(a[0] - want)[w].max() <= 1e-11 * scale
