@@ -42,7 +42,7 @@ def superbee_theta(q, Puu, Pu, Pd, du_uu, du_u, du_d, dt_over_vu, second_upwind_
 
 
 def numpy_step(g, s, P, dt, theta, schmidt_h=1.0, coef_v=1.0, bg_v=1.0e-8, tvd=False, limiter=4, advv_implicit=True,
-               null_gradient=False, bc=0, ref=None, decay_time=0.0):
+               null_gradient=False, bc=0, ref=None, decay_time=0.0, vertical_only=False):
     """One step of one property; arrays are (K+2, J+2, ld) / (J+2, ld), index order [k, j, i]."""
     K, J, I = P.shape[0] - 2, P.shape[1] - 2, g["_I"]         # the i extent may be padded: the work size comes along
     Open, Water, Land = s["OpenPoints3D"], s["WaterPoints3D"], s["LandPoints3D"]
@@ -94,12 +94,12 @@ def numpy_step(g, s, P, dt, theta, schmidt_h=1.0, coef_v=1.0, bg_v=1.0e-8, tvd=F
                 r = k - 1
                 dtv = dt / V[k, j, i]
                 is_open = Open[k, j, i] == 1
-                b[r] = P[k, j, i] * (Vold[k, j, i] / V[k, j, i]) if is_open else P[k, j, i]
+                b[r] = P[k, j, i] * (Vold[k, j, i] / V[k, j, i]) if (is_open and not vertical_only) else P[k, j, i]
                 A[r, r] = 1.0
-                if is_open and k == K:
+                if is_open and k == K and not vertical_only:
                     A[r, r] += dtv * Qz[K + 1, j, i]
                 # horizontal: inflow through the low faces, outflow through the high faces of the cell
-                for dj, di in ((1, 0), (0, 1)):
+                for dj, di in (() if vertical_only else ((1, 0), (0, 1))):
                     a_lo, d_lo = hflux(k, j, i, dj, di)
                     a_hi, d_hi = hflux(k, j + dj, i + di, dj, di) if (j + dj <= J + 1 and i + di <= I + 1) else (0.0, 0.0)
                     if dj and j + 1 > J:
@@ -251,12 +251,21 @@ def test_oracle_matches_equation_level_numpy(oracle_lib, theta, tvd):
     assert np.array_equal(a[0][~w], want[~w])
 
 
-def numpy_step_2d_implicit(g, s, P, dt, tvd, direction="xx"):
-    """K = 1, ImpExp_AdvXX = 1 or ImpExp_AdvYY = 1 (AD:1758-1841): one dense system per line of the implicit direction.
-    Advection along the line is implicit (face value from the new field, weights from the old one), everything else
-    explicit; the only layer is the surface layer, whose row carries the water flux through its top face."""
+def numpy_lines_implicit(g, s, P, dt, tvd, direction="xx"):
+    """ImpExp_AdvXX = 1 or ImpExp_AdvYY = 1: one dense system per line of the implicit direction and level.  Advection along
+    the line is implicit (face value from the new field, weights from the old one), the other horizontal terms and the
+    volume change explicit; the surface layer's row carries the water flux through its top face.  On a 2-D domain
+    (K = 1, AD:1758-1841) this is the whole step, in 3-D (AD:4132-4265) the first half: numpy_step(vertical_only=True)
+    continues from its result."""
+    out = P.copy()
+    K = P.shape[0] - 2
+    for k in range(1, K + 1):
+        _lines_of_level(g, s, P, dt, tvd, direction, k, K, out)
+    return out
+
+
+def _lines_of_level(g, s, P, dt, tvd, direction, k, K, out):
     J, I = P.shape[1] - 2, g["_I"]
-    k = 1
     Open, Land = s["OpenPoints3D"], s["LandPoints3D"]
     V, Vold, Qz = s["VolumeZ"], s["VolumeZOld"], s["Wflux_Z"]
     xx = direction == "xx"
@@ -267,7 +276,6 @@ def numpy_step_2d_implicit(g, s, P, dt, tvd, direction="xx"):
                              (s["ComputeFacesV3D"], s["Wflux_Y"], g["DVY"], g["DZY"], s["AreaV"]))
     CFC, QC, DUC, DZC, AC = ((s["ComputeFacesV3D"], s["Wflux_Y"], g["DVY"], g["DZY"], s["AreaV"]) if xx else
                              (s["ComputeFacesU3D"], s["Wflux_X"], g["DUX"], g["DZX"], s["AreaU"]))
-    out = P.copy()
 
     def face_weights(q, cells, du):
         """(cell, weight) pairs of the face value of a face with flow q; cells = a-2, a-1 | a, a+1 around the face."""
@@ -285,14 +293,15 @@ def numpy_step_2d_implicit(g, s, P, dt, tvd, direction="xx"):
         b[NL + 1] = 0.0                                         # the halo cell behind the line: identity row, 0 (MF:3803)
         for a in range(1, NL + 1):
             me = at(a, c)
-            if Land[k][me] == 1:
+            if Land[k][me] == 1 and K == 1:                        # a 3-D step fills the land cells in its vertical half
                 b[a] = NULL_REAL
                 continue
             if Open[k][me] != 1:
                 continue
             dtv = dt / V[k][me]
             b[a] = P[k][me] * Vold[k][me] / V[k][me]
-            A[a, a] += dtv * Qz[(k + 1,) + me]
+            if k == K:
+                A[a, a] += dtv * Qz[(k + 1,) + me]
             for af, sign in ((a, +1.0), (a + 1, -1.0)):          # faces along the line: low (inflow positive) and high
                 hi, lo = at(af, c), at(af - 1, c)
                 if af > NL or CFL[k][hi] != 1:
@@ -315,7 +324,6 @@ def numpy_step_2d_implicit(g, s, P, dt, tvd, direction="xx"):
         x = np.linalg.solve(A[1:, 1:], b[1:])
         for a in range(1, NL + 2):
             out[(k,) + at(a, c)] = x[a - 1]
-    return out
 
 
 @pytest.mark.parametrize("direction", ["xx", "yy"])
@@ -328,8 +336,28 @@ def test_oracle_2d_implicit_line_solve_matches_equation_level_numpy(oracle_lib, 
     prm = [dict(default_params(m, 4, m, 4), **{"ImpExp_Adv" + direction.upper(): 1.0})]
     a = [props[0].copy()]
     o.advect_batch(a, prm)
-    want = numpy_step_2d_implicit(g, s, props[0], case.dt, tvd, direction)
+    want = numpy_lines_implicit(g, s, props[0], case.dt, tvd, direction)
     w = water_mask(s)
     scale = np.abs(props[0][w]).max()
     assert np.abs(a[0] - want)[w].max() <= 1e-11 * scale
     assert np.array_equal((a[0] == NULL_REAL)[1], (want == NULL_REAL)[1])
+
+
+@pytest.mark.parametrize("direction", ["xx", "yy"])
+@pytest.mark.parametrize("tvd", [False, True])
+def test_oracle_split_implicit_step_matches_equation_level_numpy(oracle_lib, tvd, direction):
+    """3-D, one horizontal direction implicit (AD:4132-4265): line systems per level, then the vertical half restarted from
+    their result (D = 0, E = 1, F = 0, TI = PROP; vertical weights from the intermediate field)."""
+    case = make_case(12, 13, 4, nprop=1, stepped_bottom=True)
+    o, g, s, props, refs = oracle_for(case)
+    g = dict(g); g["_I"] = case.I
+    m = 4 if tvd else 1
+    prm = [dict(default_params(m, 4, m, 4, theta_difv=0.7), **{"ImpExp_Adv" + direction.upper(): 1.0})]
+    a = [props[0].copy()]
+    o.advect_batch(a, prm)
+    mid = numpy_lines_implicit(g, s, props[0], case.dt, tvd, direction)
+    want = numpy_step(g, s, mid, case.dt, 0.7, tvd=tvd, vertical_only=True)
+    w = water_mask(s)
+    scale = np.abs(props[0][w]).max()
+    assert np.abs(a[0] - want)[w].max() <= 1e-11 * scale
+    assert np.array_equal(a[0] == NULL_REAL, want == NULL_REAL)
