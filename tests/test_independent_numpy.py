@@ -14,12 +14,14 @@ from mohid_b200.synthetic import make_case, default_params
 from helpers import oracle_for, water_mask, NULL_REAL
 
 
-def superbee_theta(q, Puu, Pu, Pd, du_uu, du_u, du_d, dt_over_vu, second_upwind_open, limiter=4):
+def superbee_theta(q, Puu, Pu, Pd, du_uu, du_u, du_d, dt_over_vu, second_upwind_open, limiter=4, method=4):
     """Weight of the downwind value in the face value, theta = psi(r) (1 - Cr) / 2 (MF:10785-10858): r compares the
     upwind gradient with the face gradient (distance-weighted), Cr = Q DT / V_upwind keeps the sign of Q (quirk A.4),
     faces whose second upwind cell is not an open point fall back to first order (Upwind2)."""
     if not second_upwind_open:
         return 0.0
+    if method in (5, 6):                               # central differences / leap-frog: linear interpolation to the face (MF:10773-10783)
+        return du_u / (du_u + du_d)
     dc = (Pd - Pu) / (du_u + du_d)
     if abs(dc) < 1e-16:
         dc = 1e-16 if dc >= 0 else -1e-16
@@ -42,7 +44,7 @@ def superbee_theta(q, Puu, Pu, Pd, du_uu, du_u, du_d, dt_over_vu, second_upwind_
 
 
 def numpy_step(g, s, P, dt, theta, schmidt_h=1.0, coef_v=1.0, bg_v=1.0e-8, tvd=False, limiter=4, advv_implicit=True,
-               null_gradient=False, bc=0, ref=None, decay_time=0.0, vertical_only=False):
+               null_gradient=False, bc=0, ref=None, decay_time=0.0, vertical_only=False, method=4):
     """One step of one property; arrays are (K+2, J+2, ld) / (J+2, ld), index order [k, j, i]."""
     K, J, I = P.shape[0] - 2, P.shape[1] - 2, g["_I"]         # the i extent may be padded: the work size comes along
     Open, Water, Land = s["OpenPoints3D"], s["WaterPoints3D"], s["LandPoints3D"]
@@ -78,7 +80,7 @@ def numpy_step(g, s, P, dt, theta, schmidt_h=1.0, coef_v=1.0, bg_v=1.0e-8, tvd=F
                     uu, u, d = c[0], c[1], c[2]
                 else:
                     uu, u, d = c[3], c[2], c[1]
-                th = superbee_theta(q, P[k][uu], P[k][u], P[k][d], du[uu], du[u], du[d], dt / V[k][u], Open[k][uu] == 1, limiter)
+                th = superbee_theta(q, P[k][uu], P[k][u], P[k][d], du[uu], du[u], du[d], dt / V[k][u], Open[k][uu] == 1, limiter, method)
                 adv = q * ((1.0 - th) * P[k][u] + th * P[k][d])
         difflux = -dif * area / dz * (P[k, j, i] - P[k, jm, im])
         return adv, difflux
@@ -128,7 +130,7 @@ def numpy_step(g, s, P, dt, theta, schmidt_h=1.0, coef_v=1.0, bg_v=1.0e-8, tvd=F
                             uu = min(max(up + (up - dn), 0), K + 1)
                             dwz = s["DWZ"]
                             th = superbee_theta(q, P[uu, j, i], P[up, j, i], P[dn, j, i], dwz[uu, j, i], dwz[up, j, i],
-                                                dwz[dn, j, i], dt / V[up, j, i], Open[uu, j, i] == 1, limiter)
+                                                dwz[dn, j, i], dt / V[up, j, i], Open[uu, j, i] == 1, limiter, method)
                         if advv_implicit:
                             A[r, up - 1] -= sign * q * dtv * (1.0 - th)
                             A[r, dn - 1] -= sign * q * dtv * th
@@ -361,3 +363,20 @@ def test_oracle_split_implicit_step_matches_equation_level_numpy(oracle_lib, tvd
     scale = np.abs(props[0][w]).max()
     assert np.abs(a[0] - want)[w].max() <= 1e-11 * scale
     assert np.array_equal(a[0] == NULL_REAL, want == NULL_REAL)
+
+
+@pytest.mark.parametrize("advv", [1.0, 0.0])
+def test_oracle_matches_equation_level_numpy_central_differences(oracle_lib, advv):
+    """CentralDif (MF:10773-10783): the face value is the distance-weighted mean of the two cells, first-order upwind
+    next to a closed cell (Upwind2); horizontally explicit, vertically implicit or explicit."""
+    case = make_case(13, 11, 5, nprop=1, stepped_bottom=True)
+    o, g, s, props, refs = oracle_for(case)
+    g = dict(g); g["_I"] = case.I
+    prm = [default_params(5, 4, 5, 4, theta_difv=0.5, impexp_advv=advv)]
+    a = [props[0].copy()]
+    o.advect_batch(a, prm)
+    want = numpy_step(g, s, props[0], case.dt, 0.5, tvd=True, method=5, advv_implicit=advv == 1.0)
+    w = water_mask(s)
+    scale = np.abs(props[0][w]).max()
+    assert np.abs(a[0] - want)[w].max() <= 1e-11 * scale
+    assert np.array_equal(a[0][~w], want[~w])
