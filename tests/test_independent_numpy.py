@@ -1,4 +1,4 @@
-"""An independent, equation-level restatement of the transport step in plain numpy (first-order upwind and P2_TVD with
+"""An independent, equation-level restatement of the transport step in plain numpy (all six advection methods, P2_TVD with
 the five limiters, explicit horizontal terms, theta-weighted vertical diffusion, implicit or explicit vertical advection,
 the NullGradient, MassConservation and ImposedValue open boundaries, dense column solve with numpy.linalg.solve)
 checked against the C++ oracle.
@@ -43,10 +43,25 @@ def superbee_theta(q, Puu, Pu, Pd, du_uu, du_u, du_d, dt_over_vu, second_upwind_
     return 0.5 * psi * (1.0 - cr)
 
 
+def three_point_value(method, q, Puu, Pu, Pd, Vuu, Vu, Vd, dt, second_upwind_open, vrelmax=1.5):
+    """Explicit face value of the upwind-biased three-point schemes: method 2 the QUICK weights -1/8, 6/8, 3/8
+    (MF:11060-11083), method 3 QUICKEST with the Courant number of the upwind cell (MF:11085-11122).  First-order upwind next
+    to a closed cell (Upwind2) and where the three volumes differ by more than VolumeRelMax (MF:10746-10768)."""
+    if not second_upwind_open or max(Vuu, Vu, Vd) / min(Vuu, Vu, Vd) > vrelmax:
+        return Pu
+    if method == 2:
+        return -0.125 * Puu + 0.75 * Pu + 0.375 * Pd
+    cr = q * dt / Vu
+    c = (1.0 - 2.0 * abs(cr)) / 6.0
+    a, b, d = 0.5 + c, 0.5 - c, (1.0 - abs(cr)) / 2.0
+    return -d * b * Puu + (1.0 + d * (b - a)) * Pu + d * a * Pd
+
+
 def numpy_step(g, s, P, dt, theta, schmidt_h=1.0, coef_v=1.0, bg_v=1.0e-8, tvd=False, limiter=4, advv_implicit=True,
-               null_gradient=False, bc=0, ref=None, decay_time=0.0, vertical_only=False, method=4):
+               null_gradient=False, bc=0, ref=None, decay_time=0.0, vertical_only=False, method=4, method_v=None):
     """One step of one property; arrays are (K+2, J+2, ld) / (J+2, ld), index order [k, j, i]."""
     K, J, I = P.shape[0] - 2, P.shape[1] - 2, g["_I"]         # the i extent may be padded: the work size comes along
+    method_v = method if method_v is None else method_v
     Open, Water, Land = s["OpenPoints3D"], s["WaterPoints3D"], s["LandPoints3D"]
     CFU, CFV, CFW = s["ComputeFacesU3D"], s["ComputeFacesV3D"], s["ComputeFacesW3D"]
     V, Vold = s["VolumeZ"], s["VolumeZOld"]
@@ -80,8 +95,11 @@ def numpy_step(g, s, P, dt, theta, schmidt_h=1.0, coef_v=1.0, bg_v=1.0e-8, tvd=F
                     uu, u, d = c[0], c[1], c[2]
                 else:
                     uu, u, d = c[3], c[2], c[1]
-                th = superbee_theta(q, P[k][uu], P[k][u], P[k][d], du[uu], du[u], du[d], dt / V[k][u], Open[k][uu] == 1, limiter, method)
-                adv = q * ((1.0 - th) * P[k][u] + th * P[k][d])
+                if method in (2, 3):
+                    adv = q * three_point_value(method, q, P[k][uu], P[k][u], P[k][d], V[k][uu], V[k][u], V[k][d], dt, Open[k][uu] == 1)
+                else:
+                    th = superbee_theta(q, P[k][uu], P[k][u], P[k][d], du[uu], du[u], du[d], dt / V[k][u], Open[k][uu] == 1, limiter, method)
+                    adv = q * ((1.0 - th) * P[k][u] + th * P[k][d])
         difflux = -dif * area / dz * (P[k, j, i] - P[k, jm, im])
         return adv, difflux
 
@@ -126,12 +144,16 @@ def numpy_step(g, s, P, dt, theta, schmidt_h=1.0, coef_v=1.0, bg_v=1.0e-8, tvd=F
                         q = Qz[kf, j, i]
                         up, dn = (lo, hi) if q > 0 else (hi, lo)   # implicit: flux = q ((1-th) P_up + th P_dn)^{n+1}
                         th = 0.0
-                        if tvd:
-                            uu = min(max(up + (up - dn), 0), K + 1)
+                        uu = min(max(up + (up - dn), 0), K + 1)
+                        if tvd and method_v not in (1, 2, 3):
                             dwz = s["DWZ"]
                             th = superbee_theta(q, P[uu, j, i], P[up, j, i], P[dn, j, i], dwz[uu, j, i], dwz[up, j, i],
-                                                dwz[dn, j, i], dt / V[up, j, i], Open[uu, j, i] == 1, limiter, method)
-                        if advv_implicit:
+                                                dwz[dn, j, i], dt / V[up, j, i], Open[uu, j, i] == 1, limiter, method_v)
+                        if tvd and method_v in (2, 3):             # explicit only (AD:1229-1237 stops the implicit use)
+                            assert not advv_implicit
+                            b[r] += sign * q * dtv * three_point_value(method_v, q, P[uu, j, i], P[up, j, i], P[dn, j, i], V[uu, j, i],
+                                                                       V[up, j, i], V[dn, j, i], dt, Open[uu, j, i] == 1)
+                        elif advv_implicit:
                             A[r, up - 1] -= sign * q * dtv * (1.0 - th)
                             A[r, dn - 1] -= sign * q * dtv * th
                         else:                                      # the same face value from the field at time n
@@ -378,5 +400,24 @@ def test_oracle_matches_equation_level_numpy_central_differences(oracle_lib, adv
     want = numpy_step(g, s, props[0], case.dt, 0.5, tvd=True, method=5, advv_implicit=advv == 1.0)
     w = water_mask(s)
     scale = np.abs(props[0][w]).max()
+    assert np.abs(a[0] - want)[w].max() <= 1e-11 * scale
+    assert np.array_equal(a[0][~w], want[~w])
+
+
+@pytest.mark.parametrize("method,method_v,advv", [(2, 2, 0.0), (3, 3, 0.0), (2, 1, 1.0), (3, 1, 1.0)])
+def test_oracle_matches_equation_level_numpy_three_point_upwind(oracle_lib, method, method_v, advv):
+    """UpwindOrder2 (QUICK weights) and UpwindOrder3 (QUICKEST): explicit three-point face values with the VolumeRelMax
+    and near-boundary fall-backs to first order; vertically the same explicitly, or first-order upwind implicitly."""
+    case = make_case(13, 11, 5, nprop=1, stepped_bottom=True)
+    o, g, s, props, refs = oracle_for(case)
+    g = dict(g); g["_I"] = case.I
+    prm = [default_params(method, 4, method_v, 4, theta_difv=0.5, impexp_advv=advv)]
+    a = [props[0].copy()]
+    o.advect_batch(a, prm)
+    want = numpy_step(g, s, props[0], case.dt, 0.5, tvd=True, method=method, method_v=method_v, advv_implicit=advv == 1.0)
+    first = numpy_step(g, s, props[0], case.dt, 0.5, tvd=False, advv_implicit=advv == 1.0)
+    w = water_mask(s)
+    scale = np.abs(props[0][w]).max()
+    assert np.abs(want - first)[w].max() > 1e-6 * scale             # the higher order really acted
     assert np.abs(a[0] - want)[w].max() <= 1e-11 * scale
     assert np.array_equal(a[0][~w], want[~w])
