@@ -387,17 +387,18 @@ def test_oracle_split_implicit_step_matches_equation_level_numpy(oracle_lib, tvd
     assert np.array_equal(a[0] == NULL_REAL, want == NULL_REAL)
 
 
+@pytest.mark.parametrize("method", [5, 6])
 @pytest.mark.parametrize("advv", [1.0, 0.0])
-def test_oracle_matches_equation_level_numpy_central_differences(oracle_lib, advv):
-    """CentralDif (MF:10773-10783): the face value is the distance-weighted mean of the two cells, first-order upwind
+def test_oracle_matches_equation_level_numpy_central_differences(oracle_lib, advv, method):
+    """CentralDif and LeapFrog (the same weights, MF:10773-10783): the face value is the distance-weighted mean of the two cells, first-order upwind
     next to a closed cell (Upwind2); horizontally explicit, vertically implicit or explicit."""
     case = make_case(13, 11, 5, nprop=1, stepped_bottom=True)
     o, g, s, props, refs = oracle_for(case)
     g = dict(g); g["_I"] = case.I
-    prm = [default_params(5, 4, 5, 4, theta_difv=0.5, impexp_advv=advv)]
+    prm = [default_params(method, 4, method, 4, theta_difv=0.5, impexp_advv=advv)]
     a = [props[0].copy()]
     o.advect_batch(a, prm)
-    want = numpy_step(g, s, props[0], case.dt, 0.5, tvd=True, method=5, advv_implicit=advv == 1.0)
+    want = numpy_step(g, s, props[0], case.dt, 0.5, tvd=True, method=method, advv_implicit=advv == 1.0)
     w = water_mask(s)
     scale = np.abs(props[0][w]).max()
     assert np.abs(a[0] - want)[w].max() <= 1e-11 * scale
