@@ -160,7 +160,7 @@ def numpy_step(g, s, P, dt, theta, schmidt_h=1.0, coef_v=1.0, bg_v=1.0e-8, tvd=F
                             b[r] += sign * q * dtv * ((1.0 - th) * P[up, j, i] + th * P[dn, j, i])
                 if null_gradient and g["BoundaryPoints2D"][j, i] == 1 and is_open:
                     A[r, :] = 0.0; A[r, r] = 1.0; b[r] = P[k, j, i]        # kept through the solve, replaced below
-                if bc in (1, 2) and g["BoundaryPoints2D"][j, i] == 1 and is_open:
+                if bc in (1, 2, 7) and g["BoundaryPoints2D"][j, i] == 1 and is_open:
                     Bnd = g["BoundaryPoints2D"]
                     tdec = 1.0 / (1.0 + decay_time / dt)                   # relaxation towards the reference field (AD:5418-5419)
                     if bc == 2:
@@ -177,8 +177,15 @@ def numpy_step(g, s, P, dt, theta, schmidt_h=1.0, coef_v=1.0, bg_v=1.0e-8, tvd=F
                               + Qy[k, j, i] * (CFV[k, j, i] == 1) - Qy[k, j, i + 1] * (CFV[k, j, i + 1] == 1)
                               + Qz[k, j, i] * (CFW[k, j, i] == 1) - Qz[k + 1, j, i] * (CFW[k + 1, j, i] == 1)
                               - (V[k, j, i] - Vold[k, j, i]) / dt)
-                        if qb < 0:
+                        if qb < 0 and bc == 1:
                             b[r] -= qb * dtv * (P[k, j, i] * (1.0 - tdec) + ref[k, j, i] * tdec)
+                        elif qb < 0:
+                            # MassConservNullGrad (AD:5610-5640): an inflow cell takes the mean of the old field across its
+                            # compute faces instead
+                            nb = [(CFV[k, j, i + 1], P[k, j, i + 1]), (CFV[k, j, i], P[k, j, i - 1]),
+                                  (CFU[k, j + 1, i], P[k, j + 1, i]), (CFU[k, j, i], P[k, j - 1, i])]
+                            vals = [v for cf, v in nb if cf == 1]
+                            A[r, :] = 0.0; A[r, r] = 1.0; b[r] = sum(vals) / len(vals) if vals else P[k, j, i]
                         else:
                             A[r, r] += qb * dtv
                 if Land[k, j, i] == 1:
@@ -240,9 +247,10 @@ def test_oracle_matches_equation_level_numpy_null_gradient_boundary(oracle_lib, 
 
 
 @pytest.mark.parametrize("decay", [0.0, 900.0])
-@pytest.mark.parametrize("bc", [1, 2])
+@pytest.mark.parametrize("bc", [1, 2, 7])
 def test_oracle_matches_equation_level_numpy_flux_and_value_boundaries(oracle_lib, bc, decay):
-    """BoundaryCondition = MassConservation (1) and ImposedValue (2), with and without relaxation (DecayTime)."""
+    """BoundaryCondition = MassConservation (1), ImposedValue (2) and MassConservNullGrad (7), with and without relaxation
+    (DecayTime)."""
     case = make_case(13, 11, 5, nprop=1, stepped_bottom=True)
     o, g, s, props, refs = oracle_for(case)
     g = dict(g); g["_I"] = case.I
