@@ -58,7 +58,8 @@ def three_point_value(method, q, Puu, Pu, Pd, Vuu, Vu, Vd, dt, second_upwind_ope
 
 
 def numpy_step(g, s, P, dt, theta, schmidt_h=1.0, coef_v=1.0, bg_v=1.0e-8, tvd=False, limiter=4, advv_implicit=True,
-               null_gradient=False, bc=0, ref=None, decay_time=0.0, vertical_only=False, method=4, method_v=None):
+               null_gradient=False, bc=0, ref=None, decay_time=0.0, vertical_only=False, method=4, method_v=None,
+               cyclic=False):
     """One step of one property; arrays are (K+2, J+2, ld) / (J+2, ld), index order [k, j, i]."""
     K, J, I = P.shape[0] - 2, P.shape[1] - 2, g["_I"]         # the i extent may be padded: the work size comes along
     method_v = method if method_v is None else method_v
@@ -158,7 +159,7 @@ def numpy_step(g, s, P, dt, theta, schmidt_h=1.0, coef_v=1.0, bg_v=1.0e-8, tvd=F
                             A[r, dn - 1] -= sign * q * dtv * th
                         else:                                      # the same face value from the field at time n
                             b[r] += sign * q * dtv * ((1.0 - th) * P[up, j, i] + th * P[dn, j, i])
-                if null_gradient and g["BoundaryPoints2D"][j, i] == 1 and is_open:
+                if (null_gradient or cyclic) and g["BoundaryPoints2D"][j, i] == 1 and is_open:
                     A[r, :] = 0.0; A[r, r] = 1.0; b[r] = P[k, j, i]        # kept through the solve, replaced below
                 if bc in (1, 2, 7) and g["BoundaryPoints2D"][j, i] == 1 and is_open:
                     Bnd = g["BoundaryPoints2D"]
@@ -208,6 +209,22 @@ def numpy_step(g, s, P, dt, theta, schmidt_h=1.0, coef_v=1.0, bg_v=1.0e-8, tvd=F
                     if wsum > 0:
                         new[k, j, i] = sum(v for c, v in nb if c == 1) / wsum
         out = new
+    if cyclic:
+        # Prop_CyclicBoundary (AD:2121-2224): boundary cells <- reference field, then the opposite edges are joined: each
+        # boundary column / row takes the values next to the opposite one, from that column's bottom layer up
+        Bnd, kf = g["BoundaryPoints2D"], g["KFloorZ"]
+        for j in range(1, J + 1):
+            for i in range(1, I + 1):
+                if Bnd[j, i] == 1:
+                    out[1:K + 1, j, i] = ref[1:K + 1, j, i]
+        for i in range(2, I):
+            if Bnd[1, i] == 1 and Bnd[J, i] == 1:
+                out[kf[J - 1, i]:K + 1, 1, i] = out[kf[J - 1, i]:K + 1, J - 1, i]
+                out[kf[2, i]:K + 1, J, i] = out[kf[2, i]:K + 1, 2, i]
+        for j in range(2, J):
+            if Bnd[j, 1] == 1 and Bnd[j, I] == 1:
+                out[kf[j, I - 1]:K + 1, j, 1] = out[kf[j, I - 1]:K + 1, j, I - 1]
+                out[kf[j, 2]:K + 1, j, I] = out[kf[j, 2]:K + 1, j, 2]
     return out
 
 
@@ -428,5 +445,19 @@ def test_oracle_matches_equation_level_numpy_three_point_upwind(oracle_lib, meth
     w = water_mask(s)
     scale = np.abs(props[0][w]).max()
     assert np.abs(want - first)[w].max() > 1e-6 * scale             # the higher order really acted
+    assert np.abs(a[0] - want)[w].max() <= 1e-11 * scale
+    assert np.array_equal(a[0][~w], want[~w])
+
+
+def test_oracle_matches_equation_level_numpy_cyclic_boundary(oracle_lib):
+    case = make_case(13, 11, 5, nprop=1, stepped_bottom=True)
+    o, g, s, props, refs = oracle_for(case)
+    g = dict(g); g["_I"] = case.I
+    a = [props[0].copy()]
+    o.advect_batch(a, [default_params(4, 4, 4, 4, bc=8)], refs)
+    want = numpy_step(g, s, props[0], case.dt, 1.0, tvd=True, cyclic=True, ref=refs[0])
+    w = water_mask(s)
+    scale = np.abs(props[0][w]).max()
+    assert not np.array_equal(want, numpy_step(g, s, props[0], case.dt, 1.0, tvd=True, null_gradient=True))
     assert np.abs(a[0] - want)[w].max() <= 1e-11 * scale
     assert np.array_equal(a[0][~w], want[~w])
